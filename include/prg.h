@@ -1,0 +1,151 @@
+/* libprg.so -- C ABI of the B200-native PointRegGPT data-generation hot path.
+ *
+ * The reference (Chen-Suyi/PointRegGPT) has no FFI: its boundary for this path
+ * is the Python API of
+ *   SDD = denoising_diffusion_pytorch/successive_ddnm_diffusion.py
+ *   DC  = depth_correction_pytorch/depth_correction.py
+ * Every entry point below cites the reference function it replaces; the Python
+ * package `pointreggpt_b200` binds them with ctypes under the reference's own
+ * names and signatures.
+ *
+ * Conventions
+ *  - plain C, raw DEVICE pointers unless a parameter says "host", explicit
+ *    stream (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  - the caller owns every input/output buffer; the library owns only the
+ *    opaque network handles (packed weights, workspace, tensor maps);
+ *  - return 0 on success, <0 on error; prg_last_error() (thread-local) has the
+ *    message; no exceptions cross the boundary, no hidden host syncs on the
+ *    data path (create/destroy do synchronise);
+ *  - sm_100a only.  There is no CPU fallback: without a B200 every compute
+ *    entry returns PRG_ERR_CUDA.
+ */
+#ifndef PRG_H_
+#define PRG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRG_ABI_VERSION 1
+
+#define PRG_OK 0
+#define PRG_ERR_ARG (-1)
+#define PRG_ERR_CUDA (-2)
+#define PRG_ERR_BLOB (-3)
+#define PRG_ERR_STATE (-4)
+
+typedef void* prg_stream_t; /* cudaStream_t */
+
+const char* prg_last_error(void);
+int prg_abi_version(void);
+/* Number of kernels this library has launched in this process (all streams).
+ * bench.py reports the delta over the timed region as "gpu_launches". */
+uint64_t prg_launch_count(void);
+
+/* ------------------------------------------------------------------ geometry
+ * HBM-bound kernels; results are bit-exact against the reference. */
+
+/* reproject_tensor (SDD:268-286) = depth2pc_tensor -> R p + t -> pc2depth_tensor.
+ * depth (B,H,W) f32 metres; K (B,3,3); pose (B,4,4); valid iff clip_lo<d<clip_hi.
+ * depth_out (B,H,W) f32 (0 where empty), mask_out (B,H,W) u8 {0,1}. */
+int prg_reproject_f32(const float* depth, const float* K, const float* pose,
+                      float clip_lo, float clip_hi, float* depth_out, uint8_t* mask_out,
+                      int B, int H, int W, prg_stream_t stream);
+
+/* pc2depth_tensor (SDD:212-265) for a ragged batch: pc (sumN,3) f32, valid
+ * (sumN) u8 or NULL, offsets (B+1) i64 CSR row starts (device), K (B,3,3).
+ * pose (B,4,4) or NULL: optional rigid transform applied first (replaces the
+ * host-side `pc @ R.T + t` of Generator.generate, SDD:2533-2535). */
+int prg_pc2depth_f32(const float* pc, const uint8_t* valid, const int64_t* offsets,
+                     int64_t total_points, const float* K, const float* pose,
+                     float* depth_out, uint8_t* mask_out, int B, int H, int W,
+                     prg_stream_t stream);
+
+/* depth2pc_tensor (SDD:176-209).  use_clip=0 <=> clip=None.  invalid = the
+ * value written for invalid pixels (NaN by default in the reference).
+ * pc (B,H*W,3) f32, valid (B,H*W) u8. */
+int prg_depth2pc_f32(const float* depth, const float* K, float clip_lo, float clip_hi,
+                     int use_clip, float invalid, float* pc, uint8_t* valid,
+                     int B, int H, int W, prg_stream_t stream);
+
+/* point_cloud (SDD:122-143) applied to depth01*scale, then optionally the
+ * back-transform (pc - t) @ R of SDD:2627-2628 (pose NULL = skip).  Valid
+ * pixels are compacted in row-major order.  pc_out: B slabs of H*W*3 f64,
+ * counts (B) i64 = points written per slab.  scratch: >= B*(ceil(H*W/1024)+1)
+ * i64 of device memory. */
+int prg_depth2pc_compact_f64(const float* depth01, const float* K, const float* pose,
+                             float scale, float clip_lo, float clip_hi, double* pc_out,
+                             int64_t* counts, int64_t* scratch, int B, int H, int W,
+                             prg_stream_t stream);
+
+/* ------------------------------------------------------------------ networks
+ * tcgen05 tensor-core kernels.  A handle owns packed weights (fp16 K-major
+ * tap-major conv matrices, weight standardisation folded in at pack time),
+ * the activation workspace for up to max_batch images of size x size, and
+ * the TMA descriptors of every layer.
+ *
+ * The packed blob is produced by pointreggpt_b200.packing.pack_unet /
+ * pack_maskunet from a reference state-dict (280 / 234 entries; SDD:802-918,
+ * DC:807-869).  It is a host buffer; create copies it to the device. */
+typedef struct prg_net prg_net;
+
+#define PRG_NET_UNET 1      /* Unet, SDD:802-964 (time + intrinsics conditioning) */
+#define PRG_NET_MASKUNET 2  /* MaskUnet, DC:807-906 (DepthAugment stem, sigmoid tail) */
+
+int prg_net_create(prg_net** out, int kind, const void* blob_host, size_t nbytes,
+                   int max_batch, int size, int device);
+void prg_net_destroy(prg_net* net);
+/* Bytes of device memory held by the handle (weights + workspace). */
+size_t prg_net_device_bytes(const prg_net* net);
+
+/* Unet.forward(x, time, param_cond) (SDD:920-964).  x (B,1,S,S) f32, time (B)
+ * i64, param_cond (B,4) f32 -> out (B,1,S,S) f32. */
+int prg_unet_forward(prg_net* net, const float* x, const int64_t* time,
+                     const float* param_cond, float* out, int B, prg_stream_t stream);
+
+/* MaskUnet.forward(x) (DC:871-906) plus the caller's `> thresh` (SDD:2565,
+ * 2580).  depth01 (B,1,S,S) f32 -> prob (B,1,S,S) f32 and/or keep (B,1,S,S) u8
+ * (either may be NULL). */
+int prg_maskunet_forward(prg_net* net, const float* depth01, float* prob, uint8_t* keep,
+                         float thresh, int B, prg_stream_t stream);
+
+/* Schedule tables of GaussianDiffusion (SDD:1098-1134), host arrays of length T. */
+typedef struct prg_sched {
+  int T;
+  const float* alphas_cumprod;
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* posterior_log_variance_clipped;
+} prg_sched;
+
+#define PRG_SAMPLER_P_SAMPLE 0 /* p_sample_loop, SDD:1283-1317 */
+#define PRG_SAMPLER_DDIM 1     /* ddim_sample,  SDD:1319-1392 */
+
+/* GaussianDiffusion.sample (SDD:1394-1409), objective pred_x0, DDNM null-space
+ * replacement (SDD:1210-1218) when img_cond != NULL.
+ *  times (host, nsteps+1 ints): p_sample: T-1..0 then -1; ddim: the reversed
+ *    linspace of SDD:1331-1337 including the trailing -1.
+ *  noise: NULL => device Philox (seed, per (step, element) counter), else
+ *    (nsteps+1, B,1,S,S) f32: slab 0 = x_T, slab 1+i = i-th randn_like draw
+ *    (parity runs inject the reference's draws).
+ *  out01 (B,1,S,S) f32 in [0,1]. */
+int prg_sampler_run(prg_net* unet, const prg_sched* sched, int mode, const int* times,
+                    int nsteps, float eta, const float* param_cond, const float* img_cond,
+                    const float* noise, uint64_t philox_seed, int has_refine_step,
+                    float* out01, int B, prg_stream_t stream);
+
+/* Test hook: one implicit-GEMM convolution through the tcgen05 engine.
+ * x (B,H,W,Cin) f16 NHWC, w (Cout, taps*Cin) f16 K-major tap-major, bias (Cout)
+ * f32 or NULL -> y (B,Ho,Wo,Cout) f16.  mode: 0 = 1x1, 1 = 3x3 p1, 2 = 4x4 s2 p1. */
+int prg_test_conv_f16(const void* x, const void* w, const float* bias, void* y, int B,
+                      int H, int W, int Cin, int Cout, int mode, prg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRG_H_ */

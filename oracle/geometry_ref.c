@@ -1,0 +1,151 @@
+/* TEST INFRASTRUCTURE ONLY -- scalar C restatement of the reference geometry
+ * helpers.  It is the checker for the CUDA kernels (tests/, smoke(), the
+ * cpu_baseline leg of bench.py).  The product library never links it.
+ *
+ * Pinned against the unmodified reference (run in the build container) through
+ * tests/golden/geometry_*.npz, minted by oracle/make_golden.py.
+ *
+ * Build: gcc -O2 -ffp-contract=off -shared -fPIC   (see oracle/build.py).
+ * -ffp-contract=off matters: every fp32 operation below must round on its own,
+ * exactly like the eager torch ops it restates; the only fused operations are
+ * the explicit fmaf() calls.
+ *
+ * SDD = /root/reference/denoising_diffusion_pytorch/successive_ddnm_diffusion.py
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+/* depth2pc_tensor, SDD:176-209.  depth (B,H,W), K (B,3,3) row-major.
+ * pc (B,H*W,3), valid (B,H*W).  x = ((c - cx) * z) / fx, each op fp32. */
+void prg_ref_depth2pc_f32(const float* depth, const float* K, float clip_lo, float clip_hi,
+                          int use_clip, float invalid, float* pc, uint8_t* valid,
+                          int B, int H, int W) {
+    for (int b = 0; b < B; ++b) {
+        const float fx = K[b * 9 + 0], fy = K[b * 9 + 4], cx = K[b * 9 + 2], cy = K[b * 9 + 5];
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c) {
+                size_t i = ((size_t)b * H + r) * W + c;
+                float d = depth[i];
+                int ok = use_clip ? (d > clip_lo && d < clip_hi) : 1;   /* SDD:193-196 */
+                float z = ok ? d : invalid;
+                float t0 = (float)c - cx;
+                float t1 = t0 * z;
+                float x = t1 / fx;                                      /* SDD:200-201 */
+                float u0 = (float)r - cy;
+                float u1 = u0 * z;
+                float y = u1 / fy;                                      /* SDD:202-203 */
+                pc[i * 3 + 0] = ok ? x : invalid;
+                pc[i * 3 + 1] = ok ? y : invalid;
+                pc[i * 3 + 2] = z;
+                valid[i] = (uint8_t)ok;
+            }
+    }
+}
+
+/* One z-buffer splat, SDD:225-258: c = round_half_even((x*fx)/z + cx). */
+static inline void splat(float x, float y, float z, float fx, float fy, float cx, float cy,
+                         float* depth_img, uint8_t* mask_img, int H, int W) {
+    float cf = rintf((x * fx) / z + cx);
+    float rf = rintf((y * fy) / z + cy);
+    if (!(cf >= 0.0f && cf < (float)W)) return;                         /* SDD:232 */
+    if (!(rf >= 0.0f && rf < (float)H)) return;                         /* SDD:233 */
+    if (!(z > 0.0f)) return;                                            /* SDD:234 */
+    int ci = (int)cf, ri = (int)rf;
+    size_t i = (size_t)ri * W + ci;
+    if (!mask_img[i] || z < depth_img[i]) depth_img[i] = z;             /* amin, include_self=False */
+    mask_img[i] = 1;                                                    /* SDD:261-262 */
+}
+
+/* pc2depth_tensor for a ragged batch, SDD:212-265.  pc (sumN,3); valid (sumN)
+ * or NULL (= all true); offsets (B+1) CSR row starts; pose NULL or (B,4,4):
+ * when given, p' = R p + t is applied first with the rounding of the reference's
+ * matmul path (SDD:279-280): x' = fma(z,r02, fma(y,r01, x*r00)) then + t0. */
+void prg_ref_pc2depth_f32(const float* pc, const uint8_t* valid, const int64_t* offsets,
+                          const float* K, const float* pose, float* depth_out,
+                          uint8_t* mask_out, int B, int H, int W) {
+    memset(depth_out, 0, sizeof(float) * (size_t)B * H * W);
+    memset(mask_out, 0, (size_t)B * H * W);
+    for (int b = 0; b < B; ++b) {
+        const float fx = K[b * 9 + 0], fy = K[b * 9 + 4], cx = K[b * 9 + 2], cy = K[b * 9 + 5];
+        const float* P = pose ? pose + b * 16 : 0;
+        float* dimg = depth_out + (size_t)b * H * W;
+        uint8_t* mimg = mask_out + (size_t)b * H * W;
+        for (int64_t i = offsets[b]; i < offsets[b + 1]; ++i) {
+            if (valid && !valid[i]) continue;
+            float x = pc[i * 3 + 0], y = pc[i * 3 + 1], z = pc[i * 3 + 2];
+            if (P) {
+                float xn = fmaf(z, P[2], fmaf(y, P[1], x * P[0])) + P[3];
+                float yn = fmaf(z, P[6], fmaf(y, P[5], x * P[4])) + P[7];
+                float zn = fmaf(z, P[10], fmaf(y, P[9], x * P[8])) + P[11];
+                x = xn; y = yn; z = zn;
+            }
+            splat(x, y, z, fx, fy, cx, cy, dimg, mimg, H, W);
+        }
+    }
+}
+
+/* reproject_tensor, SDD:268-286: depth2pc -> rigid transform -> pc2depth. */
+void prg_ref_reproject_f32(const float* depth, const float* K, const float* pose,
+                           float clip_lo, float clip_hi, float* depth_out, uint8_t* mask_out,
+                           int B, int H, int W) {
+    memset(depth_out, 0, sizeof(float) * (size_t)B * H * W);
+    memset(mask_out, 0, (size_t)B * H * W);
+    for (int b = 0; b < B; ++b) {
+        const float fx = K[b * 9 + 0], fy = K[b * 9 + 4], cx = K[b * 9 + 2], cy = K[b * 9 + 5];
+        const float* P = pose + b * 16;
+        float* dimg = depth_out + (size_t)b * H * W;
+        uint8_t* mimg = mask_out + (size_t)b * H * W;
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c) {
+                float z = depth[((size_t)b * H + r) * W + c];
+                if (!(z > clip_lo && z < clip_hi)) continue;
+                float t0 = (float)c - cx;
+                float t1 = t0 * z;
+                float x = t1 / fx;
+                float u0 = (float)r - cy;
+                float u1 = u0 * z;
+                float y = u1 / fy;
+                float xn = fmaf(z, P[2], fmaf(y, P[1], x * P[0])) + P[3];
+                float yn = fmaf(z, P[6], fmaf(y, P[5], x * P[4])) + P[7];
+                float zn = fmaf(z, P[10], fmaf(y, P[9], x * P[8])) + P[11];
+                splat(xn, yn, zn, fx, fy, cx, cy, dimg, mimg, H, W);
+            }
+    }
+}
+
+/* numpy point_cloud (SDD:122-143) on depth01*scale, optionally followed by the
+ * back-transform (pc - t) @ R of SDD:2627-2628.  depth01 fp32 (B,H,W); the
+ * product depth01*scale is rounded to fp32 (numpy float32 array * python
+ * scalar, SDD:2623), everything after is float64.  Valid pixels are compacted
+ * in row-major order; pc_out holds B slabs of H*W*3 doubles, counts[b] points
+ * are meaningful in slab b. */
+void prg_ref_depth2pc_compact_f64(const float* depth01, const float* K, const float* pose,
+                                  float scale, float clip_lo, float clip_hi, double* pc_out,
+                                  int64_t* counts, int B, int H, int W) {
+    for (int b = 0; b < B; ++b) {
+        const double fx = K[b * 9 + 0], fy = K[b * 9 + 4], cx = K[b * 9 + 2], cy = K[b * 9 + 5];
+        const float* P = pose ? pose + b * 16 : 0;
+        double* out = pc_out + (size_t)b * H * W * 3;
+        int64_t n = 0;
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c) {
+                float zf = depth01[((size_t)b * H + r) * W + c] * scale;
+                if (!(zf > clip_lo && zf < clip_hi)) continue;          /* SDD:131 */
+                double z = (double)zf;
+                double x = ((double)c - cx) * z / fx;                   /* SDD:135 */
+                double y = ((double)r - cy) * z / fy;                   /* SDD:136 */
+                if (P) {
+                    double dx = x - (double)P[3], dy = y - (double)P[7], dz = z - (double)P[11];
+                    /* row-vector @ R: out_j = sum_i d_i R[i][j] */
+                    double ox = fma(dz, (double)P[8], fma(dy, (double)P[4], dx * (double)P[0]));
+                    double oy = fma(dz, (double)P[9], fma(dy, (double)P[5], dx * (double)P[1]));
+                    double oz = fma(dz, (double)P[10], fma(dy, (double)P[6], dx * (double)P[2]));
+                    x = ox; y = oy; z = oz;
+                }
+                out[n * 3 + 0] = x; out[n * 3 + 1] = y; out[n * 3 + 2] = z;
+                ++n;
+            }
+        counts[b] = n;
+    }
+}

@@ -1,0 +1,111 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy-facing wrapper of oracle/geometry_ref.c.
+
+Checker for the CUDA geometry kernels; never imported by the product package.
+The shared object is built by ``oracle/build.py`` (also called from
+``__graft_entry__.build()``); if it is missing and gcc is available it is
+built on first use.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libprg_oracle.so")
+_SRC = os.path.join(_HERE, "geometry_ref.c")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+               "-o", _SO, _SRC, "-lm"]
+        subprocess.check_call(cmd)
+    return _SO
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t)) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def depth2pc(depth, K, clip=(0, 10), invalid=float("nan")):
+    """depth (B,1,H,W) or (B,H,W) -> pc (B,H*W,3) f32, valid (B,H*W) bool."""
+    depth = _f32(depth)
+    if depth.ndim == 4:
+        depth = depth[:, 0]
+    depth = np.ascontiguousarray(depth)
+    B, H, W = depth.shape
+    K = _f32(K)
+    pc = np.empty((B, H * W, 3), np.float32)
+    valid = np.empty((B, H * W), np.uint8)
+    use_clip = clip is not None
+    lo, hi = (clip if use_clip else (0.0, 0.0))
+    _load().prg_ref_depth2pc_f32(
+        _p(depth, ctypes.c_float), _p(K, ctypes.c_float), ctypes.c_float(lo), ctypes.c_float(hi),
+        ctypes.c_int(int(use_clip)), ctypes.c_float(invalid), _p(pc, ctypes.c_float),
+        _p(valid, ctypes.c_uint8), B, H, W)
+    return pc, valid.astype(bool)
+
+
+def pc2depth(pc, valid, offsets, K, image_size, pose=None):
+    """Ragged z-buffer: pc (sumN,3), valid (sumN) or None, offsets (B+1)."""
+    pc = _f32(pc).reshape(-1, 3)
+    offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+    B = offsets.shape[0] - 1
+    H, W = image_size
+    K = _f32(K)
+    v = None if valid is None else np.ascontiguousarray(np.asarray(valid).reshape(-1).astype(np.uint8))
+    P = None if pose is None else _f32(pose)
+    depth = np.empty((B, 1, H, W), np.float32)
+    mask = np.empty((B, 1, H, W), np.uint8)
+    _load().prg_ref_pc2depth_f32(
+        _p(pc, ctypes.c_float), _p(v, ctypes.c_uint8), _p(offsets, ctypes.c_int64),
+        _p(K, ctypes.c_float), _p(P, ctypes.c_float), _p(depth, ctypes.c_float),
+        _p(mask, ctypes.c_uint8), B, H, W)
+    return depth, mask.astype(bool)
+
+
+def reproject(depth, K, pose, clip=(0, 10)):
+    """depth (B,1,H,W) metres -> (depth (B,1,H,W), mask (B,1,H,W) bool)."""
+    depth = _f32(depth)
+    if depth.ndim == 4:
+        depth = np.ascontiguousarray(depth[:, 0])
+    B, H, W = depth.shape
+    K, P = _f32(K), _f32(pose)
+    out = np.empty((B, 1, H, W), np.float32)
+    mask = np.empty((B, 1, H, W), np.uint8)
+    _load().prg_ref_reproject_f32(
+        _p(depth, ctypes.c_float), _p(K, ctypes.c_float), _p(P, ctypes.c_float),
+        ctypes.c_float(clip[0]), ctypes.c_float(clip[1]), _p(out, ctypes.c_float),
+        _p(mask, ctypes.c_uint8), B, H, W)
+    return out, mask.astype(bool)
+
+
+def depth2pc_compact(depth01, K, pose=None, scale=10.0, clip=(0.5, 10)):
+    """point_cloud(depth01*scale, K, clip) [+ (pc - t) @ R]; list of (N_b,3) f64."""
+    depth01 = _f32(depth01)
+    if depth01.ndim == 4:
+        depth01 = np.ascontiguousarray(depth01[:, 0])
+    B, H, W = depth01.shape
+    K = _f32(K)
+    P = None if pose is None else _f32(pose)
+    pc = np.empty((B, H * W, 3), np.float64)
+    counts = np.zeros((B,), np.int64)
+    _load().prg_ref_depth2pc_compact_f64(
+        _p(depth01, ctypes.c_float), _p(K, ctypes.c_float), _p(P, ctypes.c_float),
+        ctypes.c_float(scale), ctypes.c_float(clip[0]), ctypes.c_float(clip[1]),
+        _p(pc, ctypes.c_double), _p(counts, ctypes.c_int64), B, H, W)
+    return [pc[b, :counts[b]].copy() for b in range(B)]

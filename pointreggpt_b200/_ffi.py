@@ -1,0 +1,110 @@
+"""ctypes binding of libprg.so (the C ABI declared in include/prg.h).
+
+PyTorch is used here only for device memory and streams: every call forwards raw
+``data_ptr()`` values and the current CUDA stream.  There is no CPU fallback -- if the
+library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprg.so")
+
+c_void_p, c_int, c_float, c_int64, c_size_t, c_uint64 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64, ctypes.c_size_t,
+    ctypes.c_uint64)
+
+
+class PrgError(RuntimeError):
+    pass
+
+
+class Sched(ctypes.Structure):
+    """struct prg_sched (include/prg.h)."""
+    _fields_ = [("T", c_int),
+                ("alphas_cumprod", c_void_p),
+                ("sqrt_recip_alphas_cumprod", c_void_p),
+                ("sqrt_recipm1_alphas_cumprod", c_void_p),
+                ("posterior_mean_coef1", c_void_p),
+                ("posterior_mean_coef2", c_void_p),
+                ("posterior_log_variance_clipped", c_void_p)]
+
+
+# name -> (restype, argtypes); must list every symbol include/prg.h declares.
+SIGNATURES = {
+    "prg_last_error": (ctypes.c_char_p, []),
+    "prg_abi_version": (c_int, []),
+    "prg_launch_count": (c_uint64, []),
+    "prg_reproject_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_void_p]),
+    "prg_pc2depth_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "prg_depth2pc_f32": (c_int, [c_void_p, c_void_p, c_float, c_float, c_int, c_float, c_void_p,
+                                 c_void_p, c_int, c_int, c_int, c_void_p]),
+    "prg_depth2pc_compact_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_void_p]),
+    "prg_net_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_size_t, c_int, c_int,
+                               c_int]),
+    "prg_net_destroy": (None, [c_void_p]),
+    "prg_net_device_bytes": (c_size_t, [c_void_p]),
+    "prg_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p]),
+    "prg_maskunet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int,
+                                     c_void_p]),
+    "prg_sampler_run": (c_int, [c_void_p, ctypes.POINTER(Sched), c_int, c_void_p, c_int, c_float,
+                                c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_void_p, c_int,
+                                c_void_p]),
+    "prg_test_conv_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises PrgError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise PrgError(
+                "libprg.so is missing (%s); build it with `python -m pointreggpt_b200.build`. "
+                "There is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)   # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        if l.prg_abi_version() != 1:
+            raise PrgError("libprg.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PrgError("libprg error %d: %s" % (rc, lib().prg_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PrgError("pointreggpt_b200 runs on CUDA tensors only (got a %s tensor); "
+                           "there is no CPU fallback" % t.device)
+
+
+def launch_count():
+    return int(lib().prg_launch_count())

@@ -1,0 +1,62 @@
+// Shared host/device helpers for libprg.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/prg.h"
+
+namespace prg {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define PRG_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      prg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                        \
+      return PRG_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define PRG_CHECK_ARG(cond, msg)              \
+  do {                                        \
+    if (!(cond)) {                            \
+      prg::set_error("bad argument: %s", msg); \
+      return PRG_ERR_ARG;                     \
+    }                                         \
+  } while (0)
+
+// Every kernel launch in the library goes through this so prg_launch_count() is exact.
+#define PRG_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    prg::count_launch();                                                                \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      prg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                               \
+      return PRG_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace prg

@@ -1,0 +1,86 @@
+// tcgen05 implicit-GEMM convolution / GEMM engine: interface.
+//
+// One launch computes  D[m, n] = sum_k A[m, k] * W[n, k]  with
+//   m = output pixel (128-pixel tile = tile_w x tile_h patch of one image, NHWC fp16),
+//   n = output channel, k = (tap, input channel).
+// A tiles are fetched per tap by TMA (tiled mode, 4-D/5-D tensor map over the NHWC
+// activation, out-of-bounds = zero padding) straight into the 128B-swizzled K-major layout
+// tcgen05.mma consumes; accumulators live in TMEM; four epilogue warps drain them.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace prg {
+
+enum ConvEpi : int {
+  EPI_BIAS = 0,    // y = acc + bias                                   -> fp16
+  EPI_GN = 1,      // y = acc + bias, + per-(image, group) sum / sumsq -> fp16 raw + stats
+  EPI_QKV = 2,     // to_qkv: q softmax_d * scale | k (+ column max) | v -> fp16
+  EPI_LN_RES = 3,  // y = LayerNorm_c(acc + bias) * g + residual       -> fp16
+  EPI_RES = 4,     // y = acc + bias + residual                        -> fp16
+};
+
+struct ConvParams {
+  int B, Ho, Wo;         // output grid the M tiles walk (low-res grid when classes == 4)
+  int tile_w_log2;       // tile = (1 << tile_w_log2) x (128 >> tile_w_log2) pixels
+  int tiles_x, tiles_y;
+  int mode;              // 0: stride-1 taps (kh x kw, pad), 1: 4x4 stride-2 pad-1 (5-D parity view)
+  int kh, kw, pad;
+  int chunks0, chunks1;  // 64-channel K chunks taken from source 0 / source 1 (concat)
+  int cin0;              // channels of source 0 (mode 1: parity offset inside the 5-D view)
+  int classes;           // 1, or 4 = nearest-x2 upsample folded into four 2x2-tap parity classes
+  int w_batched;         // weight matrix differs per image (3rd coordinate of tmB = image)
+  // output addressing (elements)
+  __half* out;
+  long long out_img_stride;
+  int out_row_stride, out_pix_stride;
+  int out_scale;         // 1, or 2 when classes == 4
+  const float* bias;     // [Cout] or nullptr
+  const __half* res;     // residual, same addressing as out (EPI_RES / EPI_LN_RES)
+  float* stats;          // EPI_GN: [B][8][2] fp32 (sum, sumsq), zeroed by the caller
+  int gs_log2;           // EPI_GN: log2(channels per group)
+  const float* ln_g;     // EPI_LN_RES: [Cout]
+  int* colmax;           // EPI_QKV: [B][128] order-preserving int encoding of max_n k, or nullptr
+  int q_softmax;         // EPI_QKV: 1 = softmax over each 32-channel head then * q_scale
+  float q_scale;
+};
+
+struct ConvLaunch {
+  CUtensorMap tmA0, tmA1, tmB;
+  ConvParams p;
+  int bn;    // N tile: 64 / 128 / 256
+  int epi;   // ConvEpi
+  dim3 grid;
+  int cout;
+};
+
+// Description of one NHWC fp16 activation source.
+struct ActSrc {
+  const __half* ptr;   // first element of channel 0 of pixel (0,0) of image 0
+  int H, W, C;         // C = channels read from this source (multiple of 64)
+  int pix_stride;      // elements between consecutive pixels (>= C)
+};
+
+// Fills tensor maps + params.  Returns 0 or a PRG_ERR_* code (message via set_error).
+// w: [nb][classes][Cout][taps*Cin] fp16 (K-major, tap-major); nb = B if w_batched else 1.
+int conv_plan(ConvLaunch* L, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
+              int classes, const __half* w, int w_batched, int Cout);
+int conv_run(const ConvLaunch& L, cudaStream_t stream);
+
+// order-preserving float <-> int (for atomicMax on floats)
+__host__ __device__ inline int float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  int i = __float_as_int(f);
+#else
+  int i;
+  memcpy(&i, &f, 4);
+#endif
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ inline float ordered_to_float(int i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+}  // namespace prg

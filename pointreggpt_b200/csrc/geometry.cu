@@ -1,0 +1,386 @@
+// Geometry kernels of the data-generation hot path (HBM-bound, bit-exact).
+//
+// Reference semantics (SDD = denoising_diffusion_pytorch/successive_ddnm_diffusion.py):
+//   depth2pc_tensor  SDD:176-209   x = ((c - cx) * z) / fx      (each op rounded, fp32)
+//   pc2depth_tensor  SDD:212-265   c = round_half_even((x * fx) / z + cx); scatter amin
+//   reproject_tensor SDD:268-286   matmul(pc, R^T) + t  ==  fma(z,r2, fma(y,r1, x*r0)) + t
+//   point_cloud      SDD:122-143   float64 unprojection of the valid pixels, row-major
+//
+// All fp32 arithmetic uses the _rn intrinsics so nvcc can neither contract nor
+// reorder it; the z-buffer is an order-independent atomicMin on the bit pattern of
+// the (strictly positive) depth, so the result is deterministic and bit-exact.
+#include "common.cuh"
+
+namespace prg {
+
+constexpr unsigned kEmpty = 0xFFFFFFFFu;
+
+struct Intr {
+  float fx, fy, cx, cy;
+};
+
+__device__ __forceinline__ Intr load_intr(const float* __restrict__ K, int b) {
+  const float* k = K + b * 9;
+  Intr i;
+  i.fx = __ldg(k + 0);
+  i.fy = __ldg(k + 4);
+  i.cx = __ldg(k + 2);
+  i.cy = __ldg(k + 5);
+  return i;
+}
+
+__device__ __forceinline__ void unproject(int r, int c, float z, const Intr& k, float& x, float& y) {
+  x = __fdiv_rn(__fmul_rn(__fsub_rn((float)c, k.cx), z), k.fx);
+  y = __fdiv_rn(__fmul_rn(__fsub_rn((float)r, k.cy), z), k.fy);
+}
+
+__device__ __forceinline__ void rigid(const float* __restrict__ P, float& x, float& y, float& z) {
+  float xn = __fadd_rn(__fmaf_rn(z, P[2], __fmaf_rn(y, P[1], __fmul_rn(x, P[0]))), P[3]);
+  float yn = __fadd_rn(__fmaf_rn(z, P[6], __fmaf_rn(y, P[5], __fmul_rn(x, P[4]))), P[7]);
+  float zn = __fadd_rn(__fmaf_rn(z, P[10], __fmaf_rn(y, P[9], __fmul_rn(x, P[8]))), P[11]);
+  x = xn;
+  y = yn;
+  z = zn;
+}
+
+__device__ __forceinline__ void splat(float x, float y, float z, const Intr& k, int H, int W,
+                                      unsigned* __restrict__ zimg) {
+  float cf = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(x, k.fx), z), k.cx));
+  float rf = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(y, k.fy), z), k.cy));
+  bool ok = (cf >= 0.f) && (cf < (float)W) && (rf >= 0.f) && (rf < (float)H) && (z > 0.f);
+  if (ok) atomicMin(zimg + (int)rf * W + (int)cf, __float_as_uint(z));
+}
+
+// ------------------------------------------------------------------ reproject
+// One thread = 4 consecutive pixels (16-byte load).  The z-buffer lives in
+// depth_out itself (pre-filled with 0xFFFFFFFF), finalised in place.
+__global__ void __launch_bounds__(256)
+k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
+                  const float* __restrict__ pose, float lo, float hi,
+                  unsigned* __restrict__ zbuf, int HW, int H, int W) {
+  __shared__ float sP[12];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 12) sP[threadIdx.x] = __ldg(pose + b * 16 + threadIdx.x);
+  __syncthreads();
+  const Intr k = load_intr(K, b);
+  unsigned* zimg = zbuf + (size_t)b * HW;
+  const float* dimg = depth + (size_t)b * HW;
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < HW; i4 += gridDim.x * blockDim.x) {
+    const int i = i4 * 4;
+    float d[4];
+    if (i + 3 < HW) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(dimg + i));
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = (i + j < HW) ? dimg[i + j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float z0 = d[j];
+      if (i + j < HW && z0 > lo && z0 < hi) {
+        const int r = (i + j) / W, c = (i + j) - r * W;
+        float x, y, z = z0;
+        unproject(r, c, z, k, x, y);
+        rigid(sP, x, y, z);
+        splat(x, y, z, k, H, W, zimg);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_zbuf_finalize(unsigned* __restrict__ zbuf, uint8_t* __restrict__ mask, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      uint4 v = __ldcg(reinterpret_cast<const uint4*>(zbuf + i));
+      uchar4 m;
+      m.x = v.x != kEmpty; m.y = v.y != kEmpty; m.z = v.z != kEmpty; m.w = v.w != kEmpty;
+      v.x = m.x ? v.x : 0u; v.y = m.y ? v.y : 0u; v.z = m.z ? v.z : 0u; v.w = m.w ? v.w : 0u;
+      *reinterpret_cast<uint4*>(zbuf + i) = v;
+      *reinterpret_cast<uchar4*>(mask + i) = m;
+    } else {
+      for (size_t j = i; j < n; ++j) {
+        unsigned v = __ldcg(zbuf + j);
+        mask[j] = v != kEmpty;
+        zbuf[j] = v != kEmpty ? v : 0u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pc2depth (ragged)
+__global__ void __launch_bounds__(256)
+k_pc2depth_splat(const float* __restrict__ pc, const uint8_t* __restrict__ valid,
+                 const int64_t* __restrict__ offsets, int64_t total, const float* __restrict__ K,
+                 const float* __restrict__ pose, unsigned* __restrict__ zbuf, int B, int H, int W) {
+  extern __shared__ int64_t s_off[];
+  for (int i = threadIdx.x; i <= B; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  const int HW = H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (valid != nullptr && !valid[i]) continue;
+    if (i < s_off[0] || i >= s_off[B]) continue;
+    int lo = 0, hi = B;  // find b with off[b] <= i < off[b+1]
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int b = lo;
+    float x = __ldcs(pc + i * 3 + 0), y = __ldcs(pc + i * 3 + 1), z = __ldcs(pc + i * 3 + 2);
+    if (pose != nullptr) rigid(pose + b * 16, x, y, z);
+    const Intr k = load_intr(K, b);
+    splat(x, y, z, k, H, W, zbuf + (size_t)b * HW);
+  }
+}
+
+// ------------------------------------------------------------------ depth2pc (dense)
+__global__ void __launch_bounds__(256)
+k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float lo, float hi,
+           int use_clip, float invalid, float* __restrict__ pc, uint8_t* __restrict__ valid,
+           int HW, int W) {
+  const int b = blockIdx.y;
+  const Intr k = load_intr(K, b);
+  const float* dimg = depth + (size_t)b * HW;
+  float* pimg = pc + (size_t)b * HW * 3;
+  uint8_t* vimg = valid + (size_t)b * HW;
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < HW; i4 += gridDim.x * blockDim.x) {
+    const int i = i4 * 4;
+    float d[4];
+    const bool full = (i + 3 < HW);
+    if (full) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(dimg + i));
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = (i + j < HW) ? dimg[i + j] : 0.f;
+    }
+    float o[12];
+    uint8_t ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = (i + j) / W, c = (i + j) - r * W;
+      ok[j] = use_clip ? (d[j] > lo && d[j] < hi) : 1;
+      const float z = ok[j] ? d[j] : invalid;
+      float x, y;
+      unproject(r, c, z, k, x, y);
+      o[j * 3 + 0] = ok[j] ? x : invalid;
+      o[j * 3 + 1] = ok[j] ? y : invalid;
+      o[j * 3 + 2] = z;
+    }
+    if (full) {
+      float4* dst = reinterpret_cast<float4*>(pimg + (size_t)i * 3);
+      __stcs(dst + 0, make_float4(o[0], o[1], o[2], o[3]));
+      __stcs(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
+      __stcs(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
+      *reinterpret_cast<uchar4*>(vimg + i) = make_uchar4(ok[0], ok[1], ok[2], ok[3]);
+    } else {
+      for (int j = 0; j < 4 && i + j < HW; ++j) {
+        pimg[(size_t)(i + j) * 3 + 0] = o[j * 3 + 0];
+        pimg[(size_t)(i + j) * 3 + 1] = o[j * 3 + 1];
+        pimg[(size_t)(i + j) * 3 + 2] = o[j * 3 + 2];
+        vimg[i + j] = ok[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ point_cloud (f64, compacted)
+constexpr int kCompactBlock = 1024;
+
+__device__ __forceinline__ bool pc_valid(float d01, float scale, float lo, float hi, float& zf) {
+  zf = __fmul_rn(d01, scale);
+  return zf > lo && zf < hi;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+k_compact_count(const float* __restrict__ depth01, float scale, float lo, float hi,
+                int64_t* __restrict__ scratch, int HW, int nblk) {
+  const int b = blockIdx.y, i = blockIdx.x * kCompactBlock + threadIdx.x;
+  float zf;
+  const bool ok = (i < HW) && pc_valid(depth01[(size_t)b * HW + i], scale, lo, hi, zf);
+  const int n = __syncthreads_count(ok);
+  if (threadIdx.x == 0) scratch[(size_t)b * (nblk + 1) + blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(1024)
+k_compact_scan(int64_t* __restrict__ scratch, int64_t* __restrict__ counts, int nblk) {
+  // one CTA per image: exclusive scan of the per-block counts (in place).
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  int64_t* row = scratch + (size_t)blockIdx.x * (nblk + 1);
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int64_t v = (i < nblk) ? row[i] : 0;
+    int64_t s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane == 31) s_warp[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int64_t carry = s_carry;
+    const int64_t incl = s + (warp > 0 ? s_warp[warp - 1] : 0) + carry;
+    if (i < nblk) row[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    row[nblk] = s_carry;
+    counts[blockIdx.x] = s_carry;
+  }
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+k_compact_write(const float* __restrict__ depth01, const float* __restrict__ K,
+                const float* __restrict__ pose, float scale, float lo, float hi,
+                const int64_t* __restrict__ scratch, double* __restrict__ pc_out, int HW, int W,
+                int nblk) {
+  __shared__ int s_warp[32];
+  const int b = blockIdx.y, i = blockIdx.x * kCompactBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float zf = 0.f;
+  const bool ok = (i < HW) && pc_valid(depth01[(size_t)b * HW + i], scale, lo, hi, zf);
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  const int in_warp = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane], s = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    s_warp[lane] = s - w;  // exclusive
+  }
+  __syncthreads();
+  if (!ok) return;
+  const int64_t rank = scratch[(size_t)b * (nblk + 1) + blockIdx.x] + s_warp[warp] + in_warp;
+  const float* k = K + b * 9;
+  const double fx = (double)k[0], fy = (double)k[4], cx = (double)k[2], cy = (double)k[5];
+  const int r = i / W, c = i - r * W;
+  double z = (double)zf;
+  double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)c, cx), z), fx);
+  double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)r, cy), z), fy);
+  if (pose != nullptr) {
+    const float* P = pose + b * 16;
+    const double dx = __dsub_rn(x, (double)P[3]), dy = __dsub_rn(y, (double)P[7]),
+                 dz = __dsub_rn(z, (double)P[11]);
+    // numpy's float64 (N,3)@(3,3) accumulates with fused multiply-adds in k order
+    const double nx = __fma_rn(dz, (double)P[8], __fma_rn(dy, (double)P[4], __dmul_rn(dx, (double)P[0])));
+    const double ny = __fma_rn(dz, (double)P[9], __fma_rn(dy, (double)P[5], __dmul_rn(dx, (double)P[1])));
+    const double nz = __fma_rn(dz, (double)P[10], __fma_rn(dy, (double)P[6], __dmul_rn(dx, (double)P[2])));
+    x = nx;
+    y = ny;
+    z = nz;
+  }
+  double* o = pc_out + ((size_t)b * HW + rank) * 3;
+  o[0] = x;
+  o[1] = y;
+  o[2] = z;
+}
+
+}  // namespace prg
+
+using namespace prg;
+
+static int grid_for(int64_t work_items, int threads, int per_thread) {
+  int64_t blocks = (work_items + (int64_t)threads * per_thread - 1) / ((int64_t)threads * per_thread);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const float* depth, const float* K, const float* pose,
+                                 float clip_lo, float clip_hi, float* depth_out,
+                                 uint8_t* mask_out, int B, int H, int W, prg_stream_t stream) {
+  PRG_CHECK_ARG(depth && K && pose && depth_out && mask_out, "null pointer");
+  PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
+  if (B == 0) return PRG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = H * W;
+  const size_t n = (size_t)B * HW;
+  PRG_CUDA_OK(cudaMemsetAsync(depth_out, 0xFF, n * sizeof(float), s));
+  dim3 g1(grid_for(HW, 256, 4), B);
+  k_reproject_splat<<<g1, 256, 0, s>>>(depth, K, pose, clip_lo, clip_hi, (unsigned*)depth_out, HW,
+                                      H, W);
+  PRG_LAUNCH_CHECK();
+  k_zbuf_finalize<<<grid_for((int64_t)n, 256, 4), 256, 0, s>>>((unsigned*)depth_out, mask_out, n);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int prg_pc2depth_f32(const float* pc, const uint8_t* valid, const int64_t* offsets,
+                                int64_t total_points, const float* K, const float* pose,
+                                float* depth_out, uint8_t* mask_out, int B, int H, int W,
+                                prg_stream_t stream) {
+  PRG_CHECK_ARG(offsets && K && depth_out && mask_out, "null pointer");
+  PRG_CHECK_ARG(pc || total_points == 0, "null point cloud");
+  PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && total_points >= 0 && B <= 4096, "bad shape");
+  if (B == 0) return PRG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)B * H * W;
+  PRG_CUDA_OK(cudaMemsetAsync(depth_out, 0xFF, n * sizeof(float), s));
+  if (total_points > 0) {
+    k_pc2depth_splat<<<grid_for(total_points, 256, 1), 256, (B + 1) * sizeof(int64_t), s>>>(
+        pc, valid, offsets, total_points, K, pose, (unsigned*)depth_out, B, H, W);
+    PRG_LAUNCH_CHECK();
+  }
+  k_zbuf_finalize<<<grid_for((int64_t)n, 256, 4), 256, 0, s>>>((unsigned*)depth_out, mask_out, n);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int prg_depth2pc_f32(const float* depth, const float* K, float clip_lo, float clip_hi,
+                                int use_clip, float invalid, float* pc, uint8_t* valid, int B,
+                                int H, int W, prg_stream_t stream) {
+  PRG_CHECK_ARG(depth && K && pc && valid, "null pointer");
+  PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
+  if (B == 0) return PRG_OK;
+  const int HW = H * W;
+  dim3 g(grid_for(HW, 256, 4), B);
+  k_depth2pc<<<g, 256, 0, (cudaStream_t)stream>>>(depth, K, clip_lo, clip_hi, use_clip, invalid, pc,
+                                                 valid, HW, W);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int prg_depth2pc_compact_f64(const float* depth01, const float* K, const float* pose,
+                                        float scale, float clip_lo, float clip_hi, double* pc_out,
+                                        int64_t* counts, int64_t* scratch, int B, int H, int W,
+                                        prg_stream_t stream) {
+  PRG_CHECK_ARG(depth01 && K && pc_out && counts && scratch, "null pointer");
+  PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
+  if (B == 0) return PRG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = H * W;
+  const int nblk = (HW + kCompactBlock - 1) / kCompactBlock;
+  dim3 g(nblk, B);
+  k_compact_count<<<g, kCompactBlock, 0, s>>>(depth01, scale, clip_lo, clip_hi, scratch, HW, nblk);
+  PRG_LAUNCH_CHECK();
+  k_compact_scan<<<B, 1024, 0, s>>>(scratch, counts, nblk);
+  PRG_LAUNCH_CHECK();
+  k_compact_write<<<g, kCompactBlock, 0, s>>>(depth01, K, pose, scale, clip_lo, clip_hi, scratch,
+                                             pc_out, HW, W, nblk);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
