@@ -112,32 +112,38 @@ int prg_unet_forward(prg_net* net, const float* x, const int64_t* time,
 int prg_maskunet_forward(prg_net* net, const float* depth01, float* prob, uint8_t* keep,
                          float thresh, int B, prg_stream_t stream);
 
-/* Schedule tables of GaussianDiffusion (SDD:1098-1134), host arrays of length T. */
-typedef struct prg_sched {
-  int T;
-  const float* alphas_cumprod;
-  const float* sqrt_recip_alphas_cumprod;
-  const float* sqrt_recipm1_alphas_cumprod;
-  const float* posterior_mean_coef1;
-  const float* posterior_mean_coef2;
-  const float* posterior_log_variance_clipped;
-} prg_sched;
+/* One sampler step.  The host (pointreggpt_b200.diffusion) derives the coefficients from the
+ * GaussianDiffusion schedule buffers (SDD:1098-1134) with the same fp32 tensor arithmetic the
+ * reference uses, so the device only applies them.
+ *   P_SAMPLE     (SDD:1258-1281): c0 = posterior_mean_coef1[t], c1 = posterior_mean_coef2[t],
+ *                c2 = exp(0.5 * posterior_log_variance_clipped[t]); add_noise = (t > 0)
+ *   DDIM         (SDD:1343-1373): c0 = sqrt_recip_alphas_cumprod[t], c1 = sqrt_recipm1_...[t],
+ *                c2 = sqrt(alpha_next), c3 = c, c4 = sigma; add_noise = 1
+ *   DDIM_LAST    (SDD:1358-1360): x = x0 (c0, c1 as DDIM)
+ *   REFINE_P     (SDD:1307-1314) / REFINE_DDIM (SDD:1375-1389): the optional refine step
+ * A step with `unnormalize` set writes (x + 1) / 2 (SDD:1316, 1391); it must be the last. */
+typedef struct prg_step {
+  int t;
+  int kind;
+  int add_noise;
+  int unnormalize;
+  float c0, c1, c2, c3, c4;
+} prg_step;
 
-#define PRG_SAMPLER_P_SAMPLE 0 /* p_sample_loop, SDD:1283-1317 */
-#define PRG_SAMPLER_DDIM 1     /* ddim_sample,  SDD:1319-1392 */
+#define PRG_STEP_P_SAMPLE 0
+#define PRG_STEP_DDIM 1
+#define PRG_STEP_DDIM_LAST 2
+#define PRG_STEP_REFINE_P 3
+#define PRG_STEP_REFINE_DDIM 4
 
-/* GaussianDiffusion.sample (SDD:1394-1409), objective pred_x0, DDNM null-space
+/* GaussianDiffusion.sample (SDD:1394-1409) for objective pred_x0 with the DDNM null-space
  * replacement (SDD:1210-1218) when img_cond != NULL.
- *  times (host, nsteps+1 ints): p_sample: T-1..0 then -1; ddim: the reversed
- *    linspace of SDD:1331-1337 including the trailing -1.
- *  noise: NULL => device Philox (seed, per (step, element) counter), else
- *    (nsteps+1, B,1,S,S) f32: slab 0 = x_T, slab 1+i = i-th randn_like draw
- *    (parity runs inject the reference's draws).
- *  out01 (B,1,S,S) f32 in [0,1]. */
-int prg_sampler_run(prg_net* unet, const prg_sched* sched, int mode, const int* times,
-                    int nsteps, float eta, const float* param_cond, const float* img_cond,
-                    const float* noise, uint64_t philox_seed, int has_refine_step,
-                    float* out01, int B, prg_stream_t stream);
+ *  steps: host array.  noise: NULL => device Philox(seed); else (1 + #noisy steps, B,1,S,S)
+ *  f32: slab 0 = x_T, slab 1+i = the i-th randn_like draw (parity runs inject the reference's
+ *  draws).  out (B,1,S,S) f32 (in [0,1] when the last step unnormalizes).  B <= max_batch. */
+int prg_sampler_run(prg_net* unet, const prg_step* steps, int nsteps, const float* param_cond,
+                    const float* img_cond, const float* noise, uint64_t philox_seed, float* out,
+                    int B, prg_stream_t stream);
 
 /* Test hook: one implicit-GEMM convolution through the tcgen05 engine.
  * x (B,H,W,Cin) f16 NHWC, w (Cout, taps*Cin) f16 K-major tap-major, bias (Cout)

@@ -21,15 +21,14 @@ class PrgError(RuntimeError):
     pass
 
 
-class Sched(ctypes.Structure):
-    """struct prg_sched (include/prg.h)."""
-    _fields_ = [("T", c_int),
-                ("alphas_cumprod", c_void_p),
-                ("sqrt_recip_alphas_cumprod", c_void_p),
-                ("sqrt_recipm1_alphas_cumprod", c_void_p),
-                ("posterior_mean_coef1", c_void_p),
-                ("posterior_mean_coef2", c_void_p),
-                ("posterior_log_variance_clipped", c_void_p)]
+class Step(ctypes.Structure):
+    """struct prg_step (include/prg.h)."""
+    _fields_ = [("t", c_int), ("kind", c_int), ("add_noise", c_int), ("unnormalize", c_int),
+                ("c0", c_float), ("c1", c_float), ("c2", c_float), ("c3", c_float),
+                ("c4", c_float)]
+
+
+STEP_P_SAMPLE, STEP_DDIM, STEP_DDIM_LAST, STEP_REFINE_P, STEP_REFINE_DDIM = range(5)
 
 
 # name -> (restype, argtypes); must list every symbol include/prg.h declares.
@@ -54,9 +53,8 @@ SIGNATURES = {
                                  c_void_p]),
     "prg_maskunet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int,
                                      c_void_p]),
-    "prg_sampler_run": (c_int, [c_void_p, ctypes.POINTER(Sched), c_int, c_void_p, c_int, c_float,
-                                c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_void_p, c_int,
-                                c_void_p]),
+    "prg_sampler_run": (c_int, [c_void_p, ctypes.POINTER(Step), c_int, c_void_p, c_void_p,
+                                c_void_p, c_uint64, c_void_p, c_int, c_void_p]),
     "prg_test_conv_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),
 }

@@ -1,0 +1,91 @@
+// Non-GEMM kernels of the U-Net forward / sampler step (HBM- or latency-bound).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace prg {
+
+// ---- stems -------------------------------------------------------------------------------
+// Unet.init_conv (SDD:824, 929): 7x7, 1 -> 64, pad 3.  x (B,S,S) f32 -> y (B,S,S,64) f16.
+int stem_unet(const float* x, const float* w /*[64][49]*/, const float* bias, __half* y, int B,
+              int S, cudaStream_t s);
+// MaskUnet: DepthAugment (DC:582-604) + init_conv 7x7, 3 -> 64 (DC:822, 873-874).
+int stem_mask(const float* depth01, const float* w /*[64][3][49]*/, const float* bias, __half* y,
+              int B, int S, cudaStream_t s);
+
+// ---- conditioning (SDD:845-856, 709-713, 925, 932) ------------------------------------------
+struct CondWeights {
+  const float *t1w, *t1b, *t2w, *t2b;  // time_mlp: Linear(dim,4dim), Linear(4dim,4dim)
+  const float *p1w, *p1b, *p2w, *p2b;  // param_mlp: Linear(pdim,4dim), Linear(4dim,4dim)
+  int dim, pdim;
+};
+// cond_act[b][0:4dim] = SiLU(time_mlp(t_b)), [4dim:8dim] = SiLU(param_mlp(p_b)).
+// time comes either from `time` (int64 per image) or, when time == nullptr, from
+// `time_scalar` broadcast (sampler).
+int cond_embed(const CondWeights& w, const int64_t* time, int time_scalar, const float* pcond,
+               float* cond_act, int B, cudaStream_t s);
+// ss[b][r] = W[r] . cond_act[b] + bias[r] for the concatenated rows of every block MLP.
+int cond_mlp(const float* W, const float* bias, const float* cond_act, float* ss, int rows, int K,
+             int B, cudaStream_t s);
+
+// ---- GroupNorm apply (SDD:690-696) -----------------------------------------------------------
+// y = SiLU(((raw - mean_g) * rstd_g * gamma + beta) * (scale + 1) + shift) [+ res]
+// stats [B][8][2] = (sum, sumsq) over the fp32 conv outputs; ss: per-image (scale | shift)
+// rows of this block inside the cond_mlp output (nullptr = no conditioning).
+struct GnApply {
+  const __half* raw;
+  const float* stats;
+  const float *gamma, *beta;
+  const float* ss;
+  int ss_stride;     // floats per image in ss
+  int ss_off;        // offset of this block's scale row; shift row is ss_off + C
+  const __half* res; // optional residual (same layout as y)
+  int res_pix_stride;
+  __half* y;
+  int HW, C;
+};
+int gn_apply(const GnApply& a, int B, cudaStream_t s);
+
+// ---- channel LayerNorm with gain (SDD:619-628) ----------------------------------------------
+int ln_apply(const __half* x, const float* g, __half* y, int64_t npix, int C, cudaStream_t s);
+
+// ---- network tail ----------------------------------------------------------------------------
+// GroupNorm+SiLU of final_res_block.block2 + residual, final 1x1 conv (64 -> 1), then either
+//   mode 0: out = conv                                        (Unet.forward, SDD:964)
+//   mode 1: out = sigmoid(conv), keep = out > thresh         (MaskUnet tail, DC:868-869)
+//   mode 2: one sampler update x_t -> x_{t-1}                 (SDD:1199-1218, 1250-1251,
+//                                                              1173-1180, 1279-1280 / 1358-1373)
+struct TailParams {
+  const __half* raw;
+  const float* stats;
+  const float *gamma, *beta;
+  const __half* res;      // res_conv output (B,S,S,64)
+  const float* fw;        // final conv weight [64]
+  const float* fb;        // final conv bias [1]
+  int HW;
+  int mode;
+  float* out;             // mode 0/1: (B,HW) f32 ; mode 2: x_{t-1} (may alias x_t)
+  uint8_t* keep;          // mode 1 (optional)
+  float thresh;
+  // mode 2
+  const float* x_t;       // current sample (B,HW)
+  const float* img_cond;  // (B,2,HW) or nullptr
+  const float* noise;     // (B,HW) or nullptr (=> Philox)
+  unsigned long long seed, noise_offset;
+  int clip_x_start;       // ddim: clamp the network output before pred_noise
+  int use_ddnm;
+  int sampler;            // 0 = p_sample, 1 = ddim, 2 = ddim last step (x = x0), 3 = refine
+  float c0, c1, c2, c3;   // p_sample: coef1, coef2, sigma, - ; ddim: sqrt_recip, sqrt_recipm1,
+                          // sqrt(alpha_next), c ; c4 = sigma
+  float c4;
+  int add_noise;
+  int unnormalize;        // write (x+1)/2 (last step)
+};
+int net_tail(const TailParams& t, int B, cudaStream_t s);
+
+// x_T ~ N(0,1) from Philox (throughput runs)
+int fill_normal(float* x, int64_t n, unsigned long long seed, unsigned long long offset,
+                cudaStream_t s);
+
+}  // namespace prg

@@ -68,7 +68,7 @@ k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
   for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < HW; i4 += gridDim.x * blockDim.x) {
     const int i = i4 * 4;
     float d[4];
-    if (i + 3 < HW) {
+    if (i + 3 < HW && (HW & 3) == 0) {
       float4 v = __ldcs(reinterpret_cast<const float4*>(dimg + i));
       d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     } else {
@@ -149,7 +149,7 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
   for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < HW; i4 += gridDim.x * blockDim.x) {
     const int i = i4 * 4;
     float d[4];
-    const bool full = (i + 3 < HW);
+    const bool full = (i + 3 < HW) && (HW & 3) == 0;  // image bases stay 16-byte aligned
     if (full) {
       float4 v = __ldcs(reinterpret_cast<const float4*>(dimg + i));
       d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
@@ -313,6 +313,7 @@ static int grid_for(int64_t work_items, int threads, int per_thread) {
 extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const float* depth, const float* K, const float* pose,
                                  float clip_lo, float clip_hi, float* depth_out,
                                  uint8_t* mask_out, int B, int H, int W, prg_stream_t stream) {
+  if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth && K && pose && depth_out && mask_out, "null pointer");
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
   if (B == 0) return PRG_OK;
@@ -333,6 +334,7 @@ extern "C" __attribute__((visibility("default"))) int prg_pc2depth_f32(const flo
                                 int64_t total_points, const float* K, const float* pose,
                                 float* depth_out, uint8_t* mask_out, int B, int H, int W,
                                 prg_stream_t stream) {
+  if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(offsets && K && depth_out && mask_out, "null pointer");
   PRG_CHECK_ARG(pc || total_points == 0, "null point cloud");
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && total_points >= 0 && B <= 4096, "bad shape");
@@ -353,6 +355,7 @@ extern "C" __attribute__((visibility("default"))) int prg_pc2depth_f32(const flo
 extern "C" __attribute__((visibility("default"))) int prg_depth2pc_f32(const float* depth, const float* K, float clip_lo, float clip_hi,
                                 int use_clip, float invalid, float* pc, uint8_t* valid, int B,
                                 int H, int W, prg_stream_t stream) {
+  if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth && K && pc && valid, "null pointer");
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
   if (B == 0) return PRG_OK;
@@ -368,6 +371,7 @@ extern "C" __attribute__((visibility("default"))) int prg_depth2pc_compact_f64(c
                                         float scale, float clip_lo, float clip_hi, double* pc_out,
                                         int64_t* counts, int64_t* scratch, int B, int H, int W,
                                         prg_stream_t stream) {
+  if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth01 && K && pc_out && counts && scratch, "null pointer");
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
   if (B == 0) return PRG_OK;

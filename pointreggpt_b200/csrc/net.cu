@@ -1,0 +1,734 @@
+// Network handles: packed weights + workspace + per-layer launch plan, and the entry points
+// prg_net_create / prg_unet_forward / prg_maskunet_forward / prg_sampler_run.
+//
+// Mirrors Unet.forward (SDD:920-964) and MaskUnet.forward (DC:871-906): both share the same
+// encoder/decoder trunk; they differ in the stem, the conditioning and the tail.
+//
+// Data layout in HBM: every activation is NHWC fp16 ([image][y][x][channel], channel count a
+// multiple of 64) so that a 64-channel K block of any pixel is one 128-byte row of a TMA box.
+// Skip connections are never concatenated: the consuming convolution walks two sources.
+// fp32 is kept for: the sampler state x_t, GroupNorm statistics, all conditioning vectors,
+// softmax normalisers, the stem input and the final 1x1 + DDNM/posterior update.
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+#include <string.h>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "elementwise.cuh"
+
+using namespace prg;
+
+namespace {
+
+struct Entry {
+  int dtype;  // 0 f32, 1 f16
+  std::vector<int> dims;
+  size_t off, nbytes;
+};
+
+struct Act {
+  __half* p;
+  int H, W, C;
+  int pix_stride;
+};
+
+struct Run {
+  int B;
+  cudaStream_t s;
+  const float* x;          // stem input (B,S,S) f32
+  const int64_t* time;     // per-image timesteps or nullptr
+  int time_scalar;
+  const float* pcond;
+};
+
+}  // namespace
+
+struct prg_net {
+  int kind = 0, maxB = 0, S = 0, dev = 0;
+  uint8_t* d_blob = nullptr;
+  size_t blob_bytes = 0, ws_bytes = 0;
+  std::map<std::string, Entry> ent;
+  std::vector<void*> allocs;
+  std::vector<std::function<int(const Run&)>> ops;
+
+  int dim = 64, levels = 4;
+  std::vector<int> dims;  // [init, dim*m0, ...]
+
+  // conditioning
+  float* cond_act = nullptr;
+  float* ss = nullptr;
+  int ss_rows = 0;
+  CondWeights cw{};
+
+  // per-forward zeroed arena (GroupNorm stats, ctx, zsum) and the colmax arena (0x80 fill)
+  float* zero_arena = nullptr;
+  size_t zero_floats = 0, zero_cap = 0;
+  int* colmax_arena = nullptr;
+  size_t colmax_ints = 0, colmax_cap = 0;
+
+  // scratch activations
+  __half *raw = nullptr, *h1 = nullptr, *resb = nullptr, *xn = nullptr, *qkv = nullptr,
+         *ao = nullptr, *weff = nullptr;
+  size_t unit = 0;  // maxB * S * S * 64 halves
+
+  // tail (filled by the builder)
+  TailParams tail{};
+  __half* stem_out = nullptr;
+  float* x_state = nullptr;  // sampler state (maxB, S*S) f32
+
+  template <typename T>
+  T* dalloc(size_t count) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) return nullptr;
+    allocs.push_back(p);
+    ws_bytes += count * sizeof(T);
+    return reinterpret_cast<T*>(p);
+  }
+  bool has(const std::string& n) const { return ent.count(n) != 0; }
+  const Entry* find(const std::string& n) const {
+    auto it = ent.find(n);
+    if (it == ent.end()) {
+      set_error("packed blob has no entry '%s'", n.c_str());
+      return nullptr;
+    }
+    return &it->second;
+  }
+  const float* f32(const std::string& n) const {
+    const Entry* e = find(n);
+    if (!e || e->dtype != 0) {
+      if (e) set_error("blob entry '%s' is not f32", n.c_str());
+      return nullptr;
+    }
+    return reinterpret_cast<const float*>(d_blob + e->off);
+  }
+  const __half* f16(const std::string& n) const {
+    const Entry* e = find(n);
+    if (!e || e->dtype != 1) {
+      if (e) set_error("blob entry '%s' is not f16", n.c_str());
+      return nullptr;
+    }
+    return reinterpret_cast<const __half*>(d_blob + e->off);
+  }
+  float* take_zero(size_t n) {
+    float* p = zero_arena + zero_floats;
+    zero_floats += n;
+    return p;
+  }
+  int* take_colmax(size_t n) {
+    int* p = colmax_arena + colmax_ints;
+    colmax_ints += n;
+    return p;
+  }
+};
+
+namespace {
+
+#define NET_TRY(expr)      \
+  do {                     \
+    int _rc = (expr);      \
+    if (_rc) return _rc;   \
+  } while (0)
+
+#define NET_PTR(var, expr)          \
+  auto var = (expr);                \
+  if ((var) == nullptr) return PRG_ERR_BLOB;
+
+int parse_blob(prg_net* n, const uint8_t* blob, size_t nbytes) {
+  if (nbytes < 12 || memcmp(blob, "PRGW", 4) != 0) {
+    set_error("packed weights: bad magic");
+    return PRG_ERR_BLOB;
+  }
+  uint32_t version, count;
+  memcpy(&version, blob + 4, 4);
+  memcpy(&count, blob + 8, 4);
+  if (version != 1) {
+    set_error("packed weights: unsupported version %u", version);
+    return PRG_ERR_BLOB;
+  }
+  size_t p = 12;
+  for (uint32_t i = 0; i < count; ++i) {
+    if (p + 2 > nbytes) goto trunc;
+    {
+      uint16_t nl;
+      memcpy(&nl, blob + p, 2);
+      p += 2;
+      if (p + nl + 2 > nbytes) goto trunc;
+      std::string name(reinterpret_cast<const char*>(blob + p), nl);
+      p += nl;
+      Entry e;
+      e.dtype = blob[p];
+      const int nd = blob[p + 1];
+      p += 2;
+      if (p + 4 * (size_t)nd + 16 > nbytes) goto trunc;
+      for (int d = 0; d < nd; ++d) {
+        uint32_t v;
+        memcpy(&v, blob + p, 4);
+        p += 4;
+        e.dims.push_back((int)v);
+      }
+      uint64_t off, nb;
+      memcpy(&off, blob + p, 8);
+      memcpy(&nb, blob + p + 8, 8);
+      p += 16;
+      if (off + nb > nbytes || off % 256 != 0) {
+        set_error("packed weights: entry '%s' out of range", name.c_str());
+        return PRG_ERR_BLOB;
+      }
+      e.off = off;
+      e.nbytes = nb;
+      n->ent[name] = e;
+    }
+  }
+  return PRG_OK;
+trunc:
+  set_error("packed weights: truncated table");
+  return PRG_ERR_BLOB;
+}
+
+Act new_act(prg_net* n, int H, int W, int C) {
+  Act a;
+  a.p = n->dalloc<__half>((size_t)n->maxB * H * W * C);
+  a.H = H; a.W = W; a.C = C; a.pix_stride = C;
+  return a;
+}
+
+ActSrc src_of(const Act& a) { return ActSrc{a.p, a.H, a.W, a.C, a.pix_stride}; }
+
+// Plans a conv for maxB and appends the op.  `fill` may set epilogue extras on the params.
+int add_conv(prg_net* n, int epi, const Act& s0, const Act* s1, int mode, int ksize, int classes,
+             const __half* w, int w_batched, const float* bias, const Act& out,
+             std::function<void(ConvParams&)> fill = nullptr) {
+  ConvLaunch L;
+  ActSrc a0 = src_of(s0), a1;
+  if (s1) a1 = src_of(*s1);
+  NET_TRY(conv_plan(&L, epi, n->maxB, a0, s1 ? &a1 : nullptr, mode, ksize, classes, w, w_batched,
+                    out.C));
+  L.p.out = out.p;
+  L.p.out_pix_stride = out.pix_stride;
+  L.p.out_row_stride = out.W * out.pix_stride;
+  L.p.out_img_stride = (long long)out.H * out.W * out.pix_stride;
+  L.p.bias = bias;
+  if (fill) fill(L.p);
+  const int tiles = L.p.tiles_x * L.p.tiles_y;
+  n->ops.push_back([L, tiles](const Run& r) mutable {
+    L.p.B = r.B;
+    L.grid.x = (unsigned)(tiles * r.B);
+    return conv_run(L, r.s);
+  });
+  return PRG_OK;
+}
+
+int ilog2i(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+struct BlockOut {
+  Act y;                 // output (unused for the final block)
+  const float* stats2;   // final block: statistics of block2
+  const float *g2, *b2;
+};
+
+// ResnetBlock (SDD:720-734 / DC:734-740).  `last` = final_res_block: stop before the second
+// GroupNorm apply (the network tail fuses it with the final 1x1 conv).
+int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x1, int cout,
+                 int* ss_cursor, bool last, BlockOut* bo) {
+  const int H = x0.H, W = x0.W, HW = H * W;
+  const int cin = x0.C + (x1 ? x1->C : 0);
+  Act raw{n->raw, H, W, cout, cout}, h1{n->h1, H, W, cout, cout}, resb{n->resb, H, W, cout, cout};
+  float* st1 = n->take_zero((size_t)n->maxB * 16);
+  float* st2 = n->take_zero((size_t)n->maxB * 16);
+  const int gs_log2 = ilog2i(cout / 8);
+  NET_PTR(w1, n->f16(pfx + ".block1.proj.weight"));
+  NET_PTR(b1, n->f32(pfx + ".block1.proj.bias"));
+  NET_PTR(g1, n->f32(pfx + ".block1.norm.weight"));
+  NET_PTR(be1, n->f32(pfx + ".block1.norm.bias"));
+  NET_PTR(w2, n->f16(pfx + ".block2.proj.weight"));
+  NET_PTR(b2, n->f32(pfx + ".block2.proj.bias"));
+  NET_PTR(g2, n->f32(pfx + ".block2.norm.weight"));
+  NET_PTR(be2, n->f32(pfx + ".block2.norm.bias"));
+
+  NET_TRY(add_conv(n, EPI_GN, x0, x1, 0, 3, 1, w1, 0, b1, raw, [=](ConvParams& p) {
+    p.stats = st1;
+    p.gs_log2 = gs_log2;
+  }));
+  {
+    GnApply a{};
+    a.raw = raw.p; a.stats = st1; a.gamma = g1; a.beta = be1;
+    if (n->kind == PRG_NET_UNET) {
+      a.ss = n->ss;
+      a.ss_stride = n->ss_rows;
+      a.ss_off = *ss_cursor;
+      *ss_cursor += 2 * cout;
+    }
+    a.res = nullptr; a.y = h1.p; a.HW = HW; a.C = cout;
+    n->ops.push_back([a](const Run& r) { return gn_apply(a, r.B, r.s); });
+  }
+  NET_TRY(add_conv(n, EPI_GN, h1, nullptr, 0, 3, 1, w2, 0, b2, raw, [=](ConvParams& p) {
+    p.stats = st2;
+    p.gs_log2 = gs_log2;
+  }));
+  const __half* res_ptr;
+  int res_stride;
+  if (n->has(pfx + ".res_conv.weight")) {
+    NET_PTR(wr, n->f16(pfx + ".res_conv.weight"));
+    NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
+    NET_TRY(add_conv(n, EPI_BIAS, x0, x1, 0, 1, 1, wr, 0, br, resb));
+    res_ptr = resb.p;
+    res_stride = cout;
+  } else {
+    if (x1 != nullptr || cin != cout) {
+      set_error("resblock %s: identity shortcut with mismatched channels", pfx.c_str());
+      return PRG_ERR_BLOB;
+    }
+    res_ptr = x0.p;
+    res_stride = x0.pix_stride;
+  }
+  if (last) {
+    if (res_ptr != resb.p) {
+      set_error("final_res_block must have a res_conv");
+      return PRG_ERR_BLOB;
+    }
+    bo->stats2 = st2; bo->g2 = g2; bo->b2 = be2;
+    return PRG_OK;
+  }
+  Act y = new_act(n, H, W, cout);
+  if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+  {
+    GnApply a{};
+    a.raw = raw.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr;
+    a.res = res_ptr; a.res_pix_stride = res_stride; a.y = y.p; a.HW = HW; a.C = cout;
+    n->ops.push_back([a](const Run& r) { return gn_apply(a, r.B, r.s); });
+  }
+  bo->y = y;
+  return PRG_OK;
+}
+
+// Residual(PreNorm(LinearAttention)) -- SDD:748-769.
+int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
+  const int H = x.H, W = x.W, C = x.C, HW = H * W;
+  Act xn{n->xn, H, W, C, C}, qkv{n->qkv, H, W, 384, 384};
+  NET_PTR(g, n->f32(pfx + ".fn.norm.g"));
+  NET_PTR(wq, n->f16(pfx + ".fn.fn.to_qkv.weight"));
+  NET_PTR(wo, n->f32(pfx + ".fn.fn.to_out.0.weight"));
+  NET_PTR(bo, n->f32(pfx + ".fn.fn.to_out.0.bias"));
+  NET_PTR(g2, n->f32(pfx + ".fn.fn.to_out.1.g"));
+  int* cmax = n->take_colmax((size_t)n->maxB * 128);
+  float* ctx = n->take_zero((size_t)n->maxB * 4096);
+  float* zs = n->take_zero((size_t)n->maxB * 128);
+  const __half* xp = x.p;
+  __half* xnp = xn.p;
+  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, xnp, (int64_t)r.B * HW, C, r.s); });
+  NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
+    p.colmax = cmax;
+    p.q_softmax = 1;
+    p.q_scale = 0.17677669529663687f;  // 32^-0.5
+  }));
+  __half* qkvp = qkv.p;
+  __half* weff = n->weff;
+  n->ops.push_back([=](const Run& r) { return linattn_context(qkvp, cmax, ctx, zs, r.B, HW, r.s); });
+  n->ops.push_back([=](const Run& r) { return linattn_weff(wo, ctx, zs, weff, r.B, C, HW, r.s); });
+  Act y = new_act(n, H, W, C);
+  if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+  Act qsrc{qkv.p, H, W, 128, 384};
+  NET_TRY(add_conv(n, EPI_LN_RES, qsrc, nullptr, 0, 1, 1, weff, 1, bo, y, [=](ConvParams& p) {
+    p.ln_g = g2;
+    p.res = xp;
+  }));
+  *out = y;
+  return PRG_OK;
+}
+
+// Residual(PreNorm(Attention)) -- SDD:782-796.
+int add_midattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
+  const int H = x.H, W = x.W, C = x.C, HW = H * W;
+  Act xn{n->xn, H, W, C, C}, qkv{n->qkv, H, W, 384, 384}, ao{n->ao, H, W, 128, 128};
+  NET_PTR(g, n->f32(pfx + ".fn.norm.g"));
+  NET_PTR(wq, n->f16(pfx + ".fn.fn.to_qkv.weight"));
+  NET_PTR(wo, n->f16(pfx + ".fn.fn.to_out.weight"));
+  NET_PTR(bo, n->f32(pfx + ".fn.fn.to_out.bias"));
+  const __half* xp = x.p;
+  __half* xnp = xn.p;
+  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, xnp, (int64_t)r.B * HW, C, r.s); });
+  NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
+    p.colmax = nullptr;
+    p.q_softmax = 0;
+    p.q_scale = 0.17677669529663687f;
+  }));
+  __half* qkvp = qkv.p;
+  __half* aop = ao.p;
+  n->ops.push_back([=](const Run& r) { return attn_mid(qkvp, aop, r.B, HW, r.s); });
+  Act y = new_act(n, H, W, C);
+  if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+  NET_TRY(add_conv(n, EPI_RES, ao, nullptr, 0, 1, 1, wo, 0, bo, y, [=](ConvParams& p) { p.res = xp; }));
+  *out = y;
+  return PRG_OK;
+}
+
+int build(prg_net* n) {
+  const int S = n->S, B = n->maxB;
+  NET_PTR(meta_e, n->find("meta"));
+  {
+    std::vector<float> meta(meta_e->nbytes / 4);
+    if (cudaMemcpy(meta.data(), n->d_blob + meta_e->off, meta_e->nbytes, cudaMemcpyDeviceToHost) !=
+        cudaSuccess) {
+      set_error("meta readback failed");
+      return PRG_ERR_CUDA;
+    }
+    // meta = [kind, dim, groups, levels, mult_0 .. mult_{L-1}]
+    if (meta.size() < 4 || (int)meta[0] != n->kind) {
+      set_error("packed weights are for network kind %d, not %d", meta.empty() ? -1 : (int)meta[0],
+                n->kind);
+      return PRG_ERR_BLOB;
+    }
+    n->dim = (int)meta[1];
+    if ((int)meta[2] != 8) {
+      set_error("only resnet_block_groups = 8 is supported (got %d)", (int)meta[2]);
+      return PRG_ERR_BLOB;
+    }
+    n->levels = (int)meta[3];
+    if ((int)meta.size() < 4 + n->levels) {
+      set_error("meta entry too short");
+      return PRG_ERR_BLOB;
+    }
+    n->dims.push_back(n->dim);
+    for (int i = 0; i < n->levels; ++i) n->dims.push_back(n->dim * (int)meta[4 + i]);
+  }
+  if (n->dim != 64) {
+    set_error("only dim = 64 is supported by the stem/tail kernels (got %d)", n->dim);
+    return PRG_ERR_BLOB;
+  }
+  const int L = n->levels;
+  if (S % (1 << (L - 1)) != 0 || ((S >> (L - 1)) * (S >> (L - 1))) % 128 != 0) {
+    set_error("image size %d too small / not divisible for %d levels", S, L);
+    return PRG_ERR_ARG;
+  }
+  // ---- scratch sizing: `unit` = one 64-channel full-resolution tensor for maxB images
+  n->unit = (size_t)B * S * S * 64;
+  size_t max_c_hw = 0;  // max over levels of C * H * W (per image)
+  for (int i = 0; i < L; ++i) {
+    const size_t hw = (size_t)(S >> i) * (S >> i);
+    max_c_hw = std::max(max_c_hw, hw * (size_t)n->dims[i + 1]);
+    max_c_hw = std::max(max_c_hw, hw * (size_t)n->dims[i]);
+  }
+  const size_t big = (size_t)B * max_c_hw;
+  n->raw = n->dalloc<__half>(big);
+  n->h1 = n->dalloc<__half>(big);
+  n->resb = n->dalloc<__half>(big);
+  n->xn = n->dalloc<__half>(big);
+  n->qkv = n->dalloc<__half>((size_t)B * S * S * 384);
+  n->ao = n->dalloc<__half>((size_t)B * (S >> (L - 1)) * (S >> (L - 1)) * 128);
+  n->weff = n->dalloc<__half>((size_t)B * n->dims[L] * 128);
+  n->zero_cap = (size_t)B * (64 * 16 + 16 * (4096 + 128));
+  n->zero_arena = n->dalloc<float>(n->zero_cap);
+  n->colmax_cap = (size_t)B * 128 * 16;
+  n->colmax_arena = n->dalloc<int>(n->colmax_cap);
+  n->x_state = n->dalloc<float>((size_t)B * S * S);
+  if (!n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
+      !n->colmax_arena || !n->x_state) {
+    set_error("out of device memory allocating the workspace");
+    return PRG_ERR_CUDA;
+  }
+
+  // ---- conditioning
+  int ss_cursor = 0;
+  if (n->kind == PRG_NET_UNET) {
+    NET_PTR(mw, n->find("mlp_all.weight"));
+    n->ss_rows = mw->dims[0];
+    n->cond_act = n->dalloc<float>((size_t)B * 8 * n->dim);
+    n->ss = n->dalloc<float>((size_t)B * n->ss_rows);
+    if (!n->cond_act || !n->ss) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+    CondWeights& w = n->cw;
+    w.dim = n->dim;
+    NET_PTR(p1, n->find("param_mlp.0.weight"));
+    w.pdim = p1->dims[1];
+    w.t1w = n->f32("time_mlp.1.weight"); w.t1b = n->f32("time_mlp.1.bias");
+    w.t2w = n->f32("time_mlp.3.weight"); w.t2b = n->f32("time_mlp.3.bias");
+    w.p1w = n->f32("param_mlp.0.weight"); w.p1b = n->f32("param_mlp.0.bias");
+    w.p2w = n->f32("param_mlp.2.weight"); w.p2b = n->f32("param_mlp.2.bias");
+    if (!w.t1w || !w.t1b || !w.t2w || !w.t2b || !w.p1w || !w.p1b || !w.p2w || !w.p2b)
+      return PRG_ERR_BLOB;
+    NET_PTR(mlp_w, n->f32("mlp_all.weight"));
+    NET_PTR(mlp_b, n->f32("mlp_all.bias"));
+    const CondWeights cw = n->cw;
+    float* cond_act = n->cond_act;
+    float* ss = n->ss;
+    const int rows = n->ss_rows, K = 8 * n->dim;
+    n->ops.push_back([=](const Run& r) {
+      return cond_embed(cw, r.time, r.time_scalar, r.pcond, cond_act, r.B, r.s);
+    });
+    n->ops.push_back([=](const Run& r) { return cond_mlp(mlp_w, mlp_b, cond_act, ss, rows, K, r.B, r.s); });
+  }
+
+  // ---- stem
+  Act stem = new_act(n, S, S, n->dims[0]);
+  if (!stem.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+  n->stem_out = stem.p;
+  {
+    NET_PTR(sw, n->f32("init_conv.weight"));
+    NET_PTR(sb, n->f32("init_conv.bias"));
+    __half* so = stem.p;
+    if (n->kind == PRG_NET_UNET)
+      n->ops.push_back([=](const Run& r) { return stem_unet(r.x, sw, sb, so, r.B, S, r.s); });
+    else
+      n->ops.push_back([=](const Run& r) { return stem_mask(r.x, sw, sb, so, r.B, S, r.s); });
+  }
+
+  // ---- encoder
+  std::vector<Act> skips;
+  Act x = stem;
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "downs." + std::to_string(i);
+    const int cin = n->dims[i], cnext = n->dims[i + 1];
+    BlockOut bo{};
+    NET_TRY(add_resblock(n, p + ".0", x, nullptr, cin, &ss_cursor, false, &bo));
+    x = bo.y;
+    skips.push_back(x);
+    NET_TRY(add_resblock(n, p + ".1", x, nullptr, cin, &ss_cursor, false, &bo));
+    x = bo.y;
+    Act a;
+    NET_TRY(add_linattn(n, p + ".2", x, &a));
+    x = a;
+    skips.push_back(x);
+    NET_PTR(wd, n->f16(p + ".3.weight"));
+    NET_PTR(bd, n->f32(p + ".3.bias"));
+    if (i < L - 1) {
+      Act y = new_act(n, x.H / 2, x.W / 2, cnext);
+      if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+      NET_TRY(add_conv(n, EPI_BIAS, x, nullptr, 1, 4, 1, wd, 0, bd, y));
+      x = y;
+    } else {
+      Act y = new_act(n, x.H, x.W, cnext);
+      if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+      NET_TRY(add_conv(n, EPI_BIAS, x, nullptr, 0, 3, 1, wd, 0, bd, y));
+      x = y;
+    }
+  }
+  // ---- bottleneck
+  {
+    BlockOut bo{};
+    NET_TRY(add_resblock(n, "mid_block1", x, nullptr, n->dims[L], &ss_cursor, false, &bo));
+    x = bo.y;
+    Act a;
+    NET_TRY(add_midattn(n, "mid_attn", x, &a));
+    x = a;
+    NET_TRY(add_resblock(n, "mid_block2", x, nullptr, n->dims[L], &ss_cursor, false, &bo));
+    x = bo.y;
+  }
+  // ---- decoder
+  for (int j = 0; j < L; ++j) {
+    const int i = L - 1 - j;
+    const std::string p = "ups." + std::to_string(j);
+    const int cin = n->dims[i], cout = n->dims[i + 1];
+    BlockOut bo{};
+    Act sk = skips.back();
+    skips.pop_back();
+    NET_TRY(add_resblock(n, p + ".0", x, &sk, cout, &ss_cursor, false, &bo));
+    x = bo.y;
+    sk = skips.back();
+    skips.pop_back();
+    NET_TRY(add_resblock(n, p + ".1", x, &sk, cout, &ss_cursor, false, &bo));
+    x = bo.y;
+    Act a;
+    NET_TRY(add_linattn(n, p + ".2", x, &a));
+    x = a;
+    if (j < L - 1) {
+      NET_PTR(wu, n->f16(p + ".3.1.weight"));
+      NET_PTR(bu, n->f32(p + ".3.1.bias"));
+      Act y = new_act(n, x.H * 2, x.W * 2, cin);
+      if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+      NET_TRY(add_conv(n, EPI_BIAS, x, nullptr, 0, 3, 4, wu, 0, bu, y));
+      x = y;
+    } else {
+      NET_PTR(wu, n->f16(p + ".3.weight"));
+      NET_PTR(bu, n->f32(p + ".3.bias"));
+      Act y = new_act(n, x.H, x.W, cin);
+      if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+      NET_TRY(add_conv(n, EPI_BIAS, x, nullptr, 0, 3, 1, wu, 0, bu, y));
+      x = y;
+    }
+  }
+  // ---- final block (its second GroupNorm apply lives in the tail kernel)
+  {
+    BlockOut bo{};
+    NET_TRY(add_resblock(n, "final_res_block", x, &stem, n->dim, &ss_cursor, true, &bo));
+    TailParams& t = n->tail;
+    t.raw = n->raw; t.stats = bo.stats2; t.gamma = bo.g2; t.beta = bo.b2; t.res = n->resb;
+    const std::string fc = n->kind == PRG_NET_UNET ? "final_conv" : "final_conv.0";
+    t.fw = n->f32(fc + ".weight");
+    t.fb = n->f32(fc + ".bias");
+    if (!t.fw || !t.fb) return PRG_ERR_BLOB;
+    t.HW = S * S;
+  }
+  if (n->kind == PRG_NET_UNET && ss_cursor != n->ss_rows) {
+    set_error("conditioning rows mismatch: plan uses %d, blob has %d", ss_cursor, n->ss_rows);
+    return PRG_ERR_BLOB;
+  }
+  if (n->zero_floats > n->zero_cap || n->colmax_ints > n->colmax_cap) {
+    set_error("internal: arena overflow");
+    return PRG_ERR_STATE;
+  }
+  return PRG_OK;
+}
+
+int run_trunk(prg_net* n, const Run& r) {
+  PRG_CUDA_OK(cudaMemsetAsync(n->zero_arena, 0, n->zero_floats * sizeof(float), r.s));
+  if (n->colmax_ints)
+    PRG_CUDA_OK(cudaMemsetAsync(n->colmax_arena, 0x80, n->colmax_ints * sizeof(int), r.s));
+  for (auto& op : n->ops) NET_TRY(op(r));
+  return PRG_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+EXPORT int prg_net_create(prg_net** out, int kind, const void* blob_host, size_t nbytes,
+                          int max_batch, int size, int device) {
+  PRG_CHECK_ARG(out && blob_host, "null pointer");
+  PRG_CHECK_ARG(kind == PRG_NET_UNET || kind == PRG_NET_MASKUNET, "kind");
+  PRG_CHECK_ARG(max_batch >= 1 && max_batch <= 4096 && size >= 16, "max_batch / size");
+  *out = nullptr;
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    set_error("cannot select CUDA device %d (no GPU? there is no CPU fallback)", device);
+    return PRG_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  PRG_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libprg.so is built for sm_100a; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return PRG_ERR_CUDA;
+  }
+  prg_net* n = new prg_net();
+  n->kind = kind; n->maxB = max_batch; n->S = size; n->dev = device;
+  int rc = parse_blob(n, reinterpret_cast<const uint8_t*>(blob_host), nbytes);
+  if (rc == PRG_OK) {
+    n->blob_bytes = nbytes;
+    n->d_blob = n->dalloc<uint8_t>(nbytes);
+    if (!n->d_blob) {
+      set_error("out of device memory for the weights");
+      rc = PRG_ERR_CUDA;
+    } else if (cudaMemcpy(n->d_blob, blob_host, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("weight upload failed");
+      rc = PRG_ERR_CUDA;
+    }
+  }
+  if (rc == PRG_OK) rc = build(n);
+  if (rc != PRG_OK) {
+    for (void* p : n->allocs) cudaFree(p);
+    delete n;
+    return rc;
+  }
+  *out = n;
+  return PRG_OK;
+}
+
+EXPORT void prg_net_destroy(prg_net* n) {
+  if (!n) return;
+  DeviceGuard guard(n->dev);
+  cudaDeviceSynchronize();
+  for (void* p : n->allocs) cudaFree(p);
+  delete n;
+}
+
+EXPORT size_t prg_net_device_bytes(const prg_net* n) { return n ? n->ws_bytes : 0; }
+
+EXPORT int prg_unet_forward(prg_net* n, const float* x, const int64_t* time, const float* pcond,
+                            float* out, int B, prg_stream_t stream) {
+  PRG_CHECK_ARG(n && n->kind == PRG_NET_UNET, "not a Unet handle");
+  if (B == 0) return PRG_OK;
+  PRG_CHECK_ARG(x && time && pcond && out, "null pointer");
+  PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
+  Run r{B, (cudaStream_t)stream, x, time, 0, pcond};
+  NET_TRY(run_trunk(n, r));
+  TailParams t = n->tail;
+  t.mode = 0;
+  t.out = out;
+  return net_tail(t, B, r.s);
+}
+
+EXPORT int prg_maskunet_forward(prg_net* n, const float* depth01, float* prob, uint8_t* keep,
+                                float thresh, int B, prg_stream_t stream) {
+  PRG_CHECK_ARG(n && n->kind == PRG_NET_MASKUNET, "not a MaskUnet handle");
+  if (B == 0) return PRG_OK;
+  PRG_CHECK_ARG(depth01 && (prob || keep), "null pointer");
+  PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
+  Run r{B, (cudaStream_t)stream, depth01, nullptr, 0, nullptr};
+  NET_TRY(run_trunk(n, r));
+  TailParams t = n->tail;
+  t.mode = 1;
+  t.out = prob;
+  t.keep = keep;
+  t.thresh = thresh;
+  return net_tail(t, B, r.s);
+}
+
+EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const float* pcond,
+                           const float* img_cond, const float* noise, uint64_t seed, float* out,
+                           int B, prg_stream_t stream) {
+  PRG_CHECK_ARG(n && n->kind == PRG_NET_UNET, "not a Unet handle");
+  if (B == 0) return PRG_OK;
+  PRG_CHECK_ARG(steps && pcond && out && nsteps >= 1, "null pointer / no steps");
+  PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t npx = (size_t)B * n->S * n->S;
+  // x_T
+  if (noise != nullptr)
+    PRG_CUDA_OK(cudaMemcpyAsync(n->x_state, noise, npx * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  else
+    NET_TRY(fill_normal(n->x_state, (int64_t)npx, seed, 0ull, s));
+  size_t slab = 1;
+  for (int i = 0; i < nsteps; ++i) {
+    const prg_step& st = steps[i];
+    PRG_CHECK_ARG(st.kind >= 0 && st.kind <= 4, "step kind");
+    Run r{B, s, n->x_state, nullptr, st.t, pcond};
+    NET_TRY(run_trunk(n, r));
+    TailParams t = n->tail;
+    t.mode = 2;
+    t.x_t = n->x_state;
+    const bool last = (i == nsteps - 1);
+    t.out = last ? out : n->x_state;
+    t.img_cond = img_cond;
+    t.sampler = st.kind;
+    t.clip_x_start = (st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST ||
+                      st.kind == PRG_STEP_REFINE_DDIM);
+    t.use_ddnm = (img_cond != nullptr) &&
+                 (st.kind == PRG_STEP_P_SAMPLE || st.kind == PRG_STEP_DDIM ||
+                  st.kind == PRG_STEP_DDIM_LAST);
+    t.add_noise = st.add_noise;
+    t.noise = nullptr;
+    if (st.add_noise) {
+      if (noise != nullptr) t.noise = noise + slab * npx;
+      t.seed = seed;
+      t.noise_offset = (unsigned long long)slab * npx;
+      ++slab;
+    }
+    t.c0 = st.c0; t.c1 = st.c1; t.c2 = st.c2; t.c3 = st.c3; t.c4 = st.c4;
+    t.unnormalize = st.unnormalize;
+    if (st.unnormalize && !last) {
+      set_error("only the last step may unnormalize");
+      return PRG_ERR_ARG;
+    }
+    NET_TRY(net_tail(t, B, s));
+  }
+  return PRG_OK;
+}

@@ -93,3 +93,106 @@ class BlobWriter:
         for o, b in payload:
             buf[o:o + len(b)] = b
         return bytes(buf)
+
+
+# --------------------------------------------------------------------------- #
+# state-dict -> blob
+# --------------------------------------------------------------------------- #
+KIND_UNET, KIND_MASKUNET = 1, 2
+
+
+def _levels(sd):
+    n = 0
+    while ("downs.%d.0.block1.proj.weight" % n) in sd:
+        n += 1
+    return n
+
+
+def resblock_order(levels):
+    """Order in which the forward pass visits the ResnetBlocks (= row order of mlp_all)."""
+    names = []
+    for i in range(levels):
+        names += ["downs.%d.0" % i, "downs.%d.1" % i]
+    names += ["mid_block1", "mid_block2"]
+    for i in range(levels):
+        names += ["ups.%d.0" % i, "ups.%d.1" % i]
+    names.append("final_res_block")
+    return names
+
+
+def _pack_trunk(w, sd, kind, groups):
+    levels = _levels(sd)
+    dim = sd["init_conv.weight"].shape[0]
+    mults = [sd["downs.%d.3.weight" % i].shape[0] // dim for i in range(levels)]
+    w.add("meta", torch.tensor([kind, dim, groups, levels] + mults, dtype=torch.float32), "f32")
+    w.add("init_conv.weight", sd["init_conv.weight"].reshape(dim, -1), "f32")
+    w.add("init_conv.bias", sd["init_conv.bias"], "f32")
+    mlp_w, mlp_b = [], []
+    for name in resblock_order(levels):
+        for blk in ("block1", "block2"):
+            p = "%s.%s" % (name, blk)
+            w.add(p + ".proj.weight",
+                  conv_weight_kmajor(standardize(sd[p + ".proj.weight"].float())), "f16")
+            w.add(p + ".proj.bias", sd[p + ".proj.bias"], "f32")
+            w.add(p + ".norm.weight", sd[p + ".norm.weight"], "f32")
+            w.add(p + ".norm.bias", sd[p + ".norm.bias"], "f32")
+        if (name + ".res_conv.weight") in sd:
+            w.add(name + ".res_conv.weight",
+                  conv_weight_kmajor(sd[name + ".res_conv.weight"].float()), "f16")
+            w.add(name + ".res_conv.bias", sd[name + ".res_conv.bias"], "f32")
+        if (name + ".mlp.1.weight") in sd:
+            mlp_w.append(sd[name + ".mlp.1.weight"].float())
+            mlp_b.append(sd[name + ".mlp.1.bias"].float())
+    if mlp_w:
+        w.add("mlp_all.weight", torch.cat(mlp_w, 0), "f32")
+        w.add("mlp_all.bias", torch.cat(mlp_b, 0), "f32")
+    attn = ["downs.%d.2" % i for i in range(levels)] + ["ups.%d.2" % i for i in range(levels)]
+    for p in attn:
+        c = sd[p + ".fn.norm.g"].numel()
+        w.add(p + ".fn.norm.g", sd[p + ".fn.norm.g"].reshape(c), "f32")
+        w.add(p + ".fn.fn.to_qkv.weight", conv_weight_kmajor(sd[p + ".fn.fn.to_qkv.weight"].float()),
+              "f16")
+        # fp32: folded with the per-image context into W_eff on the device
+        w.add(p + ".fn.fn.to_out.0.weight", sd[p + ".fn.fn.to_out.0.weight"].reshape(c, -1), "f32")
+        w.add(p + ".fn.fn.to_out.0.bias", sd[p + ".fn.fn.to_out.0.bias"], "f32")
+        w.add(p + ".fn.fn.to_out.1.g", sd[p + ".fn.fn.to_out.1.g"].reshape(c), "f32")
+    p = "mid_attn"
+    c = sd[p + ".fn.norm.g"].numel()
+    w.add(p + ".fn.norm.g", sd[p + ".fn.norm.g"].reshape(c), "f32")
+    w.add(p + ".fn.fn.to_qkv.weight", conv_weight_kmajor(sd[p + ".fn.fn.to_qkv.weight"].float()), "f16")
+    w.add(p + ".fn.fn.to_out.weight", conv_weight_kmajor(sd[p + ".fn.fn.to_out.weight"].float()), "f16")
+    w.add(p + ".fn.fn.to_out.bias", sd[p + ".fn.fn.to_out.bias"], "f32")
+    for i in range(levels):
+        p = "downs.%d.3" % i
+        w.add(p + ".weight", conv_weight_kmajor(sd[p + ".weight"].float()), "f16")
+        w.add(p + ".bias", sd[p + ".bias"], "f32")
+        p = "ups.%d.3" % i
+        if (p + ".1.weight") in sd:
+            w.add(p + ".1.weight", upsample_fold_weight(sd[p + ".1.weight"].float()), "f16")
+            w.add(p + ".1.bias", sd[p + ".1.bias"], "f32")
+        else:
+            w.add(p + ".weight", conv_weight_kmajor(sd[p + ".weight"].float()), "f16")
+            w.add(p + ".bias", sd[p + ".bias"], "f32")
+
+
+def pack_unet(sd, groups=8):
+    """Unet state-dict (280 entries, SDD:802-918) -> blob bytes."""
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    w = BlobWriter()
+    _pack_trunk(w, sd, KIND_UNET, groups)
+    for k in ("time_mlp.1", "time_mlp.3", "param_mlp.0", "param_mlp.2"):
+        w.add(k + ".weight", sd[k + ".weight"], "f32")
+        w.add(k + ".bias", sd[k + ".bias"], "f32")
+    w.add("final_conv.weight", sd["final_conv.weight"].reshape(-1), "f32")
+    w.add("final_conv.bias", sd["final_conv.bias"], "f32")
+    return w.tobytes()
+
+
+def pack_maskunet(sd, groups=8):
+    """MaskUnet state-dict (234 entries, DC:807-869) -> blob bytes."""
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    w = BlobWriter()
+    _pack_trunk(w, sd, KIND_MASKUNET, groups)
+    w.add("final_conv.0.weight", sd["final_conv.0.weight"].reshape(-1), "f32")
+    w.add("final_conv.0.bias", sd["final_conv.0.bias"], "f32")
+    return w.tobytes()

@@ -13,6 +13,10 @@ pytestmark = pytest.mark.gpu
 def _inputs(B, H, W, seed):
     d01 = S.synthetic_depth_batch(100 + seed, B, H, W)
     K = S.synthetic_intrinsics(B, 256 if H == 256 else None, seed=seed)
+    if (H, W) not in ((256, 256), (480, 640)):      # tiny maps: principal point at the centre
+        K = K.copy()
+        K[:, 0, 0] = K[:, 1, 1] = 1.2 * W
+        K[:, 0, 2], K[:, 1, 2] = W / 2, H / 2
     P = S.synthetic_poses(B, seed=seed + 1)
     return d01, K, P
 

@@ -1,0 +1,150 @@
+"""U-Net / MaskUnet / sampler parity on the GPU (through the C ABI) against the fp32 oracle.
+
+Tolerance: north-star "fp within 1e-3 rel" -> relative L2 error <= 1e-3 per network evaluation
+(tensor-core operands are fp16, accumulation / statistics / state fp32)."""
+import pytest
+import torch
+
+from oracle import torch_ref as R
+from pointreggpt_b200 import nets
+from pointreggpt_b200.diffusion import GaussianDiffusion
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def unet():
+    torch.manual_seed(0)
+    net = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net.cuda(), sd
+
+
+@pytest.fixture(scope="module")
+def masknet():
+    torch.manual_seed(0)
+    net = nets.MaskUnet(dim=64, dim_mults=(1, 2, 4, 8))
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net.cuda(), sd
+
+
+def _pcond(b):
+    base = torch.tensor([[303.88547, 304.18253, 128.5, 128.0]])
+    return base.repeat(b, 1) * torch.linspace(1.0, 0.95, b)[:, None]
+
+
+def test_unet_forward_128(unet):
+    net, sd = unet
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, 128, 128, generator=g)
+    t = torch.tensor([999, 3])
+    pc = _pcond(2)
+    ref = R.unet_forward(sd, x, t, pc)
+    got = net(x.cuda(), t.cuda(), pc.cuda()).cpu()
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    e = rel_l2(got, ref)
+    print("unet fwd 128 rel-l2", e, "max abs", (got - ref).abs().max().item())
+    assert e <= REL_TOL
+
+
+def test_unet_forward_256_batch_independent(unet):
+    net, sd = unet
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 1, 256, 256, generator=g)
+    t = torch.tensor([500, 500, 20])
+    pc = _pcond(3)
+    got = net(x.cuda(), t.cuda(), pc.cuda()).cpu()
+    ref0 = R.unet_forward(sd, x[:1], t[:1], pc[:1])
+    e = rel_l2(got[:1], ref0)
+    print("unet fwd 256 rel-l2", e)
+    assert e <= REL_TOL
+    # images are independent: running a sub-batch alone gives the same numbers (up to the
+    # order of the fp32 atomics of the GroupNorm statistics)
+    alone = net(x[2:].cuda(), t[2:].cuda(), pc[2:].cuda()).cpu()
+    assert rel_l2(alone, got[2:]) < 1e-5
+
+
+def test_maskunet_forward(masknet):
+    net, sd = masknet
+    g = torch.Generator().manual_seed(7)
+    d = torch.rand(2, 1, 128, 128, generator=g) * 0.4
+    d[torch.rand(d.shape, generator=g) < 0.3] = 0
+    d[1, :, :40] = 0                                   # a fully invalid band (all-invalid windows)
+    ref = R.maskunet_forward(sd, d)
+    got = net(d.cuda()).cpu()
+    assert torch.isfinite(got).all()
+    e = rel_l2(got, ref)
+    print("maskunet rel-l2", e, "max abs", (got - ref).abs().max().item())
+    assert e <= REL_TOL
+    keep = net.keep_mask(d.cuda(), 0.5).cpu()
+    agree = (keep == (ref > 0.5)).float().mean().item()
+    assert agree > 0.999
+
+
+def _img_cond(b, s, g):
+    d = torch.rand(b, 1, s, s, generator=g) * 0.3
+    m = (torch.rand(b, 1, s, s, generator=g) < 0.6).float()
+    return torch.cat([d * m, m], 1) * 2 - 1
+
+
+@pytest.mark.parametrize("refine", [False, True])
+def test_p_sample_loop_injected_noise(unet, refine):
+    net, sd = unet
+    s, b, T = 128, 2, 4
+    diff = GaussianDiffusion(net, image_size=s, timesteps=T, objective='pred_x0',
+                             beta_schedule='sigmoid', is_ddnm_sampling=True).cuda()
+    g = torch.Generator().manual_seed(8)
+    n = diff.num_noise_draws(refine)
+    assert n == T          # x_T + (T - 1) draws
+    noise = torch.randn(n, b, 1, s, s, generator=g)
+    ic = _img_cond(b, s, g)
+    pc = _pcond(b)
+    ref = R.p_sample_loop(sd, R.make_schedule(T), pc, ic, list(noise), has_refine_step=refine)
+    got = diff.sample(param_cond=pc.cuda(), img_cond=ic.cuda(), has_refine_step=refine,
+                      noise=noise.cuda()).cpu()
+    e = rel_l2(got, ref)
+    print("p_sample_loop rel-l2", e, "max abs", (got - ref).abs().max().item())
+    assert e <= 2e-3       # T chained evaluations
+    # DDNM: conditioned pixels reproduce the condition exactly at t = 0 (SDD:1218)
+    mask = ic[:, 1:2] > 0
+    if not refine:
+        want = ((ic[:, 0:1] + 1) * 0.5)[mask]
+        assert torch.allclose(got[mask], want, atol=1e-6)
+
+
+def test_ddim_injected_noise(unet):
+    net, sd = unet
+    s, b, T, K = 128, 1, 12, 3
+    diff = GaussianDiffusion(net, image_size=s, timesteps=T, sampling_timesteps=K,
+                             objective='pred_x0', beta_schedule='sigmoid',
+                             ddim_sampling_eta=1.0, is_ddnm_sampling=True).cuda()
+    g = torch.Generator().manual_seed(9)
+    n = diff.num_noise_draws(True)
+    noise = torch.randn(n, b, 1, s, s, generator=g)
+    ic = _img_cond(b, s, g)
+    pc = _pcond(b)
+    ref = R.ddim_sample(sd, R.make_schedule(T), pc, ic, list(noise), K, 1.0, has_refine_step=True)
+    got = diff.sample(param_cond=pc.cuda(), img_cond=ic.cuda(), has_refine_step=True,
+                      noise=noise.cuda()).cpu()
+    e = rel_l2(got, ref)
+    print("ddim rel-l2", e)
+    assert e <= 2e-3
+
+
+def test_sampler_philox_runs_and_is_seeded(unet):
+    net, _ = unet
+    diff = GaussianDiffusion(net, image_size=128, timesteps=3, objective='pred_x0',
+                             beta_schedule='sigmoid').cuda()
+    pc = _pcond(2).cuda()
+    a = diff.sample(param_cond=pc, seed=11)
+    b = diff.sample(param_cond=pc, seed=11)
+    c = diff.sample(param_cond=pc, seed=12)
+    assert torch.isfinite(a).all() and a.min() >= 0 and a.max() <= 1
+    assert (a - b).abs().max().item() < 1e-4
+    assert (a - c).abs().max().item() > 1e-3
