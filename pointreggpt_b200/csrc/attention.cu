@@ -49,10 +49,11 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // linear attention: context accumulation
 // ------------------------------------------------------------------------------------------
 constexpr int kCtxTile = 64;  // pixels per smem tile
+constexpr double kCtxScale = 16777216.0;  // 2^24 fixed point for the cross-CTA sums
 
 __global__ void __launch_bounds__(128)
 k_linattn_context(const __half* __restrict__ qkv, const int* __restrict__ colmax,
-                  float* __restrict__ ctx, float* __restrict__ zsum, int n, int chunk) {
+                  long long* __restrict__ ctx, long long* __restrict__ zsum, int n, int chunk) {
   // [row][16 chunks of 16 B], chunk index XOR (row & 7): conflict-free ldmatrix
   __shared__ __align__(16) __half sK[kCtxTile * 128];
   __shared__ __align__(16) __half sV[kCtxTile * 128];
@@ -128,22 +129,25 @@ k_linattn_context(const __half* __restrict__ qkv, const int* __restrict__ colmax
     }
     __syncthreads();
   }
-  // ---- flush: ctx [b][h][d][e], zsum [b][h*32+d]
-  float* cb = ctx + ((size_t)b * 4 + h) * 1024;
+  // ---- flush: ctx [b][h][d][e], zsum [b][h*32+d]; fixed-point integer atomics so the sum over
+  // pixel chunks does not depend on CTA arrival order
+  unsigned long long* cb = reinterpret_cast<unsigned long long*>(ctx) + ((size_t)b * 4 + h) * 1024;
+  unsigned long long* zb = reinterpret_cast<unsigned long long*>(zsum) + (size_t)b * 128 + h * 32;
+  auto fx = [](float v) { return (unsigned long long)__double2ll_rn((double)v * kCtxScale); };
 #pragma unroll
   for (int mb = 0; mb < 2; ++mb) {
     const int d = mb * 16 + (lane >> 2);
 #pragma unroll
     for (int eb = 0; eb < 4; ++eb) {
       const int e = eb * 8 + (lane & 3) * 2;
-      atomicAdd(cb + d * 32 + e, acc[mb][eb][0]);
-      atomicAdd(cb + d * 32 + e + 1, acc[mb][eb][1]);
-      atomicAdd(cb + (d + 8) * 32 + e, acc[mb][eb][2]);
-      atomicAdd(cb + (d + 8) * 32 + e + 1, acc[mb][eb][3]);
+      atomicAdd(cb + d * 32 + e, fx(acc[mb][eb][0]));
+      atomicAdd(cb + d * 32 + e + 1, fx(acc[mb][eb][1]));
+      atomicAdd(cb + (d + 8) * 32 + e, fx(acc[mb][eb][2]));
+      atomicAdd(cb + (d + 8) * 32 + e + 1, fx(acc[mb][eb][3]));
     }
     if ((lane & 3) == 0) {
-      atomicAdd(zsum + (size_t)b * 128 + h * 32 + d, zacc[mb][0]);
-      atomicAdd(zsum + (size_t)b * 128 + h * 32 + d + 8, zacc[mb][2]);
+      atomicAdd(zb + d, fx(zacc[mb][0]));
+      atomicAdd(zb + d + 8, fx(zacc[mb][2]));
     }
   }
 }
@@ -154,7 +158,7 @@ k_linattn_context(const __half* __restrict__ qkv, const int* __restrict__ colmax
 // and .trans hands thread (lane) the element [pixel = 2*(lane%4)+{0,1}][channel = lane/4],
 // i.e. A[row = channel][k = pixel]: exactly the m16n8k16 A fragment order a0a1|a2a3|a4a5|a6a7.
 
-int linattn_context(const __half* qkv, const int* colmax, float* ctx, float* zsum, int B, int n,
+int linattn_context(const __half* qkv, const int* colmax, long long* ctx, long long* zsum, int B, int n,
                     cudaStream_t s) {
   if (n % kCtxTile != 0) {
     set_error("linattn_context: n=%d is not a multiple of %d", n, kCtxTile);
@@ -172,13 +176,13 @@ int linattn_context(const __half* qkv, const int* colmax, float* ctx, float* zsu
 
 // W_eff[b][c][h*32+d] = sum_e W_out[c][h*32+e] * ctx[b][h][d][e] / (Z[b][h*32+d] * n)
 __global__ void __launch_bounds__(128)
-k_linattn_weff(const float* __restrict__ wout, const float* __restrict__ ctx,
-               const float* __restrict__ zsum, __half* __restrict__ weff, int C, float inv_n) {
+k_linattn_weff(const float* __restrict__ wout, const long long* __restrict__ ctx,
+               const long long* __restrict__ zsum, __half* __restrict__ weff, int C, float inv_n) {
   __shared__ float sC[4 * 32 * 33];
   const int b = blockIdx.y, c = blockIdx.x, hd = threadIdx.x;
   for (int i = threadIdx.x; i < 4096; i += 128) {
     const int hh = i >> 10, d = (i >> 5) & 31, e = i & 31;
-    sC[(hh * 32 + d) * 33 + e] = ctx[(size_t)b * 4096 + i];
+    sC[(hh * 32 + d) * 33 + e] = (float)((double)ctx[(size_t)b * 4096 + i] * (1.0 / kCtxScale));
   }
   __syncthreads();
   const int h = hd >> 5;
@@ -186,11 +190,11 @@ k_linattn_weff(const float* __restrict__ wout, const float* __restrict__ ctx,
   float a = 0.f;
 #pragma unroll
   for (int e = 0; e < 32; ++e) a = fmaf(__ldg(w + e), sC[hd * 33 + e], a);
-  a = a * inv_n / zsum[(size_t)b * 128 + hd];
+  a = a * inv_n / (float)((double)zsum[(size_t)b * 128 + hd] * (1.0 / kCtxScale));
   weff[((size_t)b * C + c) * 128 + hd] = __float2half_rn(a);
 }
 
-int linattn_weff(const float* wout, const float* ctx, const float* zsum, __half* weff, int B, int C,
+int linattn_weff(const float* wout, const long long* ctx, const long long* zsum, __half* weff, int B, int C,
                  int n, cudaStream_t s) {
   dim3 g(C, B);
   k_linattn_weff<<<g, 128, 0, s>>>(wout, ctx, zsum, weff, C, 1.f / (float)n);

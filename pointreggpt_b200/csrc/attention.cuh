@@ -6,11 +6,12 @@
 namespace prg {
 
 // qkv (B, n, 384) fp16: [0,128) q', [128,256) k, [256,384) v.  colmax (B,128): max_n k as
-// ordered ints.  ctx (B,4,32,32) and zsum (B,128) fp32 must be zero on entry.
-int linattn_context(const __half* qkv, const int* colmax, float* ctx, float* zsum, int B, int n,
+// ordered ints.  ctx (B,4,32,32) and zsum (B,128) are 2^-24 fixed-point int64 sums (order-independent,
+// bit-reproducible), zero on entry.
+int linattn_context(const __half* qkv, const int* colmax, long long* ctx, long long* zsum, int B, int n,
                     cudaStream_t s);
 // weff (B, C, 128) fp16 = W_out (C,128) fp32 folded with the normalised context.
-int linattn_weff(const float* wout, const float* ctx, const float* zsum, __half* weff, int B, int C,
+int linattn_weff(const float* wout, const long long* ctx, const long long* zsum, __half* weff, int B, int C,
                  int n, cudaStream_t s);
 // out (B, n, 128) fp16 = softmax(q k^T) v per head (q already scaled).
 int attn_mid(const __half* qkv, __half* out, int B, int n, cudaStream_t s);

@@ -41,10 +41,12 @@ struct alignas(8) SmemCtl {
   uint64_t tmem_full;
   uint32_t tmem_addr;
   uint32_t pad;
-  float stats[16];      // EPI_GN: up to 8 groups x (sum, sumsq)
+  float stats[64];      // EPI_GN: [epilogue warp][up to 8 groups][sum, sumsq]
   int colmax[128];      // EPI_QKV (k tile): per-column max across the 4 epilogue warps
 };
 static_assert(sizeof(SmemCtl) <= 1024, "control block too large");
+
+constexpr double kStatScale = 1048576.0;  // 2^20 fixed point, see conv_tc.cuh
 
 __device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
 
@@ -92,7 +94,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     tmem_alloc(&ctl->tmem_addr, BN);
     tmem_relinquish();
   }
-  if (EPI == EPI_GN && threadIdx.x < 16) ctl->stats[threadIdx.x] = 0.f;
+  if (EPI == EPI_GN && threadIdx.x < 64) ctl->stats[threadIdx.x] = 0.f;
   if (EPI == EPI_QKV && threadIdx.x < 128) ctl->colmax[threadIdx.x] = INT_MIN;
   tc_fence_before();
   __syncthreads();
@@ -234,11 +236,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
           }
         }
         if (lane == 0) {
+          // this warp's private slots, accumulated in program order (deterministic)
+          float* ws = ctl->stats + quarter * 16;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int grp = (c + g * 8) >> p.gs_log2;  // group index inside this tile
-            atomicAdd(&ctl->stats[grp * 2 + 0], s4[g]);
-            atomicAdd(&ctl->stats[grp * 2 + 1], q4[g]);
+            ws[grp * 2 + 0] += s4[g];
+            ws[grp * 2 + 1] += q4[g];
           }
         }
       } else if (EPI == EPI_QKV) {
@@ -310,13 +314,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
 
     if (EPI == EPI_GN) {
-      // 4 epilogue warps -> one global atomic per (group, moment) of this tile
+      // 4 epilogue warps -> one global atomic per (group, moment) of this tile.  The cross-CTA
+      // sum is a 64-bit fixed-point integer add: order-independent, hence bit-reproducible
+      // (an fp32 atomic's rounding would depend on arrival order, and the fp16 re-rounding of
+      // the activations amplifies even 1e-7 differences to the 5e-4 level a few layers on).
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 64;
       const int ngrp = BN >> p.gs_log2;
       if (e < ngrp * 2) {
         const int g0 = n0 >> p.gs_log2;
-        atomicAdd(p.stats + ((size_t)img * 8 + g0) * 2 + e, ctl->stats[e]);
+        const float v = (ctl->stats[e] + ctl->stats[16 + e]) + (ctl->stats[32 + e] + ctl->stats[48 + e]);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)img * 8 + g0) * 2 + e,
+                  (unsigned long long)__double2ll_rn((double)v * kStatScale));
       }
     }
     if (EPI == EPI_QKV) {

@@ -39,7 +39,7 @@ struct ConvParams {
   int out_scale;         // 1, or 2 when classes == 4
   const float* bias;     // [Cout] or nullptr
   const __half* res;     // residual, same addressing as out (EPI_RES / EPI_LN_RES)
-  float* stats;          // EPI_GN: [B][8][2] fp32 (sum, sumsq), zeroed by the caller
+  long long* stats;      // EPI_GN: [B][8][2] (sum, sumsq) as 2^-20 fixed point, zeroed by the caller
   int gs_log2;           // EPI_GN: log2(channels per group)
   const float* ln_g;     // EPI_LN_RES: [Cout]
   int* colmax;           // EPI_QKV: [B][128] order-preserving int encoding of max_n k, or nullptr
@@ -68,6 +68,8 @@ struct ActSrc {
 int conv_plan(ConvLaunch* L, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
               int classes, const __half* w, int w_batched, int Cout);
 int conv_run(const ConvLaunch& L, cudaStream_t stream);
+
+constexpr float kStatUnscale = 1.0f / 1048576.0f;  // fixed-point statistics -> float
 
 // order-preserving float <-> int (for atomicMax on floats)
 __host__ __device__ inline int float_to_ordered(float f) {

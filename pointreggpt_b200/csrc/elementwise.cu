@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the U-Net forward / sampler step.  See elementwise.cuh for semantics.
 #include "common.cuh"
 #include "elementwise.cuh"
+#include "conv_tc.cuh"
 
 namespace prg {
 
@@ -224,16 +225,19 @@ int cond_mlp(const float* W, const float* bias, const float* cond_act, float* ss
 // ------------------------------------------------------------------------------------------
 // GroupNorm apply (+ scale/shift, SiLU, optional residual).  One thread = 8 channels of a pixel.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gn_coeffs(const float* stats, const float* gamma, const float* beta,
+__device__ __forceinline__ void gn_coeffs(const long long* stats, const float* gamma, const float* beta,
                                           const float* ss_row, int C, int HW, int b, float* sA,
                                           float* sB) {
   const int gs = C >> 3;
   const float inv_n = 1.f / ((float)gs * (float)HW);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / gs;
-    const float sum = stats[((size_t)b * 8 + g) * 2 + 0], sq = stats[((size_t)b * 8 + g) * 2 + 1];
-    const float mean = sum * inv_n;
-    const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+    // exact integer sums -> double for the mean/variance (no cancellation issue), then fp32
+    const double sum = (double)stats[((size_t)b * 8 + g) * 2 + 0] * (double)kStatUnscale;
+    const double sq = (double)stats[((size_t)b * 8 + g) * 2 + 1] * (double)kStatUnscale;
+    const double meand = sum * (double)inv_n;
+    const float mean = (float)meand;
+    const float var = fmaxf((float)(sq * (double)inv_n - meand * meand), 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
     float a = rstd * gamma[c], d = beta[c] - mean * rstd * gamma[c];
     if (ss_row != nullptr) {
@@ -314,8 +318,8 @@ int gn_apply(const GnApply& a, int B, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256)
-k_ln_apply(const __half* __restrict__ x, const float* __restrict__ g, __half* __restrict__ y,
-           int64_t npix) {
+k_ln_apply(const __half* __restrict__ x, const float* __restrict__ g,
+           const __half* __restrict__ res, __half* __restrict__ y, int64_t npix) {
   constexpr int PER = C / 32;  // channels per lane (2, 4, 8 or 16), contiguous
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -365,22 +369,28 @@ k_ln_apply(const __half* __restrict__ x, const float* __restrict__ g, __half* __
     __half* dst = y + p * C + lane * PER;
 #pragma unroll
     for (int j = 0; j < PER; j += 2) {
-      *reinterpret_cast<__half2*>(dst + j) =
-          __floats2half2_rn((f[j] - mean) * rstd * gl[j], (f[j + 1] - mean) * rstd * gl[j + 1]);
+      float o0 = (f[j] - mean) * rstd * gl[j], o1 = (f[j + 1] - mean) * rstd * gl[j + 1];
+      if (res != nullptr) {
+        const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(res + p * C + lane * PER + j));
+        o0 += r2.x;
+        o1 += r2.y;
+      }
+      *reinterpret_cast<__half2*>(dst + j) = __floats2half2_rn(o0, o1);
     }
   }
 }
 
-int ln_apply(const __half* x, const float* g, __half* y, int64_t npix, int C, cudaStream_t s) {
+int ln_apply(const __half* x, const float* g, const __half* res, __half* y, int64_t npix, int C,
+             cudaStream_t s) {
   int64_t blocks = (npix * 32 + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   switch (C) {
-    case 64: k_ln_apply<64><<<(int)blocks, 256, 0, s>>>(x, g, y, npix); break;
-    case 128: k_ln_apply<128><<<(int)blocks, 256, 0, s>>>(x, g, y, npix); break;
-    case 256: k_ln_apply<256><<<(int)blocks, 256, 0, s>>>(x, g, y, npix); break;
-    case 512: k_ln_apply<512><<<(int)blocks, 256, 0, s>>>(x, g, y, npix); break;
+    case 64: k_ln_apply<64><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
+    case 128: k_ln_apply<128><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
+    case 256: k_ln_apply<256><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
+    case 512: k_ln_apply<512><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
     default:
       set_error("ln_apply: unsupported channel count %d", C);
       return PRG_ERR_ARG;

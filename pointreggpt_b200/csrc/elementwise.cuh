@@ -35,7 +35,7 @@ int cond_mlp(const float* W, const float* bias, const float* cond_act, float* ss
 // rows of this block inside the cond_mlp output (nullptr = no conditioning).
 struct GnApply {
   const __half* raw;
-  const float* stats;
+  const long long* stats;  // fixed point (2^-20), see conv_tc.cuh
   const float *gamma, *beta;
   const float* ss;
   int ss_stride;     // floats per image in ss
@@ -47,8 +47,9 @@ struct GnApply {
 };
 int gn_apply(const GnApply& a, int B, cudaStream_t s);
 
-// ---- channel LayerNorm with gain (SDD:619-628) ----------------------------------------------
-int ln_apply(const __half* x, const float* g, __half* y, int64_t npix, int C, cudaStream_t s);
+// ---- channel LayerNorm with gain (SDD:619-628): y = LN_c(x) * g [+ res] -----------------------
+int ln_apply(const __half* x, const float* g, const __half* res, __half* y, int64_t npix, int C,
+             cudaStream_t s);
 
 // ---- network tail ----------------------------------------------------------------------------
 // GroupNorm+SiLU of final_res_block.block2 + residual, final 1x1 conv (64 -> 1), then either
@@ -58,7 +59,7 @@ int ln_apply(const __half* x, const float* g, __half* y, int64_t npix, int C, cu
 //                                                              1173-1180, 1279-1280 / 1358-1373)
 struct TailParams {
   const __half* raw;
-  const float* stats;
+  const long long* stats;
   const float *gamma, *beta;
   const __half* res;      // res_conv output (B,S,S,64)
   const float* fw;        // final conv weight [64]

@@ -231,7 +231,7 @@ int ilog2i(int v) {
 
 struct BlockOut {
   Act y;                 // output (unused for the final block)
-  const float* stats2;   // final block: statistics of block2
+  const long long* stats2;  // final block: statistics of block2
   const float *g2, *b2;
 };
 
@@ -242,8 +242,8 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
   const int H = x0.H, W = x0.W, HW = H * W;
   const int cin = x0.C + (x1 ? x1->C : 0);
   Act raw{n->raw, H, W, cout, cout}, h1{n->h1, H, W, cout, cout}, resb{n->resb, H, W, cout, cout};
-  float* st1 = n->take_zero((size_t)n->maxB * 16);
-  float* st2 = n->take_zero((size_t)n->maxB * 16);
+  long long* st1 = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 32));
+  long long* st2 = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 32));
   const int gs_log2 = ilog2i(cout / 8);
   NET_PTR(w1, n->f16(pfx + ".block1.proj.weight"));
   NET_PTR(b1, n->f32(pfx + ".block1.proj.bias"));
@@ -320,11 +320,11 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   NET_PTR(bo, n->f32(pfx + ".fn.fn.to_out.0.bias"));
   NET_PTR(g2, n->f32(pfx + ".fn.fn.to_out.1.g"));
   int* cmax = n->take_colmax((size_t)n->maxB * 128);
-  float* ctx = n->take_zero((size_t)n->maxB * 4096);
-  float* zs = n->take_zero((size_t)n->maxB * 128);
+  long long* ctx = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 4096 * 2));
+  long long* zs = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 128 * 2));
   const __half* xp = x.p;
   __half* xnp = xn.p;
-  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, xnp, (int64_t)r.B * HW, C, r.s); });
+  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
   NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
     p.colmax = cmax;
     p.q_softmax = 1;
@@ -337,10 +337,19 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   Act y = new_act(n, H, W, C);
   if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
   Act qsrc{qkv.p, H, W, 128, 384};
-  NET_TRY(add_conv(n, EPI_LN_RES, qsrc, nullptr, 0, 1, 1, weff, 1, bo, y, [=](ConvParams& p) {
-    p.ln_g = g2;
-    p.res = xp;
-  }));
+  if (C <= 256) {
+    NET_TRY(add_conv(n, EPI_LN_RES, qsrc, nullptr, 0, 1, 1, weff, 1, bo, y, [=](ConvParams& p) {
+      p.ln_g = g2;
+      p.res = xp;
+    }));
+  } else {
+    // a 512-channel row does not fit one UMMA N tile: plain GEMM, then LayerNorm + residual
+    Act tmp{n->h1, H, W, C, C};
+    NET_TRY(add_conv(n, EPI_BIAS, qsrc, nullptr, 0, 1, 1, weff, 1, bo, tmp));
+    const __half* tp = tmp.p;
+    __half* yp = y.p;
+    n->ops.push_back([=](const Run& r) { return ln_apply(tp, g2, xp, yp, (int64_t)r.B * HW, C, r.s); });
+  }
   *out = y;
   return PRG_OK;
 }
@@ -355,7 +364,7 @@ int add_midattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   NET_PTR(bo, n->f32(pfx + ".fn.fn.to_out.bias"));
   const __half* xp = x.p;
   __half* xnp = xn.p;
-  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, xnp, (int64_t)r.B * HW, C, r.s); });
+  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
   NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
     p.colmax = nullptr;
     p.q_softmax = 0;
@@ -425,7 +434,7 @@ int build(prg_net* n) {
   n->qkv = n->dalloc<__half>((size_t)B * S * S * 384);
   n->ao = n->dalloc<__half>((size_t)B * (S >> (L - 1)) * (S >> (L - 1)) * 128);
   n->weff = n->dalloc<__half>((size_t)B * n->dims[L] * 128);
-  n->zero_cap = (size_t)B * (64 * 16 + 16 * (4096 + 128));
+  n->zero_cap = (size_t)B * 2 * (64 * 16 + 16 * (4096 + 128));
   n->zero_arena = n->dalloc<float>(n->zero_cap);
   n->colmax_cap = (size_t)B * 128 * 16;
   n->colmax_arena = n->dalloc<int>(n->colmax_cap);
