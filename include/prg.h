@@ -145,6 +145,19 @@ int prg_sampler_run(prg_net* unet, const prg_step* steps, int nsteps, const floa
                     const float* img_cond, const float* noise, uint64_t philox_seed, float* out,
                     int B, prg_stream_t stream);
 
+/* Sampled kernel timing for bench.py's roofline: every n-th network evaluation (0 = off) each
+ * launch is bracketed by CUDA events on the launching stream.  prg_profile_read synchronises
+ * on the recorded events and returns one entry per kernel family: total device ms, launches,
+ * and the number of profiled network evaluations. */
+typedef struct prg_profile {
+  char name[32];
+  uint64_t launches;
+  double ms;
+  uint64_t forwards;
+} prg_profile;
+int prg_profile_set(int every_n_forwards);
+int prg_profile_read(prg_profile* out, int max_entries, int reset);
+
 /* Test hook: one implicit-GEMM convolution through the tcgen05 engine.
  * x (B,H,W,Cin) f16 NHWC, w (Cout, taps*Cin) f16 K-major tap-major, bias (Cout)
  * f32 or NULL -> y (B,Ho,Wo,Cout) f16.  mode: 0 = 1x1, 1 = 3x3 p1, 2 = 4x4 s2 p1. */

@@ -28,6 +28,12 @@ class Step(ctypes.Structure):
                 ("c4", c_float)]
 
 
+class Profile(ctypes.Structure):
+    """struct prg_profile (include/prg.h)."""
+    _fields_ = [("name", ctypes.c_char * 32), ("launches", c_uint64), ("ms", ctypes.c_double),
+                ("forwards", c_uint64)]
+
+
 STEP_P_SAMPLE, STEP_DDIM, STEP_DDIM_LAST, STEP_REFINE_P, STEP_REFINE_DDIM = range(5)
 
 
@@ -55,6 +61,8 @@ SIGNATURES = {
                                      c_void_p]),
     "prg_sampler_run": (c_int, [c_void_p, ctypes.POINTER(Step), c_int, c_void_p, c_void_p,
                                 c_void_p, c_uint64, c_void_p, c_int, c_void_p]),
+    "prg_profile_set": (c_int, [c_int]),
+    "prg_profile_read": (c_int, [ctypes.POINTER(Profile), c_int, c_int]),
     "prg_test_conv_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),
 }
@@ -106,3 +114,15 @@ def require_cuda(*tensors):
 
 def launch_count():
     return int(lib().prg_launch_count())
+
+
+def profile_set(every):
+    check(lib().prg_profile_set(int(every)))
+
+
+def profile_read(reset=True):
+    """{family: dict(launches, ms, forwards)} of the sampled launches since the last reset."""
+    arr = (Profile * 16)()
+    n = lib().prg_profile_read(arr, 16, int(reset))
+    return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=float(arr[i].ms),
+                                       forwards=int(arr[i].forwards)) for i in range(n)}

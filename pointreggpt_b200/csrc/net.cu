@@ -25,6 +25,40 @@ using namespace prg;
 
 namespace {
 
+enum OpCat { CAT_CONV = 0, CAT_GN, CAT_LN, CAT_CTX, CAT_WEFF, CAT_ATTN, CAT_STEM, CAT_COND, CAT_TAIL, CAT_COUNT };
+const char* const kCatNames[CAT_COUNT] = {"conv_tc", "gn_apply", "ln_apply", "linattn_context",
+                                          "linattn_weff", "attn_mid", "stem", "cond", "tail"};
+
+// Sampled per-op timing with CUDA events on the launching stream (bench.py's roofline leg).
+struct Profiler {
+  int every = 0;                  // profile every n-th forward (0 = off)
+  std::vector<cudaEvent_t> pool;  // recycled events
+  struct Rec { cudaEvent_t a, b; int cat; };
+  std::vector<Rec> recs;
+  double ms[CAT_COUNT] = {0};
+  uint64_t launches[CAT_COUNT] = {0};
+  uint64_t forwards = 0;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void drain() {
+    for (auto& r : recs) {
+      float t = 0.f;
+      if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+        ms[r.cat] += t;
+        launches[r.cat] += 1;
+      }
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+};
+Profiler g_prof;
+
 struct Entry {
   int dtype;  // 0 f32, 1 f16
   std::vector<int> dims;
@@ -55,6 +89,12 @@ struct prg_net {
   std::map<std::string, Entry> ent;
   std::vector<void*> allocs;
   std::vector<std::function<int(const Run&)>> ops;
+  std::vector<int> op_cat;
+  uint64_t forwards = 0;
+  void add_op(int cat, std::function<int(const Run&)> f) {
+    ops.push_back(std::move(f));
+    op_cat.push_back(cat);
+  }
 
   int dim = 64, levels = 4;
   std::vector<int> dims;  // [init, dim*m0, ...]
@@ -215,7 +255,7 @@ int add_conv(prg_net* n, int epi, const Act& s0, const Act* s1, int mode, int ks
   L.p.bias = bias;
   if (fill) fill(L.p);
   const int tiles = L.p.tiles_x * L.p.tiles_y;
-  n->ops.push_back([L, tiles](const Run& r) mutable {
+  n->add_op(CAT_CONV, [L, tiles](const Run& r) mutable {
     L.p.B = r.B;
     L.grid.x = (unsigned)(tiles * r.B);
     return conv_run(L, r.s);
@@ -268,7 +308,7 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
       *ss_cursor += 2 * cout;
     }
     a.res = nullptr; a.y = h1.p; a.HW = HW; a.C = cout;
-    n->ops.push_back([a](const Run& r) { return gn_apply(a, r.B, r.s); });
+    n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); });
   }
   NET_TRY(add_conv(n, EPI_GN, h1, nullptr, 0, 3, 1, w2, 0, b2, raw, [=](ConvParams& p) {
     p.stats = st2;
@@ -304,7 +344,7 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
     GnApply a{};
     a.raw = raw.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr;
     a.res = res_ptr; a.res_pix_stride = res_stride; a.y = y.p; a.HW = HW; a.C = cout;
-    n->ops.push_back([a](const Run& r) { return gn_apply(a, r.B, r.s); });
+    n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); });
   }
   bo->y = y;
   return PRG_OK;
@@ -324,7 +364,7 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   long long* zs = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 128 * 2));
   const __half* xp = x.p;
   __half* xnp = xn.p;
-  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
+  n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
   NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
     p.colmax = cmax;
     p.q_softmax = 1;
@@ -332,8 +372,8 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   }));
   __half* qkvp = qkv.p;
   __half* weff = n->weff;
-  n->ops.push_back([=](const Run& r) { return linattn_context(qkvp, cmax, ctx, zs, r.B, HW, r.s); });
-  n->ops.push_back([=](const Run& r) { return linattn_weff(wo, ctx, zs, weff, r.B, C, HW, r.s); });
+  n->add_op(CAT_CTX, [=](const Run& r) { return linattn_context(qkvp, cmax, ctx, zs, r.B, HW, r.s); });
+  n->add_op(CAT_WEFF, [=](const Run& r) { return linattn_weff(wo, ctx, zs, weff, r.B, C, HW, r.s); });
   Act y = new_act(n, H, W, C);
   if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
   Act qsrc{qkv.p, H, W, 128, 384};
@@ -348,7 +388,7 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
     NET_TRY(add_conv(n, EPI_BIAS, qsrc, nullptr, 0, 1, 1, weff, 1, bo, tmp));
     const __half* tp = tmp.p;
     __half* yp = y.p;
-    n->ops.push_back([=](const Run& r) { return ln_apply(tp, g2, xp, yp, (int64_t)r.B * HW, C, r.s); });
+    n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(tp, g2, xp, yp, (int64_t)r.B * HW, C, r.s); });
   }
   *out = y;
   return PRG_OK;
@@ -364,7 +404,7 @@ int add_midattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   NET_PTR(bo, n->f32(pfx + ".fn.fn.to_out.bias"));
   const __half* xp = x.p;
   __half* xnp = xn.p;
-  n->ops.push_back([=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
+  n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
   NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
     p.colmax = nullptr;
     p.q_softmax = 0;
@@ -372,7 +412,7 @@ int add_midattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   }));
   __half* qkvp = qkv.p;
   __half* aop = ao.p;
-  n->ops.push_back([=](const Run& r) { return attn_mid(qkvp, aop, r.B, HW, r.s); });
+  n->add_op(CAT_ATTN, [=](const Run& r) { return attn_mid(qkvp, aop, r.B, HW, r.s); });
   Act y = new_act(n, H, W, C);
   if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
   NET_TRY(add_conv(n, EPI_RES, ao, nullptr, 0, 1, 1, wo, 0, bo, y, [=](ConvParams& p) { p.res = xp; }));
@@ -469,10 +509,10 @@ int build(prg_net* n) {
     float* cond_act = n->cond_act;
     float* ss = n->ss;
     const int rows = n->ss_rows, K = 8 * n->dim;
-    n->ops.push_back([=](const Run& r) {
+    n->add_op(CAT_COND, [=](const Run& r) {
       return cond_embed(cw, r.time, r.time_scalar, r.pcond, cond_act, r.B, r.s);
     });
-    n->ops.push_back([=](const Run& r) { return cond_mlp(mlp_w, mlp_b, cond_act, ss, rows, K, r.B, r.s); });
+    n->add_op(CAT_COND, [=](const Run& r) { return cond_mlp(mlp_w, mlp_b, cond_act, ss, rows, K, r.B, r.s); });
   }
 
   // ---- stem
@@ -484,9 +524,9 @@ int build(prg_net* n) {
     NET_PTR(sb, n->f32("init_conv.bias"));
     __half* so = stem.p;
     if (n->kind == PRG_NET_UNET)
-      n->ops.push_back([=](const Run& r) { return stem_unet(r.x, sw, sb, so, r.B, S, r.s); });
+      n->add_op(CAT_STEM, [=](const Run& r) { return stem_unet(r.x, sw, sb, so, r.B, S, r.s); });
     else
-      n->ops.push_back([=](const Run& r) { return stem_mask(r.x, sw, sb, so, r.B, S, r.s); });
+      n->add_op(CAT_STEM, [=](const Run& r) { return stem_mask(r.x, sw, sb, so, r.B, S, r.s); });
   }
 
   // ---- encoder
@@ -590,8 +630,33 @@ int run_trunk(prg_net* n, const Run& r) {
   PRG_CUDA_OK(cudaMemsetAsync(n->zero_arena, 0, n->zero_floats * sizeof(float), r.s));
   if (n->colmax_ints)
     PRG_CUDA_OK(cudaMemsetAsync(n->colmax_arena, 0x80, n->colmax_ints * sizeof(int), r.s));
-  for (auto& op : n->ops) NET_TRY(op(r));
+  const bool prof = g_prof.every > 0 && (n->forwards % (uint64_t)g_prof.every) == 0;
+  n->forwards++;
+  if (!prof) {
+    for (auto& op : n->ops) NET_TRY(op(r));
+    return PRG_OK;
+  }
+  g_prof.forwards++;
+  for (size_t i = 0; i < n->ops.size(); ++i) {
+    Profiler::Rec rec{g_prof.get(), g_prof.get(), n->op_cat[i]};
+    cudaEventRecord(rec.a, r.s);
+    const int rc = n->ops[i](r);
+    cudaEventRecord(rec.b, r.s);
+    g_prof.recs.push_back(rec);
+    if (rc) return rc;
+  }
   return PRG_OK;
+}
+
+int run_tail(prg_net* n, const TailParams& t, int B, cudaStream_t s) {
+  const bool prof = g_prof.every > 0 && ((n->forwards - 1) % (uint64_t)g_prof.every) == 0;
+  if (!prof) return net_tail(t, B, s);
+  Profiler::Rec rec{g_prof.get(), g_prof.get(), CAT_TAIL};
+  cudaEventRecord(rec.a, s);
+  const int rc = net_tail(t, B, s);
+  cudaEventRecord(rec.b, s);
+  g_prof.recs.push_back(rec);
+  return rc;
 }
 
 struct DeviceGuard {
@@ -672,7 +737,7 @@ EXPORT int prg_unet_forward(prg_net* n, const float* x, const int64_t* time, con
   TailParams t = n->tail;
   t.mode = 0;
   t.out = out;
-  return net_tail(t, B, r.s);
+  return run_tail(n, t, B, r.s);
 }
 
 EXPORT int prg_maskunet_forward(prg_net* n, const float* depth01, float* prob, uint8_t* keep,
@@ -688,7 +753,7 @@ EXPORT int prg_maskunet_forward(prg_net* n, const float* depth01, float* prob, u
   t.out = prob;
   t.keep = keep;
   t.thresh = thresh;
-  return net_tail(t, B, r.s);
+  return run_tail(n, t, B, r.s);
 }
 
 EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const float* pcond,
@@ -737,7 +802,32 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
       set_error("only the last step may unnormalize");
       return PRG_ERR_ARG;
     }
-    NET_TRY(net_tail(t, B, s));
+    NET_TRY(run_tail(n, t, B, s));
   }
   return PRG_OK;
+}
+
+EXPORT int prg_profile_set(int every_n_forwards) {
+  g_prof.drain();
+  g_prof.every = every_n_forwards < 0 ? 0 : every_n_forwards;
+  return PRG_OK;
+}
+
+EXPORT int prg_profile_read(prg_profile* out, int max_entries, int reset) {
+  g_prof.drain();
+  int n = 0;
+  for (int c = 0; c < CAT_COUNT && n < max_entries; ++c) {
+    if (g_prof.launches[c] == 0) continue;
+    prg_profile& e = out[n++];
+    memset(&e, 0, sizeof(e));
+    strncpy(e.name, kCatNames[c], sizeof(e.name) - 1);
+    e.launches = g_prof.launches[c];
+    e.ms = g_prof.ms[c];
+    e.forwards = g_prof.forwards;
+  }
+  if (reset) {
+    for (int c = 0; c < CAT_COUNT; ++c) { g_prof.ms[c] = 0; g_prof.launches[c] = 0; }
+    g_prof.forwards = 0;
+  }
+  return n;
 }
