@@ -1,0 +1,837 @@
+// tcgen05 implicit-GEMM convolution / GEMM engine, persistent version (sm_100a).
+//
+// Replaces, for the U-Net denoiser and the depth-correction U-Net, the cuDNN/cuBLAS calls
+// behind F.conv2d / nn.Conv2d at SDD:594-598, 615, 717, 743-745, 779-780 (same lines in DC).
+//
+// One CTA per SM walks a static list of work items.  Warp roles (192 threads):
+//   warp 0   : TMA producer.  A operand, two modes:
+//                per-tap : one 4-D/5-D box per (tap, 64-channel chunk) -- shifted window of the
+//                          NHWC activation, zero padding = TMA out-of-bounds fill;
+//                halo    : (3x3, stride 1, Cin = 64, row tiles) a ring of input rows, each loaded
+//                          ONCE (130 pixels x 64 ch, 128B-swizzled); the nine taps are nine
+//                          shifted views (start address + dx*128 B, row slot y+dy) of that ring,
+//                          so L2->SM traffic drops ~9x.
+//              B operand (weights): resident in shared memory for the whole kernel when it
+//              fits (loaded once per CTA), otherwise streamed next to A.
+//   warp 1   : one lane issues tcgen05.mma (M=128, N=BN, K=16), accumulating in one of TWO
+//              TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 2-5: epilogue: tcgen05.ld -> fused bias / GroupNorm statistics / softmax /
+//              LayerNorm / residual -> fp16 -> 128B-swizzled staging tile -> TMA store.
+#include <limits.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace prg {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KiB per-tap A stage
+constexpr int kHaloPix = kBlockM + 2;              // 130 pixels per ring row
+constexpr int kHaloBytes = kHaloPix * 128;         // 16640 B written by TMA
+constexpr int kHaloSlot = 17 * 1024;               // slot pitch (1024-aligned)
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 12;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kCtlBytes = 2048;
+constexpr double kStatScale = 1048576.0;           // 2^20 fixed point (see conv_tc.cuh)
+
+struct alignas(8) Ctl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t wfull;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_addr;
+  uint32_t pad;
+  float stats[64];   // EPI_GN: [epilogue warp][8 groups][sum, sumsq]
+  int colmax[128];   // EPI_QKV k tile
+};
+static_assert(sizeof(Ctl) <= kCtlBytes, "control block too large");
+
+__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct Item {
+  int img, x0, y0, n_tile, cls;
+};
+
+}  // namespace
+
+struct Conv2Params {
+  ConvParams c;
+  int halo, wres, n_tiles, stages;
+  int total_items;      // per-tap: m_tiles * n_tiles * classes ; halo: number of row segments
+  int m_tiles;          // per-tap: tiles_x * tiles_y * B
+  int rseg, segs_per_strip;
+  int num_kb;           // K blocks per tile
+  int a_slot;           // bytes per A stage / ring slot
+  int w_bytes;          // resident weight bytes
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+        const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
+        const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
+        const __grid_constant__ CUtensorMap tmO3, const Conv2Params P) {
+  const ConvParams& p = P.c;
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kStageOut = (BN / 64) * kABytes;   // fp16 staging tile, 64-channel boxes
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sW = smem;                               // resident weights (may be empty)
+  uint8_t* sA = sW + P.w_bytes;                     // A ring
+  uint8_t* sB = sA + P.stages * P.a_slot;           // streamed B ring (when !wres)
+  uint8_t* sO = sB + (P.wres ? 0 : P.stages * kBBytes);
+  Ctl* ctl = reinterpret_cast<Ctl*>(sO + kStageOut);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_w = 1 << p.tile_w_log2;
+  const int tile_h = kBlockM >> p.tile_w_log2;
+  const int chunks = p.chunks0 + p.chunks1;
+  const int num_kb = P.num_kb;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    if (p.chunks1 > 0) prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmO0);
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    mbar_init(&ctl->wfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ctl->tmem_full[a], 1);
+      mbar_init(&ctl->tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_addr, 2 * BN);
+    tmem_relinquish();
+  }
+  if (EPI == EPI_QKV && threadIdx.x < 128) ctl->colmax[threadIdx.x] = INT_MIN;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = ctl->tmem_addr;
+
+  // item -> coordinates (per-tap mode)
+  auto decode = [&](int item) {
+    Item it;
+    it.n_tile = item % P.n_tiles;
+    int m = item / P.n_tiles;
+    it.cls = m / P.m_tiles;
+    m -= it.cls * P.m_tiles;
+    it.img = m / tiles_per_img;
+    const int t_in = m - it.img * tiles_per_img;
+    const int tyi = t_in / p.tiles_x, txi = t_in - tyi * p.tiles_x;
+    it.x0 = txi << p.tile_w_log2;
+    it.y0 = tyi * tile_h;
+    return it;
+  };
+  // segment -> coordinates (halo mode): (img, strip x0, first row, rows)
+  auto decode_seg = [&](int seg, int& img, int& x0, int& y0, int& nr) {
+    const int strips = p.tiles_x;
+    const int per_img = strips * P.segs_per_strip;
+    img = seg / per_img;
+    const int r = seg - img * per_img;
+    const int strip = r / P.segs_per_strip, sidx = r - strip * P.segs_per_strip;
+    x0 = strip * kBlockM;
+    y0 = sidx * P.rseg;
+    nr = min(P.rseg, p.Ho - y0);
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      if (P.wres) {
+        mbar_arrive_expect_tx(&ctl->wfull, (uint32_t)P.w_bytes);
+        for (int nt = 0; nt < P.n_tiles; ++nt)
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)(nt * num_kb + kb) * kBBytes, kb * kBlockK,
+                        nt * BN, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      if (P.halo) {
+        for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+          int img, x0, y0, nr;
+          decode_seg(seg, img, x0, y0, nr);
+          for (int r = 0; r < nr + 2; ++r) {
+            mbar_wait(&ctl->empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&ctl->full[stage], kHaloBytes);
+            tma_load_4d(&tmA0, &ctl->full[stage], sA + (size_t)stage * P.a_slot, 0, x0 - 1,
+                        y0 - 1 + r, img);
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+          const Item it = decode(item);
+          int pad_y = p.pad, pad_x = p.pad;
+          if (p.classes == 4) { pad_y = 1 - (it.cls >> 1); pad_x = 1 - (it.cls & 1); }
+          const int wz = p.w_batched ? it.img : 0;
+          const int wk0 = it.cls * num_kb * kBlockK;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int tap = kb / chunks, cc = kb - tap * chunks;
+            mbar_wait(&ctl->empty[stage], phase ^ 1);
+            uint8_t* a_dst = sA + (size_t)stage * P.a_slot;
+            mbar_arrive_expect_tx(&ctl->full[stage], kABytes + (P.wres ? 0 : kBBytes));
+            if (p.mode == 0) {
+              const int ky = tap / p.kw, kx = tap - ky * p.kw;
+              const int dy = ky - pad_y, dx = kx - pad_x;
+              if (cc < p.chunks0)
+                tma_load_4d(&tmA0, &ctl->full[stage], a_dst, cc * kBlockK, it.x0 + dx, it.y0 + dy,
+                            it.img);
+              else
+                tma_load_4d(&tmA1, &ctl->full[stage], a_dst, (cc - p.chunks0) * kBlockK, it.x0 + dx,
+                            it.y0 + dy, it.img);
+            } else {
+              const int ey = (tap >> 2) - 1, ex = (tap & 3) - 1;
+              const int qy = ey >> 1, ry = ey & 1, qx = ex >> 1, rx = ex & 1;
+              tma_load_5d(&tmA0, &ctl->full[stage], a_dst, rx * p.cin0 + cc * kBlockK, it.x0 + qx,
+                          ry, it.y0 + qy, it.img);
+            }
+            if (!P.wres)
+              tma_load_3d(&tmB, &ctl->full[stage], sB + (size_t)stage * kBBytes, wk0 + kb * kBlockK,
+                          it.n_tile * BN, wz);
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    constexpr uint32_t idesc = idesc_f16(kBlockM, BN);
+    if (P.wres) mbar_wait(&ctl->wfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t tcount = 0;  // tiles issued by this CTA
+    if (P.halo) {
+      for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+        int img, x0, y0, nr;
+        decode_seg(seg, img, x0, y0, nr);
+        // ring positions of this segment's rows: stage .. stage + nr + 1 (mod stages)
+        int wait_stage = stage;
+        uint32_t wait_phase = phase;
+        int waited = 0;
+        for (int j = 0; j < nr; ++j) {
+          while (waited < j + 3) {
+            mbar_wait(&ctl->full[wait_stage], wait_phase);
+            if (++wait_stage == P.stages) { wait_stage = 0; wait_phase ^= 1; }
+            ++waited;
+          }
+          const uint32_t acc = tcount & 1;
+          mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t d_addr = taddr + acc * BN;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              int slot = stage + dy;   // row j + dy of the segment
+              if (slot >= P.stages) slot -= P.stages;
+              const uint32_t a_addr = smem_u32(sA + (size_t)slot * P.a_slot) + dx * 128;
+              const uint32_t b_addr = smem_u32(sW + (size_t)tap * kBBytes);
+              // shifted view: the start sits dx rows into a swizzle atom.  The 128B swizzle is a
+              // function of the absolute shared-memory address (measured: base_offset must stay
+              // 0), so the descriptor needs nothing beyond the displaced start address.
+              const uint64_t da = smem_desc_sw128(a_addr);
+              const uint64_t db = smem_desc_sw128(b_addr);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (tap > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&ctl->tmem_full[acc]);
+            umma_commit(&ctl->empty[stage]);           // top row of this tile is done
+            if (j == nr - 1) {                          // segment end: release the two halo rows
+              int s1 = stage + 1, s2 = stage + 2;
+              if (s1 >= P.stages) s1 -= P.stages;
+              if (s2 >= P.stages) s2 -= P.stages;
+              umma_commit(&ctl->empty[s1]);
+              umma_commit(&ctl->empty[s2]);
+            }
+          }
+          __syncwarp();
+          ++tcount;
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        // skip the two trailing halo rows in the ring position
+        for (int e = 0; e < 2; ++e)
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+      }
+    } else {
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        const Item it = decode(item);
+        const uint32_t acc = tcount & 1;
+        mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = taddr + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(sA + (size_t)stage * P.a_slot);
+            const uint32_t b_addr =
+                P.wres ? smem_u32(sW + (size_t)(it.n_tile * num_kb + kb) * kBBytes)
+                       : smem_u32(sB + (size_t)stage * kBBytes);
+            const uint64_t da = smem_desc_sw128(a_addr);
+            const uint64_t db = smem_desc_sw128(b_addr);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                       (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&ctl->empty[stage]);
+            if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        ++tcount;
+      }
+    }
+  } else {
+    // =============================== epilogue ===================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int e = threadIdx.x - 64;                 // 0..127
+    const int tyr = row >> p.tile_w_log2, txr = row & (tile_w - 1);
+    uint32_t tcount = 0;
+
+    auto do_tile = [&](int img, int x0, int y0, int n_tile, int cls) {
+      const int n0 = n_tile * BN;
+      const int cpy = cls >> 1, cpx = cls & 1;
+      const uint32_t acc = tcount & 1;
+      // (1) previous TMA store must have finished reading the staging tile
+      if (e == 0) bulk_wait_read0();
+      epi_bar();
+      // every thread is past the previous tile's cross-warp reads: reset this warp's own slots
+      if (EPI == EPI_GN && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ctl->stats[quarter * 16 + i] = 0.f;
+      }
+      mbar_wait(&ctl->tmem_full[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = taddr + acc * BN + ((uint32_t)(quarter * 32) << 16);
+
+      const int oy = (y0 + tyr) * p.out_scale + cpy, ox = (x0 + txr) * p.out_scale + cpx;
+      const long long off = (long long)img * p.out_img_stride + (long long)oy * p.out_row_stride +
+                            (long long)ox * p.out_pix_stride + n0;
+
+      float ln_mean = 0.f, ln_rstd = 0.f;
+      if (EPI == EPI_LN_RES) {
+        float s = 0.f;
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(trow + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += __uint_as_float(v[j]) + __ldg(p.bias + n0 + c + j);
+        }
+        ln_mean = s * (1.f / BN);
+        float ss = 0.f;
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(trow + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(v[j]) + __ldg(p.bias + n0 + c + j) - ln_mean;
+            ss += d * d;
+          }
+        }
+        ln_rstd = rsqrtf(ss * (1.f / BN) + 1e-5f);
+      }
+      const int qkv_part = (EPI == EPI_QKV) ? (n0 >> 7) : 0;
+
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + c, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n0 + c + j);
+        }
+        if (EPI == EPI_GN) {
+          float s4[4], q4[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = f[g * 8 + j];
+              s += x;
+              q = fmaf(x, x, q);
+            }
+            s4[g] = s;
+            q4[g] = q;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              s4[g] += __shfl_xor_sync(0xffffffffu, s4[g], o);
+              q4[g] += __shfl_xor_sync(0xffffffffu, q4[g], o);
+            }
+          }
+          if (lane == 0) {
+            float* ws = ctl->stats + quarter * 16;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int grp = (c + g * 8) >> p.gs_log2;
+              ws[grp * 2 + 0] += s4[g];
+              ws[grp * 2 + 1] += q4[g];
+            }
+          }
+        } else if (EPI == EPI_QKV) {
+          if (qkv_part == 0) {
+            if (p.q_softmax) {
+              float m = f[0];
+#pragma unroll
+              for (int j = 1; j < 32; ++j) m = fmaxf(m, f[j]);
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                f[j] = fast_exp(f[j] - m);
+                s += f[j];
+              }
+              const float inv = p.q_scale / s;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= inv;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= p.q_scale;
+            }
+          } else if (qkv_part == 1 && p.colmax != nullptr) {
+            int mine = INT_MIN;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = __half2float(__float2half_rn(f[j]));
+              const int m = __reduce_max_sync(0xffffffffu, float_to_ordered(r));
+              if (lane == j) mine = m;
+            }
+            atomicMax(&ctl->colmax[c + lane], mine);
+          }
+        } else if (EPI == EPI_LN_RES) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            f[j] = (f[j] - ln_mean) * ln_rstd * __ldg(p.ln_g + n0 + c + j);
+        }
+        if (EPI == EPI_RES || EPI == EPI_LN_RES) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = __ldg(rp + q);
+            const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 r2 = __half22float2(h[j]);
+              f[q * 8 + j * 2 + 0] += r2.x;
+              f[q * 8 + j * 2 + 1] += r2.y;
+            }
+          }
+        }
+        // fp16 -> staging tile: box (c / 64), row `row`, 16-byte chunk index XOR (row & 7)
+        uint8_t* box = sO + (size_t)(c >> 6) * kABytes + (size_t)row * 128;
+        const int ch0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          __half2 h0 = __floats2half2_rn(f[q * 8 + 0], f[q * 8 + 1]);
+          __half2 h1 = __floats2half2_rn(f[q * 8 + 2], f[q * 8 + 3]);
+          __half2 h2 = __floats2half2_rn(f[q * 8 + 4], f[q * 8 + 5]);
+          __half2 h3 = __floats2half2_rn(f[q * 8 + 6], f[q * 8 + 7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2);
+          o.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(box + (((ch0 + q) ^ (row & 7)) << 4)) = o;
+        }
+      }
+      // (3) accumulator drained -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&ctl->tmem_empty[acc]);
+      // (4) staging tile complete and visible to the async proxy
+      fence_proxy_async();
+      epi_bar();
+      if (e == 0) {
+        const CUtensorMap* tmo = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
+#pragma unroll
+        for (int bx = 0; bx < BN / 64; ++bx)
+          tma_store_4d(tmo, sO + (size_t)bx * kABytes, n0 + bx * 64, x0, y0, img);
+        bulk_commit();
+      }
+      if (EPI == EPI_GN) {
+        const int ngrp = BN >> p.gs_log2;
+        if (e < ngrp * 2) {
+          const int g0 = n0 >> p.gs_log2;
+          const float v = (ctl->stats[e] + ctl->stats[16 + e]) + (ctl->stats[32 + e] + ctl->stats[48 + e]);
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)img * 8 + g0) * 2 + e,
+                    (unsigned long long)__double2ll_rn((double)v * kStatScale));
+        }
+      }
+      if (EPI == EPI_QKV) {
+        if (qkv_part == 1 && p.colmax != nullptr) {
+          atomicMax(&p.colmax[img * 128 + e], ctl->colmax[e]);
+          ctl->colmax[e] = INT_MIN;   // slot e is read only by thread e; next tile's atomics come
+        }                             // after the next epi_bar
+      }
+      ++tcount;
+    };
+
+    if (P.halo) {
+      for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+        int img, x0, y0, nr;
+        decode_seg(seg, img, x0, y0, nr);
+        for (int j = 0; j < nr; ++j) do_tile(img, x0, y0 + j, 0, 0);
+      }
+    } else {
+      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        const Item it = decode(item);
+        do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls);
+      }
+    }
+    if (e == 0) bulk_wait0();
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(taddr, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return PRG_ERR_CUDA;
+  }
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    e[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s,
+                  b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box "
+              "%u,%u,%u)", (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+    return PRG_ERR_CUDA;
+  }
+  return PRG_OK;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+struct Conv2Launch {
+  CUtensorMap tmA0, tmA1, tmB, tmO[4];
+  Conv2Params P;
+  int bn, epi, smem;
+  int grid;
+};
+
+static int g_conv_flags = -1;  // PRG_CONV_FLAGS bit0: disable the halo-ring mode (A/B measurements)
+static int conv_flags() {
+  if (g_conv_flags < 0) {
+    const char* e = getenv("PRG_CONV_FLAGS");
+    g_conv_flags = e ? atoi(e) : 0;
+  }
+  return g_conv_flags;
+}
+
+static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode,
+                      int ksize, int classes, const __half* w, int w_batched, int Cout,
+                      const ActSrc& out) {
+  memset(L, 0, sizeof(*L));
+  Conv2Params& P = L->P;
+  ConvParams& p = P.c;
+  const int Ho = (mode == 1) ? s0.H / 2 : s0.H, Wo = (mode == 1) ? s0.W / 2 : s0.W;
+  if (s0.C % 64 != 0 || (s1 && s1->C % 64 != 0) || Cout % 64 != 0) {
+    set_error("conv_plan: channel counts must be multiples of 64 (%d,%d->%d)", s0.C, s1 ? s1->C : 0,
+              Cout);
+    return PRG_ERR_ARG;
+  }
+  if ((Ho * Wo) % kBlockM != 0) {
+    set_error("conv_plan: %dx%d output is not a multiple of the 128-pixel tile", Ho, Wo);
+    return PRG_ERR_ARG;
+  }
+  if (mode == 1 && (s1 != nullptr || ksize != 4 || classes != 1)) {
+    set_error("conv_plan: stride-2 mode takes one source, 4x4 taps");
+    return PRG_ERR_ARG;
+  }
+  const int tile_w = Wo < kBlockM ? Wo : kBlockM;
+  if ((tile_w & (tile_w - 1)) != 0 || tile_w < 8 || (kBlockM / tile_w) > Ho ||
+      Ho % (kBlockM / tile_w) != 0 || Wo % tile_w != 0) {
+    set_error("conv_plan: unsupported spatial size %dx%d", Ho, Wo);
+    return PRG_ERR_ARG;
+  }
+  const int tile_h = kBlockM / tile_w;
+  p.B = B; p.Ho = Ho; p.Wo = Wo;
+  p.tile_w_log2 = ilog2(tile_w);
+  p.tiles_x = Wo / tile_w; p.tiles_y = Ho / tile_h;
+  p.mode = mode;
+  p.kh = p.kw = (classes == 4) ? 2 : ksize;
+  p.pad = (ksize == 3) ? 1 : 0;
+  p.chunks0 = s0.C / 64; p.chunks1 = s1 ? s1->C / 64 : 0;
+  p.cin0 = s0.C;
+  p.classes = classes;
+  p.w_batched = w_batched;
+  p.out_scale = (classes == 4) ? 2 : 1;
+  L->epi = epi;
+
+  int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
+  if (epi == EPI_QKV) bn = 128;
+  if (epi == EPI_LN_RES) bn = Cout;
+  if (bn != 64 && bn != 128 && bn != 256) {
+    set_error("conv_plan: unsupported N tile %d", bn);
+    return PRG_ERR_ARG;
+  }
+  L->bn = bn;
+  P.n_tiles = Cout / bn;
+  const int cin = s0.C + (s1 ? s1->C : 0);
+  const int ntaps = (mode == 1) ? 16 : p.kh * p.kw;
+  P.num_kb = ntaps * (cin / 64);
+  P.m_tiles = p.tiles_x * p.tiles_y * B;
+  const int b_bytes = bn * 128;
+  const int stage_out = (bn / 64) * kABytes;
+  const int fixed = stage_out + kCtlBytes + 1024;
+
+  // ---- mode selection
+  const long long w_all = (long long)P.n_tiles * P.num_kb * b_bytes;   // all weights of one class
+  P.halo = 0;
+  P.wres = 0;
+  if (!w_batched && classes == 1 && w_all + fixed + 4 * kABytes <= kSmemBudget) P.wres = 1;
+  if (P.wres && mode == 0 && ksize == 3 && s1 == nullptr && cin == 64 && tile_w == kBlockM &&
+      P.n_tiles == 1 && !(conv_flags() & 1) &&
+      w_all + fixed + 5 * kHaloSlot <= kSmemBudget)
+    P.halo = 1;
+  P.w_bytes = P.wres ? (int)w_all : 0;
+  P.a_slot = P.halo ? kHaloSlot : kABytes;
+  const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes);
+  int stages = (kSmemBudget - fixed - P.w_bytes) / per_stage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    set_error("conv_plan: shared memory budget too small (%d stages)", stages);
+    return PRG_ERR_ARG;
+  }
+  P.stages = stages;
+  L->smem = P.w_bytes + stages * per_stage + fixed;
+
+  const int sms = num_sms();
+  if (P.halo) {
+    // split every 128-pixel strip into row segments; pick the segment length that best fills
+    // the SMs (each segment re-reads 2 halo rows)
+    int best_r = 8;
+    double best_eff = 0.0;
+    for (int r = 4; r <= Ho; ++r) {
+      const int segs = (Ho + r - 1) / r;
+      const long long items = (long long)B * p.tiles_x * segs;
+      const long long waves = (items + sms - 1) / sms;
+      const double eff = ((double)B * p.tiles_x * Ho) / ((double)waves * sms * (r + 2));
+      if (eff > best_eff + 1e-9) { best_eff = eff; best_r = r; }
+    }
+    P.rseg = best_r;
+    P.segs_per_strip = (Ho + best_r - 1) / best_r;
+    P.total_items = B * p.tiles_x * P.segs_per_strip;
+  } else {
+    P.total_items = P.m_tiles * P.n_tiles * classes;
+  }
+  L->grid = std::min(P.total_items, sms);
+
+  // ---- tensor maps: activations
+  for (int si = 0; si < 2; ++si) {
+    const ActSrc* s = si == 0 ? &s0 : s1;
+    CUtensorMap* tm = si == 0 ? &L->tmA0 : &L->tmA1;
+    if (s == nullptr) { *tm = L->tmA0; continue; }
+    const uint64_t ps = (uint64_t)s->pix_stride * 2;
+    if (mode == 0) {
+      uint64_t dims[4] = {(uint64_t)s->C, (uint64_t)s->W, (uint64_t)s->H, (uint64_t)B};
+      uint64_t str[3] = {ps, ps * s->W, ps * s->W * s->H};
+      uint32_t box[4] = {64, (uint32_t)(P.halo ? kHaloPix : tile_w), (uint32_t)(P.halo ? 1 : tile_h), 1};
+      int rc = encode(tm, s->ptr, 4, dims, str, box);
+      if (rc) return rc;
+    } else {
+      if (s->pix_stride != s->C) {
+        set_error("conv_plan: stride-2 source must be dense");
+        return PRG_ERR_ARG;
+      }
+      uint64_t dims[5] = {(uint64_t)2 * s->C, (uint64_t)s->W / 2, 2, (uint64_t)s->H / 2, (uint64_t)B};
+      uint64_t str[4] = {2 * ps, ps * s->W, 2 * ps * s->W, ps * s->W * s->H};
+      uint32_t box[5] = {64, (uint32_t)tile_w, 1, (uint32_t)tile_h, 1};
+      int rc = encode(tm, s->ptr, 5, dims, str, box);
+      if (rc) return rc;
+    }
+  }
+  // ---- weights: [nb][Cout][classes*ntaps*cin]
+  {
+    const uint64_t ktot = (uint64_t)classes * ntaps * cin;
+    uint64_t dims[3] = {ktot, (uint64_t)Cout, (uint64_t)(w_batched ? B : 1)};
+    uint64_t str[2] = {ktot * 2, ktot * 2 * Cout};
+    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    int rc = encode(&L->tmB, w, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  // ---- output maps (one per upsample parity class)
+  {
+    const int sc = p.out_scale;
+    const uint64_t ps = (uint64_t)out.pix_stride * 2;
+    for (int cls = 0; cls < 4; ++cls) {
+      if (cls >= classes) { L->tmO[cls] = L->tmO[0]; continue; }
+      const int cpy = cls >> 1, cpx = cls & 1;
+      const __half* base = out.ptr + ((size_t)cpy * out.W + cpx) * out.pix_stride;
+      uint64_t dims[4] = {(uint64_t)out.C, (uint64_t)(out.W / sc), (uint64_t)(out.H / sc), (uint64_t)B};
+      uint64_t str[3] = {ps * sc, ps * out.W * sc, ps * out.W * out.H};
+      uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, 1};
+      int rc = encode(&L->tmO[cls], base, 4, dims, str, box);
+      if (rc) return rc;
+    }
+  }
+  p.out = const_cast<__half*>(out.ptr);
+  p.out_pix_stride = out.pix_stride;
+  p.out_row_stride = out.W * out.pix_stride;
+  p.out_img_stride = (long long)out.H * out.W * out.pix_stride;
+  return PRG_OK;
+}
+
+template <int BN, int EPI>
+static int launch2(const Conv2Launch& L, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < L.smem) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_conv2<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemBudget));
+    configured = kSmemBudget;
+  }
+  k_conv2<BN, EPI><<<L.grid, kThreads, L.smem, stream>>>(L.tmA0, L.tmA1, L.tmB, L.tmO[0], L.tmO[1],
+                                                       L.tmO[2], L.tmO[3], L.P);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+static int conv2_run(const Conv2Launch& L, cudaStream_t stream) {
+#define PRG_CASE(BN_, EPI_) \
+  if (L.bn == BN_ && L.epi == EPI_) return launch2<BN_, EPI_>(L, stream);
+  PRG_CASE(64, EPI_BIAS) PRG_CASE(128, EPI_BIAS) PRG_CASE(256, EPI_BIAS)
+  PRG_CASE(64, EPI_GN) PRG_CASE(128, EPI_GN) PRG_CASE(256, EPI_GN)
+  PRG_CASE(128, EPI_QKV)
+  PRG_CASE(64, EPI_LN_RES) PRG_CASE(128, EPI_LN_RES) PRG_CASE(256, EPI_LN_RES)
+  PRG_CASE(64, EPI_RES) PRG_CASE(128, EPI_RES) PRG_CASE(256, EPI_RES)
+#undef PRG_CASE
+  set_error("conv_run: no kernel for N tile %d / epilogue %d", L.bn, L.epi);
+  return PRG_ERR_ARG;
+}
+
+// ---- public wrappers (conv_tc.cuh) ---------------------------------------------------------
+ConvOp::ConvOp() : impl(nullptr) {}
+ConvOp::~ConvOp() { delete reinterpret_cast<Conv2Launch*>(impl); }
+ConvOp::ConvOp(const ConvOp& o) : impl(nullptr) {
+  if (o.impl) impl = new Conv2Launch(*reinterpret_cast<Conv2Launch*>(o.impl));
+}
+ConvOp& ConvOp::operator=(const ConvOp& o) {
+  if (this != &o) {
+    delete reinterpret_cast<Conv2Launch*>(impl);
+    impl = o.impl ? new Conv2Launch(*reinterpret_cast<Conv2Launch*>(o.impl)) : nullptr;
+  }
+  return *this;
+}
+ConvParams& ConvOp::params() { return reinterpret_cast<Conv2Launch*>(impl)->P.c; }
+
+int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
+                 int classes, const __half* w, int w_batched, int Cout, const ActSrc& out) {
+  Conv2Launch* L = new Conv2Launch();
+  int rc = conv2_plan(L, epi, B, s0, s1, mode, ksize, classes, w, w_batched, Cout, out);
+  if (rc) {
+    delete L;
+    return rc;
+  }
+  delete reinterpret_cast<Conv2Launch*>(op->impl);
+  op->impl = L;
+  return PRG_OK;
+}
+
+// Runs the planned conv on the first `B` images (B <= the planned batch).
+int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
+  Conv2Launch L = *reinterpret_cast<Conv2Launch*>(op.impl);
+  Conv2Params& P = L.P;
+  P.c.B = B;
+  P.m_tiles = P.c.tiles_x * P.c.tiles_y * B;
+  if (P.halo)
+    P.total_items = B * P.c.tiles_x * P.segs_per_strip;
+  else
+    P.total_items = P.m_tiles * P.n_tiles * P.c.classes;
+  L.grid = std::min(P.total_items, num_sms());
+  return conv2_run(L, stream);
+}
+
+const char* conv_op_describe(const ConvOp& op, char* buf, int n) {
+  const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
+  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
+           L->P.halo, L->P.wres, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
+  return buf;
+}
+
+}  // namespace prg

@@ -1,4 +1,4 @@
-// tcgen05 implicit-GEMM convolution / GEMM engine: interface.
+// tcgen05 implicit-GEMM convolution / GEMM engine: interface (implementation: conv2_tc.cu).
 //
 // One launch computes  D[m, n] = sum_k A[m, k] * W[n, k]  with
 //   m = output pixel (128-pixel tile = tile_w x tile_h patch of one image, NHWC fp16),
@@ -47,27 +47,27 @@ struct ConvParams {
   float q_scale;
 };
 
-struct ConvLaunch {
-  CUtensorMap tmA0, tmA1, tmB;
-  ConvParams p;
-  int bn;    // N tile: 64 / 128 / 256
-  int epi;   // ConvEpi
-  dim3 grid;
-  int cout;
-};
-
-// Description of one NHWC fp16 activation source.
+// Description of one NHWC fp16 activation tensor (source or destination).
 struct ActSrc {
   const __half* ptr;   // first element of channel 0 of pixel (0,0) of image 0
-  int H, W, C;         // C = channels read from this source (multiple of 64)
+  int H, W, C;         // C = channels used (multiple of 64)
   int pix_stride;      // elements between consecutive pixels (>= C)
 };
 
-// Fills tensor maps + params.  Returns 0 or a PRG_ERR_* code (message via set_error).
-// w: [nb][classes][Cout][taps*Cin] fp16 (K-major, tap-major); nb = B if w_batched else 1.
-int conv_plan(ConvLaunch* L, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
-              int classes, const __half* w, int w_batched, int Cout);
-int conv_run(const ConvLaunch& L, cudaStream_t stream);
+// ---- persistent engine (conv2_tc.cu): plan once for the maximum batch, run for any B <= that.
+struct ConvOp {
+  void* impl;
+  ConvOp();
+  ~ConvOp();
+  ConvOp(const ConvOp&);
+  ConvOp& operator=(const ConvOp&);
+  ConvParams& params();   // epilogue extras (bias, stats, res, ...) are filled in by the caller
+};
+// out: destination tensor (H, W = full output size, C = Cout, pix_stride).
+int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
+                 int classes, const __half* w, int w_batched, int Cout, const ActSrc& out);
+int conv_op_run(ConvOp& op, int B, cudaStream_t stream);
+const char* conv_op_describe(const ConvOp& op, char* buf, int n);
 
 constexpr float kStatUnscale = 1.0f / 1048576.0f;  // fixed-point statistics -> float
 

@@ -14,6 +14,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <stdlib.h>
 #include <string.h>
 
 #include "attention.cuh"
@@ -243,23 +244,19 @@ ActSrc src_of(const Act& a) { return ActSrc{a.p, a.H, a.W, a.C, a.pix_stride}; }
 int add_conv(prg_net* n, int epi, const Act& s0, const Act* s1, int mode, int ksize, int classes,
              const __half* w, int w_batched, const float* bias, const Act& out,
              std::function<void(ConvParams&)> fill = nullptr) {
-  ConvLaunch L;
+  ConvOp op;
   ActSrc a0 = src_of(s0), a1;
   if (s1) a1 = src_of(*s1);
-  NET_TRY(conv_plan(&L, epi, n->maxB, a0, s1 ? &a1 : nullptr, mode, ksize, classes, w, w_batched,
-                    out.C));
-  L.p.out = out.p;
-  L.p.out_pix_stride = out.pix_stride;
-  L.p.out_row_stride = out.W * out.pix_stride;
-  L.p.out_img_stride = (long long)out.H * out.W * out.pix_stride;
-  L.p.bias = bias;
-  if (fill) fill(L.p);
-  const int tiles = L.p.tiles_x * L.p.tiles_y;
-  n->add_op(CAT_CONV, [L, tiles](const Run& r) mutable {
-    L.p.B = r.B;
-    L.grid.x = (unsigned)(tiles * r.B);
-    return conv_run(L, r.s);
-  });
+  NET_TRY(conv_op_plan(&op, epi, n->maxB, a0, s1 ? &a1 : nullptr, mode, ksize, classes, w, w_batched,
+                       out.C, src_of(out)));
+  op.params().bias = bias;
+  if (fill) fill(op.params());
+  if (getenv("PRG_DEBUG_PLAN")) {
+    char buf[160];
+    fprintf(stderr, "conv %dx%d %d->%d k%d m%d c%d: %s\n", s0.H, s0.W, s0.C + (s1 ? s1->C : 0), out.C,
+            ksize, mode, classes, conv_op_describe(op, buf, sizeof(buf)));
+  }
+  n->add_op(CAT_CONV, [op](const Run& r) mutable { return conv_op_run(op, r.B, r.s); });
   return PRG_OK;
 }
 

@@ -9,26 +9,16 @@ extern "C" __attribute__((visibility("default"))) int prg_test_conv_f16(
     int mode, prg_stream_t stream) {
   PRG_CHECK_ARG(x && w && y, "null pointer");
   PRG_CHECK_ARG(mode >= 0 && mode <= 3, "mode");
-  ConvLaunch L;
   ActSrc s{(const __half*)x, H, W, Cin, Cin};
-  int rc;
   int Ho = H, Wo = W;
-  if (mode == 0) {
-    rc = conv_plan(&L, EPI_BIAS, B, s, nullptr, 0, 1, 1, (const __half*)w, 0, Cout);
-  } else if (mode == 1) {
-    rc = conv_plan(&L, EPI_BIAS, B, s, nullptr, 0, 3, 1, (const __half*)w, 0, Cout);
-  } else if (mode == 2) {
-    rc = conv_plan(&L, EPI_BIAS, B, s, nullptr, 1, 4, 1, (const __half*)w, 0, Cout);
-    Ho = H / 2; Wo = W / 2;
-  } else {  // nearest x2 upsample folded into four 2x2 parity classes (weights pre-combined)
-    rc = conv_plan(&L, EPI_BIAS, B, s, nullptr, 0, 3, 4, (const __half*)w, 0, Cout);
-    Ho = H * 2; Wo = W * 2;
-  }
+  int cmode = 0, ksize = 1, classes = 1;
+  if (mode == 1) { ksize = 3; }
+  else if (mode == 2) { cmode = 1; ksize = 4; Ho = H / 2; Wo = W / 2; }
+  else if (mode == 3) { ksize = 3; classes = 4; Ho = H * 2; Wo = W * 2; }
+  ActSrc o{(const __half*)y, Ho, Wo, Cout, Cout};
+  ConvOp op;
+  int rc = conv_op_plan(&op, EPI_BIAS, B, s, nullptr, cmode, ksize, classes, (const __half*)w, 0, Cout, o);
   if (rc) return rc;
-  L.p.out = (__half*)y;
-  L.p.out_pix_stride = Cout;
-  L.p.out_row_stride = Wo * Cout;
-  L.p.out_img_stride = (long long)Ho * Wo * Cout;
-  L.p.bias = bias;
-  return conv_run(L, (cudaStream_t)stream);
+  op.params().bias = bias;
+  return conv_op_run(op, B, (cudaStream_t)stream);
 }

@@ -86,3 +86,17 @@ def test_conv_no_bias():
     got = _run(x, w, None, 1)
     ref = _ref(x, w, None, 1)
     assert ((got - ref).norm() / ref.norm()).item() < 5e-4
+
+
+def test_conv_halo_ring_many_rows():
+    """3x3, Cin = Cout = 64 on >=128-wide maps takes the halo-ring path (each input row loaded
+    once, nine shifted smem views); check several images / strips / segment boundaries."""
+    g = torch.Generator().manual_seed(3)
+    for (B, H, W) in [(3, 128, 128), (2, 256, 256), (1, 40, 128)]:
+        x = torch.randn(B, 64, H, W, generator=g)
+        w = torch.randn(64, 64, 3, 3, generator=g) * 0.06
+        bias = torch.randn(64, generator=g)
+        got = _run(x, w, bias, 1)
+        ref = _ref(x, w, bias, 1)
+        rel = ((got - ref).norm() / ref.norm()).item()
+        assert rel < 5e-4, (B, H, W, rel)
