@@ -164,8 +164,10 @@ int linattn_context(const __half* qkv, const int* colmax, long long* ctx, long l
     set_error("linattn_context: n=%d is not a multiple of %d", n, kCtxTile);
     return PRG_ERR_ARG;
   }
-  int chunk = n / 16;
-  if (chunk < 1024) chunk = 1024;
+  // enough CTAs per image to hide the load->mma latency chain, few enough to keep the
+  // cross-CTA atomics cheap
+  int chunk = n / 32;
+  if (chunk < 256) chunk = 256;
   if (chunk > n) chunk = n;
   chunk = (chunk + kCtxTile - 1) / kCtxTile * kCtxTile;
   dim3 g((n + chunk - 1) / chunk, B);

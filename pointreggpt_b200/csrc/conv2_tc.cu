@@ -15,7 +15,7 @@
 //              fits (loaded once per CTA), otherwise streamed next to A.
 //   warp 1   : one lane issues tcgen05.mma (M=128, N=BN, K=16), accumulating in one of TWO
 //              TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warps 2-5: epilogue: tcgen05.ld -> fused bias / GroupNorm statistics / softmax /
+//   warps 2-9: epilogue (two warps per TMEM lane quarter, each draining half the columns): tcgen05.ld -> fused bias / GroupNorm statistics / softmax /
 //              LayerNorm / residual -> fp16 -> 128B-swizzled staging tile -> TMA store.
 #include <limits.h>
 #include <string.h>
@@ -38,10 +38,11 @@ constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KiB per-tap A stage
 constexpr int kHaloPix = kBlockM + 2;              // 130 pixels per ring row
 constexpr int kHaloBytes = kHaloPix * 128;         // 16640 B written by TMA
 constexpr int kHaloSlot = 17 * 1024;               // slot pitch (1024-aligned)
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                     // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kCtlBytes = 2048;
+constexpr int kCtlBytes = 8192;
 constexpr double kStatScale = 1048576.0;           // 2^20 fixed point (see conv_tc.cuh)
 
 struct alignas(8) Ctl {
@@ -52,8 +53,11 @@ struct alignas(8) Ctl {
   uint64_t tmem_empty[2];
   uint32_t tmem_addr;
   uint32_t pad;
-  float stats[64];   // EPI_GN: [epilogue warp][8 groups][sum, sumsq]
-  int colmax[128];   // EPI_QKV k tile
+  float stats[4 * 32 * 2];  // EPI_GN: [TMEM quarter][8-column sub-block][sum, sumsq], written once per tile
+  int colmax[128];          // EPI_QKV k tile
+  float rowsum[2][128];     // EPI_LN_RES: per-row partial sums of the two column halves
+  float bias[512];          // bias of every output channel (0 when absent)
+  float gain[256];          // EPI_LN_RES: LayerNorm gain
 };
 static_assert(sizeof(Ctl) <= kCtlBytes, "control block too large");
 
@@ -71,8 +75,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct Item {
   int img, x0, y0, n_tile, cls;
@@ -100,6 +107,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   const ConvParams& p = P.c;
   constexpr int kBBytes = BN * kBlockK * 2;
   constexpr int kStageOut = (BN / 64) * kABytes;   // fp16 staging tile, 64-channel boxes
+  constexpr int kOutBufs = (BN <= 128) ? 2 : 1;    // double-buffered: the TMA store of tile i drains
+                                                   // while tile i+1 is being written
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -107,7 +116,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   uint8_t* sA = sW + P.w_bytes;                     // A ring
   uint8_t* sB = sA + P.stages * P.a_slot;           // streamed B ring (when !wres)
   uint8_t* sO = sB + (P.wres ? 0 : P.stages * kBBytes);
-  Ctl* ctl = reinterpret_cast<Ctl*>(sO + kStageOut);
+  Ctl* ctl = reinterpret_cast<Ctl*>(sO + kOutBufs * kStageOut);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_w = 1 << p.tile_w_log2;
@@ -128,7 +137,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     mbar_init(&ctl->wfull, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&ctl->tmem_full[a], 1);
-      mbar_init(&ctl->tmem_empty[a], 128);
+      mbar_init(&ctl->tmem_empty[a], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -137,6 +146,10 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     tmem_relinquish();
   }
   if (EPI == EPI_QKV && threadIdx.x < 128) ctl->colmax[threadIdx.x] = INT_MIN;
+  for (int i = threadIdx.x; i < BN * P.n_tiles; i += kThreads)
+    ctl->bias[i] = (p.bias != nullptr) ? __ldg(p.bias + i) : 0.f;
+  if (EPI == EPI_LN_RES)
+    for (int i = threadIdx.x; i < BN; i += kThreads) ctl->gain[i] = __ldg(p.ln_g + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,7 +169,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     it.y0 = tyi * tile_h;
     return it;
   };
-  // segment -> coordinates (halo mode): (img, strip x0, first row, rows)
+  // halo mode: every 128-pixel strip is cut into row segments that are dealt round-robin to
+  // the CTAs (concurrently running CTAs work inside one small address window).
   auto decode_seg = [&](int seg, int& img, int& x0, int& y0, int& nr) {
     const int strips = p.tiles_x;
     const int per_img = strips * P.segs_per_strip;
@@ -231,6 +245,17 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     // =============================== MMA issuer =================================
     constexpr uint32_t idesc = idesc_f16(kBlockM, BN);
     if (P.wres) mbar_wait(&ctl->wfull, 0);
+    // The warp stays converged: every lane computes the (warp-uniform) descriptors, only the
+    // leader lane's tcgen05 instructions are predicated on.
+    const uint32_t leader = (lane == 0) ? 1u : 0u;
+    // warp-reductions return provably uniform values: lets the compiler keep the TMEM address
+    // and the descriptors in uniform registers instead of re-broadcasting them per MMA
+    const uint32_t taddr_u = __reduce_or_sync(0xffffffffu, taddr);
+    const uint32_t sA_u = __reduce_or_sync(0xffffffffu, smem_u32(sA));
+    const uint32_t sB_u = __reduce_or_sync(0xffffffffu, smem_u32(sB));
+    const uint32_t sW_u = __reduce_or_sync(0xffffffffu, smem_u32(sW));
+    const uint64_t desc_hi = smem_desc_sw128(0);     // everything but the start-address field
+    auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)((addr >> 4) & 0x3FFFu); };
     int stage = 0;
     uint32_t phase = 0;
     uint32_t tcount = 0;  // tiles issued by this CTA
@@ -251,36 +276,31 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const uint32_t acc = tcount & 1;
           mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t d_addr = taddr + acc * BN;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              int slot = stage + dy;   // row j + dy of the segment
-              if (slot >= P.stages) slot -= P.stages;
-              const uint32_t a_addr = smem_u32(sA + (size_t)slot * P.a_slot) + dx * 128;
-              const uint32_t b_addr = smem_u32(sW + (size_t)tap * kBBytes);
-              // shifted view: the start sits dx rows into a swizzle atom.  The 128B swizzle is a
-              // function of the absolute shared-memory address (measured: base_offset must stay
-              // 0), so the descriptor needs nothing beyond the displaced start address.
-              const uint64_t da = smem_desc_sw128(a_addr);
-              const uint64_t db = smem_desc_sw128(b_addr);
+          const uint32_t d_addr = taddr_u + acc * BN;
+          int s1 = stage + 1, s2 = stage + 2;
+          if (s1 >= P.stages) s1 -= P.stages;
+          if (s2 >= P.stages) s2 -= P.stages;
+          const uint32_t row_addr[3] = {sA_u + (uint32_t)stage * P.a_slot, sA_u + (uint32_t)s1 * P.a_slot,
+                                        sA_u + (uint32_t)s2 * P.a_slot};
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                         (tap > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(&ctl->tmem_full[acc]);
-            umma_commit(&ctl->empty[stage]);           // top row of this tile is done
-            if (j == nr - 1) {                          // segment end: release the two halo rows
-              int s1 = stage + 1, s2 = stage + 2;
-              if (s1 >= P.stages) s1 -= P.stages;
-              if (s2 >= P.stages) s2 -= P.stages;
-              umma_commit(&ctl->empty[s1]);
-              umma_commit(&ctl->empty[s2]);
-            }
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            // shifted view: the start sits dx rows into a swizzle atom.  The 128B swizzle is a
+            // function of the absolute shared-memory address (measured: base_offset must stay
+            // 0), so the descriptor needs nothing beyond the displaced start address.
+            const uint64_t da = mkdesc(row_addr[dy] + dx * 128);
+            const uint64_t db = mkdesc(sW_u + tap * kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16_pred(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                            (tap > 0 || k > 0) ? 1u : 0u, leader);
           }
-          __syncwarp();
+          umma_commit_pred(&ctl->tmem_full[acc], leader);
+          umma_commit_pred(&ctl->empty[stage], leader);     // top row of this tile is done
+          if (j == nr - 1) {                                // segment end: release the halo rows
+            umma_commit_pred(&ctl->empty[s1], leader);
+            umma_commit_pred(&ctl->empty[s2], leader);
+          }
           ++tcount;
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
@@ -294,25 +314,22 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const uint32_t acc = tcount & 1;
         mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_addr = taddr + acc * BN;
+        const uint32_t d_addr = taddr_u + acc * BN;
+        const uint32_t w_base = sW_u + (uint32_t)(it.n_tile * num_kb) * kBBytes;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(sA + (size_t)stage * P.a_slot);
-            const uint32_t b_addr =
-                P.wres ? smem_u32(sW + (size_t)(it.n_tile * num_kb + kb) * kBBytes)
-                       : smem_u32(sB + (size_t)stage * kBBytes);
-            const uint64_t da = smem_desc_sw128(a_addr);
-            const uint64_t db = smem_desc_sw128(b_addr);
+          const uint32_t a_addr = sA_u + (uint32_t)stage * P.a_slot;
+          const uint32_t b_addr = P.wres ? w_base + (uint32_t)kb * kBBytes
+                                         : sB_u + (uint32_t)stage * kBBytes;
+          const uint64_t da = mkdesc(a_addr);
+          const uint64_t db = mkdesc(b_addr);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                       (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&ctl->empty[stage]);
-            if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
-          }
-          __syncwarp();
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16_pred(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u, leader);
+          umma_commit_pred(&ctl->empty[stage], leader);
+          if (kb == num_kb - 1) umma_commit_pred(&ctl->tmem_full[acc], leader);
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         ++tcount;
@@ -320,27 +337,28 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     }
   } else {
     // =============================== epilogue ===================================
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;               // which half of the columns this warp drains
     const int row = quarter * 32 + lane;
-    const int e = threadIdx.x - 64;                 // 0..127
+    const int e = threadIdx.x - 64;                 // 0..255
     const int tyr = row >> p.tile_w_log2, txr = row & (tile_w - 1);
+    constexpr int kHalfCols = BN / 2;
     uint32_t tcount = 0;
 
     auto do_tile = [&](int img, int x0, int y0, int n_tile, int cls) {
       const int n0 = n_tile * BN;
       const int cpy = cls >> 1, cpx = cls & 1;
       const uint32_t acc = tcount & 1;
-      // (1) previous TMA store must have finished reading the staging tile
-      if (e == 0) bulk_wait_read0();
-      epi_bar();
-      // every thread is past the previous tile's cross-warp reads: reset this warp's own slots
-      if (EPI == EPI_GN && lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) ctl->stats[quarter * 16 + i] = 0.f;
+      // (1) the TMA store that last used this staging buffer must have finished reading it
+      uint8_t* sOut = sO + (kOutBufs == 2 ? (tcount & 1) * kStageOut : 0);
+      if (e == 0) {
+        if (kOutBufs == 2) bulk_wait_read1(); else bulk_wait_read0();
       }
+      epi_bar();
       mbar_wait(&ctl->tmem_full[acc], (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = taddr + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      const float* sbias = ctl->bias + n0;
 
       const int oy = (y0 + tyr) * p.out_scale + cpy, ox = (x0 + txr) * p.out_scale + cpx;
       const long long off = (long long)img * p.out_img_stride + (long long)oy * p.out_row_stride +
@@ -348,72 +366,83 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 
       float ln_mean = 0.f, ln_rstd = 0.f;
       if (EPI == EPI_LN_RES) {
+        // channel LayerNorm over the whole row (BN == Cout); the two threads that share a row
+        // exchange their half-row partial sums through shared memory (exact two-pass variance)
         float s = 0.f;
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * kHalfCols; c < (half + 1) * kHalfCols; c += 32) {
           uint32_t v[32];
           tmem_ld32(trow + c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += __uint_as_float(v[j]) + __ldg(p.bias + n0 + c + j);
+          for (int j = 0; j < 32; ++j) s += __uint_as_float(v[j]) + sbias[c + j];
         }
-        ln_mean = s * (1.f / BN);
+        ctl->rowsum[half][row] = s;
+        epi_bar();
+        ln_mean = (ctl->rowsum[0][row] + ctl->rowsum[1][row]) * (1.f / BN);
+        epi_bar();
         float ss = 0.f;
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * kHalfCols; c < (half + 1) * kHalfCols; c += 32) {
           uint32_t v[32];
           tmem_ld32(trow + c, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(v[j]) + __ldg(p.bias + n0 + c + j) - ln_mean;
+            const float d = __uint_as_float(v[j]) + sbias[c + j] - ln_mean;
             ss += d * d;
           }
         }
-        ln_rstd = rsqrtf(ss * (1.f / BN) + 1e-5f);
+        ctl->rowsum[half][row] = ss;
+        epi_bar();
+        ln_rstd = rsqrtf((ctl->rowsum[0][row] + ctl->rowsum[1][row]) * (1.f / BN) + 1e-5f);
       }
       const int qkv_part = (EPI == EPI_QKV) ? (n0 >> 7) : 0;
 
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * kHalfCols; c < (half + 1) * kHalfCols; c += 32) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n0 + c + j);
-        }
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + sbias[c + j];
+
         if (EPI == EPI_GN) {
-          float s4[4], q4[4];
+          // per 8-column sub-block (sum, sumsq) of this row, then a halving butterfly over the
+          // warp: 8 values x 32 lanes -> 9 shuffles, fixed order (bit-reproducible)
+          float w8[8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float s = 0.f, q = 0.f;
+            float sm = 0.f, sq = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float x = f[g * 8 + j];
-              s += x;
-              q = fmaf(x, x, q);
+              sm += x;
+              sq = fmaf(x, x, sq);
             }
-            s4[g] = s;
-            q4[g] = q;
+            w8[g * 2] = sm;
+            w8[g * 2 + 1] = sq;
+          }
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+          float w4[4], w2[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = h16 ? w8[i] : w8[i + 4];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            w4[i] = (h16 ? w8[i + 4] : w8[i]) + recv;
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              s4[g] += __shfl_xor_sync(0xffffffffu, s4[g], o);
-              q4[g] += __shfl_xor_sync(0xffffffffu, q4[g], o);
-            }
+          for (int i = 0; i < 2; ++i) {
+            const float send = h8 ? w4[i] : w4[i + 2];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            w2[i] = (h8 ? w4[i + 2] : w4[i]) + recv;
           }
-          if (lane == 0) {
-            float* ws = ctl->stats + quarter * 16;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int grp = (c + g * 8) >> p.gs_log2;
-              ws[grp * 2 + 0] += s4[g];
-              ws[grp * 2 + 1] += q4[g];
-            }
+          const float send = h4 ? w2[0] : w2[1];
+          float t = (h4 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          if ((lane & 3) == 0) {
+            const int idx = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);   // = sub-block*2 + moment
+            ctl->stats[(quarter * 32 + (c >> 3)) * 2 + idx] = t;
           }
         } else if (EPI == EPI_QKV) {
           if (qkv_part == 0) {
@@ -446,8 +475,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           }
         } else if (EPI == EPI_LN_RES) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            f[j] = (f[j] - ln_mean) * ln_rstd * __ldg(p.ln_g + n0 + c + j);
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] - ln_mean) * ln_rstd * ctl->gain[c + j];
         }
         if (EPI == EPI_RES || EPI == EPI_LN_RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + c);
@@ -464,7 +492,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           }
         }
         // fp16 -> staging tile: box (c / 64), row `row`, 16-byte chunk index XOR (row & 7)
-        uint8_t* box = sO + (size_t)(c >> 6) * kABytes + (size_t)row * 128;
+        uint8_t* box = sOut + (size_t)(c >> 6) * kABytes + (size_t)row * 128;
         const int ch0 = (c & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -490,23 +518,31 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const CUtensorMap* tmo = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx)
-          tma_store_4d(tmo, sO + (size_t)bx * kABytes, n0 + bx * 64, x0, y0, img);
+          tma_store_4d(tmo, sOut + (size_t)bx * kABytes, n0 + bx * 64, x0, y0, img);
         bulk_commit();
       }
       if (EPI == EPI_GN) {
+        // one 64-bit fixed-point atomic per (group, moment) of this tile: order-independent.
+        // Slots were each written exactly once above; summed here in a fixed order.
         const int ngrp = BN >> p.gs_log2;
         if (e < ngrp * 2) {
+          const int grp = e >> 1, m = e & 1;
+          const int sb0 = grp << (p.gs_log2 - 3), nsb = 1 << (p.gs_log2 - 3);
+          float v = 0.f;
+          for (int sb = sb0; sb < sb0 + nsb; ++sb) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v += ctl->stats[(q * 32 + sb) * 2 + m];
+          }
           const int g0 = n0 >> p.gs_log2;
-          const float v = (ctl->stats[e] + ctl->stats[16 + e]) + (ctl->stats[32 + e] + ctl->stats[48 + e]);
           atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)img * 8 + g0) * 2 + e,
                     (unsigned long long)__double2ll_rn((double)v * kStatScale));
         }
       }
       if (EPI == EPI_QKV) {
-        if (qkv_part == 1 && p.colmax != nullptr) {
+        if (qkv_part == 1 && p.colmax != nullptr && e < 128) {
           atomicMax(&p.colmax[img * 128 + e], ctl->colmax[e]);
-          ctl->colmax[e] = INT_MIN;   // slot e is read only by thread e; next tile's atomics come
-        }                             // after the next epi_bar
+          ctl->colmax[e] = INT_MIN;   // slot e is touched again only after the next epi_bar
+        }
       }
       ++tcount;
     };
@@ -604,6 +640,25 @@ static int conv_flags() {
   return g_conv_flags;
 }
 
+// Segment length for the halo mode: MMA time scales with the rows a CTA owns, the two extra halo
+// rows per segment only cost a TMA load each; pick the length that minimises the busiest CTA.
+static void halo_segments(Conv2Params* P, int B, int sms) {
+  const int Ho = P->c.Ho, strips = P->c.tiles_x;
+  int best_r = 8;
+  double best_cost = 1e30;
+  for (int r = 4; r <= 32 && r <= Ho; ++r) {
+    const int segs = (Ho + r - 1) / r;
+    const long long items = (long long)B * strips * segs;
+    const long long waves = (items + sms - 1) / sms;
+    const double cost = (double)waves * (r + 0.6);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_r = r; }
+  }
+  if (const char* e = getenv("PRG_HALO_RSEG")) best_r = std::max(1, atoi(e));  // tuning override
+  P->rseg = best_r;
+  P->segs_per_strip = (Ho + best_r - 1) / best_r;
+  P->total_items = B * strips * P->segs_per_strip;
+}
+
 static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode,
                       int ksize, int classes, const __half* w, int w_batched, int Cout,
                       const ActSrc& out) {
@@ -658,18 +713,23 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   P.num_kb = ntaps * (cin / 64);
   P.m_tiles = p.tiles_x * p.tiles_y * B;
   const int b_bytes = bn * 128;
-  const int stage_out = (bn / 64) * kABytes;
+  const int stage_out = (bn / 64) * kABytes * (bn <= 128 ? 2 : 1);
   const int fixed = stage_out + kCtlBytes + 1024;
 
   // ---- mode selection
   const long long w_all = (long long)P.n_tiles * P.num_kb * b_bytes;   // all weights of one class
   P.halo = 0;
   P.wres = 0;
-  if (!w_batched && classes == 1 && w_all + fixed + 4 * kABytes <= kSmemBudget) P.wres = 1;
-  if (P.wres && mode == 0 && ksize == 3 && s1 == nullptr && cin == 64 && tile_w == kBlockM &&
-      P.n_tiles == 1 && !(conv_flags() & 1) &&
-      w_all + fixed + 5 * kHaloSlot <= kSmemBudget)
+  const bool halo_ok = !w_batched && classes == 1 && mode == 0 && ksize == 3 && s1 == nullptr &&
+                       cin == 64 && tile_w == kBlockM && P.n_tiles == 1 && !(conv_flags() & 1) &&
+                       w_all + fixed + 5 * kHaloSlot <= kSmemBudget;
+  if (halo_ok) {
     P.halo = 1;
+    P.wres = 1;
+  } else if (!w_batched && classes == 1 && w_all + fixed + 8 * kABytes <= kSmemBudget) {
+    // resident weights only when enough A stages remain to keep ~128 KiB of loads in flight
+    P.wres = 1;
+  }
   P.w_bytes = P.wres ? (int)w_all : 0;
   P.a_slot = P.halo ? kHaloSlot : kABytes;
   const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes);
@@ -684,20 +744,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
 
   const int sms = num_sms();
   if (P.halo) {
-    // split every 128-pixel strip into row segments; pick the segment length that best fills
-    // the SMs (each segment re-reads 2 halo rows)
-    int best_r = 8;
-    double best_eff = 0.0;
-    for (int r = 4; r <= Ho; ++r) {
-      const int segs = (Ho + r - 1) / r;
-      const long long items = (long long)B * p.tiles_x * segs;
-      const long long waves = (items + sms - 1) / sms;
-      const double eff = ((double)B * p.tiles_x * Ho) / ((double)waves * sms * (r + 2));
-      if (eff > best_eff + 1e-9) { best_eff = eff; best_r = r; }
-    }
-    P.rseg = best_r;
-    P.segs_per_strip = (Ho + best_r - 1) / best_r;
-    P.total_items = B * p.tiles_x * P.segs_per_strip;
+    halo_segments(&P, B, sms);
   } else {
     P.total_items = P.m_tiles * P.n_tiles * classes;
   }
@@ -820,7 +867,7 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
   P.c.B = B;
   P.m_tiles = P.c.tiles_x * P.c.tiles_y * B;
   if (P.halo)
-    P.total_items = B * P.c.tiles_x * P.segs_per_strip;
+    halo_segments(&P, B, num_sms());
   else
     P.total_items = P.m_tiles * P.n_tiles * P.c.classes;
   L.grid = std::min(P.total_items, num_sms());

@@ -148,7 +148,7 @@ int stem_mask(const float* depth01, const float* w, const float* bias, __half* y
 // ------------------------------------------------------------------------------------------
 // One CTA per image: sinusoidal embedding -> Linear -> GELU -> Linear, param MLP likewise,
 // SiLU of both written to cond_act (every block MLP starts with SiLU, SDD:709-710).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_cond_embed(CondWeights w, const int64_t* __restrict__ time, int time_scalar,
              const float* __restrict__ pcond, float* __restrict__ cond_act) {
   extern __shared__ float sm[];
@@ -170,30 +170,38 @@ k_cond_embed(CondWeights w, const int64_t* __restrict__ time, int time_scalar,
   }
   for (int i = threadIdx.x; i < w.pdim; i += blockDim.x) pin[i] = pcond[b * w.pdim + i];
   __syncthreads();
-  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-    float a = w.t1b[j];
-    for (int k = 0; k < dim; ++k) a = fmaf(w.t1w[j * dim + k], emb[k], a);
-    h1[j] = gelu_erf(a);
-    float c = w.p1b[j];
-    for (int k = 0; k < w.pdim; ++k) c = fmaf(w.p1w[j * w.pdim + k], pin[k], c);
-    h2[j] = gelu_erf(c);
+  // warp-per-row GEMVs (lanes stride K -> coalesced weight reads, fixed-order shuffle reduction)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < 2 * hid; j += nwarps) {
+    const bool is_p = j >= hid;
+    const int r = is_p ? j - hid : j;
+    const int K = is_p ? w.pdim : dim;
+    const float* wr = (is_p ? w.p1w : w.t1w) + (size_t)r * K;
+    const float* in = is_p ? pin : emb;
+    float a = 0.f;
+    for (int k = lane; k < K; k += 32) a = fmaf(__ldg(wr + k), in[k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) (is_p ? h2 : h1)[r] = gelu_erf(a + (is_p ? w.p1b : w.t1b)[r]);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-    float a = w.t2b[j], c = w.p2b[j];
-    for (int k = 0; k < hid; ++k) {
-      a = fmaf(w.t2w[j * hid + k], h1[k], a);
-      c = fmaf(w.p2w[j * hid + k], h2[k], c);
-    }
-    cond_act[(size_t)b * 2 * hid + j] = silu(a);
-    cond_act[(size_t)b * 2 * hid + hid + j] = silu(c);
+  for (int j = warp; j < 2 * hid; j += nwarps) {
+    const bool is_p = j >= hid;
+    const int r = is_p ? j - hid : j;
+    const float* wr = (is_p ? w.p2w : w.t2w) + (size_t)r * hid;
+    const float* in = is_p ? h2 : h1;
+    float a = 0.f;
+    for (int k = lane; k < hid; k += 32) a = fmaf(__ldg(wr + k), in[k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) cond_act[(size_t)b * 2 * hid + j] = silu(a + (is_p ? w.p2b : w.t2b)[r]);
   }
 }
 
 int cond_embed(const CondWeights& w, const int64_t* time, int time_scalar, const float* pcond,
                float* cond_act, int B, cudaStream_t s) {
   const size_t smem = sizeof(float) * (w.dim + 8 * w.dim + w.pdim);
-  k_cond_embed<<<B, 256, smem, s>>>(w, time, time_scalar, pcond, cond_act);
+  k_cond_embed<<<B, 512, smem, s>>>(w, time, time_scalar, pcond, cond_act);
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
