@@ -406,6 +406,22 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + sbias[c + j];
 
+        if (EPI == EPI_GN && p.res != nullptr) {
+          // second half of a source-split convolution: add the partial sum of the first half
+          // (so the GroupNorm statistics see the complete convolution output)
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = __ldg(rp + q);
+            const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 r2 = __half22float2(h[j]);
+              f[q * 8 + j * 2 + 0] += r2.x;
+              f[q * 8 + j * 2 + 1] += r2.y;
+            }
+          }
+        }
         if (EPI == EPI_GN) {
           // per 8-column sub-block (sum, sumsq) of this row, then a halving butterfly over the
           // warp: 8 values x 32 lanes -> 9 shuffles, fixed order (bit-reproducible)

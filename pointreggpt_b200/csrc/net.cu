@@ -291,10 +291,25 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
   NET_PTR(g2, n->f32(pfx + ".block2.norm.weight"));
   NET_PTR(be2, n->f32(pfx + ".block2.norm.bias"));
 
-  NET_TRY(add_conv(n, EPI_GN, x0, x1, 0, 3, 1, w1, 0, b1, raw, [=](ConvParams& p) {
-    p.stats = st1;
-    p.gs_log2 = gs_log2;
-  }));
+  if (x1 != nullptr && n->has(pfx + ".block1.proj.weight.a")) {
+    // 64 + 64 -> 64 at >= 128-pixel rows: neither the 147 KB weight matrix nor a 128-channel
+    // row ring fits beside the other in one SM, so the concat conv is split by source into two
+    // halo-ring convs; the second adds the first's fp16 partial before the GN statistics.
+    NET_PTR(wa, n->f16(pfx + ".block1.proj.weight.a"));
+    NET_PTR(wb, n->f16(pfx + ".block1.proj.weight.b"));
+    NET_TRY(add_conv(n, EPI_BIAS, x0, nullptr, 0, 3, 1, wa, 0, nullptr, h1));
+    const __half* partial = h1.p;
+    NET_TRY(add_conv(n, EPI_GN, *x1, nullptr, 0, 3, 1, wb, 0, b1, raw, [=](ConvParams& p) {
+      p.stats = st1;
+      p.gs_log2 = gs_log2;
+      p.res = partial;
+    }));
+  } else {
+    NET_TRY(add_conv(n, EPI_GN, x0, x1, 0, 3, 1, w1, 0, b1, raw, [=](ConvParams& p) {
+      p.stats = st1;
+      p.gs_log2 = gs_log2;
+    }));
+  }
   {
     GnApply a{};
     a.raw = raw.p; a.stats = st1; a.gamma = g1; a.beta = be1;

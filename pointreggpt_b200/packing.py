@@ -131,8 +131,12 @@ def _pack_trunk(w, sd, kind, groups):
     for name in resblock_order(levels):
         for blk in ("block1", "block2"):
             p = "%s.%s" % (name, blk)
-            w.add(p + ".proj.weight",
-                  conv_weight_kmajor(standardize(sd[p + ".proj.weight"].float())), "f16")
+            ws = standardize(sd[p + ".proj.weight"].float())
+            w.add(p + ".proj.weight", conv_weight_kmajor(ws), "f16")
+            if blk == "block1" and ws.shape[0] == 64 and ws.shape[1] == 128:
+                # source-split copies for the two-pass halo convolution of cat(x, skip)
+                w.add(p + ".proj.weight.a", conv_weight_kmajor(ws[:, :64].contiguous()), "f16")
+                w.add(p + ".proj.weight.b", conv_weight_kmajor(ws[:, 64:].contiguous()), "f16")
             w.add(p + ".proj.bias", sd[p + ".proj.bias"], "f32")
             w.add(p + ".norm.weight", sd[p + ".norm.weight"], "f32")
             w.add(p + ".norm.bias", sd[p + ".norm.bias"], "f32")

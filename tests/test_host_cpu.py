@@ -1,0 +1,173 @@
+"""CPU-side checks of the product package: the C ABI loads and exports every symbol of
+include/prg.h, compute entries fail loudly without a GPU (no CPU fallback), packing, sampler
+step tables, state-dict compatibility, rank sharding (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import torch_ref as R
+from pointreggpt_b200 import _ffi, dist as pdist, geometry as pg, nets, packing
+from pointreggpt_b200.diffusion import GaussianDiffusion
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NO_GPU = not torch.cuda.is_available()
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "prg.h")).read()
+    declared = set(re.findall(r"\b(prg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libprg.so does not export " + name
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    assert _ffi.lib().prg_abi_version() == 1
+
+
+@pytest.mark.skipif(not NO_GPU, reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    x = torch.zeros(1, 1, 8, 8)
+    K = torch.eye(3)[None]
+    with pytest.raises(_ffi.PrgError):
+        pg.reproject_tensor(x, K, torch.eye(4)[None])
+    torch.manual_seed(0)
+    net = nets.MaskUnet(dim=64, dim_mults=(1, 2, 4, 8))
+    with pytest.raises(_ffi.PrgError):
+        net(torch.zeros(1, 1, 128, 128))
+    # creating a handle without a device must fail with an error code, not crash
+    h = ctypes.c_void_p()
+    blob = net._pack()
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    rc = _ffi.lib().prg_net_create(ctypes.byref(h), packing.KIND_MASKUNET, buf, len(blob), 1, 128, 0)
+    assert rc != 0 and _ffi.lib().prg_last_error()
+
+
+def test_packing_layouts():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(5, 3, 3, 3, generator=g)
+    k = packing.conv_weight_kmajor(w)
+    assert k.shape == (5, 27)
+    assert torch.equal(k[2, (1 * 3 + 2) * 3 + 1], w[2, 1, 1, 2])
+    # folded nearest-x2 upsample + conv3x3 == four 2x2 parity convs
+    x = torch.randn(1, 3, 6, 6, generator=g)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest"),
+                                     w, padding=1)
+    f = packing.upsample_fold_weight(w).reshape(5, 4, 4, 3)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    dy, dx = ty - (1 - py), tx - (1 - px)
+                    patch = xp[:, :, 1 + dy:1 + dy + 6, 1 + dx:1 + dx + 6]
+                    out[:, :, py::2, px::2] += torch.einsum("oc,bchw->bohw", f[:, py * 2 + px, ty * 2 + tx], patch)
+    assert torch.allclose(out, ref, atol=1e-5)
+    ws = packing.standardize(w)
+    assert torch.allclose(ws, R.standardize_weight(w))
+
+
+def test_blob_roundtrip_header():
+    torch.manual_seed(0)
+    net = nets.MaskUnet(dim=64, dim_mults=(1, 2, 4, 8))
+    blob = net._pack()
+    assert blob[:4] == b"PRGW"
+    assert len(blob) % 256 == 0 and len(blob) > 60e6
+
+
+def test_state_dict_layout_and_loading():
+    torch.manual_seed(0)
+    u = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
+    d = GaussianDiffusion(u, image_size=256, timesteps=1000, sampling_timesteps=250,
+                          objective="pred_x0", beta_schedule="sigmoid")
+    sd = d.state_dict()
+    assert len(sd) == 293 and len(u.state_dict()) == 280
+    assert list(sd)[:3] == ["betas", "alphas_cumprod", "alphas_cumprod_prev"]
+    assert "model.downs.0.2.fn.fn.to_out.1.g" in sd and "model.ups.0.3.1.weight" in sd
+    assert len(nets.MaskUnet(dim=64, dim_mults=(1, 2, 4, 8)).state_dict()) == 234
+    d.load_state_dict(sd)     # a reference checkpoint's 'model' entry has exactly this layout
+    assert d.is_ddim_sampling and d.num_timesteps == 1000
+
+
+def test_sampling_step_tables_follow_reference_arithmetic():
+    torch.manual_seed(0)
+    u = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
+    d = GaussianDiffusion(u, image_size=256, timesteps=50, objective="pred_x0", beta_schedule="sigmoid")
+    sch = R.make_schedule(50)
+    steps = d.sampling_steps(has_refine_step=True)
+    assert len(steps) == 51 and d.num_noise_draws(True) == 50
+    assert [s.t for s in steps[:50]] == list(reversed(range(50)))
+    for s in steps[:50]:
+        assert s.kind == _ffi.STEP_P_SAMPLE and s.add_noise == int(s.t > 0)
+        assert s.c0 == float(sch["posterior_mean_coef1"][s.t])
+        assert s.c2 == float((0.5 * sch["posterior_log_variance_clipped"][s.t]).exp())
+    assert steps[-1].kind == _ffi.STEP_REFINE_P and steps[-1].unnormalize == 1
+    d2 = GaussianDiffusion(u, image_size=256, timesteps=1000, sampling_timesteps=250,
+                           objective="pred_x0", beta_schedule="sigmoid", ddim_sampling_eta=1.0)
+    st = d2.sampling_steps()
+    assert len(st) == 250 and st[0].t == 999 and st[-1].kind == _ffi.STEP_DDIM_LAST
+    ac = R.make_schedule(1000)["alphas_cumprod"]
+    t, tn = st[0].t, st[1].t
+    sigma = 1.0 * ((1 - ac[t] / ac[tn]) * (1 - ac[tn]) / (1 - ac[t])).sqrt()
+    assert st[0].c4 == float(sigma) and st[0].c2 == float(ac[tn].sqrt())
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        nets.Unet(dim=64, param_cond_dim=4, learned_variance=True)
+    torch.manual_seed(0)
+    u = nets.Unet(dim=64, param_cond_dim=4)
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion(u, image_size=256, objective="pred_noise")
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion(u, image_size=256, objective="pred_x0", ddnm_sampling_dropout=0.1)
+
+
+def test_shard_range_covers_everything_once():
+    for n, w in [(10, 4), (3, 8), (256, 8), (0, 2), (7, 1)]:
+        seen = []
+        for r in range(w):
+            lo, hi = pdist.shard_range(100, 100 + n, r, w)
+            assert 100 <= lo <= hi <= 100 + n
+            seen += list(range(lo, hi))
+        assert seen == list(range(100, 100 + n))
+    assert pg.num_to_groups(10, 4) == [4, 4, 2]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)            # different init per rank ...
+    net = nets.MaskUnet(dim=64, dim_mults=(1,))
+    nbytes = pdist.broadcast_weights([net], src=0)   # ... identical after the broadcast
+    fp = sum(float(p.double().abs().sum()) for p in net.parameters())
+    lo, hi = pdist.shard_range(0, 5, rank, world)
+    tot = pdist.sum_counters([hi - lo, 1.0], torch.device("cpu"))
+    ret[rank] = (fp, nbytes, lo, hi, tot)
+    dist.destroy_process_group()
+
+
+def test_two_rank_weight_broadcast_and_sharding_gloo():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    (fp0, nb0, lo0, hi0, tot0), (fp1, nb1, lo1, hi1, tot1) = ret[0], ret[1]
+    assert fp0 == fp1 and nb0 == nb1 > 0
+    assert (lo0, hi0, lo1, hi1) == (0, 3, 3, 5)
+    assert tot0 == tot1 == [5.0, 2.0]

@@ -1,0 +1,71 @@
+"""Live cross-check of the oracle against the unmodified reference modules.  Only runs where
+/root/reference exists (the build container); skipped on the GPU box."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry_ref as G
+from oracle import torch_ref as R
+from oracle.ref_import import load_reference, reference_available
+from pointreggpt_b200 import synthetic as S
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return load_reference()
+
+
+def test_geometry_bit_exact(ref):
+    sdd, _ = ref
+    B, H, W = 3, 96, 128
+    d01 = S.synthetic_depth_batch(7, B, H, W)
+    K = S.synthetic_intrinsics(B, None, seed=1).copy()
+    K[:, 0, 0] = K[:, 1, 1] = 150.0
+    K[:, 0, 2], K[:, 1, 2] = W / 2, H / 2
+    P = S.synthetic_poses(B, seed=2)
+    dm = d01 * 10
+    rd, rm = sdd.reproject_tensor(dm, torch.tensor(K), torch.tensor(P))
+    od, om = G.reproject(dm.numpy(), K, P)
+    assert np.array_equal(rd.numpy(), od) and np.array_equal(rm.numpy(), om) and om.any()
+    rpc, rv = sdd.depth2pc_tensor(dm, torch.tensor(K), clip=[0.5, 10], invalid_num=0)
+    opc, ov = G.depth2pc(dm.numpy(), K, clip=(0.5, 10), invalid=0.0)
+    assert np.array_equal(rpc.numpy(), opc) and np.array_equal(rv.numpy(), ov)
+    rp = sdd.point_cloud(d01[0, 0].numpy() * 10, K[0], clip=[0.5, 10])
+    op = G.depth2pc_compact(d01[:1].numpy(), K[:1], None)[0]
+    assert rp.dtype == np.float64 and np.array_equal(rp, op)
+
+
+def test_unet_and_sampler_bit_exact(ref):
+    sdd, dc = ref
+    torch.manual_seed(3)
+    net = sdd.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1).eval()
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 1, 64, 64, generator=g)
+    t = torch.tensor([11, 800])
+    pc = torch.tensor([[304., 304., 128.5, 128.], [290., 291., 128.5, 128.]])
+    with torch.no_grad():
+        assert torch.equal(net(x, t, pc), R.unet_forward(sd, x, t, pc))
+    torch.manual_seed(3)
+    m = dc.MaskUnet(dim=64, dim_mults=(1, 2, 4, 8)).eval()
+    msd = {k: v.detach() for k, v in m.state_dict().items()}
+    d = torch.rand(2, 1, 64, 64, generator=g)
+    d[d < 0.3] = 0
+    with torch.no_grad():
+        assert torch.equal(m(d), R.maskunet_forward(msd, d))
+    diff = sdd.GaussianDiffusion(net, image_size=64, timesteps=4, objective='pred_x0',
+                                 beta_schedule='sigmoid', is_ddnm_sampling=True)
+    noises = [torch.randn(2, 1, 64, 64, generator=g) for _ in range(5)]
+    ic = torch.cat([d, (d > 0).float()], 1) * 2 - 1
+    it = iter(noises)
+    o1, o2 = torch.randn, torch.randn_like
+    torch.randn = lambda *a, **k: next(it).clone()
+    torch.randn_like = lambda *a, **k: next(it).clone()
+    try:
+        want = diff.sample(param_cond=pc, img_cond=ic, disable_tqdm=True, has_refine_step=True)
+    finally:
+        torch.randn, torch.randn_like = o1, o2
+    got = R.p_sample_loop(sd, R.make_schedule(4), pc, ic, noises, has_refine_step=True)
+    assert torch.equal(want, got)
