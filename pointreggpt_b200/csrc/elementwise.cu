@@ -1,4 +1,6 @@
 // Non-GEMM kernels of the U-Net forward / sampler step.  See elementwise.cuh for semantics.
+#include <algorithm>
+
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "conv_tc.cuh"
@@ -258,65 +260,144 @@ __device__ __forceinline__ void gn_coeffs(const long long* stats, const float* g
   }
 }
 
+// LN: also emit LayerNorm_c(y) * g (the PreNorm of the attention that follows) from the same
+// registers -- the lanes holding one pixel (C/8 consecutive lanes) reduce with shuffles.
+template <bool LN>
 __global__ void __launch_bounds__(256)
 k_gn_apply(GnApply a) {
   extern __shared__ float sm[];
   float* sA = sm;
   float* sB = sm + a.C;
-  const int b = blockIdx.y;
+  float* sG = sm + 2 * a.C;
+  // Reverse traversal (last image first, highest addresses first): `raw` was just written front
+  // to back by the convolution, so its tail is what still sits in the 126 MB L2; and the front
+  // of `y`, written last here, is what the next convolution (front to back) reads first.
+  const int b = gridDim.y - 1 - blockIdx.y;
   gn_coeffs(a.stats, a.gamma, a.beta,
             a.ss ? a.ss + (size_t)b * a.ss_stride + a.ss_off : nullptr, a.C, a.HW, b, sA, sB);
+  if (LN)
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) sG[c] = a.ln_g[c];
   __syncthreads();
-  const int cvec = a.C >> 3;                       // 16-byte vectors per pixel
+  const int cvec = a.C >> 3;                       // 16-byte vectors per pixel (power of two)
   const int64_t nvec = (int64_t)a.HW * cvec;
   const uint4* src = reinterpret_cast<const uint4*>(a.raw + (size_t)b * a.HW * a.C);
   uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)b * a.HW * a.C);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % cvec);
-    const int64_t pix = i / cvec;
-    const uint4 v = __ldcs(src + i);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-    float f[8];
+  uint4* ldst = LN ? reinterpret_cast<uint4*>(a.ln_out + (size_t)b * a.HW * a.C) : nullptr;
+  constexpr int U = 4;                             // independent 16-byte loads in flight per thread
+  const float inv_c = 1.f / (float)a.C;
+  int cvec_log2 = 0;
+  while ((1 << cvec_log2) < cvec) ++cvec_log2;
+  // a block-iteration covers U * 256 consecutive vectors (16 KiB); blocks stride over the image
+  const int64_t stride = 256;
+  const int64_t nblk = (nvec + 256 * U - 1) / (256 * U);
+  for (int64_t blk = nblk - 1 - blockIdx.x; blk >= 0; blk -= gridDim.x) {
+    const int64_t i0 = blk * (256 * U) + threadIdx.x;
+    uint4 v[U], rv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __half22float2(h[j]);
-      f[2 * j] = t.x;
-      f[2 * j + 1] = t.y;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < nvec) v[u] = __ldcs(src + i);
     }
-    const int c0 = cv * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = silu(fmaf(f[j], sA[c0 + j], sB[c0 + j]));
     if (a.res != nullptr) {
-      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
-          a.res + ((size_t)b * a.HW + pix) * a.res_pix_stride + c0));
-      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 t = __half22float2(rh[j]);
-        f[2 * j] += t.x;
-        f[2 * j + 1] += t.y;
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < nvec) {
+          const int cv = (int)(i & (cvec - 1));
+          const int64_t pix = i >> cvec_log2;
+          rv[u] = __ldg(reinterpret_cast<const uint4*>(
+              a.res + ((size_t)b * a.HW + pix) * a.res_pix_stride + cv * 8));
+        }
       }
     }
-    uint4 o;
-    __half2 o0 = __floats2half2_rn(f[0], f[1]), o1 = __floats2half2_rn(f[2], f[3]),
-            o2 = __floats2half2_rn(f[4], f[5]), o3 = __floats2half2_rn(f[6], f[7]);
-    o.x = *reinterpret_cast<uint32_t*>(&o0);
-    o.y = *reinterpret_cast<uint32_t*>(&o1);
-    o.z = *reinterpret_cast<uint32_t*>(&o2);
-    o.w = *reinterpret_cast<uint32_t*>(&o3);
-    dst[i] = o;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      // nvec is a multiple of the warp size (HW % 128 == 0), so a warp is all-in or all-out
+      if (i >= nvec) continue;
+      const int c0 = (int)(i & (cvec - 1)) * 8;
+      const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h[j]);
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu(fmaf(f[j], sA[c0 + j], sB[c0 + j]));
+      if (a.res != nullptr) {
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(rh[j]);
+          f[2 * j] += t.x;
+          f[2 * j + 1] += t.y;
+        }
+      }
+      uint4 o;
+      __half2 o0 = __floats2half2_rn(f[0], f[1]), o1 = __floats2half2_rn(f[2], f[3]),
+              o2 = __floats2half2_rn(f[4], f[5]), o3 = __floats2half2_rn(f[6], f[7]);
+      o.x = *reinterpret_cast<uint32_t*>(&o0);
+      o.y = *reinterpret_cast<uint32_t*>(&o1);
+      o.z = *reinterpret_cast<uint32_t*>(&o2);
+      o.w = *reinterpret_cast<uint32_t*>(&o3);
+      dst[i] = o;
+      if (LN) {
+        // LayerNorm of the fp16-rounded values the attention would otherwise re-read
+        float g8[8];
+        {
+          const float2 t0 = __half22float2(o0), t1 = __half22float2(o1), t2 = __half22float2(o2),
+                       t3 = __half22float2(o3);
+          g8[0] = t0.x; g8[1] = t0.y; g8[2] = t1.x; g8[3] = t1.y;
+          g8[4] = t2.x; g8[5] = t2.y; g8[6] = t3.x; g8[7] = t3.y;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += g8[j];
+        for (int o2s = cvec >> 1; o2s > 0; o2s >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2s);
+        const float mean = s * inv_c;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = g8[j] - mean;
+          q = fmaf(d, d, q);
+        }
+        for (int o2s = cvec >> 1; o2s > 0; o2s >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o2s);
+        const float rstd = rsqrtf(q * inv_c + 1e-5f);
+        uint4 lo;
+        __half2 l0 = __floats2half2_rn((g8[0] - mean) * rstd * sG[c0 + 0], (g8[1] - mean) * rstd * sG[c0 + 1]);
+        __half2 l1 = __floats2half2_rn((g8[2] - mean) * rstd * sG[c0 + 2], (g8[3] - mean) * rstd * sG[c0 + 3]);
+        __half2 l2 = __floats2half2_rn((g8[4] - mean) * rstd * sG[c0 + 4], (g8[5] - mean) * rstd * sG[c0 + 5]);
+        __half2 l3 = __floats2half2_rn((g8[6] - mean) * rstd * sG[c0 + 6], (g8[7] - mean) * rstd * sG[c0 + 7]);
+        lo.x = *reinterpret_cast<uint32_t*>(&l0);
+        lo.y = *reinterpret_cast<uint32_t*>(&l1);
+        lo.z = *reinterpret_cast<uint32_t*>(&l2);
+        lo.w = *reinterpret_cast<uint32_t*>(&l3);
+        ldst[i] = lo;
+      }
+    }
   }
 }
 
 int gn_apply(const GnApply& a, int B, cudaStream_t s) {
   const int64_t nvec = (int64_t)a.HW * (a.C >> 3);
+  // many thin CTAs, launched in address order: the set of CTAs in flight covers a narrow window
+  // of pages (fat strided CTAs measured 8 % slower)
   int gx = (int)((nvec + 256 * 4 - 1) / (256 * 4));
   const int cap = num_sms() * 8;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 g(gx, B);
-  k_gn_apply<<<g, 256, 2 * a.C * sizeof(float), s>>>(a);
+  const bool ln = a.ln_out != nullptr;
+  if (ln && (a.C > 256)) {
+    set_error("gn_apply: fused LayerNorm needs C <= 256 (got %d)", a.C);
+    return PRG_ERR_ARG;
+  }
+  if (ln)
+    k_gn_apply<true><<<g, 256, 3 * a.C * sizeof(float), s>>>(a);
+  else
+    k_gn_apply<false><<<g, 256, 3 * a.C * sizeof(float), s>>>(a);
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }

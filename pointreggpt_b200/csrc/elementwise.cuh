@@ -44,6 +44,8 @@ struct GnApply {
   int res_pix_stride;
   __half* y;
   int HW, C;
+  const float* ln_g;  // optional fused channel LayerNorm of y (C <= 256): gain ...
+  __half* ln_out;     // ... and destination
 };
 int gn_apply(const GnApply& a, int B, cudaStream_t s);
 

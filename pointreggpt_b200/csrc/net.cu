@@ -275,7 +275,7 @@ struct BlockOut {
 // ResnetBlock (SDD:720-734 / DC:734-740).  `last` = final_res_block: stop before the second
 // GroupNorm apply (the network tail fuses it with the final 1x1 conv).
 int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x1, int cout,
-                 int* ss_cursor, bool last, BlockOut* bo) {
+                 int* ss_cursor, bool last, BlockOut* bo, const float* fuse_ln_g = nullptr) {
   const int H = x0.H, W = x0.W, HW = H * W;
   const int cin = x0.C + (x1 ? x1->C : 0);
   Act raw{n->raw, H, W, cout, cout}, h1{n->h1, H, W, cout, cout}, resb{n->resb, H, W, cout, cout};
@@ -356,6 +356,10 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
     GnApply a{};
     a.raw = raw.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr;
     a.res = res_ptr; a.res_pix_stride = res_stride; a.y = y.p; a.HW = HW; a.C = cout;
+    if (fuse_ln_g != nullptr) {   // PreNorm of the attention that consumes y, written to n->xn
+      a.ln_g = fuse_ln_g;
+      a.ln_out = n->xn;
+    }
     n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); });
   }
   bo->y = y;
@@ -363,7 +367,7 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
 }
 
 // Residual(PreNorm(LinearAttention)) -- SDD:748-769.
-int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
+int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out, bool ln_done = false) {
   const int H = x.H, W = x.W, C = x.C, HW = H * W;
   Act xn{n->xn, H, W, C, C}, qkv{n->qkv, H, W, 384, 384};
   NET_PTR(g, n->f32(pfx + ".fn.norm.g"));
@@ -376,7 +380,8 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   long long* zs = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 128 * 2));
   const __half* xp = x.p;
   __half* xnp = xn.p;
-  n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
+  if (!ln_done)
+    n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
   NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
     p.colmax = cmax;
     p.q_softmax = 1;
@@ -551,10 +556,11 @@ int build(prg_net* n) {
     NET_TRY(add_resblock(n, p + ".0", x, nullptr, cin, &ss_cursor, false, &bo));
     x = bo.y;
     skips.push_back(x);
-    NET_TRY(add_resblock(n, p + ".1", x, nullptr, cin, &ss_cursor, false, &bo));
+    const float* ln_g = (cin <= 256) ? n->f32(p + ".2.fn.norm.g") : nullptr;
+    NET_TRY(add_resblock(n, p + ".1", x, nullptr, cin, &ss_cursor, false, &bo, ln_g));
     x = bo.y;
     Act a;
-    NET_TRY(add_linattn(n, p + ".2", x, &a));
+    NET_TRY(add_linattn(n, p + ".2", x, &a, ln_g != nullptr));
     x = a;
     skips.push_back(x);
     NET_PTR(wd, n->f16(p + ".3.weight"));
@@ -594,10 +600,11 @@ int build(prg_net* n) {
     x = bo.y;
     sk = skips.back();
     skips.pop_back();
-    NET_TRY(add_resblock(n, p + ".1", x, &sk, cout, &ss_cursor, false, &bo));
+    const float* ln_g = (cout <= 256) ? n->f32(p + ".2.fn.norm.g") : nullptr;
+    NET_TRY(add_resblock(n, p + ".1", x, &sk, cout, &ss_cursor, false, &bo, ln_g));
     x = bo.y;
     Act a;
-    NET_TRY(add_linattn(n, p + ".2", x, &a));
+    NET_TRY(add_linattn(n, p + ".2", x, &a, ln_g != nullptr));
     x = a;
     if (j < L - 1) {
       NET_PTR(wu, n->f16(p + ".3.1.weight"));
