@@ -78,6 +78,9 @@ __device__ __forceinline__ void bulk_wait_read0() {
 __device__ __forceinline__ void bulk_wait_read1() {
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_wait_read2() {
+  asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -96,6 +99,8 @@ struct Conv2Params {
   int num_kb;           // K blocks per tile
   int a_slot;           // bytes per A stage / ring slot
   int w_bytes;          // resident weight bytes
+  long long* trace;     // debug: per-tile clock64 stamps of CTA 0 (nullptr = off)
+  int dbg_flags;        // debug: bit2 = skip the output TMA store, bit3 = skip GN flush
 };
 
 template <int BN, int EPI>
@@ -194,12 +199,15 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       }
       int stage = 0;
       uint32_t phase = 0;
+      int dbg_row = 0;
       if (P.halo) {
         for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
           for (int r = 0; r < nr + 2; ++r) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
+            if (P.trace != nullptr && blockIdx.x == 0 && dbg_row < 96) P.trace[512 + 2 * dbg_row] = clock64();
+            ++dbg_row;
             mbar_arrive_expect_tx(&ctl->full[stage], kHaloBytes);
             tma_load_4d(&tmA0, &ctl->full[stage], sA + (size_t)stage * P.a_slot, 0, x0 - 1,
                         y0 - 1 + r, img);
@@ -245,9 +253,6 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     // =============================== MMA issuer =================================
     constexpr uint32_t idesc = idesc_f16(kBlockM, BN);
     if (P.wres) mbar_wait(&ctl->wfull, 0);
-    // The warp stays converged: every lane computes the (warp-uniform) descriptors, only the
-    // leader lane's tcgen05 instructions are predicated on.
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
     // warp-reductions return provably uniform values: lets the compiler keep the TMEM address
     // and the descriptors in uniform registers instead of re-broadcasting them per MMA
     const uint32_t taddr_u = __reduce_or_sync(0xffffffffu, taddr);
@@ -259,6 +264,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     int stage = 0;
     uint32_t phase = 0;
     uint32_t tcount = 0;  // tiles issued by this CTA
+    int dbg_row = 0;
     if (P.halo) {
       for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
         int img, x0, y0, nr;
@@ -268,39 +274,55 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         uint32_t wait_phase = phase;
         int waited = 0;
         for (int j = 0; j < nr; ++j) {
+          if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && tcount < 64)
+            P.trace[tcount * 8 + 3] = clock64();             // loop top (before the row waits)
           while (waited < j + 3) {
             mbar_wait(&ctl->full[wait_stage], wait_phase);
+            if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && dbg_row < 96)
+              P.trace[512 + 2 * dbg_row + 1] = clock64();
+            ++dbg_row;
             if (++wait_stage == P.stages) { wait_stage = 0; wait_phase ^= 1; }
             ++waited;
           }
           const uint32_t acc = tcount & 1;
+          const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && tcount < 64;
+          if (tr) P.trace[tcount * 8 + 0] = clock64();     // rows ready
           mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
           tc_fence_after();
+          if (tr) P.trace[tcount * 8 + 1] = clock64();     // accumulator free
           const uint32_t d_addr = taddr_u + acc * BN;
           int s1 = stage + 1, s2 = stage + 2;
           if (s1 >= P.stages) s1 -= P.stages;
           if (s2 >= P.stages) s2 -= P.stages;
           const uint32_t row_addr[3] = {sA_u + (uint32_t)stage * P.a_slot, sA_u + (uint32_t)s1 * P.a_slot,
                                         sA_u + (uint32_t)s2 * P.a_slot};
+          // One elect.sync region for the whole tile: ptxas knows exactly one thread is active,
+          // keeps descriptors / TMEM address in uniform registers and emits ~4 SASS instructions
+          // per UTCHMMA (a `lane == 0` test or per-instruction predicates cost 16-17 and made the
+          // kernel MMA-issue bound at ~67 cycles per MMA -- see profiles/r1_conv_summary.txt).
+          if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            // shifted view: the start sits dx rows into a swizzle atom.  The 128B swizzle is a
-            // function of the absolute shared-memory address (measured: base_offset must stay
-            // 0), so the descriptor needs nothing beyond the displaced start address.
-            const uint64_t da = mkdesc(row_addr[dy] + dx * 128);
-            const uint64_t db = mkdesc(sW_u + tap * kBBytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              // shifted view: the start sits dx rows into a swizzle atom.  The 128B swizzle is a
+              // function of the absolute shared-memory address (measured: base_offset must
+              // stay 0), so the descriptor needs nothing beyond the displaced start address.
+              const uint64_t da = mkdesc(row_addr[dy] + dx * 128);
+              const uint64_t db = mkdesc(sW_u + tap * kBBytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16_pred(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                            (tap > 0 || k > 0) ? 1u : 0u, leader);
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (tap > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&ctl->tmem_full[acc]);
+            umma_commit(&ctl->empty[stage]);                // top row of this tile is done
+            if (j == nr - 1) {                              // segment end: release the halo rows
+              umma_commit(&ctl->empty[s1]);
+              umma_commit(&ctl->empty[s2]);
+            }
           }
-          umma_commit_pred(&ctl->tmem_full[acc], leader);
-          umma_commit_pred(&ctl->empty[stage], leader);     // top row of this tile is done
-          if (j == nr - 1) {                                // segment end: release the halo rows
-            umma_commit_pred(&ctl->empty[s1], leader);
-            umma_commit_pred(&ctl->empty[s2], leader);
-          }
+          __syncwarp();
+          if (tr) P.trace[tcount * 8 + 2] = clock64();     // all MMAs issued
           ++tcount;
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
@@ -322,14 +344,17 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const uint32_t a_addr = sA_u + (uint32_t)stage * P.a_slot;
           const uint32_t b_addr = P.wres ? w_base + (uint32_t)kb * kBBytes
                                          : sB_u + (uint32_t)stage * kBBytes;
-          const uint64_t da = mkdesc(a_addr);
-          const uint64_t db = mkdesc(b_addr);
+          if (elect_one()) {
+            const uint64_t da = mkdesc(a_addr);
+            const uint64_t db = mkdesc(b_addr);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16_pred(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u, leader);
-          umma_commit_pred(&ctl->empty[stage], leader);
-          if (kb == num_kb - 1) umma_commit_pred(&ctl->tmem_full[acc], leader);
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                       (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&ctl->empty[stage]);
+            if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
+          }
+          __syncwarp();
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         ++tcount;
@@ -350,13 +375,18 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       const int cpy = cls >> 1, cpx = cls & 1;
       const uint32_t acc = tcount & 1;
       // (1) the TMA store that last used this staging buffer must have finished reading it
-      uint8_t* sOut = sO + (kOutBufs == 2 ? (tcount & 1) * kStageOut : 0);
+      uint8_t* sOut = sO + (tcount % kOutBufs) * kStageOut;
       if (e == 0) {
-        if (kOutBufs == 2) bulk_wait_read1(); else bulk_wait_read0();
+        if (kOutBufs == 3) bulk_wait_read2();
+        else if (kOutBufs == 2) bulk_wait_read1();
+        else bulk_wait_read0();
       }
+      const bool tr = P.trace != nullptr && blockIdx.x == 0 && e == 0 && tcount < 64;
       epi_bar();
+      if (tr) P.trace[tcount * 8 + 4] = clock64();       // all epilogue warps arrived
       mbar_wait(&ctl->tmem_full[acc], (tcount >> 1) & 1);
       tc_fence_after();
+      if (tr) P.trace[tcount * 8 + 5] = clock64();       // accumulator complete
       const uint32_t trow = taddr + acc * BN + ((uint32_t)(quarter * 32) << 16);
       const float* sbias = ctl->bias + n0;
 
@@ -527,10 +557,11 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       // (3) accumulator drained -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&ctl->tmem_empty[acc]);
+      if (tr) P.trace[tcount * 8 + 6] = clock64();       // accumulator drained
       // (4) staging tile complete and visible to the async proxy
       fence_proxy_async();
       epi_bar();
-      if (e == 0) {
+      if (e == 0 && !(P.dbg_flags & 4)) {
         const CUtensorMap* tmo = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx)
@@ -554,6 +585,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
                     (unsigned long long)__double2ll_rn((double)v * kStatScale));
         }
       }
+      if (tr) P.trace[tcount * 8 + 7] = clock64();       // tile done
       if (EPI == EPI_QKV) {
         if (qkv_part == 1 && p.colmax != nullptr && e < 128) {
           atomicMax(&p.colmax[img * 128 + e], ctl->colmax[e]);
@@ -746,6 +778,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
     // resident weights only when enough A stages remain to keep ~128 KiB of loads in flight
     P.wres = 1;
   }
+  P.dbg_flags = conv_flags();
   P.w_bytes = P.wres ? (int)w_all : 0;
   P.a_slot = P.halo ? kHaloSlot : kABytes;
   const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes);
@@ -862,6 +895,7 @@ ConvOp& ConvOp::operator=(const ConvOp& o) {
   return *this;
 }
 ConvParams& ConvOp::params() { return reinterpret_cast<Conv2Launch*>(impl)->P.c; }
+void conv_op_set_trace(ConvOp& op, long long* buf) { reinterpret_cast<Conv2Launch*>(op.impl)->P.trace = buf; }
 
 int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
                  int classes, const __half* w, int w_batched, int Cout, const ActSrc& out) {

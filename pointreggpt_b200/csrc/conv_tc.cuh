@@ -68,6 +68,7 @@ int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1,
                  int classes, const __half* w, int w_batched, int Cout, const ActSrc& out);
 int conv_op_run(ConvOp& op, int B, cudaStream_t stream);
 const char* conv_op_describe(const ConvOp& op, char* buf, int n);
+void conv_op_set_trace(ConvOp& op, long long* buf);  // debug: clock64 stamps of CTA 0 (64 tiles x 8)
 
 constexpr float kStatUnscale = 1.0f / 1048576.0f;  // fixed-point statistics -> float
 

@@ -1,4 +1,6 @@
 // Test hooks exported through the C ABI (single-layer entry points for parity tests).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_tc.cuh"
 
@@ -20,5 +22,26 @@ extern "C" __attribute__((visibility("default"))) int prg_test_conv_f16(
   int rc = conv_op_plan(&op, EPI_BIAS, B, s, nullptr, cmode, ksize, classes, (const __half*)w, 0, Cout, o);
   if (rc) return rc;
   op.params().bias = bias;
+  if (getenv("PRG_CONV_TRACE") != nullptr) {
+    // debug timeline of CTA 0: stamps per tile = rows ready | acc free | MMAs issued | staging
+    // free | epilogue warps arrived | acc complete | acc drained | tile done
+    long long* d = nullptr;
+    PRG_CUDA_OK(cudaMalloc(&d, (64 * 8 + 192) * sizeof(long long)));
+    PRG_CUDA_OK(cudaMemset(d, 0, (64 * 8 + 192) * sizeof(long long)));
+    conv_op_set_trace(op, d);
+    rc = conv_op_run(op, B, (cudaStream_t)stream);
+    long long h[64 * 8 + 192];
+    PRG_CUDA_OK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    const long long t0 = h[0];
+    for (int t = 0; t < 24; ++t) {
+      fprintf(stderr, "tile %2d:", t);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", h[t * 8 + k] ? h[t * 8 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+    for (int r = 0; r < 40; ++r)
+      fprintf(stderr, "row %2d: issued %7lld  seen %7lld\n", r, h[512 + 2 * r] - t0, h[512 + 2 * r + 1] - t0);
+    return rc;
+  }
   return conv_op_run(op, B, (cudaStream_t)stream);
 }
