@@ -157,6 +157,10 @@ typedef struct prg_profile {
 } prg_profile;
 int prg_profile_set(int every_n_forwards);
 int prg_profile_read(prg_profile* out, int max_entries, int reset);
+/* Per-layer view of the same samples: writes one text line per op,
+ * "<U|M><op index>:<description>\t<launches>\t<total ms>\t<algorithmic FLOP per image>\n",
+ * into buf (host, cap bytes); returns the bytes written. */
+int prg_profile_ops(char* buf, int cap, int reset);
 
 /* Test hook: one implicit-GEMM convolution through the tcgen05 engine.
  * x (B,H,W,Cin) f16 NHWC, w (Cout, taps*Cin) f16 K-major tap-major, bias (Cout)

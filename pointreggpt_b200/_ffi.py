@@ -63,6 +63,7 @@ SIGNATURES = {
                                 c_void_p, c_uint64, c_void_p, c_int, c_void_p]),
     "prg_profile_set": (c_int, [c_int]),
     "prg_profile_read": (c_int, [ctypes.POINTER(Profile), c_int, c_int]),
+    "prg_profile_ops": (c_int, [ctypes.c_char_p, c_int, c_int]),
     "prg_test_conv_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),
 }
@@ -126,3 +127,14 @@ def profile_read(reset=True):
     n = lib().prg_profile_read(arr, 16, int(reset))
     return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=float(arr[i].ms),
                                        forwards=int(arr[i].forwards)) for i in range(n)}
+
+
+def profile_ops(reset=True):
+    """[(label, launches, ms, flops_per_image)] per layer of the sampled network evaluations."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib().prg_profile_ops(buf, len(buf), int(reset))
+    rows = []
+    for ln in buf.raw[:n].decode().splitlines():
+        lab, launches, ms, fl = ln.split("\t")
+        rows.append((lab, int(launches), float(ms), float(fl)))
+    return rows

@@ -34,8 +34,18 @@ const char* const kCatNames[CAT_COUNT] = {"conv_tc", "gn_apply", "ln_apply", "li
 struct Profiler {
   int every = 0;                  // profile every n-th forward (0 = off)
   std::vector<cudaEvent_t> pool;  // recycled events
-  struct Rec { cudaEvent_t a, b; int cat; };
+  struct Rec { cudaEvent_t a, b; int cat; int op; };
   std::vector<Rec> recs;
+  struct OpStat { std::string label; double flops = 0, ms = 0; uint64_t launches = 0; };
+  std::vector<OpStat> op_stats;             // per-layer totals (prg_profile_ops)
+  std::map<std::string, int> op_index;
+  int op_id(const std::string& label, double flops) {
+    auto it = op_index.find(label);
+    if (it != op_index.end()) return it->second;
+    op_stats.push_back(OpStat{label, flops, 0, 0});
+    op_index[label] = (int)op_stats.size() - 1;
+    return (int)op_stats.size() - 1;
+  }
   double ms[CAT_COUNT] = {0};
   uint64_t launches[CAT_COUNT] = {0};
   uint64_t forwards = 0;
@@ -51,6 +61,10 @@ struct Profiler {
       if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
         ms[r.cat] += t;
         launches[r.cat] += 1;
+        if (r.op >= 0 && r.op < (int)op_stats.size()) {
+          op_stats[r.op].ms += t;
+          op_stats[r.op].launches += 1;
+        }
       }
       pool.push_back(r.a);
       pool.push_back(r.b);
@@ -91,10 +105,15 @@ struct prg_net {
   std::vector<void*> allocs;
   std::vector<std::function<int(const Run&)>> ops;
   std::vector<int> op_cat;
+  std::vector<std::string> op_label;   // per-layer description (prg_profile_ops)
+  std::vector<double> op_flops;        // algorithmic FLOP per image of the op (0 = not a contraction)
   uint64_t forwards = 0;
-  void add_op(int cat, std::function<int(const Run&)> f) {
+  void add_op(int cat, std::function<int(const Run&)> f, const std::string& label = "",
+              double flops = 0) {
     ops.push_back(std::move(f));
     op_cat.push_back(cat);
+    op_label.push_back(std::to_string(ops.size() - 1) + ":" + (label.empty() ? kCatNames[cat] : label));
+    op_flops.push_back(flops);
   }
 
   int dim = 64, levels = 4;
@@ -256,7 +275,15 @@ int add_conv(prg_net* n, int epi, const Act& s0, const Act* s1, int mode, int ks
     fprintf(stderr, "conv %dx%d %d->%d k%d m%d c%d: %s\n", s0.H, s0.W, s0.C + (s1 ? s1->C : 0), out.C,
             ksize, mode, classes, conv_op_describe(op, buf, sizeof(buf)));
   }
-  n->add_op(CAT_CONV, [op](const Run& r) mutable { return conv_op_run(op, r.B, r.s); });
+  {
+    char buf[160], lab[256];
+    const int cin = s0.C + (s1 ? s1->C : 0);
+    const int eff_taps = (mode == 1) ? 16 : ksize * ksize;   // algorithmic taps of the reference op
+    const double flops = 2.0 * out.H * out.W * (double)out.C * eff_taps * cin;
+    snprintf(lab, sizeof(lab), "conv %dx%d %d->%d k%d m%d c%d [%s]", out.H, out.W, cin, out.C, ksize,
+             mode, classes, conv_op_describe(op, buf, sizeof(buf)));
+    n->add_op(CAT_CONV, [op](const Run& r) mutable { return conv_op_run(op, r.B, r.s); }, lab, flops);
+  }
   return PRG_OK;
 }
 
@@ -320,7 +347,9 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
       *ss_cursor += 2 * cout;
     }
     a.res = nullptr; a.y = h1.p; a.HW = HW; a.C = cout;
-    n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); });
+    n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); },
+              "gn_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(cout) +
+                  (a.res ? " +res" : "") + (a.ln_g ? " +ln" : ""));
   }
   NET_TRY(add_conv(n, EPI_GN, h1, nullptr, 0, 3, 1, w2, 0, b2, raw, [=](ConvParams& p) {
     p.stats = st2;
@@ -360,7 +389,9 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
       a.ln_g = fuse_ln_g;
       a.ln_out = n->xn;
     }
-    n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); });
+    n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); },
+              "gn_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(cout) +
+                  (a.res ? " +res" : "") + (a.ln_g ? " +ln" : ""));
   }
   bo->y = y;
   return PRG_OK;
@@ -381,7 +412,8 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out, bool
   const __half* xp = x.p;
   __half* xnp = xn.p;
   if (!ln_done)
-    n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
+    n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); },
+              "ln_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(C));
   NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
     p.colmax = cmax;
     p.q_softmax = 1;
@@ -389,7 +421,8 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out, bool
   }));
   __half* qkvp = qkv.p;
   __half* weff = n->weff;
-  n->add_op(CAT_CTX, [=](const Run& r) { return linattn_context(qkvp, cmax, ctx, zs, r.B, HW, r.s); });
+  n->add_op(CAT_CTX, [=](const Run& r) { return linattn_context(qkvp, cmax, ctx, zs, r.B, HW, r.s); },
+            "linattn_context " + std::to_string(H) + "x" + std::to_string(W));
   n->add_op(CAT_WEFF, [=](const Run& r) { return linattn_weff(wo, ctx, zs, weff, r.B, C, HW, r.s); });
   Act y = new_act(n, H, W, C);
   if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
@@ -405,7 +438,8 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out, bool
     NET_TRY(add_conv(n, EPI_BIAS, qsrc, nullptr, 0, 1, 1, weff, 1, bo, tmp));
     const __half* tp = tmp.p;
     __half* yp = y.p;
-    n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(tp, g2, xp, yp, (int64_t)r.B * HW, C, r.s); });
+    n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(tp, g2, xp, yp, (int64_t)r.B * HW, C, r.s); },
+              "ln_apply+res " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(C));
   }
   *out = y;
   return PRG_OK;
@@ -421,7 +455,8 @@ int add_midattn(prg_net* n, const std::string& pfx, const Act& x, Act* out) {
   NET_PTR(bo, n->f32(pfx + ".fn.fn.to_out.bias"));
   const __half* xp = x.p;
   __half* xnp = xn.p;
-  n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); });
+  n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); },
+              "ln_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(C));
   NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
     p.colmax = nullptr;
     p.q_softmax = 0;
@@ -657,7 +692,8 @@ int run_trunk(prg_net* n, const Run& r) {
   }
   g_prof.forwards++;
   for (size_t i = 0; i < n->ops.size(); ++i) {
-    Profiler::Rec rec{g_prof.get(), g_prof.get(), n->op_cat[i]};
+    Profiler::Rec rec{g_prof.get(), g_prof.get(), n->op_cat[i],
+                      g_prof.op_id((n->kind == PRG_NET_UNET ? "U" : "M") + n->op_label[i], n->op_flops[i])};
     cudaEventRecord(rec.a, r.s);
     const int rc = n->ops[i](r);
     cudaEventRecord(rec.b, r.s);
@@ -670,7 +706,8 @@ int run_trunk(prg_net* n, const Run& r) {
 int run_tail(prg_net* n, const TailParams& t, int B, cudaStream_t s) {
   const bool prof = g_prof.every > 0 && ((n->forwards - 1) % (uint64_t)g_prof.every) == 0;
   if (!prof) return net_tail(t, B, s);
-  Profiler::Rec rec{g_prof.get(), g_prof.get(), CAT_TAIL};
+  Profiler::Rec rec{g_prof.get(), g_prof.get(), CAT_TAIL,
+                    g_prof.op_id(n->kind == PRG_NET_UNET ? "Utail" : "Mtail", 0)};
   cudaEventRecord(rec.a, s);
   const int rc = net_tail(t, B, s);
   cudaEventRecord(rec.b, s);
@@ -849,4 +886,19 @@ EXPORT int prg_profile_read(prg_profile* out, int max_entries, int reset) {
     g_prof.forwards = 0;
   }
   return n;
+}
+
+EXPORT int prg_profile_ops(char* buf, int cap, int reset) {
+  g_prof.drain();
+  int w = 0;
+  for (const auto& o : g_prof.op_stats) {
+    if (o.launches == 0) continue;
+    const int k = snprintf(buf + w, w < cap ? cap - w : 0, "%s\t%llu\t%.6f\t%.0f\n", o.label.c_str(),
+                           (unsigned long long)o.launches, o.ms, o.flops);
+    if (k < 0 || w + k >= cap) break;
+    w += k;
+  }
+  if (reset)
+    for (auto& o : g_prof.op_stats) { o.ms = 0; o.launches = 0; }
+  return w;
 }
