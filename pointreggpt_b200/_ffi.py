@@ -63,6 +63,7 @@ SIGNATURES = {
                                 c_void_p, c_uint64, c_void_p, c_int, c_void_p]),
     "prg_profile_set": (c_int, [c_int]),
     "prg_profile_read": (c_int, [ctypes.POINTER(Profile), c_int, c_int]),
+    "prg_test_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "prg_profile_ops": (c_int, [ctypes.c_char_p, c_int, c_int]),
     "prg_test_conv_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),

@@ -7,10 +7,15 @@
 //   warp 0   : TMA producer.  A operand, two modes:
 //                per-tap : one 4-D/5-D box per (tap, 64-channel chunk) -- shifted window of the
 //                          NHWC activation, zero padding = TMA out-of-bounds fill;
-//                halo    : (3x3, stride 1, Cin = 64, row tiles) a ring of input rows, each loaded
-//                          ONCE (130 pixels x 64 ch, 128B-swizzled); the nine taps are nine
-//                          shifted views (start address + dx*128 B, row slot y+dy) of that ring,
-//                          so L2->SM traffic drops ~9x.
+//                halo    : (3x3, stride 1, Cin = Cout = 64, row tiles) input rows stream through a
+//                          ring, each loaded ONCE (130 pixels x 64 ch, 128B-swizzled).  One input
+//                          row feeds the THREE output rows it touches in a single N = 192 MMA per
+//                          (dx, k16): the weights sit in shared memory stacked [dy=2; dy=1; dy=0]
+//                          per dx and the three output rows own neighbouring 64-column TMEM
+//                          accumulators (a ring of eight).  dx = shifted view (start address +
+//                          dx*128 B).  12-13 MMAs of N = 192 per output row instead of 36 of
+//                          N = 64: the A operand is read from shared memory 3x less often
+//                          (N = 64 MMAs are shared-memory-bandwidth bound: 6 KB per 32 cycles).
 //              B operand (weights): resident in shared memory for the whole kernel when it
 //              fits (loaded once per CTA), otherwise streamed next to A.
 //   warp 1   : one lane issues tcgen05.mma (M=128, N=BN, K=16), accumulating in one of TWO
@@ -49,8 +54,8 @@ struct alignas(8) Ctl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t wfull;
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[8];
+  uint64_t tmem_empty[8];
   uint32_t tmem_addr;
   uint32_t pad;
   float stats[4 * 32 * 2];  // EPI_GN: [TMEM quarter][8-column sub-block][sum, sumsq], written once per tile
@@ -114,6 +119,11 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   constexpr int kStageOut = (BN / 64) * kABytes;   // fp16 staging tile, 64-channel boxes
   constexpr int kOutBufs = (BN <= 128) ? 2 : 1;    // double-buffered: the TMA store of tile i drains
                                                    // while tile i+1 is being written
+  // TMEM: BN = 64 owns all 512 columns (eight accumulators, halo mode walks them as a ring),
+  // the wider tiles two accumulators.
+  constexpr int kTmemCols = (BN == 64) ? 512 : 2 * BN;
+  const uint32_t acc_mask = P.halo ? 7u : 1u;      // accumulator slots - 1
+  const int acc_log2 = P.halo ? 3 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -140,14 +150,14 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       mbar_init(&ctl->empty[s], 1);
     }
     mbar_init(&ctl->wfull, 1);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 8; ++a) {
       mbar_init(&ctl->tmem_full[a], 1);
-      mbar_init(&ctl->tmem_empty[a], kEpiThreads);
+      mbar_init(&ctl->tmem_empty[a], BN == 64 ? kEpiThreads / 2 : kEpiThreads);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&ctl->tmem_addr, 2 * BN);
+    tmem_alloc(&ctl->tmem_addr, kTmemCols);
     tmem_relinquish();
   }
   if (EPI == EPI_QKV && threadIdx.x < 128) ctl->colmax[threadIdx.x] = INT_MIN;
@@ -193,9 +203,12 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       if (P.wres) {
         mbar_arrive_expect_tx(&ctl->wfull, (uint32_t)P.w_bytes);
         for (int nt = 0; nt < P.n_tiles; ++nt)
-          for (int kb = 0; kb < num_kb; ++kb)
-            tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)(nt * num_kb + kb) * kBBytes, kb * kBlockK,
-                        nt * BN, 0);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            // halo mode: tap (dy, dx) goes to block dx*3 + (2 - dy), so that for one dx the taps
+            // dy = 2, 1, 0 are one contiguous N = 192 B operand
+            const int blk = P.halo ? (kb % 3) * 3 + (2 - kb / 3) : nt * num_kb + kb;
+            tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)blk * kBBytes, kb * kBlockK, nt * BN, 0);
+          }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -264,71 +277,80 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     int stage = 0;
     uint32_t phase = 0;
     uint32_t tcount = 0;  // tiles issued by this CTA
-    int dbg_row = 0;
     if (P.halo) {
+      // Row-streaming 3x3: input row ri (image row y0 - 1 + ri) of a segment contributes to the
+      // output rows j = ri - dy (dy = 0, 1, 2).  Their accumulators are neighbouring 64-column
+      // TMEM slots ((tiles so far + j) & 7), and the weights of one dx are stacked [dy=2; dy=1;
+      // dy=0], so the whole contribution is ONE MMA with N = 64 * (number of targets) per
+      // (dx, k16) -- split in two only where the slot ring wraps, and on the very first
+      // (dx, k16) = (0, 0) step, where the new target (dy = 0) must overwrite, not accumulate.
+      constexpr uint32_t idesc0 = idesc_f16(kBlockM, 0);   // + (N >> 3) << 17
       for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
         int img, x0, y0, nr;
         decode_seg(seg, img, x0, y0, nr);
-        // ring positions of this segment's rows: stage .. stage + nr + 1 (mod stages)
-        int wait_stage = stage;
-        uint32_t wait_phase = phase;
-        int waited = 0;
-        for (int j = 0; j < nr; ++j) {
-          if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && tcount < 64)
-            P.trace[tcount * 8 + 3] = clock64();             // loop top (before the row waits)
-          while (waited < j + 3) {
-            mbar_wait(&ctl->full[wait_stage], wait_phase);
-            if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && dbg_row < 96)
-              P.trace[512 + 2 * dbg_row + 1] = clock64();
-            ++dbg_row;
-            if (++wait_stage == P.stages) { wait_stage = 0; wait_phase ^= 1; }
-            ++waited;
+        for (int ri = 0; ri < nr + 2; ++ri) {
+          mbar_wait(&ctl->full[stage], phase);
+          if (ri < nr) {   // slot of the new target must have been drained
+            const uint32_t tn = tcount + (uint32_t)ri;
+            mbar_wait(&ctl->tmem_empty[tn & 7u], ((tn >> 3) & 1u) ^ 1u);
           }
-          const uint32_t acc = tcount & 1;
-          const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && tcount < 64;
-          if (tr) P.trace[tcount * 8 + 0] = clock64();     // rows ready
-          mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
           tc_fence_after();
-          if (tr) P.trace[tcount * 8 + 1] = clock64();     // accumulator free
-          const uint32_t d_addr = taddr_u + acc * BN;
-          int s1 = stage + 1, s2 = stage + 2;
-          if (s1 >= P.stages) s1 -= P.stages;
-          if (s2 >= P.stages) s2 -= P.stages;
-          const uint32_t row_addr[3] = {sA_u + (uint32_t)stage * P.a_slot, sA_u + (uint32_t)s1 * P.a_slot,
-                                        sA_u + (uint32_t)s2 * P.a_slot};
-          // One elect.sync region for the whole tile: ptxas knows exactly one thread is active,
-          // keeps descriptors / TMEM address in uniform registers and emits ~4 SASS instructions
-          // per UTCHMMA (a `lane == 0` test or per-instruction predicates cost 16-17 and made the
-          // kernel MMA-issue bound at ~67 cycles per MMA -- see profiles/r1_conv_summary.txt).
+          const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && ri >= 2 &&
+                          tcount + (uint32_t)ri - 2u < 64u;
+          if (tr) P.trace[(tcount + ri - 2) * 8 + 0] = clock64();   // last input row + slot ready
+          const int j_lo = max(ri - 2, 0), j_hi = min(ri, nr - 1);
+          const uint32_t row_lo = (sA_u + (uint32_t)stage * P.a_slot) >> 4;
+          const uint32_t w_lo = sW_u >> 4;
           if (elect_one()) {
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              // shifted view: the start sits dx rows into a swizzle atom.  The 128B swizzle is a
-              // function of the absolute shared-memory address (measured: base_offset must
-              // stay 0), so the descriptor needs nothing beyond the displaced start address.
-              const uint64_t da = mkdesc(row_addr[dy] + dx * 128);
-              const uint64_t db = mkdesc(sW_u + tap * kBBytes);
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                         (tap > 0 || k > 0) ? 1u : 0u);
+            // Descriptors of step s = dx*4 + k: A = row + 2*s (dx*128 B + k*32 B, in 16-byte
+            // units), B = first target's block + dx*3 blocks + 2*k.  All twelve are the row's base
+            // descriptor plus a compile-time constant: independent 64-bit adds, no chains.
+            constexpr uint32_t kBlk = kBBytes >> 4;                 // one 64x64 weight block
+            const uint64_t da0 = desc_hi | (uint64_t)row_lo;
+            const uint32_t sa = (tcount + (uint32_t)j_lo) & 7u;      // TMEM slot of the first target
+            const int cnt = j_hi - j_lo + 1;
+            const int c1 = min(cnt, 8 - (int)sa);                    // targets before the slot ring wraps
+            const uint64_t db0 = desc_hi | (uint64_t)(w_lo + (uint32_t)(2 - ri + j_lo) * kBlk);
+            const uint32_t d0 = taddr_u + sa * 64u;
+            // step 0: targets that already hold a partial sum accumulate, the new one (j = ri)
+            // overwrites its slot
+            const int n_old = (ri < nr) ? cnt - 1 : cnt;             // old targets come first
+            {
+              const int o1 = min(n_old, c1);                         // old targets before the wrap
+              if (o1 > 0) umma_f16(d0, da0, db0, idesc0 | ((uint32_t)(o1 * 8) << 17), 1u);
+              if (n_old > o1)
+                umma_f16(taddr_u, da0, db0 + (uint64_t)(o1 * kBlk),
+                         idesc0 | ((uint32_t)((n_old - o1) * 8) << 17), 1u);
+              if (ri < nr) {
+                const uint32_t sn = (tcount + (uint32_t)ri) & 7u;
+                umma_f16(taddr_u + sn * 64u, da0, db0 + (uint64_t)(n_old * kBlk), idesc0 | (8u << 17), 0u);
+              }
             }
-            umma_commit(&ctl->tmem_full[acc]);
-            umma_commit(&ctl->empty[stage]);                // top row of this tile is done
-            if (j == nr - 1) {                              // segment end: release the halo rows
-              umma_commit(&ctl->empty[s1]);
-              umma_commit(&ctl->empty[s2]);
+            if (c1 == cnt) {
+              const uint32_t id = idesc0 | ((uint32_t)(cnt * 8) << 17);
+#pragma unroll
+              for (int s = 1; s < 12; ++s)
+                umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + (uint64_t)((s >> 2) * 3 * kBlk + (s & 3) * 2),
+                         id, 1u);
+            } else {
+              const uint32_t id1 = idesc0 | ((uint32_t)(c1 * 8) << 17);
+              const uint32_t id2 = idesc0 | ((uint32_t)((cnt - c1) * 8) << 17);
+              const uint64_t db1 = db0 + (uint64_t)(c1 * kBlk);
+#pragma unroll
+              for (int s = 1; s < 12; ++s) {
+                const uint64_t bo = (uint64_t)((s >> 2) * 3 * kBlk + (s & 3) * 2);
+                umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + bo, id1, 1u);
+                umma_f16(taddr_u, da0 + (uint64_t)(2 * s), db1 + bo, id2, 1u);
+              }
             }
+            umma_commit(&ctl->empty[stage]);                       // input row consumed
+            if (ri >= 2) umma_commit(&ctl->tmem_full[(tcount + (uint32_t)(ri - 2)) & 7u]);
           }
           __syncwarp();
-          if (tr) P.trace[tcount * 8 + 2] = clock64();     // all MMAs issued
-          ++tcount;
+          if (tr) P.trace[(tcount + ri - 2) * 8 + 2] = clock64();   // row's MMAs issued
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        // skip the two trailing halo rows in the ring position
-        for (int e = 0; e < 2; ++e)
-          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        tcount += (uint32_t)nr;
       }
     } else {
       for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
@@ -373,7 +395,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     auto do_tile = [&](int img, int x0, int y0, int n_tile, int cls) {
       const int n0 = n_tile * BN;
       const int cpy = cls >> 1, cpx = cls & 1;
-      const uint32_t acc = tcount & 1;
+      const uint32_t acc = tcount & acc_mask;
       // (1) the TMA store that last used this staging buffer must have finished reading it
       uint8_t* sOut = sO + (tcount % kOutBufs) * kStageOut;
       if (e == 0) {
@@ -384,7 +406,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       const bool tr = P.trace != nullptr && blockIdx.x == 0 && e == 0 && tcount < 64;
       epi_bar();
       if (tr) P.trace[tcount * 8 + 4] = clock64();       // all epilogue warps arrived
-      mbar_wait(&ctl->tmem_full[acc], (tcount >> 1) & 1);
+      mbar_wait(&ctl->tmem_full[acc], (tcount >> acc_log2) & 1);
       tc_fence_after();
       if (tr) P.trace[tcount * 8 + 5] = clock64();       // accumulator complete
       const uint32_t trow = taddr + acc * BN + ((uint32_t)(quarter * 32) << 16);
@@ -582,7 +604,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           }
           const int g0 = n0 >> p.gs_log2;
           atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)img * 8 + g0) * 2 + e,
-                    (unsigned long long)__double2ll_rn((double)v * kStatScale));
+                    (unsigned long long)__float2ll_rn(v * (float)kStatScale));
         }
       }
       if (tr) P.trace[tcount * 8 + 7] = clock64();       // tile done
@@ -595,26 +617,203 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       ++tcount;
     };
 
-    if (P.halo) {
-      for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
-        int img, x0, y0, nr;
-        decode_seg(seg, img, x0, y0, nr);
-        for (int j = 0; j < nr; ++j) do_tile(img, x0, y0 + j, 0, 0);
+
+    // ---- BN = 64: warp-independent epilogue.  The eight warps form two groups that take tiles
+    // alternately (tile t -> group t & 1); inside a group each warp owns its TMEM lane quarter =
+    // 32 pixels x all 64 channels, stages them in its own 4 KB slab and stores the slab with its
+    // own TMA box (32 pixels x 64 ch).  No CTA-level barrier: the latency chains of consecutive
+    // tiles overlap instead of adding up (the eight-slot accumulator ring gives the slack).
+    auto do_tile64 = [&](int img, int x0, int y0, int cls) {
+      const int grp = (warp - 2) >> 2;
+      if ((int)(tcount & 1u) != grp) { ++tcount; return; }
+      const uint32_t acc = tcount & acc_mask;
+      const int cpy = cls >> 1, cpx = cls & 1;
+      const int oy = (y0 + tyr) * p.out_scale + cpy, ox = (x0 + txr) * p.out_scale + cpx;
+      const long long off = (long long)img * p.out_img_stride + (long long)oy * p.out_row_stride +
+                            (long long)ox * p.out_pix_stride;
+      const bool has_res = (EPI == EPI_RES || EPI == EPI_LN_RES || (EPI == EPI_GN && p.res != nullptr));
+      uint4 rv[8];
+      if (has_res) {   // this pixel's 64 residual channels = one 128-byte line; issued before the wait
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q);
       }
+      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 2 + 4 * grp && lane == 0 && tcount < 64;
+      if (tr) P.trace[tcount * 8 + 4] = clock64();
+      mbar_wait(&ctl->tmem_full[acc], (tcount >> acc_log2) & 1);
+      tc_fence_after();
+      if (tr) P.trace[tcount * 8 + 5] = clock64();       // accumulator complete
+      const uint32_t trow = taddr + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      uint32_t v0[32], v1[32];
+      tmem_ld32(trow, v0);
+      tmem_ld32(trow + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&ctl->tmem_empty[acc]);                // accumulator back to the MMA warp
+      if (tr) P.trace[tcount * 8 + 6] = clock64();       // accumulator drained
+      float f[64];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 ba = *reinterpret_cast<const float4*>(ctl->bias + q * 8);
+        const float4 bb = *reinterpret_cast<const float4*>(ctl->bias + q * 8 + 4);
+        const uint32_t* vv = (q < 4) ? (v0 + q * 8) : (v1 + (q - 4) * 8);
+        f[q * 8 + 0] = __uint_as_float(vv[0]) + ba.x; f[q * 8 + 1] = __uint_as_float(vv[1]) + ba.y;
+        f[q * 8 + 2] = __uint_as_float(vv[2]) + ba.z; f[q * 8 + 3] = __uint_as_float(vv[3]) + ba.w;
+        f[q * 8 + 4] = __uint_as_float(vv[4]) + bb.x; f[q * 8 + 5] = __uint_as_float(vv[5]) + bb.y;
+        f[q * 8 + 6] = __uint_as_float(vv[6]) + bb.z; f[q * 8 + 7] = __uint_as_float(vv[7]) + bb.w;
+      }
+      if (EPI == EPI_GN && p.res != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __half2* h = reinterpret_cast<const __half2*>(&rv[q]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 r2 = __half22float2(h[j]);
+            f[q * 8 + j * 2 + 0] += r2.x;
+            f[q * 8 + j * 2 + 1] += r2.y;
+          }
+        }
+      }
+      if (EPI == EPI_GN) {
+        // (sum, sumsq) of the eight 8-channel sub-blocks of this row, then a halving butterfly over
+        // the 32 rows of the warp: 16 values x 32 lanes -> 16 shuffles, fixed order.  Lanes 0, 2,
+        // .., 30 end up with one (sub-block, moment) total each and add it to the image's
+        // fixed-point statistics (64-bit integer atomics: order-independent, bit-reproducible).
+        float w16[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float sm = 0.f, sq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = f[g * 8 + j];
+            sm += x;
+            sq = fmaf(x, x, sq);
+          }
+          w16[g * 2] = sm;
+          w16[g * 2 + 1] = sq;
+        }
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+        float w8[8], w4[4], w2[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float send = h16 ? w16[i] : w16[i + 8];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+          w8[i] = (h16 ? w16[i + 8] : w16[i]) + recv;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = h8 ? w8[i] : w8[i + 4];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+          w4[i] = (h8 ? w8[i + 4] : w8[i]) + recv;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = h4 ? w4[i] : w4[i + 2];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+          w2[i] = (h4 ? w4[i + 2] : w4[i]) + recv;
+        }
+        const float send = h2 ? w2[0] : w2[1];
+        float t = (h2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, send, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        if ((lane & 1) == 0 && !(P.dbg_flags & 8)) {
+          const int idx = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);  // sub-block*2 + moment
+          const int grp_c = (idx >> 1) >> (p.gs_log2 - 3);
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)img * 8 + grp_c) * 2 + (idx & 1),
+                    (unsigned long long)__float2ll_rn(t * (float)kStatScale));
+        }
+      } else if (EPI == EPI_LN_RES) {
+        float sm = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) sm += f[j];
+        const float mean = sm * (1.f / 64.f);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float d = f[j] - mean;
+          ss = fmaf(d, d, ss);
+        }
+        const float rstd = rsqrtf(ss * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] = (f[j] - mean) * rstd * ctl->gain[j];
+      }
+      if (EPI == EPI_RES || EPI == EPI_LN_RES) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __half2* h = reinterpret_cast<const __half2*>(&rv[q]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 r2 = __half22float2(h[j]);
+            f[q * 8 + j * 2 + 0] += r2.x;
+            f[q * 8 + j * 2 + 1] += r2.y;
+          }
+        }
+      }
+      // the slab's previous TMA store must have finished reading it
+      uint8_t* slab = sO + (size_t)(grp * 4 + quarter) * 4096;
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      uint8_t* srow = slab + (size_t)lane * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 o;
+        __half2 h0 = __floats2half2_rn(f[q * 8 + 0], f[q * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(f[q * 8 + 2], f[q * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(f[q * 8 + 4], f[q * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(f[q * 8 + 6], f[q * 8 + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0);
+        o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2);
+        o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(srow + ((q ^ (lane & 7)) << 4)) = o;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && !(P.dbg_flags & 4)) {
+        const CUtensorMap* tmo = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
+        const int px = quarter * 32;
+        tma_store_4d(tmo, slab, 0, x0 + (px & (tile_w - 1)), y0 + (px >> p.tile_w_log2), img);
+        bulk_commit();
+      }
+      if (tr) P.trace[tcount * 8 + 7] = clock64();       // tile done
+      ++tcount;
+    };
+
+    if constexpr (BN == 64) {
+      if (P.halo) {
+        for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+          int img, x0, y0, nr;
+          decode_seg(seg, img, x0, y0, nr);
+          for (int j = 0; j < nr; ++j) do_tile64(img, x0, y0 + j, 0);
+        }
+      } else {
+        for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+          const Item it = decode(item);
+          do_tile64(it.img, it.x0, it.y0, it.cls);
+        }
+      }
+      if (lane == 0) bulk_wait0();
     } else {
-      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-        const Item it = decode(item);
-        do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls);
+      if (P.halo) {
+        for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+          int img, x0, y0, nr;
+          decode_seg(seg, img, x0, y0, nr);
+          for (int j = 0; j < nr; ++j) do_tile(img, x0, y0 + j, 0, 0);
+        }
+      } else {
+        for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+          const Item it = decode(item);
+          do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls);
+        }
       }
+      if (e == 0) bulk_wait0();
     }
-    if (e == 0) bulk_wait0();
     tc_fence_before();
   }
 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(taddr, 2 * BN);
+    tmem_dealloc(taddr, kTmemCols);
   }
 }
 
@@ -688,8 +887,9 @@ static int conv_flags() {
   return g_conv_flags;
 }
 
-// Segment length for the halo mode: MMA time scales with the rows a CTA owns, the two extra halo
-// rows per segment only cost a TMA load each; pick the length that minimises the busiest CTA.
+// Segment length for the halo mode: MMA time scales with the rows a CTA owns; the two extra halo
+// rows per segment cost a TMA load and twelve N = 64 MMAs each (about half an output row); pick
+// the length that minimises the busiest CTA.
 static void halo_segments(Conv2Params* P, int B, int sms) {
   const int Ho = P->c.Ho, strips = P->c.tiles_x;
   int best_r = 8;
@@ -698,7 +898,7 @@ static void halo_segments(Conv2Params* P, int B, int sms) {
     const int segs = (Ho + r - 1) / r;
     const long long items = (long long)B * strips * segs;
     const long long waves = (items + sms - 1) / sms;
-    const double cost = (double)waves * (r + 0.6);
+    const double cost = (double)waves * (r + 1.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_r = r; }
   }
   if (const char* e = getenv("PRG_HALO_RSEG")) best_r = std::max(1, atoi(e));  // tuning override
@@ -769,7 +969,8 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   P.halo = 0;
   P.wres = 0;
   const bool halo_ok = !w_batched && classes == 1 && mode == 0 && ksize == 3 && s1 == nullptr &&
-                       cin == 64 && tile_w == kBlockM && P.n_tiles == 1 && !(conv_flags() & 1) &&
+                       cin == 64 && bn == 64 && tile_w == kBlockM && P.n_tiles == 1 &&
+                       !(conv_flags() & 1) &&
                        w_all + fixed + 5 * kHaloSlot <= kSmemBudget;
   if (halo_ok) {
     P.halo = 1;
@@ -843,6 +1044,10 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
       uint64_t dims[4] = {(uint64_t)out.C, (uint64_t)(out.W / sc), (uint64_t)(out.H / sc), (uint64_t)B};
       uint64_t str[3] = {ps * sc, ps * out.W * sc, ps * out.W * out.H};
       uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, 1};
+      if (bn == 64) {   // warp-independent epilogue: one box per TMEM lane quarter (32 pixels)
+        box[1] = (uint32_t)std::min(tile_w, 32);
+        box[2] = 32u / box[1];
+      }
       int rc = encode(&L->tmO[cls], base, 4, dims, str, box);
       if (rc) return rc;
     }
@@ -931,4 +1136,78 @@ const char* conv_op_describe(const ConvOp& op, char* buf, int n) {
   return buf;
 }
 
+}  // namespace prg
+
+// ------------------------------------------------------------------------------------------
+// Tensor-pipe micro-benchmark (test hook): one thread per CTA issues `iters` back-to-back
+// tcgen05.mma (M = 128, N = n, K = 16) on whatever shared memory holds; reports SM cycles per MMA.
+// a_shift: byte displacement of the A start address (0 / 128 / 256 = the dx views of the halo
+// mode), used to check that displaced 128B-swizzled views run at full rate.
+// ------------------------------------------------------------------------------------------
+namespace prg {
+__global__ void __launch_bounds__(128, 1)
+k_mma_rate(int n, int iters, int a_shift, int same_ab, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_addr;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    ptx::tmem_alloc(&tmem_addr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t taddr = tmem_addr;
+  if (threadIdx.x < 32) {
+    const uint32_t idesc = ptx::idesc_f16(128, 0) | ((uint32_t)(n >> 3) << 17);
+    const uint32_t a0 = ptx::smem_u32(smem) + a_shift, b0 = ptx::smem_u32(smem) + 32 * 1024;
+    const uint64_t hi = ptx::smem_desc_sw128(0);
+    long long t0 = 0, t1 = 0;
+    if (ptx::elect_one()) {
+      t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // walk A over 16 KB and B over 48 KB like a real K loop (same_ab: hammer one address)
+          const uint32_t ao = same_ab ? 0u : (uint32_t)(((i >> 2) & 0) * 0 + k * 32);
+          const uint32_t bo = same_ab ? 0u : (uint32_t)((((i >> 2) % 3) * 8192 * 0) + k * 32);
+          ptx::umma_f16(taddr + ((i >> 2) & 1) * 256u, hi | (uint64_t)(((a0 + ao) >> 4) & 0x3FFFu),
+                        hi | (uint64_t)(((b0 + bo) >> 4) & 0x3FFFu), idesc, 1u);
+        }
+      }
+      ptx::umma_commit(&bar);
+    }
+    __syncwarp();
+    ptx::mbar_wait(&bar, 0);
+    t1 = clock64();
+    t0 = __shfl_sync(0xffffffffu, t0, 0);   // elected lane is lane 0 on current hardware
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(taddr, 512);
+  }
+}
+
+int mma_rate_probe(int grid, int n, int iters, int a_shift, int same_ab, long long* out_dev,
+                   cudaStream_t s) {
+  static bool cfg = false;
+  if (!cfg) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    cfg = true;
+  }
+  k_mma_rate<<<grid, 128, 100 * 1024, s>>>(n, iters, a_shift, same_ab, out_dev);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
 }  // namespace prg

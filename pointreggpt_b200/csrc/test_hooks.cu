@@ -45,3 +45,15 @@ extern "C" __attribute__((visibility("default"))) int prg_test_conv_f16(
   }
   return conv_op_run(op, B, (cudaStream_t)stream);
 }
+
+namespace prg {
+int mma_rate_probe(int grid, int n, int iters, int a_shift, int same_ab, long long* out_dev,
+                   cudaStream_t s);
+}
+// Test hook: tensor-pipe rate probe.  out (grid) i64 device: SM cycles for `iters` MMAs per CTA.
+extern "C" __attribute__((visibility("default"))) int prg_test_mma_rate(
+    int grid, int n, int iters, int a_shift, int same_ab, int64_t* out, prg_stream_t stream) {
+  PRG_CHECK_ARG(out && grid >= 1 && n >= 16 && n <= 256 && n % 16 == 0 && iters % 4 == 0, "args");
+  return mma_rate_probe(grid, n, iters, a_shift, same_ab, reinterpret_cast<long long*>(out),
+                        (cudaStream_t)stream);
+}
