@@ -838,8 +838,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box) {
+int tmap_encode_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -1010,7 +1010,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
       uint64_t dims[4] = {(uint64_t)s->C, (uint64_t)s->W, (uint64_t)s->H, (uint64_t)B};
       uint64_t str[3] = {ps, ps * s->W, ps * s->W * s->H};
       uint32_t box[4] = {64, (uint32_t)(P.halo ? kHaloPix : tile_w), (uint32_t)(P.halo ? 1 : tile_h), 1};
-      int rc = encode(tm, s->ptr, 4, dims, str, box);
+      int rc = tmap_encode_f16(tm, s->ptr, 4, dims, str, box);
       if (rc) return rc;
     } else {
       if (s->pix_stride != s->C) {
@@ -1020,7 +1020,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
       uint64_t dims[5] = {(uint64_t)2 * s->C, (uint64_t)s->W / 2, 2, (uint64_t)s->H / 2, (uint64_t)B};
       uint64_t str[4] = {2 * ps, ps * s->W, 2 * ps * s->W, ps * s->W * s->H};
       uint32_t box[5] = {64, (uint32_t)tile_w, 1, (uint32_t)tile_h, 1};
-      int rc = encode(tm, s->ptr, 5, dims, str, box);
+      int rc = tmap_encode_f16(tm, s->ptr, 5, dims, str, box);
       if (rc) return rc;
     }
   }
@@ -1030,7 +1030,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
     uint64_t dims[3] = {ktot, (uint64_t)Cout, (uint64_t)(w_batched ? B : 1)};
     uint64_t str[2] = {ktot * 2, ktot * 2 * Cout};
     uint32_t box[3] = {64, (uint32_t)bn, 1};
-    int rc = encode(&L->tmB, w, 3, dims, str, box);
+    int rc = tmap_encode_f16(&L->tmB, w, 3, dims, str, box);
     if (rc) return rc;
   }
   // ---- output maps (one per upsample parity class)
@@ -1048,7 +1048,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
         box[1] = (uint32_t)std::min(tile_w, 32);
         box[2] = 32u / box[1];
       }
-      int rc = encode(&L->tmO[cls], base, 4, dims, str, box);
+      int rc = tmap_encode_f16(&L->tmO[cls], base, 4, dims, str, box);
       if (rc) return rc;
     }
   }

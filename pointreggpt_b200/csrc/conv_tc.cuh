@@ -70,6 +70,11 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream);
 const char* conv_op_describe(const ConvOp& op, char* buf, int n);
 void conv_op_set_trace(ConvOp& op, long long* buf);  // debug: clock64 stamps of CTA 0 (64 tiles x 8)
 
+// fp16 tiled tensor map, 128B swizzle, zero out-of-bounds fill (dims innermost first; strides in
+// bytes for dims 1..rank-1).
+int tmap_encode_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
+
 constexpr float kStatUnscale = 1.0f / 1048576.0f;  // fixed-point statistics -> float
 
 // order-preserving float <-> int (for atomicMax on floats)

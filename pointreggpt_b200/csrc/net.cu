@@ -134,6 +134,7 @@ struct prg_net {
   // scratch activations
   __half *raw = nullptr, *h1 = nullptr, *resb = nullptr, *xn = nullptr, *qkv = nullptr,
          *ao = nullptr, *weff = nullptr;
+  float* kv_partials = nullptr;   // LinearAttention context partials (shared by all attention layers)
   size_t unit = 0;  // maxB * S * S * 64 halves
 
   // tail (filled by the builder)
@@ -400,33 +401,38 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
 // Residual(PreNorm(LinearAttention)) -- SDD:748-769.
 int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out, bool ln_done = false) {
   const int H = x.H, W = x.W, C = x.C, HW = H * W;
-  Act xn{n->xn, H, W, C, C}, qkv{n->qkv, H, W, 384, 384};
+  Act xn{n->xn, H, W, C, C};
   NET_PTR(g, n->f32(pfx + ".fn.norm.g"));
   NET_PTR(wq, n->f16(pfx + ".fn.fn.to_qkv.weight"));
   NET_PTR(wo, n->f32(pfx + ".fn.fn.to_out.0.weight"));
   NET_PTR(bo, n->f32(pfx + ".fn.fn.to_out.0.bias"));
   NET_PTR(g2, n->f32(pfx + ".fn.fn.to_out.1.g"));
-  int* cmax = n->take_colmax((size_t)n->maxB * 128);
-  long long* ctx = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 4096 * 2));
-  long long* zs = reinterpret_cast<long long*>(n->take_zero((size_t)n->maxB * 128 * 2));
   const __half* xp = x.p;
   __half* xnp = xn.p;
   if (!ln_done)
     n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); },
               "ln_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(C));
-  NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, qkv, [=](ConvParams& p) {
-    p.colmax = cmax;
+  // q = softmax_d(W_q xn) * scale: the first 128 rows of to_qkv through the conv engine
+  Act q{n->qkv, H, W, 128, 128};
+  NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, q, [=](ConvParams& p) {
+    p.colmax = nullptr;
     p.q_softmax = 1;
     p.q_scale = 0.17677669529663687f;  // 32^-0.5
   }));
-  __half* qkvp = qkv.p;
+  // k, v and the context never reach HBM: fused projection + softmax_n + k v^T, then W_eff
   __half* weff = n->weff;
-  n->add_op(CAT_CTX, [=](const Run& r) { return linattn_context(qkvp, cmax, ctx, zs, r.B, HW, r.s); },
-            "linattn_context " + std::to_string(H) + "x" + std::to_string(W));
-  n->add_op(CAT_WEFF, [=](const Run& r) { return linattn_weff(wo, ctx, zs, weff, r.B, C, HW, r.s); });
+  {
+    KvCtxOp op;
+    NET_TRY(kvctx_plan(&op, n->maxB, xn.p, H, W, C, C, wq, n->kv_partials));
+    char lab[96];
+    snprintf(lab, sizeof(lab), "linattn_kvctx %dx%d c%d", H, W, C);
+    // algorithmic FLOP: k, v projection (2 * 256 * C) + k v^T (2 * 4 heads * 32 * 32) per pixel
+    n->add_op(CAT_CTX, [op, wo, weff, C](const Run& r) mutable { return kvctx_run(op, r.B, wo, weff, C, r.s); },
+              lab, (double)HW * (2.0 * 256 * C + 2.0 * 4 * 32 * 32));
+  }
   Act y = new_act(n, H, W, C);
   if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
-  Act qsrc{qkv.p, H, W, 128, 384};
+  Act qsrc{q.p, H, W, 128, 128};
   if (C <= 256) {
     NET_TRY(add_conv(n, EPI_LN_RES, qsrc, nullptr, 0, 1, 1, weff, 1, bo, y, [=](ConvParams& p) {
       p.ln_g = g2;
@@ -531,7 +537,8 @@ int build(prg_net* n) {
   n->colmax_cap = (size_t)B * 128 * 16;
   n->colmax_arena = n->dalloc<int>(n->colmax_cap);
   n->x_state = n->dalloc<float>((size_t)B * S * S);
-  if (!n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
+  n->kv_partials = n->dalloc<float>((size_t)B * kvctx_max_slots(B) * kPartialFloats);
+  if (!n->kv_partials || !n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
       !n->colmax_arena || !n->x_state) {
     set_error("out of device memory allocating the workspace");
     return PRG_ERR_CUDA;
