@@ -7,7 +7,9 @@
 
 namespace prg {
 
-__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// x * sigmoid(x) with the hardware reciprocal (<= 2 ulp; an IEEE division costs ~10 instructions and
+// made the GroupNorm-apply pass issue-bound instead of HBM-bound)
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
@@ -263,59 +265,74 @@ __device__ __forceinline__ void gn_coeffs(const long long* stats, const float* g
 // LN: also emit LayerNorm_c(y) * g (the PreNorm of the attention that follows) from the same
 // registers -- the lanes holding one pixel (C/8 consecutive lanes) reduce with shuffles.
 template <bool LN>
-__global__ void __launch_bounds__(256)
-k_gn_apply(GnApply a) {
+__global__ void __launch_bounds__(256, LN ? 3 : 4)
+k_gn_apply(GnApply a, int total_blocks, int nblk) {
   extern __shared__ float sm[];
   float* sA = sm;
   float* sB = sm + a.C;
   float* sG = sm + 2 * a.C;
-  // Reverse traversal (last image first, highest addresses first): `raw` was just written front
-  // to back by the convolution, so its tail is what still sits in the 126 MB L2; and the front
-  // of `y`, written last here, is what the next convolution (front to back) reads first.
-  const int b = gridDim.y - 1 - blockIdx.y;
-  gn_coeffs(a.stats, a.gamma, a.beta,
-            a.ss ? a.ss + (size_t)b * a.ss_stride + a.ss_off : nullptr, a.C, a.HW, b, sA, sB);
+  // Persistent: the (image, 16 KiB block) pairs are dealt to the CTAs in contiguous ranges, so
+  // the per-image coefficient prologue (fp64 mean / variance from the integer statistics) runs
+  // once or twice per CTA instead of once per 16 KiB of data.
+  const int g_begin = (int)(((long long)blockIdx.x * total_blocks) / gridDim.x);
+  const int g_end = (int)(((long long)(blockIdx.x + 1) * total_blocks) / gridDim.x);
   if (LN)
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) sG[c] = a.ln_g[c];
-  __syncthreads();
   const int cvec = a.C >> 3;                       // 16-byte vectors per pixel (power of two)
-  const int64_t nvec = (int64_t)a.HW * cvec;
-  const uint4* src = reinterpret_cast<const uint4*>(a.raw + (size_t)b * a.HW * a.C);
-  uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)b * a.HW * a.C);
-  uint4* ldst = LN ? reinterpret_cast<uint4*>(a.ln_out + (size_t)b * a.HW * a.C) : nullptr;
+  const int nvec = a.HW * cvec;                    // per image: fits 32 bits (HW * C / 8)
   constexpr int U = 4;                             // independent 16-byte loads in flight per thread
   const float inv_c = 1.f / (float)a.C;
   int cvec_log2 = 0;
   while ((1 << cvec_log2) < cvec) ++cvec_log2;
-  // a block-iteration covers U * 256 consecutive vectors (16 KiB); blocks stride over the image
-  const int64_t stride = 256;
-  const int64_t nblk = (nvec + 256 * U - 1) / (256 * U);
-  for (int64_t blk = nblk - 1 - blockIdx.x; blk >= 0; blk -= gridDim.x) {
-    const int64_t i0 = blk * (256 * U) + threadIdx.x;
+  // 256 is a multiple of the vectors per pixel, so a thread meets the same eight channels in
+  // every vector it touches: their coefficients live in registers
+  const int cv = threadIdx.x & (cvec - 1);
+  const int c0 = cv * 8;
+  float cA[8], cB[8], cG[8];
+  int b = -1;
+  const uint4* src = nullptr;
+  uint4* dst = nullptr;
+  uint4* ldst = nullptr;
+  const __half* resb = nullptr;
+  for (int g = g_begin; g < g_end; ++g) {
+    const int gb = g / nblk, blk = g - gb * nblk;
+    if (gb != b) {
+      b = gb;
+      __syncthreads();   // everyone is done with the previous image's coefficients
+      gn_coeffs(a.stats, a.gamma, a.beta, a.ss ? a.ss + (size_t)b * a.ss_stride + a.ss_off : nullptr,
+                a.C, a.HW, b, sA, sB);
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        cA[j] = sA[c0 + j];
+        cB[j] = sB[c0 + j];
+        cG[j] = LN ? sG[c0 + j] : 0.f;
+      }
+      src = reinterpret_cast<const uint4*>(a.raw + (size_t)b * a.HW * a.C);
+      dst = reinterpret_cast<uint4*>(a.y + (size_t)b * a.HW * a.C);
+      ldst = LN ? reinterpret_cast<uint4*>(a.ln_out + (size_t)b * a.HW * a.C) : nullptr;
+      resb = a.res ? a.res + (size_t)b * a.HW * a.res_pix_stride + c0 : nullptr;
+    }
+    const int i0 = blk * (256 * U) + (int)threadIdx.x;
     uint4 v[U], rv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
+      const int i = i0 + u * 256;
       if (i < nvec) v[u] = __ldcs(src + i);
     }
     if (a.res != nullptr) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t i = i0 + u * stride;
-        if (i < nvec) {
-          const int cv = (int)(i & (cvec - 1));
-          const int64_t pix = i >> cvec_log2;
-          rv[u] = __ldg(reinterpret_cast<const uint4*>(
-              a.res + ((size_t)b * a.HW + pix) * a.res_pix_stride + cv * 8));
-        }
+        const int i = i0 + u * 256;
+        if (i < nvec)
+          rv[u] = __ldg(reinterpret_cast<const uint4*>(resb + (size_t)(i >> cvec_log2) * a.res_pix_stride));
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
+      const int i = i0 + u * 256;
       // nvec is a multiple of the warp size (HW % 128 == 0), so a warp is all-in or all-out
       if (i >= nvec) continue;
-      const int c0 = (int)(i & (cvec - 1)) * 8;
       const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
       float f[8];
 #pragma unroll
@@ -325,7 +342,7 @@ k_gn_apply(GnApply a) {
         f[2 * j + 1] = t.y;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu(fmaf(f[j], sA[c0 + j], sB[c0 + j]));
+      for (int j = 0; j < 8; ++j) f[j] = silu(fmaf(f[j], cA[j], cB[j]));
       if (a.res != nullptr) {
         const __half2* rh = reinterpret_cast<const __half2*>(&rv[u]);
 #pragma unroll
@@ -366,10 +383,10 @@ k_gn_apply(GnApply a) {
         for (int o2s = cvec >> 1; o2s > 0; o2s >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o2s);
         const float rstd = rsqrtf(q * inv_c + 1e-5f);
         uint4 lo;
-        __half2 l0 = __floats2half2_rn((g8[0] - mean) * rstd * sG[c0 + 0], (g8[1] - mean) * rstd * sG[c0 + 1]);
-        __half2 l1 = __floats2half2_rn((g8[2] - mean) * rstd * sG[c0 + 2], (g8[3] - mean) * rstd * sG[c0 + 3]);
-        __half2 l2 = __floats2half2_rn((g8[4] - mean) * rstd * sG[c0 + 4], (g8[5] - mean) * rstd * sG[c0 + 5]);
-        __half2 l3 = __floats2half2_rn((g8[6] - mean) * rstd * sG[c0 + 6], (g8[7] - mean) * rstd * sG[c0 + 7]);
+        __half2 l0 = __floats2half2_rn((g8[0] - mean) * rstd * cG[0], (g8[1] - mean) * rstd * cG[1]);
+        __half2 l1 = __floats2half2_rn((g8[2] - mean) * rstd * cG[2], (g8[3] - mean) * rstd * cG[3]);
+        __half2 l2 = __floats2half2_rn((g8[4] - mean) * rstd * cG[4], (g8[5] - mean) * rstd * cG[5]);
+        __half2 l3 = __floats2half2_rn((g8[6] - mean) * rstd * cG[6], (g8[7] - mean) * rstd * cG[7]);
         lo.x = *reinterpret_cast<uint32_t*>(&l0);
         lo.y = *reinterpret_cast<uint32_t*>(&l1);
         lo.z = *reinterpret_cast<uint32_t*>(&l2);
@@ -381,23 +398,21 @@ k_gn_apply(GnApply a) {
 }
 
 int gn_apply(const GnApply& a, int B, cudaStream_t s) {
-  const int64_t nvec = (int64_t)a.HW * (a.C >> 3);
-  // many thin CTAs, launched in address order: the set of CTAs in flight covers a narrow window
-  // of pages (fat strided CTAs measured 8 % slower)
-  int gx = (int)((nvec + 256 * 4 - 1) / (256 * 4));
-  const int cap = num_sms() * 8;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  dim3 g(gx, B);
+  const int nvec = a.HW * (a.C >> 3);
+  const int nblk = (nvec + 256 * 4 - 1) / (256 * 4);     // 16 KiB blocks per image
+  const int total = nblk * B;
   const bool ln = a.ln_out != nullptr;
   if (ln && (a.C > 256)) {
     set_error("gn_apply: fused LayerNorm needs C <= 256 (got %d)", a.C);
     return PRG_ERR_ARG;
   }
+  int grid = num_sms() * (ln ? 3 : 4);                    // one resident wave
+  if (grid > total) grid = total;
+  if (grid < 1) grid = 1;
   if (ln)
-    k_gn_apply<true><<<g, 256, 3 * a.C * sizeof(float), s>>>(a);
+    k_gn_apply<true><<<grid, 256, 3 * a.C * sizeof(float), s>>>(a, total, nblk);
   else
-    k_gn_apply<false><<<g, 256, 3 * a.C * sizeof(float), s>>>(a);
+    k_gn_apply<false><<<grid, 256, 3 * a.C * sizeof(float), s>>>(a, total, nblk);
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }

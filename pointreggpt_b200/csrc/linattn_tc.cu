@@ -7,15 +7,20 @@
 //   MMA1   D_k[d][px] = W_k[d][:] . xn[px][:]   and   D_v[e][px] = W_v[e][:] . xn[px][:]
 //          (weights are the M operand, pixels the N operand: TMEM lane = channel, column = pixel,
 //          so everything a softmax over pixels needs is local to one thread)
-//   k-warps (one thread per channel d): tile max m, p = exp(k - m) as fp16 -> P[d][px] in
-//          shared memory (K-major, 128B swizzle), z = sum p
-//   v-warps (one thread per channel e): v as fp16 -> Vt[e][px] in shared memory
-//   MMA2   D2[d][e] = sum_px P[d][px] Vt[e][px]   (M = N = K = 128; the four 32x32 diagonal
-//          blocks are the per-head contexts)
-//   k-warps: flash-style running (m, z, ctx[32]) per thread, rescaled when the running max moves.
-// A CTA owns a contiguous range of tiles; per image it touches it writes one partial
-// (m[128], z[128], ctx[128][32]); k_linattn_fold combines the partials of an image in a fixed
-// order (bit-reproducible, no atomics) and folds the normalised context into the to_out weight:
+//   eight epilogue warps = 4 TMEM lane quarters (32 channels = one head) x 2 pixel halves; the
+//   thread of (channel c, half hf) handles the 64 pixels of its half for BOTH k row c and v row c:
+//          max m over its 64 pixels, p = exp(k - m) as fp16 -> P[c][px] (shared memory, K-major,
+//          128B swizzle), z = sum p;  v as fp16 -> Vt[c][px]
+//   MMA2   D2_hf[d][e] = sum_{px in half hf} P[d][px] Vt[e][px]   (M = N = 128, K = 64 per half;
+//          the four 32x32 diagonal blocks are the per-head contexts)
+//   each thread keeps a flash-style running (m, z, ctx[32]) for its (channel, half) pixel stream,
+//   rescaled when the running max moves.
+// An image is cut into fixed chunks of tiles (a function of the image size only); a CTA owns a
+// contiguous range of chunks and writes two partials (one per pixel half; m[128], z[128],
+// ctx[128][32]) per chunk, so
+// the numbers do not depend on the batch size or the grid.  k_linattn_fold combines the partials
+// of an image in a fixed order (bit-reproducible, no atomics) and folds the normalised context
+// into the to_out weight:
 //   W_eff[b][c][h*32+d] = sum_e W_out[c][h*32+e] ctx_b[h][d][e] / (z_b[h*32+d] n)      (SDD:763-769)
 #include <algorithm>
 #include <limits.h>
@@ -32,7 +37,7 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kThreads = 320;           // TMA warp, MMA warp, 4 k-warps, 4 v-warps
+constexpr int kThreads = 320;           // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kXBytes = 128 * 128;      // xn K block: 128 pixels x 64 ch
 constexpr int kWBytes = 256 * 128;      // W K block: (k rows, v rows) x 64 ch
 constexpr int kStageBytes = kXBytes + kWBytes;
@@ -50,8 +55,9 @@ struct alignas(8) Ctl {
 
 struct Params {
   int tile_w_log2, tiles_x, tpi;   // tile geometry, tiles per image
-  int total_tiles, num_kb, stages, max_slots;
-  float* partials;                 // [B][max_slots][kPartialFloats]
+  int tpc, total_chunks;           // tiles per chunk, chunks of this launch (B * tpi / tpc)
+  int num_kb, stages;
+  float* partials;                 // [total_chunks][2 halves][kPartialFloats]
 };
 
 __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {   // packed fp16 exp2
@@ -65,18 +71,22 @@ __device__ __forceinline__ float ex2_f(float x) {
   return y;
 }
 
+__device__ __forceinline__ void tma_store_4d_(const CUtensorMap* m, const void* src, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0_() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0_() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // first tile of CTA c when `total` tiles are dealt in contiguous ranges to `grid` CTAs
 __host__ __device__ inline int range_begin(int c, int total, int grid) {
   return (int)(((long long)c * total) / grid);
 }
-// the CTA whose range contains tile t
-__host__ __device__ inline int range_owner(int t, int total, int grid) {
-  int c = (int)(((long long)t * grid) / total);
-  while (c + 1 < grid && range_begin(c + 1, total, grid) <= t) ++c;
-  while (c > 0 && range_begin(c, total, grid) > t) --c;
-  return c;
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
         const Params P) {
@@ -90,8 +100,8 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_h = 128 >> P.tile_w_log2;
-  const int t_begin = range_begin(blockIdx.x, P.total_tiles, gridDim.x);
-  const int t_end = range_begin(blockIdx.x + 1, P.total_tiles, gridDim.x);
+  const int t_begin = range_begin(blockIdx.x, P.total_chunks, gridDim.x) * P.tpc;
+  const int t_end = range_begin(blockIdx.x + 1, P.total_chunks, gridDim.x) * P.tpc;
   const int ntiles = t_end - t_begin;
 
   if (warp == 0 && lane == 0) {
@@ -119,7 +129,7 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t taddr = ctl->tmem_addr;
-  // TMEM columns: [K0 | V0 | K1 | V1], 128 each; D2 of tile i reuses V(i & 1)
+  // TMEM columns: [K0 | V0 | K1 | V1], 128 each; D2 of tile i, half 0 / 1 reuses K(i & 1) / V(i & 1)
   auto k_cols = [&](int b) { return taddr + (uint32_t)(b * 256); };
   auto v_cols = [&](int b) { return taddr + (uint32_t)(b * 256 + 128); };
 
@@ -189,38 +199,41 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
         mbar_wait(&ctl->pv_ready, (uint32_t)j & 1u);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d2 = taddr_u + (uint32_t)(bj * 256 + 128);
+          const uint32_t d2 = taddr_u + (uint32_t)(bj * 256);   // half 0 -> K(bj), half 1 -> V(bj)
           const uint64_t dp = desc_hi | (uint64_t)(sP_u >> 4), dvt = desc_hi | (uint64_t)(sVt_u >> 4);
 #pragma unroll
           for (int s = 0; s < 8; ++s) {
             const uint64_t o = (uint64_t)((s >> 2) * (16384 >> 4) + (s & 3) * 2);
-            umma_f16(d2, dp + o, dvt + o, idesc, s > 0 ? 1u : 0u);
+            umma_f16(d2 + (uint32_t)((s >> 2) * 128), dp + o, dvt + o, idesc, (s & 3) ? 1u : 0u);
           }
           umma_commit(&ctl->d2_full[bj]);
         }
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
-    // =============================== k-warps ====================================
+  } else {
+    // =============================== epilogue warps ==============================
     const int quarter = warp & 3;            // TMEM lane quarter = head
-    const int d = quarter * 32 + lane;
+    const int hf = (warp - 2) >> 2;          // pixel half of the tile this warp owns
+    const int d = quarter * 32 + lane;       // k channel and v channel of this thread
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     float m_run = -INFINITY, z = 0.f;
     float acc[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-    float m_prev = 0.f, z_prev = 0.f;        // tile-local max / sum of the tile whose D2 is pending
+    float m_prev = 0.f, z_prev = 0.f;        // max / sum of the tile whose D2 is pending
+    uint8_t* prow = sP + (size_t)hf * 16384 + (size_t)d * 128;    // K block hf, row d
+    uint8_t* vrow = sVt + (size_t)hf * 16384 + (size_t)d * 128;
 
-    auto epi2 = [&](int j) {                 // fold tile j's D2 into the running state
+    auto epi2 = [&](int j) {                 // fold tile j's D2 (this half) into the running state
       const int bj = j & 1;
       mbar_wait(&ctl->d2_full[bj], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld32(v_cols(bj) + lane_off + (uint32_t)(quarter * 32), v);
+      tmem_ld32((hf ? v_cols(bj) : k_cols(bj)) + lane_off + (uint32_t)(quarter * 32), v);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&ctl->v_empty[bj]);
+      mbar_arrive(hf ? &ctl->v_empty[bj] : &ctl->k_empty[bj]);
       const float m_new = fmaxf(m_run, m_prev);
       const float so = ex2_f((m_run - m_new) * kLog2e), sn = ex2_f((m_prev - m_new) * kLog2e);
 #pragma unroll
@@ -228,9 +241,8 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
       z = fmaf(z, so, z_prev * sn);
       m_run = m_new;
     };
-    auto flush = [&](int img) {
-      const int first = range_owner(img * P.tpi, P.total_tiles, gridDim.x);
-      float* dst = P.partials + ((size_t)img * P.max_slots + (blockIdx.x - first)) * kPartialFloats;
+    auto flush = [&](int chunk) {
+      float* dst = P.partials + ((size_t)chunk * 2 + hf) * kPartialFloats;
       dst[d] = m_run;
       dst[128 + d] = z;
       float4* c4 = reinterpret_cast<float4*>(dst + 256 + d * 32);
@@ -246,30 +258,30 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
       const int b = i & 1;
       mbar_wait(&ctl->k_full[b], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
-      const uint32_t kaddr = k_cols(b) + lane_off;
-      // pass 1: this channel's maximum over the tile's 128 pixels
+      const uint32_t kaddr = k_cols(b) + lane_off + (uint32_t)(hf * 64);
+      // pass 1: this channel's maximum over the 64 pixels of this half
       float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(kaddr + (uint32_t)(c * 32), v);
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(kaddr, v0);
+        tmem_ld32(kaddr + 32, v1);
         tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 32; jj += 2)
-          m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1])));
+        for (int jj = 0; jj < 32; jj += 2) {
+          m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v0[jj]), __uint_as_float(v0[jj + 1])));
+          m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v1[jj]), __uint_as_float(v1[jj + 1])));
+        }
       }
       // tile i-1: its P / Vt have been consumed once D2 is complete
       if (i > 0) {
         epi2(i - 1);
-        const int img_prev = (t_begin + i - 1) / P.tpi, img_cur = (t_begin + i) / P.tpi;
-        if (img_prev != img_cur) flush(img_prev);
+        if (i % P.tpc == 0) flush((t_begin + i - 1) / P.tpc);   // chunk boundary
       }
       // pass 2: p = exp(k - m_tile) -> fp16 -> P[d][px]
       const float mb = m_tile * kLog2e;
       float zt = 0.f;
-      uint8_t* prow = sP + (size_t)d * 128;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld32(kaddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
@@ -282,38 +294,17 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
           const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&h[jj]));
           zt += pf.x + pf.y;
         }
-        uint8_t* blk = prow + (size_t)(c >> 1) * 16384;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + q) ^ (d & 7)) << 4)) =
+          *reinterpret_cast<uint4*>(prow + (((c * 4 + q) ^ (d & 7)) << 4)) =
               make_uint4(h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
       }
-      tc_fence_before();
-      mbar_arrive(&ctl->k_empty[b]);
-      fence_proxy_async();
-      mbar_arrive(&ctl->pv_ready);
-      m_prev = m_tile;
-      z_prev = zt;
-    }
-    if (ntiles > 0) {
-      epi2(ntiles - 1);
-      flush((t_end - 1) / P.tpi);
-    }
-    tc_fence_before();
-  } else {
-    // =============================== v-warps ====================================
-    const int quarter = warp & 3;
-    const int e = quarter * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    uint8_t* vrow = sVt + (size_t)e * 128;
-    for (int i = 0; i < ntiles; ++i) {
-      const int b = i & 1;
+      // v row of the same channel / half -> Vt
       mbar_wait(&ctl->v_full[b], (uint32_t)(i >> 1) & 1u);
-      if (i > 0) mbar_wait(&ctl->d2_full[(i - 1) & 1], (uint32_t)((i - 1) >> 1) & 1u);   // Vt free
       tc_fence_after();
-      const uint32_t vaddr = v_cols(b) + lane_off;
+      const uint32_t vaddr = v_cols(b) + lane_off + (uint32_t)(hf * 64);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld32(vaddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
@@ -323,15 +314,20 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
           const __half2 x = __floats2half2_rn(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
           h[jj] = *reinterpret_cast<const uint32_t*>(&x);
         }
-        uint8_t* blk = vrow + (size_t)(c >> 1) * 16384;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + q) ^ (e & 7)) << 4)) =
+          *reinterpret_cast<uint4*>(vrow + (((c * 4 + q) ^ (d & 7)) << 4)) =
               make_uint4(h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
       }
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(&ctl->pv_ready);
+      m_prev = m_tile;
+      z_prev = zt;
+    }
+    if (ntiles > 0) {
+      epi2(ntiles - 1);
+      flush((t_end - 1) / P.tpc);
     }
     tc_fence_before();
   }
@@ -343,60 +339,412 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
   }
 }
 
-// Combine the per-CTA partials of one image (fixed order) and fold the normalised context into
-// the to_out weight.  grid (B, 4): blockIdx.y takes a quarter of the output channels.
+// Combine the chunk partials of one image (fixed order) and fold the normalised context into
+// the to_out weight.  grid (B, 4 heads): one CTA per (image, head); up to 32 chunks.
+constexpr int kMaxChunks = 64;      // partial slots per image (two pixel halves per chunk)
 __global__ void __launch_bounds__(256)
 k_linattn_fold(const float* __restrict__ partials, const float* __restrict__ wout,
-               __half* __restrict__ weff, int C, int tpi, int total_tiles, int grid_kv, int max_slots,
-               float inv_n) {
-  __shared__ float sM[128];
-  __shared__ float sZ[128];
-  __shared__ float sC[128 * 33];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int first = range_owner(b * tpi, total_tiles, grid_kv);
-  int nslots = 0;
-  for (int k = 0; k < max_slots; ++k) {
-    const int c = first + k;
-    if (c < grid_kv && range_begin(c, total_tiles, grid_kv) < (b + 1) * tpi) nslots = k + 1;
-  }
-  const float* base = partials + (size_t)b * max_slots * kPartialFloats;
-  if (tid < 128) {
+               __half* __restrict__ weff, int C, int cpi, float inv_n) {
+  __shared__ float sS[kMaxChunks][32];   // exp(m_k - m) per chunk and channel of this head
+  __shared__ float sN[32];               // 1 / (z n)
+  __shared__ float sC[32 * 33];          // combined context [d][e]
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const float* base = partials + (size_t)b * cpi * kPartialFloats;
+  if (tid < 32) {
+    const int hd = h * 32 + tid;
+    float mk[kMaxChunks];
     float m = -INFINITY;
-    for (int k = 0; k < nslots; ++k) m = fmaxf(m, base[(size_t)k * kPartialFloats + tid]);
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+      mk[k] = (k < cpi) ? base[(size_t)k * kPartialFloats + hd] : -INFINITY;
+      m = fmaxf(m, mk[k]);
+    }
     float zz = 0.f;
-    for (int k = 0; k < nslots; ++k)
-      zz = fmaf(base[(size_t)k * kPartialFloats + 128 + tid],
-                exp2f((base[(size_t)k * kPartialFloats + tid] - m) * kLog2e), zz);
-    sM[tid] = m;
-    sZ[tid] = zz;
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+      const float sc = exp2f((mk[k] - m) * kLog2e);   // 0 for the unused slots
+      sS[k][tid] = sc;
+      if (k < cpi) zz = fmaf(base[(size_t)k * kPartialFloats + 128 + hd], sc, zz);
+    }
+    sN[tid] = inv_n / zz;
   }
   __syncthreads();
-  for (int i = tid; i < 4096; i += 256) {
+  for (int i = tid; i < 1024; i += 256) {
     const int dd = i >> 5;
+    const float* src = base + 256 + (h * 32) * 32 + i;
+    float v[kMaxChunks];
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) v[k] = (k < cpi) ? src[(size_t)k * kPartialFloats] : 0.f;
     float a = 0.f;
-    for (int k = 0; k < nslots; ++k)
-      a = fmaf(base[(size_t)k * kPartialFloats + 256 + i],
-               exp2f((base[(size_t)k * kPartialFloats + dd] - sM[dd]) * kLog2e), a);
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) a = fmaf(v[k], sS[k][dd], a);
     sC[dd * 33 + (i & 31)] = a;
   }
   __syncthreads();
-  const int hd = tid & 127, h = hd >> 5;
-  const float norm = inv_n / sZ[hd];
-  const int cq = C >> 2;
-  for (int c = blockIdx.y * cq + (tid >> 7); c < (blockIdx.y + 1) * cq; c += 2) {
-    const float* w = wout + (size_t)c * 128 + h * 32;
+  const int dd = tid & 31;
+  const float norm = sN[dd];
+  for (int c = tid >> 5; c < C; c += 8) {
+    const float4* w4 = reinterpret_cast<const float4*>(wout + (size_t)c * 128 + h * 32);
     float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) a = fmaf(__ldg(w + e), sC[hd * 33 + e], a);
-    weff[((size_t)b * C + c) * 128 + hd] = __float2half_rn(a * norm);
+    for (int q = 0; q < 8; ++q) {
+      const float4 w = __ldg(w4 + q);
+      a = fmaf(w.x, sC[dd * 33 + q * 4 + 0], a);
+      a = fmaf(w.y, sC[dd * 33 + q * 4 + 1], a);
+      a = fmaf(w.z, sC[dd * 33 + q * 4 + 2], a);
+      a = fmaf(w.w, sC[dd * 33 + q * 4 + 3], a);
+    }
+    weff[((size_t)b * C + c) * 128 + h * 32 + dd] = __float2half_rn(a * norm);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// LinearAttention, fused q projection + softmax_d + (context . q) + to_out + LayerNorm + residual
+// (SDD:750-756, 763-769, Residual SDD:583-589): q never reaches HBM.
+//
+// Per 128-pixel tile:  MMA1  D_q[px][128] = xn[px][:] . W_q^T          (TMEM, double-buffered)
+//   q-warps (thread = pixel): softmax over each 32-channel head * scale -> fp16 Q tile in
+//          shared memory (K-major, 128B swizzle) = the M operand of
+//   MMA2   D_o[px][C] = Q[px][:] . W_eff[b]^T    (W_eff = to_out weight folded with the image's
+//          normalised context, one [C][128] fp16 matrix per image, resident in shared memory)
+//   o-warps (thread = pixel): + bias, channel LayerNorm * g, + residual x -> fp16 -> per-warp
+//          staging slab -> TMA store.
+// ------------------------------------------------------------------------------------------
+struct alignas(8) QCtl {
+  uint64_t full[kMaxStages], empty[kMaxStages];
+  uint64_t dq_full[2], dq_empty[2];
+  uint64_t q_ready[2], q_free[2], do_full[2], do_empty[2];
+  uint64_t weff_full, weff_free;
+  uint32_t tmem_addr, pad;
+};
+
+struct QParams {
+  int tile_w_log2, tiles_x, tpi, total_tiles, num_kb, stages, H, W;
+  const float *bias, *gain;
+  const __half* res;          // residual x, NHWC, C channels dense
+  float q_scale;
+};
+
+constexpr int kQStage = 128 * 128 + 128 * 128;   // xn K block + W_q K block
+
+// C <= 128: the Q tile and the D_o accumulator are double-buffered (shared memory and TMEM allow
+// it), so softmax (tile i+1), MMA2 (tile i) and the LayerNorm/store (tile i-1) overlap.
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1)
+k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+       const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
+       const QParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr int NB = (C <= 128) ? 2 : 1;         // Q tiles / D_o accumulators
+  constexpr int kWeffBytes = C * 256;            // two K blocks of [C rows][64]
+  constexpr int kSlabBytes = 32 * C * 2;         // one o-warp: 32 pixels x C channels
+  uint8_t* sStage = smem;
+  uint8_t* sQ = sStage + (size_t)P.stages * kQStage;   // NB x 2 K blocks x [128 px][64 ch]
+  uint8_t* sE = sQ + NB * 32768;
+  uint8_t* sO = sE + kWeffBytes;
+  QCtl* ctl = reinterpret_cast<QCtl*>(sO + 4 * kSlabBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_w = 1 << P.tile_w_log2, tile_h = 128 >> P.tile_w_log2;
+  const int t_begin = range_begin(blockIdx.x, P.total_tiles, gridDim.x);
+  const int t_end = range_begin(blockIdx.x + 1, P.total_tiles, gridDim.x);
+  const int ntiles = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    prefetch_tmap(&tmE);
+    prefetch_tmap(&tmO);
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctl->dq_full[b], 1);
+      mbar_init(&ctl->dq_empty[b], 128);
+      mbar_init(&ctl->q_ready[b], 128);
+      mbar_init(&ctl->q_free[b], 1);
+      mbar_init(&ctl->do_full[b], 1);
+      mbar_init(&ctl->do_empty[b], 128);
+    }
+    mbar_init(&ctl->weff_full, 1);
+    mbar_init(&ctl->weff_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = ctl->tmem_addr;     // columns: [Dq0 | Dq1 | Do0 (C) | Do1 (C)]
+
+  auto tile_xy = [&](int t, int& img, int& x0, int& y0) {
+    img = t / P.tpi;
+    const int r = t - img * P.tpi;
+    const int tyi = r / P.tiles_x, txi = r - tyi * P.tiles_x;
+    x0 = txi << P.tile_w_log2;
+    y0 = tyi * tile_h;
+  };
+  // buffer index / wait parity of the n-th use of an NB-deep ring
+  auto ring_b = [](int n) { return NB == 2 ? (n & 1) : 0; };
+  auto ring_par = [](int n) { return (uint32_t)(NB == 2 ? (n >> 1) : n) & 1u; };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < ntiles; ++i) {
+        int img, x0, y0;
+        tile_xy(t_begin + i, img, x0, y0);
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          uint8_t* dst = sStage + (size_t)stage * kQStage;
+          mbar_arrive_expect_tx(&ctl->full[stage], kQStage);
+          tma_load_4d(&tmX, &ctl->full[stage], dst, kb * 64, x0, y0, img);
+          tma_load_3d(&tmW, &ctl->full[stage], dst + 16384, kb * 64, 0, 0);   // rows 0..127 = q
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    constexpr uint32_t idesc1 = idesc_f16(128, 128);
+    constexpr uint32_t idesc2 = idesc_f16(128, C);
+    const uint32_t taddr_u = __reduce_or_sync(0xffffffffu, taddr);
+    const uint32_t sStage_u = __reduce_or_sync(0xffffffffu, smem_u32(sStage));
+    const uint32_t sQ_u = __reduce_or_sync(0xffffffffu, smem_u32(sQ));
+    const uint32_t sE_u = __reduce_or_sync(0xffffffffu, smem_u32(sE));
+    const uint64_t desc_hi = smem_desc_sw128(0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int cur_img = -1;
+    uint32_t n_weff = 0;      // W_eff loads so far (phase of weff_full / weff_free)
+    for (int i = 0; i <= ntiles; ++i) {
+      if (i < ntiles) {
+        const int b = i & 1;
+        mbar_wait(&ctl->dq_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t dq = taddr_u + (uint32_t)(b * 128);
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t x_lo = (sStage_u + (uint32_t)stage * kQStage) >> 4;
+          if (elect_one()) {
+            const uint64_t dx = desc_hi | (uint64_t)x_lo;
+            const uint64_t dw = desc_hi | (uint64_t)(x_lo + (16384 >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(dq, dx + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&ctl->empty[stage]);
+            if (kb == P.num_kb - 1) umma_commit(&ctl->dq_full[b]);
+          }
+          __syncwarp();
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (i >= 1) {
+        const int j = i - 1;
+        const int img = (t_begin + j) / P.tpi;
+        if (img != cur_img) {
+          // new image: its W_eff replaces the resident one once every MMA2 that read it is done
+          if (cur_img >= 0) {
+            if (elect_one()) umma_commit(&ctl->weff_free);
+            __syncwarp();
+            mbar_wait(&ctl->weff_free, (n_weff - 1u) & 1u);
+          }
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&ctl->weff_full, kWeffBytes);
+            tma_load_3d(&tmE, &ctl->weff_full, sE, 0, 0, img);
+            tma_load_3d(&tmE, &ctl->weff_full, sE + C * 128, 64, 0, img);
+          }
+          __syncwarp();
+          mbar_wait(&ctl->weff_full, n_weff & 1u);
+          ++n_weff;
+          cur_img = img;
+        }
+        const int bj = ring_b(j);
+        mbar_wait(&ctl->q_ready[bj], ring_par(j));
+        mbar_wait(&ctl->do_empty[bj], ring_par(j) ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t dout = taddr_u + 256u + (uint32_t)(bj * C);
+          const uint64_t dq_ = desc_hi | (uint64_t)((sQ_u + (uint32_t)bj * 32768u) >> 4);
+          const uint64_t de = desc_hi | (uint64_t)(sE_u >> 4);
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            umma_f16(dout, dq_ + (uint64_t)((s >> 2) * (16384 >> 4) + (s & 3) * 2),
+                     de + (uint64_t)((s >> 2) * ((C * 128) >> 4) + (s & 3) * 2), idesc2, s > 0 ? 1u : 0u);
+          umma_commit(&ctl->q_free[bj]);
+          umma_commit(&ctl->do_full[bj]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // =============================== q-warps: softmax_d ==========================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float qs = P.q_scale;
+    for (int i = 0; i < ntiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(&ctl->dq_full[b], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      uint32_t hq[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {       // one head per 32-column chunk
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(b * 128 + c * 32) + lane_off, v);
+        tmem_ld_wait();
+        float m = __uint_as_float(v[0]);
+#pragma unroll
+        for (int jj = 1; jj < 32; ++jj) m = fmaxf(m, __uint_as_float(v[jj]));
+        const float mb = m * kLog2e;
+        float f[32];
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          f[jj] = ex2_f(fmaf(__uint_as_float(v[jj]), kLog2e, -mb));
+          sum += f[jj];
+        }
+        const float inv = __fdividef(qs, sum);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const __half2 x = __floats2half2_rn(f[2 * jj] * inv, f[2 * jj + 1] * inv);
+          hq[c][jj] = *reinterpret_cast<const uint32_t*>(&x);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ctl->dq_empty[b]);
+      const int bq = ring_b(i);
+      if (i >= NB) mbar_wait(&ctl->q_free[bq], ring_par(i - NB));   // MMA2(i - NB) has read this Q tile
+      uint8_t* qrow = sQ + (size_t)bq * 32768 + (size_t)row * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* blk = qrow + (size_t)(c >> 1) * 16384;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + q) ^ (row & 7)) << 4)) =
+              make_uint4(hq[c][q * 4], hq[c][q * 4 + 1], hq[c][q * 4 + 2], hq[c][q * 4 + 3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&ctl->q_ready[bq]);
+    }
+  } else {
+    // =============================== o-warps: LayerNorm + residual + store =======
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int tyr = row >> P.tile_w_log2, txr = row & (tile_w - 1);
+    uint8_t* slab = sO + (size_t)quarter * kSlabBytes;
+    for (int i = 0; i < ntiles; ++i) {
+      int img, x0, y0;
+      tile_xy(t_begin + i, img, x0, y0);
+      const __half* rp = P.res + (((size_t)img * P.H + (y0 + tyr)) * P.W + (x0 + txr)) * C;
+      const int bo = ring_b(i);
+      const uint32_t dout = taddr + 256u + (uint32_t)(bo * C) + lane_off;
+      mbar_wait(&ctl->do_full[bo], ring_par(i));
+      tc_fence_after();
+      // pass 1: mean and variance of (acc + bias) over the C channels of this pixel, shifted by
+      // the first channel's value (single sweep, no cancellation)
+      float sh = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < C; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(dout + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c == 0) sh = __uint_as_float(v[0]) + __ldg(P.bias);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float dlt = __uint_as_float(v[jj]) + __ldg(P.bias + c + jj) - sh;
+          s1 += dlt;
+          s2 = fmaf(dlt, dlt, s2);
+        }
+      }
+      const float dm = s1 * (1.f / C);
+      const float mean = sh + dm;
+      const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - dm * dm, 0.f) + 1e-5f);
+      if (lane == 0) bulk_wait_read0_();     // the slab's previous TMA store has read it
+      __syncwarp();
+#pragma unroll 1
+      for (int c = 0; c < C; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(dout + (uint32_t)c, v);
+        const uint4* r4 = reinterpret_cast<const uint4*>(rp + c);
+        uint4 rv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rv[q] = __ldg(r4 + q);
+        tmem_ld_wait();
+        if (c + 32 >= C) {                   // last read of this accumulator
+          tc_fence_before();
+          mbar_arrive(&ctl->do_empty[bo]);
+        }
+        uint8_t* blk = slab + (size_t)(c >> 6) * (32 * 128) + (size_t)lane * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
+          uint32_t o[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int ch = c + q * 8 + jj * 2;
+            const float2 r2 = __half22float2(rh[jj]);
+            const float y0f = (__uint_as_float(v[q * 8 + jj * 2]) + __ldg(P.bias + ch) - mean) * rstd * __ldg(P.gain + ch) + r2.x;
+            const float y1f = (__uint_as_float(v[q * 8 + jj * 2 + 1]) + __ldg(P.bias + ch + 1) - mean) * rstd * __ldg(P.gain + ch + 1) + r2.y;
+            const __half2 hh = __floats2half2_rn(y0f, y1f);
+            o[jj] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+          *reinterpret_cast<uint4*>(blk + (((((c & 63) >> 3) + q) ^ (lane & 7)) << 4)) =
+              make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        const int px = quarter * 32;
+#pragma unroll
+        for (int cb = 0; cb < C / 64; ++cb)
+          tma_store_4d_(&tmO, slab + (size_t)cb * (32 * 128), cb * 64, x0 + (px & (tile_w - 1)),
+                        y0 + (px >> P.tile_w_log2), img);
+        bulk_commit_();
+      }
+    }
+    if (lane == 0) bulk_wait0_();
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(taddr, 512);
+  }
+}
+
+struct QOutLaunch {
+  CUtensorMap tmX, tmW, tmE, tmO;
+  QParams P;
+  int smem, C;
+};
 
 struct KvCtxLaunch {
   CUtensorMap tmX, tmW;
   Params P;
-  int smem, maxB, tpi;
+  int smem, maxB, cpi;
 };
+
+// tiles per chunk: a function of the image size only (batch-invariant results); about 32 chunks
+// per image, at most 16 tiles each
+int tiles_per_chunk(int tpi) {
+  int t = tpi / 32;
+  if (t < 1) t = 1;
+  if (t > 16) t = 16;
+  while (tpi % t != 0) --t;
+  return t;
+}
 
 }  // namespace
 
@@ -413,9 +761,9 @@ KvCtxOp& KvCtxOp::operator=(const KvCtxOp& o) {
   return *this;
 }
 
-int kvctx_max_slots(int maxB) {
-  // an image's tiles are spread over at most ceil(grid / B) + 1 contiguous CTA ranges
-  return (num_sms() + maxB - 1) / maxB + 2;
+size_t kvctx_partial_floats(int maxB, int H, int W) {
+  const int tpi = (H * W) / 128;
+  return (size_t)maxB * (tpi / tiles_per_chunk(tpi)) * 2 * kPartialFloats;
 }
 
 int kvctx_plan(KvCtxOp* op, int maxB, const __half* xn, int H, int W, int C, int pix_stride,
@@ -439,14 +787,14 @@ int kvctx_plan(KvCtxOp* op, int maxB, const __half* xn, int H, int W, int C, int
   P.tiles_x = W / tile_w;
   P.tpi = (H * W) / 128;
   P.num_kb = C / 64;
-  P.max_slots = kvctx_max_slots(maxB);
+  P.tpc = tiles_per_chunk(P.tpi);
   P.partials = partials;
   int stages = (kSmemBudget - 2 * kPvBytes - 2048) / kStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   P.stages = stages;
   L->smem = stages * kStageBytes + 2 * kPvBytes + 1024 + (int)sizeof(Ctl) + 64;
   L->maxB = maxB;
-  L->tpi = P.tpi;
+  L->cpi = P.tpi / P.tpc;
   int rc;
   {
     const uint64_t ps = (uint64_t)pix_stride * 2;
@@ -474,10 +822,8 @@ int kvctx_plan(KvCtxOp* op, int maxB, const __half* xn, int H, int W, int C, int
 int kvctx_run(KvCtxOp& op, int B, const float* wout, __half* weff, int C, cudaStream_t s) {
   KvCtxLaunch L = *reinterpret_cast<KvCtxLaunch*>(op.impl);
   Params& P = L.P;
-  P.total_tiles = B * L.tpi;
-  // The partial slots were sized for maxB images over all SMs; with fewer images use fewer CTAs,
-  // so that an image never spans more contiguous CTA ranges than it has slots.
-  const int grid = std::max(1, std::min(std::min(P.total_tiles, num_sms()), (P.max_slots - 2) * B));
+  P.total_chunks = B * L.cpi;
+  const int grid = std::min(P.total_chunks, num_sms());
   static int configured = 0;
   if (!configured) {
     PRG_CUDA_OK(cudaFuncSetAttribute(k_kvctx, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -486,10 +832,115 @@ int kvctx_run(KvCtxOp& op, int B, const float* wout, __half* weff, int C, cudaSt
   k_kvctx<<<grid, kThreads, L.smem, s>>>(L.tmX, L.tmW, P);
   PRG_LAUNCH_CHECK();
   dim3 g(B, 4);
-  k_linattn_fold<<<g, 256, 0, s>>>(P.partials, wout, weff, C, L.tpi, P.total_tiles, grid, P.max_slots,
-                                   1.f / (float)(L.tpi * 128));
+  k_linattn_fold<<<g, 256, 0, s>>>(P.partials, wout, weff, C, 2 * L.cpi, 1.f / (float)(P.tpi * 128));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
+}
+
+QOutOp::QOutOp() : impl(nullptr) {}
+QOutOp::~QOutOp() { delete reinterpret_cast<QOutLaunch*>(impl); }
+QOutOp::QOutOp(const QOutOp& o) : impl(nullptr) {
+  if (o.impl) impl = new QOutLaunch(*reinterpret_cast<QOutLaunch*>(o.impl));
+}
+QOutOp& QOutOp::operator=(const QOutOp& o) {
+  if (this != &o) {
+    delete reinterpret_cast<QOutLaunch*>(impl);
+    impl = o.impl ? new QOutLaunch(*reinterpret_cast<QOutLaunch*>(o.impl)) : nullptr;
+  }
+  return *this;
+}
+
+int qout_plan(QOutOp* op, int maxB, const __half* xn, int H, int W, int C, const __half* wqkv,
+              const __half* weff, const float* bias, const float* gain, const __half* res, __half* out) {
+  if ((C != 64 && C != 128 && C != 256) || (H * W) % 128 != 0) {
+    set_error("qout_plan: unsupported shape %dx%d C=%d", H, W, C);
+    return PRG_ERR_ARG;
+  }
+  const int tile_w = W < 128 ? W : 128;
+  if ((tile_w & (tile_w - 1)) != 0 || tile_w < 8 || W % tile_w != 0 || H % (128 / tile_w) != 0) {
+    set_error("qout_plan: unsupported spatial size %dx%d", H, W);
+    return PRG_ERR_ARG;
+  }
+  QOutLaunch* L = new QOutLaunch();
+  memset(L, 0, sizeof(*L));
+  const int tile_h = 128 / tile_w;
+  int l2 = 0;
+  while ((1 << l2) < tile_w) ++l2;
+  QParams& P = L->P;
+  P.tile_w_log2 = l2;
+  P.tiles_x = W / tile_w;
+  P.tpi = (H * W) / 128;
+  P.num_kb = C / 64;
+  P.H = H;
+  P.W = W;
+  P.bias = bias;
+  P.gain = gain;
+  P.res = res;
+  P.q_scale = 0.17677669529663687f;   // 32^-0.5 (SDD:742)
+  const int fixed = (C <= 128 ? 2 : 1) * 32768 + 2 * C * 256 + 1024 + (int)sizeof(QCtl) + 64;
+  int stages = (kSmemBudget - fixed) / kQStage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    delete L;
+    set_error("qout_plan: shared memory budget too small");
+    return PRG_ERR_ARG;
+  }
+  P.stages = stages;
+  L->smem = stages * kQStage + fixed;
+  L->C = C;
+  int rc;
+  const uint64_t ps = (uint64_t)C * 2;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)maxB};
+    uint64_t str[3] = {ps, ps * W, ps * W * H};
+    uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, 1};
+    rc = tmap_encode_f16(&L->tmX, xn, 4, dims, str, box);
+    if (rc == PRG_OK) {
+      uint32_t sbox[4] = {64, (uint32_t)std::min(tile_w, 32), 0, 1};
+      sbox[2] = 32u / sbox[1];
+      rc = tmap_encode_f16(&L->tmO, out, 4, dims, str, sbox);
+    }
+  }
+  if (rc == PRG_OK) {
+    uint64_t dims[3] = {(uint64_t)C, 384, 1};
+    uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * 2 * 384};
+    uint32_t box[3] = {64, 128, 1};
+    rc = tmap_encode_f16(&L->tmW, wqkv, 3, dims, str, box);
+  }
+  if (rc == PRG_OK) {
+    uint64_t dims[3] = {128, (uint64_t)C, (uint64_t)maxB};
+    uint64_t str[2] = {256, (uint64_t)C * 256};
+    uint32_t box[3] = {64, (uint32_t)C, 1};
+    rc = tmap_encode_f16(&L->tmE, weff, 3, dims, str, box);
+  }
+  if (rc != PRG_OK) {
+    delete L;
+    return rc;
+  }
+  delete reinterpret_cast<QOutLaunch*>(op->impl);
+  op->impl = L;
+  return PRG_OK;
+}
+
+template <int C>
+static int qout_launch(const QOutLaunch& L, int grid, cudaStream_t s) {
+  static int configured = 0;
+  if (!configured) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_qout<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = 1;
+  }
+  k_qout<C><<<grid, kThreads, L.smem, s>>>(L.tmX, L.tmW, L.tmE, L.tmO, L.P);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+int qout_run(QOutOp& op, int B, cudaStream_t s) {
+  QOutLaunch L = *reinterpret_cast<QOutLaunch*>(op.impl);
+  L.P.total_tiles = B * L.P.tpi;
+  const int grid = std::min(L.P.total_tiles, num_sms());
+  if (L.C == 64) return qout_launch<64>(L, grid, s);
+  if (L.C == 128) return qout_launch<128>(L, grid, s);
+  return qout_launch<256>(L, grid, s);
 }
 
 }  // namespace prg

@@ -26,9 +26,9 @@ using namespace prg;
 
 namespace {
 
-enum OpCat { CAT_CONV = 0, CAT_GN, CAT_LN, CAT_CTX, CAT_WEFF, CAT_ATTN, CAT_STEM, CAT_COND, CAT_TAIL, CAT_COUNT };
-const char* const kCatNames[CAT_COUNT] = {"conv_tc", "gn_apply", "ln_apply", "linattn_context",
-                                          "linattn_weff", "attn_mid", "stem", "cond", "tail"};
+enum OpCat { CAT_CONV = 0, CAT_GN, CAT_LN, CAT_CTX, CAT_QOUT, CAT_ATTN, CAT_STEM, CAT_COND, CAT_TAIL, CAT_COUNT };
+const char* const kCatNames[CAT_COUNT] = {"conv_tc", "gn_apply", "ln_apply", "linattn_kvctx",
+                                          "linattn_qout", "attn_mid", "stem", "cond", "tail"};
 
 // Sampled per-op timing with CUDA events on the launching stream (bench.py's roofline leg).
 struct Profiler {
@@ -412,13 +412,6 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out, bool
   if (!ln_done)
     n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(xp, g, nullptr, xnp, (int64_t)r.B * HW, C, r.s); },
               "ln_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(C));
-  // q = softmax_d(W_q xn) * scale: the first 128 rows of to_qkv through the conv engine
-  Act q{n->qkv, H, W, 128, 128};
-  NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, q, [=](ConvParams& p) {
-    p.colmax = nullptr;
-    p.q_softmax = 1;
-    p.q_scale = 0.17677669529663687f;  // 32^-0.5
-  }));
   // k, v and the context never reach HBM: fused projection + softmax_n + k v^T, then W_eff
   __half* weff = n->weff;
   {
@@ -432,16 +425,25 @@ int add_linattn(prg_net* n, const std::string& pfx, const Act& x, Act* out, bool
   }
   Act y = new_act(n, H, W, C);
   if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
-  Act qsrc{q.p, H, W, 128, 128};
   if (C <= 256) {
-    NET_TRY(add_conv(n, EPI_LN_RES, qsrc, nullptr, 0, 1, 1, weff, 1, bo, y, [=](ConvParams& p) {
-      p.ln_g = g2;
-      p.res = xp;
-    }));
+    // q projection + softmax_d + W_eff + LayerNorm + residual in one kernel: q never reaches HBM
+    QOutOp op;
+    NET_TRY(qout_plan(&op, n->maxB, xn.p, H, W, C, wq, weff, bo, g2, xp, y.p));
+    char lab[96];
+    snprintf(lab, sizeof(lab), "linattn_qout %dx%d c%d", H, W, C);
+    n->add_op(CAT_QOUT, [op](const Run& r) mutable { return qout_run(op, r.B, r.s); }, lab,
+              (double)HW * (2.0 * 128 * C + 2.0 * 128 * C));
   } else {
-    // a 512-channel row does not fit one UMMA N tile: plain GEMM, then LayerNorm + residual
+    // a 512-channel row does not fit the TMEM budget of the fused kernel: q through the conv
+    // engine, plain GEMM with W_eff, then LayerNorm + residual
+    Act q{n->qkv, H, W, 128, 128};
+    NET_TRY(add_conv(n, EPI_QKV, xn, nullptr, 0, 1, 1, wq, 0, nullptr, q, [=](ConvParams& p) {
+      p.colmax = nullptr;
+      p.q_softmax = 1;
+      p.q_scale = 0.17677669529663687f;  // 32^-0.5
+    }));
     Act tmp{n->h1, H, W, C, C};
-    NET_TRY(add_conv(n, EPI_BIAS, qsrc, nullptr, 0, 1, 1, weff, 1, bo, tmp));
+    NET_TRY(add_conv(n, EPI_BIAS, q, nullptr, 0, 1, 1, weff, 1, bo, tmp));
     const __half* tp = tmp.p;
     __half* yp = y.p;
     n->add_op(CAT_LN, [=](const Run& r) { return ln_apply(tp, g2, xp, yp, (int64_t)r.B * HW, C, r.s); },
@@ -537,7 +539,11 @@ int build(prg_net* n) {
   n->colmax_cap = (size_t)B * 128 * 16;
   n->colmax_arena = n->dalloc<int>(n->colmax_cap);
   n->x_state = n->dalloc<float>((size_t)B * S * S);
-  n->kv_partials = n->dalloc<float>((size_t)B * kvctx_max_slots(B) * kPartialFloats);
+  {
+    size_t pf = 0;   // the largest level decides (chunks per image <= 32)
+    for (int i = 0; i < L; ++i) pf = std::max(pf, kvctx_partial_floats(B, S >> i, S >> i));
+    n->kv_partials = n->dalloc<float>(pf);
+  }
   if (!n->kv_partials || !n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
       !n->colmax_arena || !n->x_state) {
     set_error("out of device memory allocating the workspace");
