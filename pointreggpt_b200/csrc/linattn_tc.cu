@@ -24,6 +24,7 @@
 //   W_eff[b][c][h*32+d] = sum_e W_out[c][h*32+e] ctx_b[h][d][e] / (z_b[h*32+d] n)      (SDD:763-769)
 #include <algorithm>
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "attention.cuh"
@@ -266,11 +267,13 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
         tmem_ld32(kaddr, v0);
         tmem_ld32(kaddr + 32, v1);
         tmem_ld_wait();
+        float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 2) {
-          m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v0[jj]), __uint_as_float(v0[jj + 1])));
-          m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v1[jj]), __uint_as_float(v1[jj + 1])));
+          mp[(jj >> 1) & 1] = fmaxf(mp[(jj >> 1) & 1], fmaxf(__uint_as_float(v0[jj]), __uint_as_float(v0[jj + 1])));
+          mp[2 + ((jj >> 1) & 1)] = fmaxf(mp[2 + ((jj >> 1) & 1)], fmaxf(__uint_as_float(v1[jj]), __uint_as_float(v1[jj + 1])));
         }
+        m_tile = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       }
       // tile i-1: its P / Vt have been consumed once D2 is complete
       if (i > 0) {
@@ -279,45 +282,60 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
       }
       // pass 2: p = exp(k - m_tile) -> fp16 -> P[d][px]
       const float mb = m_tile * kLog2e;
-      float zt = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(kaddr + (uint32_t)(c * 32), v);
+      float zt;
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(kaddr, v0);
+        tmem_ld32(kaddr + 32, v1);
         tmem_ld_wait();
-        uint32_t h[16];
+        uint32_t h0[16], h1[16];
+        float zp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const __half2 x = __floats2half2_rn(fmaf(__uint_as_float(v[2 * jj]), kLog2e, -mb),
-                                              fmaf(__uint_as_float(v[2 * jj + 1]), kLog2e, -mb));
-          h[jj] = ex2_h2(*reinterpret_cast<const uint32_t*>(&x));
-          const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&h[jj]));
-          zt += pf.x + pf.y;
+          const __half2 x0 = __floats2half2_rn(fmaf(__uint_as_float(v0[2 * jj]), kLog2e, -mb),
+                                               fmaf(__uint_as_float(v0[2 * jj + 1]), kLog2e, -mb));
+          const __half2 x1 = __floats2half2_rn(fmaf(__uint_as_float(v1[2 * jj]), kLog2e, -mb),
+                                               fmaf(__uint_as_float(v1[2 * jj + 1]), kLog2e, -mb));
+          h0[jj] = ex2_h2(*reinterpret_cast<const uint32_t*>(&x0));
+          h1[jj] = ex2_h2(*reinterpret_cast<const uint32_t*>(&x1));
+          const float2 pf0 = __half22float2(*reinterpret_cast<const __half2*>(&h0[jj]));
+          const float2 pf1 = __half22float2(*reinterpret_cast<const __half2*>(&h1[jj]));
+          zp[jj & 1] += pf0.x + pf0.y;
+          zp[2 + (jj & 1)] += pf1.x + pf1.y;
         }
+        zt = (zp[0] + zp[1]) + (zp[2] + zp[3]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(prow + (((c * 4 + q) ^ (d & 7)) << 4)) =
-              make_uint4(h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<uint4*>(prow + ((q ^ (d & 7)) << 4)) =
+              make_uint4(h0[q * 4], h0[q * 4 + 1], h0[q * 4 + 2], h0[q * 4 + 3]);
+          *reinterpret_cast<uint4*>(prow + (((4 + q) ^ (d & 7)) << 4)) =
+              make_uint4(h1[q * 4], h1[q * 4 + 1], h1[q * 4 + 2], h1[q * 4 + 3]);
+        }
       }
       // v row of the same channel / half -> Vt
       mbar_wait(&ctl->v_full[b], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       const uint32_t vaddr = v_cols(b) + lane_off + (uint32_t)(hf * 64);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(vaddr + (uint32_t)(c * 32), v);
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(vaddr, v0);
+        tmem_ld32(vaddr + 32, v1);
         tmem_ld_wait();
-        uint32_t h[16];
+        uint32_t h0[16], h1[16];
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const __half2 x = __floats2half2_rn(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
-          h[jj] = *reinterpret_cast<const uint32_t*>(&x);
+          const __half2 x0 = __floats2half2_rn(__uint_as_float(v0[2 * jj]), __uint_as_float(v0[2 * jj + 1]));
+          const __half2 x1 = __floats2half2_rn(__uint_as_float(v1[2 * jj]), __uint_as_float(v1[2 * jj + 1]));
+          h0[jj] = *reinterpret_cast<const uint32_t*>(&x0);
+          h1[jj] = *reinterpret_cast<const uint32_t*>(&x1);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(vrow + (((c * 4 + q) ^ (d & 7)) << 4)) =
-              make_uint4(h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<uint4*>(vrow + ((q ^ (d & 7)) << 4)) =
+              make_uint4(h0[q * 4], h0[q * 4 + 1], h0[q * 4 + 2], h0[q * 4 + 3]);
+          *reinterpret_cast<uint4*>(vrow + (((4 + q) ^ (d & 7)) << 4)) =
+              make_uint4(h1[q * 4], h1[q * 4 + 1], h1[q * 4 + 2], h1[q * 4 + 3]);
+        }
       }
       tc_fence_before();
       fence_proxy_async();
@@ -423,6 +441,7 @@ struct QParams {
   const float *bias, *gain;
   const __half* res;          // residual x, NHWC, C channels dense
   float q_scale;
+  long long* trace;           // debug: clock64 stamps of CTA 0 (nullptr = off), 16 per tile
 };
 
 constexpr int kQStage = 128 * 128 + 128 * 128;   // xn K block + W_q K block
@@ -445,9 +464,18 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
   uint8_t* sE = sQ + NB * 32768;
   uint8_t* sO = sE + kWeffBytes;
   QCtl* ctl = reinterpret_cast<QCtl*>(sO + 4 * kSlabBytes);
+  // bias / gain: shared-memory copies when they fit (C <= 128), else read through L1
+  float* scoef = reinterpret_cast<float*>(ctl + 1);
+  const float* sbias = (C <= 128) ? scoef : P.bias;
+  const float* sgain = (C <= 128) ? scoef + C : P.gain;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_w = 1 << P.tile_w_log2, tile_h = 128 >> P.tile_w_log2;
+  if (C <= 128)
+    for (int i = threadIdx.x; i < C; i += kThreads) {
+      scoef[i] = __ldg(P.bias + i);
+      scoef[C + i] = __ldg(P.gain + i);
+    }
   const int t_begin = range_begin(blockIdx.x, P.total_tiles, gridDim.x);
   const int t_end = range_begin(blockIdx.x + 1, P.total_tiles, gridDim.x);
   const int ntiles = t_end - t_begin;
@@ -529,6 +557,7 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
         const int b = i & 1;
         mbar_wait(&ctl->dq_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < 48) P.trace[i * 16 + 5] = clock64();
         const uint32_t dq = taddr_u + (uint32_t)(b * 128);
         for (int kb = 0; kb < P.num_kb; ++kb) {
           mbar_wait(&ctl->full[stage], phase);
@@ -568,9 +597,11 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
           cur_img = img;
         }
         const int bj = ring_b(j);
+        if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && j < 48) P.trace[j * 16 + 6] = clock64();
         mbar_wait(&ctl->q_ready[bj], ring_par(j));
         mbar_wait(&ctl->do_empty[bj], ring_par(j) ^ 1u);
         tc_fence_after();
+        if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && j < 48) P.trace[j * 16 + 7] = clock64();
         if (elect_one()) {
           const uint32_t dout = taddr_u + 256u + (uint32_t)(bj * C);
           const uint64_t dq_ = desc_hi | (uint64_t)((sQ_u + (uint32_t)bj * 32768u) >> 4);
@@ -593,36 +624,55 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
     const float qs = P.q_scale;
     for (int i = 0; i < ntiles; ++i) {
       const int b = i & 1;
+      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 48;
+      if (tr) P.trace[i * 16 + 0] = clock64();
       mbar_wait(&ctl->dq_full[b], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
+      if (tr) P.trace[i * 16 + 1] = clock64();
       uint32_t hq[4][16];
+      // one head per 32-column chunk; two heads per step with independent reduction trees, so a
+      // lone warp per scheduler still finds independent instructions to issue
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {       // one head per 32-column chunk
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)(b * 128 + c * 32) + lane_off, v);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr + (uint32_t)(b * 128 + c * 32) + lane_off, va);
+        tmem_ld32(taddr + (uint32_t)(b * 128 + c * 32 + 32) + lane_off, vb);
         tmem_ld_wait();
-        float m = __uint_as_float(v[0]);
+        float ma[4], mq[4];
 #pragma unroll
-        for (int jj = 1; jj < 32; ++jj) m = fmaxf(m, __uint_as_float(v[jj]));
-        const float mb = m * kLog2e;
-        float f[32];
-        float sum = 0.f;
+        for (int r = 0; r < 4; ++r) { ma[r] = __uint_as_float(va[r]); mq[r] = __uint_as_float(vb[r]); }
+#pragma unroll
+        for (int jj = 4; jj < 32; ++jj) {
+          ma[jj & 3] = fmaxf(ma[jj & 3], __uint_as_float(va[jj]));
+          mq[jj & 3] = fmaxf(mq[jj & 3], __uint_as_float(vb[jj]));
+        }
+        const float mba = fmaxf(fmaxf(ma[0], ma[1]), fmaxf(ma[2], ma[3])) * kLog2e;
+        const float mbb = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])) * kLog2e;
+        float fa[32], fb[32];
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          f[jj] = ex2_f(fmaf(__uint_as_float(v[jj]), kLog2e, -mb));
-          sum += f[jj];
+          fa[jj] = ex2_f(fmaf(__uint_as_float(va[jj]), kLog2e, -mba));
+          fb[jj] = ex2_f(fmaf(__uint_as_float(vb[jj]), kLog2e, -mbb));
+          sa[jj & 3] += fa[jj];
+          sb[jj & 3] += fb[jj];
         }
-        const float inv = __fdividef(qs, sum);
+        const float inva = __fdividef(qs, (sa[0] + sa[1]) + (sa[2] + sa[3]));
+        const float invb = __fdividef(qs, (sb[0] + sb[1]) + (sb[2] + sb[3]));
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const __half2 x = __floats2half2_rn(f[2 * jj] * inv, f[2 * jj + 1] * inv);
-          hq[c][jj] = *reinterpret_cast<const uint32_t*>(&x);
+          const __half2 xa = __floats2half2_rn(fa[2 * jj] * inva, fa[2 * jj + 1] * inva);
+          const __half2 xb = __floats2half2_rn(fb[2 * jj] * invb, fb[2 * jj + 1] * invb);
+          hq[c][jj] = *reinterpret_cast<const uint32_t*>(&xa);
+          hq[c + 1][jj] = *reinterpret_cast<const uint32_t*>(&xb);
         }
       }
       tc_fence_before();
       mbar_arrive(&ctl->dq_empty[b]);
+      if (tr) P.trace[i * 16 + 2] = clock64();
       const int bq = ring_b(i);
       if (i >= NB) mbar_wait(&ctl->q_free[bq], ring_par(i - NB));   // MMA2(i - NB) has read this Q tile
+      if (tr) P.trace[i * 16 + 3] = clock64();
       uint8_t* qrow = sQ + (size_t)bq * 32768 + (size_t)row * 128;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -634,6 +684,7 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
       }
       fence_proxy_async();
       mbar_arrive(&ctl->q_ready[bq]);
+      if (tr) P.trace[i * 16 + 4] = clock64();
     }
   } else {
     // =============================== o-warps: LayerNorm + residual + store =======
@@ -648,58 +699,75 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
       const __half* rp = P.res + (((size_t)img * P.H + (y0 + tyr)) * P.W + (x0 + txr)) * C;
       const int bo = ring_b(i);
       const uint32_t dout = taddr + 256u + (uint32_t)(bo * C) + lane_off;
+      // residual of the first 64 channels: issued before the wait so its latency hides behind it
+      uint4 rv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 6 && lane == 0 && i < 48;
+      if (tr) P.trace[i * 16 + 8] = clock64();
       mbar_wait(&ctl->do_full[bo], ring_par(i));
       tc_fence_after();
+      if (tr) P.trace[i * 16 + 9] = clock64();
       // pass 1: mean and variance of (acc + bias) over the C channels of this pixel, shifted by
       // the first channel's value (single sweep, no cancellation)
-      float sh = 0.f, s1 = 0.f, s2 = 0.f;
+      float sh = 0.f;
+      float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c = 0; c < C; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(dout + (uint32_t)c, v);
+      for (int c = 0; c < C; c += 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(dout + (uint32_t)c, v0);
+        tmem_ld32(dout + (uint32_t)c + 32, v1);
         tmem_ld_wait();
-        if (c == 0) sh = __uint_as_float(v[0]) + __ldg(P.bias);
+        if (c == 0) sh = __uint_as_float(v0[0]) + sbias[0];
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const float dlt = __uint_as_float(v[jj]) + __ldg(P.bias + c + jj) - sh;
-          s1 += dlt;
-          s2 = fmaf(dlt, dlt, s2);
+          const float d0 = __uint_as_float(v0[jj]) + sbias[c + jj] - sh;
+          const float d1 = __uint_as_float(v1[jj]) + sbias[c + 32 + jj] - sh;
+          p1[jj & 1] += d0;
+          p1[2 + (jj & 1)] += d1;
+          p2[jj & 1] = fmaf(d0, d0, p2[jj & 1]);
+          p2[2 + (jj & 1)] = fmaf(d1, d1, p2[2 + (jj & 1)]);
         }
       }
+      const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
       const float dm = s1 * (1.f / C);
       const float mean = sh + dm;
       const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - dm * dm, 0.f) + 1e-5f);
+      if (tr) P.trace[i * 16 + 10] = clock64();
       if (lane == 0) bulk_wait_read0_();     // the slab's previous TMA store has read it
       __syncwarp();
+      if (tr) P.trace[i * 16 + 11] = clock64();
 #pragma unroll 1
-      for (int c = 0; c < C; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(dout + (uint32_t)c, v);
-        const uint4* r4 = reinterpret_cast<const uint4*>(rp + c);
-        uint4 rv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rv[q] = __ldg(r4 + q);
+      for (int c0 = 0; c0 < C; c0 += 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(dout + (uint32_t)c0, v0);
+        tmem_ld32(dout + (uint32_t)c0 + 32, v1);
         tmem_ld_wait();
-        if (c + 32 >= C) {                   // last read of this accumulator
+        if (c0 + 64 >= C) {                  // last read of this accumulator
           tc_fence_before();
           mbar_arrive(&ctl->do_empty[bo]);
         }
-        uint8_t* blk = slab + (size_t)(c >> 6) * (32 * 128) + (size_t)lane * 128;
+        uint8_t* blk = slab + (size_t)(c0 >> 6) * (32 * 128) + (size_t)lane * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
           uint32_t o[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const int ch = c + q * 8 + jj * 2;
+            const int ch = c0 + q * 8 + jj * 2;
             const float2 r2 = __half22float2(rh[jj]);
-            const float y0f = (__uint_as_float(v[q * 8 + jj * 2]) + __ldg(P.bias + ch) - mean) * rstd * __ldg(P.gain + ch) + r2.x;
-            const float y1f = (__uint_as_float(v[q * 8 + jj * 2 + 1]) + __ldg(P.bias + ch + 1) - mean) * rstd * __ldg(P.gain + ch + 1) + r2.y;
+            const float a0 = __uint_as_float(q < 4 ? v0[q * 8 + jj * 2] : v1[(q - 4) * 8 + jj * 2]);
+            const float a1 = __uint_as_float(q < 4 ? v0[q * 8 + jj * 2 + 1] : v1[(q - 4) * 8 + jj * 2 + 1]);
+            const float y0f = (a0 + sbias[ch] - mean) * rstd * sgain[ch] + r2.x;
+            const float y1f = (a1 + sbias[ch + 1] - mean) * rstd * sgain[ch + 1] + r2.y;
             const __half2 hh = __floats2half2_rn(y0f, y1f);
             o[jj] = *reinterpret_cast<const uint32_t*>(&hh);
           }
-          *reinterpret_cast<uint4*>(blk + (((((c & 63) >> 3) + q) ^ (lane & 7)) << 4)) =
-              make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(blk + ((q ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (c0 + 64 < C) {                   // residual of the next 64 channels
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rp + c0 + 64) + q);
         }
       }
       fence_proxy_async();
@@ -712,6 +780,7 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
                         y0 + (px >> P.tile_w_log2), img);
         bulk_commit_();
       }
+      if (tr) P.trace[i * 16 + 12] = clock64();
     }
     if (lane == 0) bulk_wait0_();
     tc_fence_before();
@@ -877,7 +946,7 @@ int qout_plan(QOutOp* op, int maxB, const __half* xn, int H, int W, int C, const
   P.gain = gain;
   P.res = res;
   P.q_scale = 0.17677669529663687f;   // 32^-0.5 (SDD:742)
-  const int fixed = (C <= 128 ? 2 : 1) * 32768 + 2 * C * 256 + 1024 + (int)sizeof(QCtl) + 64;
+  const int fixed = (C <= 128 ? 2 : 1) * 32768 + 2 * C * 256 + 1024 + (int)sizeof(QCtl) + (C <= 128 ? 8 * C : 0) + 64;
   int stages = (kSmemBudget - fixed) / kQStage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
@@ -938,6 +1007,26 @@ int qout_run(QOutOp& op, int B, cudaStream_t s) {
   QOutLaunch L = *reinterpret_cast<QOutLaunch*>(op.impl);
   L.P.total_tiles = B * L.P.tpi;
   const int grid = std::min(L.P.total_tiles, num_sms());
+  if (getenv("PRG_QOUT_TRACE") != nullptr && L.C == 64) {
+    // debug timeline of CTA 0 (synchronous): q-warp  0 loop top | 1 Dq ready | 2 softmax done |
+    // 3 Q tile free | 4 Q written;  MMA warp  5 MMA1 go | 6 MMA2 loop top | 7 MMA2 go;
+    // o-warp  8 loop top | 9 Do ready | 10 stats done | 11 slab free | 12 stored
+    long long* d = nullptr;
+    PRG_CUDA_OK(cudaMalloc(&d, 48 * 16 * sizeof(long long)));
+    PRG_CUDA_OK(cudaMemset(d, 0, 48 * 16 * sizeof(long long)));
+    L.P.trace = d;
+    int rc = qout_launch<64>(L, grid, s);
+    long long h[48 * 16];
+    PRG_CUDA_OK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    const long long t0 = h[1];
+    for (int t = 0; t < 32; ++t) {
+      fprintf(stderr, "tile %2d:", t);
+      for (int k = 0; k < 13; ++k) fprintf(stderr, " %6lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+    return rc;
+  }
   if (L.C == 64) return qout_launch<64>(L, grid, s);
   if (L.C == 128) return qout_launch<128>(L, grid, s);
   return qout_launch<256>(L, grid, s);
