@@ -98,6 +98,7 @@ struct Item {
 struct Conv2Params {
   ConvParams c;
   int halo, wres, n_tiles, stages;
+  int pair;             // per-tap mode, BN = 128: an item is TWO adjacent M tiles sharing every B stage
   int total_items;      // per-tap: m_tiles * n_tiles * classes ; halo: number of row segments
   int m_tiles;          // per-tap: tiles_x * tiles_y * B
   int rseg, segs_per_strip;
@@ -121,7 +122,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
                                                    // while tile i+1 is being written
   // TMEM: BN = 64 owns all 512 columns (eight accumulators, halo mode walks them as a ring),
   // the wider tiles two accumulators.
-  constexpr int kTmemCols = (BN == 64) ? 512 : 2 * BN;
+  constexpr int kTmemCols = 512;
   const uint32_t acc_mask = P.halo ? 7u : 1u;      // accumulator slots - 1
   const int acc_log2 = P.halo ? 3 : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -171,12 +172,13 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   const uint32_t taddr = ctl->tmem_addr;
 
   // item -> coordinates (per-tap mode)
-  auto decode = [&](int item) {
+  auto decode = [&](int item, int sub = 0) {
     Item it;
     it.n_tile = item % P.n_tiles;
     int m = item / P.n_tiles;
-    it.cls = m / P.m_tiles;
-    m -= it.cls * P.m_tiles;
+    const int m_items = P.m_tiles >> P.pair;      // pair mode: item m covers tiles 2m, 2m + 1
+    it.cls = m / m_items;
+    m = ((m - it.cls * m_items) << P.pair) + sub;
     it.img = m / tiles_per_img;
     const int t_in = m - it.img * tiles_per_img;
     const int tyi = t_in / p.tiles_x, txi = t_in - tyi * p.tiles_x;
@@ -234,11 +236,12 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           if (p.classes == 4) { pad_y = 1 - (it.cls >> 1); pad_x = 1 - (it.cls & 1); }
           const int wz = p.w_batched ? it.img : 0;
           const int wk0 = it.cls * num_kb * kBlockK;
+          const Item i2 = P.pair ? decode(item, 1) : it;
           for (int kb = 0; kb < num_kb; ++kb) {
             const int tap = kb / chunks, cc = kb - tap * chunks;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* a_dst = sA + (size_t)stage * P.a_slot;
-            mbar_arrive_expect_tx(&ctl->full[stage], kABytes + (P.wres ? 0 : kBBytes));
+            mbar_arrive_expect_tx(&ctl->full[stage], (kABytes << P.pair) + (P.wres ? 0 : kBBytes));
             if (p.mode == 0) {
               const int ky = tap / p.kw, kx = tap - ky * p.kw;
               const int dy = ky - pad_y, dx = kx - pad_x;
@@ -248,6 +251,14 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               else
                 tma_load_4d(&tmA1, &ctl->full[stage], a_dst, (cc - p.chunks0) * kBlockK, it.x0 + dx,
                             it.y0 + dy, it.img);
+              if (P.pair) {   // second M tile of the item, same tap / channel chunk
+                if (cc < p.chunks0)
+                  tma_load_4d(&tmA0, &ctl->full[stage], a_dst + kABytes, cc * kBlockK, i2.x0 + dx,
+                              i2.y0 + dy, i2.img);
+                else
+                  tma_load_4d(&tmA1, &ctl->full[stage], a_dst + kABytes, (cc - p.chunks0) * kBlockK,
+                              i2.x0 + dx, i2.y0 + dy, i2.img);
+              }
             } else {
               const int ey = (tap >> 2) - 1, ex = (tap & 3) - 1;
               const int qy = ey >> 1, ry = ey & 1, qx = ex >> 1, rx = ex & 1;
@@ -358,7 +369,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const uint32_t acc = tcount & 1;
         mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_addr = taddr_u + acc * BN;
+        const uint32_t d_addr = taddr_u + ((acc * BN) << P.pair);
         const uint32_t w_base = sW_u + (uint32_t)(it.n_tile * num_kb) * kBBytes;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&ctl->full[stage], phase);
@@ -373,6 +384,13 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                        (kb > 0 || k > 0) ? 1u : 0u);
+            if (P.pair) {   // the second M tile reuses the B stage
+              const uint64_t da2 = mkdesc(a_addr + kABytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16(d_addr + BN, da2 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+            }
             umma_commit(&ctl->empty[stage]);
             if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
           }
@@ -392,12 +410,13 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     constexpr int kHalfCols = BN / 2;
     uint32_t tcount = 0;
 
-    auto do_tile = [&](int img, int x0, int y0, int n_tile, int cls) {
+    uint32_t scount = 0;   // tiles staged so far (tcount counts items: one or, in pair mode, two tiles)
+    auto do_tile = [&](int img, int x0, int y0, int n_tile, int cls, int sub = 0, bool last = true) {
       const int n0 = n_tile * BN;
       const int cpy = cls >> 1, cpx = cls & 1;
       const uint32_t acc = tcount & acc_mask;
       // (1) the TMA store that last used this staging buffer must have finished reading it
-      uint8_t* sOut = sO + (tcount % kOutBufs) * kStageOut;
+      uint8_t* sOut = sO + (scount % kOutBufs) * kStageOut;
       if (e == 0) {
         if (kOutBufs == 3) bulk_wait_read2();
         else if (kOutBufs == 2) bulk_wait_read1();
@@ -409,7 +428,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       mbar_wait(&ctl->tmem_full[acc], (tcount >> acc_log2) & 1);
       tc_fence_after();
       if (tr) P.trace[tcount * 8 + 5] = clock64();       // accumulator complete
-      const uint32_t trow = taddr + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t trow = taddr + ((acc * BN) << P.pair) + (uint32_t)(sub * BN) +
+                            ((uint32_t)(quarter * 32) << 16);
       const float* sbias = ctl->bias + n0;
 
       const int oy = (y0 + tyr) * p.out_scale + cpy, ox = (x0 + txr) * p.out_scale + cpx;
@@ -576,9 +596,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           *reinterpret_cast<uint4*>(box + (((ch0 + q) ^ (row & 7)) << 4)) = o;
         }
       }
-      // (3) accumulator drained -> hand it back to the MMA warp
+      // (3) accumulator drained -> hand it back to the MMA warp (pair mode: after both tiles)
       tc_fence_before();
-      mbar_arrive(&ctl->tmem_empty[acc]);
+      if (last) mbar_arrive(&ctl->tmem_empty[acc]);
       if (tr) P.trace[tcount * 8 + 6] = clock64();       // accumulator drained
       // (4) staging tile complete and visible to the async proxy
       fence_proxy_async();
@@ -614,7 +634,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           ctl->colmax[e] = INT_MIN;   // slot e is touched again only after the next epi_bar
         }
       }
-      ++tcount;
+      ++scount;
+      if (last) ++tcount;
     };
 
 
@@ -801,8 +822,10 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         }
       } else {
         for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-          const Item it = decode(item);
-          do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls);
+          for (int sub = 0; sub <= P.pair; ++sub) {
+            const Item it = decode(item, sub);
+            do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls, sub, sub == P.pair);
+          }
         }
       }
       if (e == 0) bulk_wait0();
@@ -981,7 +1004,11 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   }
   P.dbg_flags = conv_flags();
   P.w_bytes = P.wres ? (int)w_all : 0;
-  P.a_slot = P.halo ? kHaloSlot : kABytes;
+  // pair mode: with N = 128 one B stage (16 KB) only feeds 256 MMA cycles, and the loads in
+  // flight (not L2 bandwidth) bound the kernel; two M tiles per B stage need a third less
+  P.pair = (bn == 128 && !P.halo && !P.wres && mode == 0 && epi != EPI_QKV && !(conv_flags() & 2) &&
+            (p.tiles_x * p.tiles_y) % 2 == 0) ? 1 : 0;
+  P.a_slot = P.halo ? kHaloSlot : (kABytes << P.pair);
   const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes);
   int stages = (kSmemBudget - fixed - P.w_bytes) / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -996,7 +1023,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   if (P.halo) {
     halo_segments(&P, B, sms);
   } else {
-    P.total_items = P.m_tiles * P.n_tiles * classes;
+    P.total_items = (P.m_tiles >> P.pair) * P.n_tiles * classes;
   }
   L->grid = std::min(P.total_items, sms);
 
@@ -1124,15 +1151,15 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
   if (P.halo)
     halo_segments(&P, B, num_sms());
   else
-    P.total_items = P.m_tiles * P.n_tiles * P.c.classes;
+    P.total_items = (P.m_tiles >> P.pair) * P.n_tiles * P.c.classes;
   L.grid = std::min(P.total_items, num_sms());
   return conv2_run(L, stream);
 }
 
 const char* conv_op_describe(const ConvOp& op, char* buf, int n) {
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
-  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
-           L->P.halo, L->P.wres, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
+  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
+           L->P.halo, L->P.wres, L->P.pair, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
   return buf;
 }
 
