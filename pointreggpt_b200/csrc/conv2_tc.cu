@@ -117,9 +117,11 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const __grid_constant__ CUtensorMap tmO3, const Conv2Params P) {
   const ConvParams& p = P.c;
   constexpr int kBBytes = BN * kBlockK * 2;
-  constexpr int kStageOut = (BN / 64) * kABytes;   // fp16 staging tile, 64-channel boxes
-  constexpr int kOutBufs = (BN <= 128) ? 2 : 1;    // double-buffered: the TMA store of tile i drains
-                                                   // while tile i+1 is being written
+  // fp16 staging.  BN = 64: eight per-warp 4 KB slabs.  BN >= 128: ONE 64-channel box (16 KB) that
+  // the epilogue fills and stores BN/64 times per tile -- the shared memory this frees buys a
+  // fourth load stage, and these layers are bound by the bytes in flight, not by the epilogue.
+  constexpr int kStageOut = (BN == 64) ? 2 * kABytes : kABytes;
+  constexpr int kOutBufs = 1;
   // TMEM: BN = 64 owns all 512 columns (eight accumulators, halo mode walks them as a ring),
   // the wider tiles two accumulators.
   constexpr int kTmemCols = 512;
@@ -441,7 +443,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         // channel LayerNorm over the whole row (BN == Cout); the two threads that share a row
         // exchange their half-row partial sums through shared memory (exact two-pass variance)
         float s = 0.f;
-        for (int c = half * kHalfCols; c < (half + 1) * kHalfCols; c += 32) {
+        for (int c = half * 32; c < BN; c += 64) {
           uint32_t v[32];
           tmem_ld32(trow + c, v);
           tmem_ld_wait();
@@ -453,7 +455,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         ln_mean = (ctl->rowsum[0][row] + ctl->rowsum[1][row]) * (1.f / BN);
         epi_bar();
         float ss = 0.f;
-        for (int c = half * kHalfCols; c < (half + 1) * kHalfCols; c += 32) {
+        for (int c = half * 32; c < BN; c += 64) {
           uint32_t v[32];
           tmem_ld32(trow + c, v);
           tmem_ld_wait();
@@ -469,11 +471,20 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       }
       const int qkv_part = (EPI == EPI_QKV) ? (n0 >> 7) : 0;
 
+      // one 64-column box per pass; inside it this warp owns columns [half * 32, half * 32 + 32)
 #pragma unroll 1
-      for (int c = half * kHalfCols; c < (half + 1) * kHalfCols; c += 32) {
+      for (int c = half * 32; c < BN; c += 64) {
+        if (c >= 64) {   // the previous box's TMA store must have read the staging tile
+          if (e == 0) bulk_wait_read0();
+          epi_bar();
+        }
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
+        if (c + 64 >= BN) {   // last read of this accumulator (pair mode: of the item's last tile)
+          tc_fence_before();
+          if (last) mbar_arrive(&ctl->tmem_empty[acc]);
+        }
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + sbias[c + j];
@@ -580,7 +591,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           }
         }
         // fp16 -> staging tile: box (c / 64), row `row`, 16-byte chunk index XOR (row & 7)
-        uint8_t* box = sOut + (size_t)(c >> 6) * kABytes + (size_t)row * 128;
+        uint8_t* box = sOut + (size_t)row * 128;
         const int ch0 = (c & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -595,21 +606,16 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           o.w = *reinterpret_cast<uint32_t*>(&h3);
           *reinterpret_cast<uint4*>(box + (((ch0 + q) ^ (row & 7)) << 4)) = o;
         }
+        // box complete and visible to the async proxy -> store it
+        fence_proxy_async();
+        epi_bar();
+        if (e == 0 && !(P.dbg_flags & 4)) {
+          const CUtensorMap* tmo = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
+          tma_store_4d(tmo, sOut, n0 + (c & ~63), x0, y0, img);
+          bulk_commit();
+        }
       }
-      // (3) accumulator drained -> hand it back to the MMA warp (pair mode: after both tiles)
-      tc_fence_before();
-      if (last) mbar_arrive(&ctl->tmem_empty[acc]);
       if (tr) P.trace[tcount * 8 + 6] = clock64();       // accumulator drained
-      // (4) staging tile complete and visible to the async proxy
-      fence_proxy_async();
-      epi_bar();
-      if (e == 0 && !(P.dbg_flags & 4)) {
-        const CUtensorMap* tmo = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
-#pragma unroll
-        for (int bx = 0; bx < BN / 64; ++bx)
-          tma_store_4d(tmo, sOut + (size_t)bx * kABytes, n0 + bx * 64, x0, y0, img);
-        bulk_commit();
-      }
       if (EPI == EPI_GN) {
         // one 64-bit fixed-point atomic per (group, moment) of this tile: order-independent.
         // Slots were each written exactly once above; summed here in a fixed order.
@@ -984,7 +990,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   P.num_kb = ntaps * (cin / 64);
   P.m_tiles = p.tiles_x * p.tiles_y * B;
   const int b_bytes = bn * 128;
-  const int stage_out = (bn / 64) * kABytes * (bn <= 128 ? 2 : 1);
+  const int stage_out = (bn == 64) ? 2 * kABytes : kABytes;
   const int fixed = stage_out + kCtlBytes + 1024;
 
   // ---- mode selection
