@@ -109,14 +109,22 @@ struct Conv2Params {
   int dbg_flags;        // debug: bit2 = skip the output TMA store, bit3 = skip GN flush
 };
 
-template <int BN, int EPI>
+// CG = 2 (per-tap mode, BN = 256): the two CTAs of a cluster work as a tcgen05 CTA pair on M = 256
+// (two adjacent M tiles): each CTA loads its own A tile and HALF of every B stage, the leader CTA
+// issues tcgen05.mma.cta_group::2, and each CTA drains its own 128 accumulator rows.  Per SM a
+// K block costs 32 KB of loads instead of 48 KB -- these layers sit at the ~64 B/clk/SM the TMA
+// path sustains, not at the tensor-pipe limit.
+template <int BN, int EPI, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
         const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
         const __grid_constant__ CUtensorMap tmO3, const Conv2Params P) {
   const ConvParams& p = P.c;
-  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kBBytes = (BN / CG) * kBlockK * 2;   // B rows this CTA stages per K block
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int item0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // per-tap item walk
+  const int istep = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // fp16 staging.  BN = 64: eight per-warp 4 KB slabs.  BN >= 128: ONE 64-channel box (16 KB) that
   // the epilogue fills and stores BN/64 times per tile -- the shared memory this frees buys a
   // fourth load stage, and these layers are bound by the bytes in flight, not by the epilogue.
@@ -155,13 +163,18 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     mbar_init(&ctl->wfull, 1);
     for (int a = 0; a < 8; ++a) {
       mbar_init(&ctl->tmem_full[a], 1);
-      mbar_init(&ctl->tmem_empty[a], BN == 64 ? kEpiThreads / 2 : kEpiThreads);
+      mbar_init(&ctl->tmem_empty[a], (BN == 64 ? kEpiThreads / 2 : kEpiThreads) * CG);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&ctl->tmem_addr, kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_2cta(&ctl->tmem_addr, kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(&ctl->tmem_addr, kTmemCols);
+      tmem_relinquish();
+    }
   }
   if (EPI == EPI_QKV && threadIdx.x < 128) ctl->colmax[threadIdx.x] = INT_MIN;
   for (int i = threadIdx.x; i < BN * P.n_tiles; i += kThreads)
@@ -169,7 +182,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   if (EPI == EPI_LN_RES)
     for (int i = threadIdx.x; i < BN; i += kThreads) ctl->gain[i] = __ldg(p.ln_g + i);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t taddr = ctl->tmem_addr;
 
@@ -178,9 +192,10 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     Item it;
     it.n_tile = item % P.n_tiles;
     int m = item / P.n_tiles;
-    const int m_items = P.m_tiles >> P.pair;      // pair mode: item m covers tiles 2m, 2m + 1
+    const int msh = (CG == 2) ? 1 : P.pair;       // pair mode / CTA pair: item m covers tiles 2m, 2m + 1
+    const int m_items = P.m_tiles >> msh;
     it.cls = m / m_items;
-    m = ((m - it.cls * m_items) << P.pair) + sub;
+    m = ((m - it.cls * m_items) << msh) + sub;
     it.img = m / tiles_per_img;
     const int t_in = m - it.img * tiles_per_img;
     const int tyi = t_in / p.tiles_x, txi = t_in - tyi * p.tiles_x;
@@ -232,8 +247,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           }
         }
       } else {
-        for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-          const Item it = decode(item);
+        const uint32_t full0 = (CG == 2) ? mapa_u32(smem_u32(&ctl->full[0]), 0) : 0u;   // leader's barriers
+        for (int item = item0; item < P.total_items; item += istep) {
+          const Item it = decode(item, (int)cta_rank);
           int pad_y = p.pad, pad_x = p.pad;
           if (p.classes == 4) { pad_y = 1 - (it.cls >> 1); pad_x = 1 - (it.cls & 1); }
           const int wz = p.w_batched ? it.img : 0;
@@ -243,6 +259,27 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             const int tap = kb / chunks, cc = kb - tap * chunks;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* a_dst = sA + (size_t)stage * P.a_slot;
+            if (CG == 2) {
+              // both CTAs' bytes are counted on the leader's barrier
+              const uint32_t fb = full0 + (uint32_t)stage * 8u;
+              if (cta_rank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2 * (kABytes + kBBytes));
+              if (p.mode == 0) {
+                const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                const int dy = ky - pad_y, dx = kx - pad_x;
+                if (cc < p.chunks0)
+                  tma_load_4d_2cta(&tmA0, fb, a_dst, cc * kBlockK, it.x0 + dx, it.y0 + dy, it.img);
+                else
+                  tma_load_4d_2cta(&tmA1, fb, a_dst, (cc - p.chunks0) * kBlockK, it.x0 + dx, it.y0 + dy, it.img);
+              } else {
+                const int ey = (tap >> 2) - 1, ex = (tap & 3) - 1;
+                const int qy = ey >> 1, ry = ey & 1, qx = ex >> 1, rx = ex & 1;
+                tma_load_5d_2cta(&tmA0, fb, a_dst, rx * p.cin0 + cc * kBlockK, it.x0 + qx, ry, it.y0 + qy, it.img);
+              }
+              tma_load_3d_2cta(&tmB, fb, sB + (size_t)stage * kBBytes, wk0 + kb * kBlockK,
+                               it.n_tile * BN + (int)cta_rank * (BN / 2), wz);
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_arrive_expect_tx(&ctl->full[stage], (kABytes << P.pair) + (P.wres ? 0 : kBBytes));
             if (p.mode == 0) {
               const int ky = tap / p.kw, kx = tap - ky * p.kw;
@@ -366,7 +403,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         tcount += (uint32_t)nr;
       }
     } else {
-      for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+      for (int item = item0; item < P.total_items; item += istep) {
+        if (CG == 2 && cta_rank != 0) break;    // only the leader CTA of a pair issues MMAs
         const Item it = decode(item);
         const uint32_t acc = tcount & 1;
         mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
@@ -382,19 +420,29 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           if (elect_one()) {
             const uint64_t da = mkdesc(a_addr);
             const uint64_t db = mkdesc(b_addr);
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                       (kb > 0 || k > 0) ? 1u : 0u);
-            if (P.pair) {   // the second M tile reuses the B stage
-              const uint64_t da2 = mkdesc(a_addr + kABytes);
+            if (CG == 2) {
+              constexpr uint32_t idesc2 = idesc_f16(2 * kBlockM, BN);
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
-                umma_f16(d_addr + BN, da2 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                umma_f16_2cta(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2,
+                              (kb > 0 || k > 0) ? 1u : 0u);
+              umma_commit_2cta(&ctl->empty[stage]);
+              if (kb == num_kb - 1) umma_commit_2cta(&ctl->tmem_full[acc]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                          (kb > 0 || k > 0) ? 1u : 0u);
+              if (P.pair) {   // the second M tile reuses the B stage
+                const uint64_t da2 = mkdesc(a_addr + kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16(d_addr + BN, da2 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit(&ctl->empty[stage]);
+              if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
             }
-            umma_commit(&ctl->empty[stage]);
-            if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
           }
           __syncwarp();
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -483,7 +531,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         tmem_ld_wait();
         if (c + 64 >= BN) {   // last read of this accumulator (pair mode: of the item's last tile)
           tc_fence_before();
-          if (last) mbar_arrive(&ctl->tmem_empty[acc]);
+          if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->tmem_empty[acc]), 0));   // leader's barrier
+          else if (last) mbar_arrive(&ctl->tmem_empty[acc]);
         }
         float f[32];
 #pragma unroll
@@ -827,7 +876,12 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           for (int j = 0; j < nr; ++j) do_tile(img, x0, y0 + j, 0, 0);
         }
       } else {
-        for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+        for (int item = item0; item < P.total_items; item += istep) {
+          if (CG == 2) {
+            const Item it = decode(item, (int)cta_rank);
+            do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls);
+            continue;
+          }
           for (int sub = 0; sub <= P.pair; ++sub) {
             const Item it = decode(item, sub);
             do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls, sub, sub == P.pair);
@@ -839,10 +893,12 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     tc_fence_before();
   }
 
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // neither CTA leaves while the other may still signal it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(taddr, kTmemCols);
+    if (CG == 2) tmem_dealloc_2cta(taddr, kTmemCols);
+    else tmem_dealloc(taddr, kTmemCols);
   }
 }
 
@@ -905,6 +961,7 @@ struct Conv2Launch {
   Conv2Params P;
   int bn, epi, smem;
   int grid;
+  int cg;   // 2 = CTA-pair kernel (cluster of two, tcgen05 cta_group::2)
 };
 
 static int g_conv_flags = -1;  // PRG_CONV_FLAGS bit0: disable the halo-ring mode (A/B measurements)
@@ -1015,7 +1072,11 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   P.pair = (bn == 128 && !P.halo && !P.wres && mode == 0 && epi != EPI_QKV && !(conv_flags() & 2) &&
             (p.tiles_x * p.tiles_y) % 2 == 0) ? 1 : 0;
   P.a_slot = P.halo ? kHaloSlot : (kABytes << P.pair);
-  const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes);
+  // CTA pair: N = 256 per-tap layers are bound by the bytes each SM pulls through TMA; as a pair
+  // each CTA stages only half of B
+  L->cg = (bn == 256 && !P.halo && !P.wres && !P.pair && !w_batched && (epi == EPI_BIAS || epi == EPI_GN) &&
+           (p.tiles_x * p.tiles_y) % 2 == 0 && !(conv_flags() & 16)) ? 2 : 1;
+  const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes / L->cg);
   int stages = (kSmemBudget - fixed - P.w_bytes) / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
@@ -1029,9 +1090,9 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   if (P.halo) {
     halo_segments(&P, B, sms);
   } else {
-    P.total_items = (P.m_tiles >> P.pair) * P.n_tiles * classes;
+    P.total_items = (P.m_tiles >> (P.pair | (L->cg == 2))) * P.n_tiles * classes;
   }
-  L->grid = std::min(P.total_items, sms);
+  L->grid = (L->cg == 2) ? 2 * std::min(P.total_items, sms / 2) : std::min(P.total_items, sms);
 
   // ---- tensor maps: activations
   for (int si = 0; si < 2; ++si) {
@@ -1062,7 +1123,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
     const uint64_t ktot = (uint64_t)classes * ntaps * cin;
     uint64_t dims[3] = {ktot, (uint64_t)Cout, (uint64_t)(w_batched ? B : 1)};
     uint64_t str[2] = {ktot * 2, ktot * 2 * Cout};
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint32_t box[3] = {64, (uint32_t)(bn / L->cg), 1};
     int rc = tmap_encode_f16(&L->tmB, w, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -1106,7 +1167,40 @@ static int launch2(const Conv2Launch& L, cudaStream_t stream) {
   return PRG_OK;
 }
 
+template <int BN, int EPI>
+static int launch2_pair(const Conv2Launch& L, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < L.smem) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_conv2<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemBudget));
+    configured = kSmemBudget;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PRG_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv2<BN, EPI, 2>, L.tmA0, L.tmA1, L.tmB, L.tmO[0], L.tmO[1], L.tmO[2],
+                                 L.tmO[3], L.P));
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
 static int conv2_run(const Conv2Launch& L, cudaStream_t stream) {
+  if (L.cg == 2) {
+    if (L.bn == 256 && L.epi == EPI_BIAS) return launch2_pair<256, EPI_BIAS>(L, stream);
+    if (L.bn == 256 && L.epi == EPI_GN) return launch2_pair<256, EPI_GN>(L, stream);
+    set_error("conv_run: no CTA-pair kernel for N tile %d / epilogue %d", L.bn, L.epi);
+    return PRG_ERR_ARG;
+  }
 #define PRG_CASE(BN_, EPI_) \
   if (L.bn == BN_ && L.epi == EPI_) return launch2<BN_, EPI_>(L, stream);
   PRG_CASE(64, EPI_BIAS) PRG_CASE(128, EPI_BIAS) PRG_CASE(256, EPI_BIAS)
@@ -1157,15 +1251,15 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
   if (P.halo)
     halo_segments(&P, B, num_sms());
   else
-    P.total_items = (P.m_tiles >> P.pair) * P.n_tiles * P.c.classes;
-  L.grid = std::min(P.total_items, num_sms());
+    P.total_items = (P.m_tiles >> (P.pair | (L.cg == 2))) * P.n_tiles * P.c.classes;
+  L.grid = (L.cg == 2) ? 2 * std::min(P.total_items, num_sms() / 2) : std::min(P.total_items, num_sms());
   return conv2_run(L, stream);
 }
 
 const char* conv_op_describe(const ConvOp& op, char* buf, int n) {
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
-  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
-           L->P.halo, L->P.wres, L->P.pair, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
+  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d cg=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
+           L->P.halo, L->P.wres, L->P.pair, L->cg, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
   return buf;
 }
 
