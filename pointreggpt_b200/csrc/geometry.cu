@@ -9,6 +9,8 @@
 // All fp32 arithmetic uses the _rn intrinsics so nvcc can neither contract nor
 // reorder it; the z-buffer is an order-independent atomicMin on the bit pattern of
 // the (strictly positive) depth, so the result is deterministic and bit-exact.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace prg {
@@ -27,6 +29,14 @@ __device__ __forceinline__ Intr load_intr(const float* __restrict__ K, int b) {
   i.cx = __ldg(k + 2);
   i.cy = __ldg(k + 5);
   return i;
+}
+
+// row / column of pixel i (i < 2^23) without an integer division: float estimate + fix-up
+__device__ __forceinline__ void row_col(int i, int W, float inv_w, int& r, int& c) {
+  r = __float2int_rz(__fmul_rn((float)i, inv_w));
+  c = i - r * W;
+  if (c < 0) { c += W; --r; }
+  if (c >= W) { c -= W; ++r; }
 }
 
 __device__ __forceinline__ void unproject(int r, int c, float z, const Intr& k, float& x, float& y) {
@@ -65,6 +75,7 @@ k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
   const Intr k = load_intr(K, b);
   unsigned* zimg = zbuf + (size_t)b * HW;
   const float* dimg = depth + (size_t)b * HW;
+  const float inv_w = 1.f / (float)W;
   for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < HW; i4 += gridDim.x * blockDim.x) {
     const int i = i4 * 4;
     float d[4];
@@ -75,11 +86,14 @@ k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
 #pragma unroll
       for (int j = 0; j < 4; ++j) d[j] = (i + j < HW) ? dimg[i + j] : 0.f;
     }
+    int r0, c0;
+    row_col(i, W, inv_w, r0, c0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float z0 = d[j];
       if (i + j < HW && z0 > lo && z0 < hi) {
-        const int r = (i + j) / W, c = (i + j) - r * W;
+        int r = r0, c = c0 + j;
+        if (c >= W) { c -= W; ++r; }
         float x, y, z = z0;
         unproject(r, c, z, k, x, y);
         rigid(sP, x, y, z);
@@ -146,7 +160,13 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
   const float* dimg = depth + (size_t)b * HW;
   float* pimg = pc + (size_t)b * HW * 3;
   uint8_t* vimg = valid + (size_t)b * HW;
-  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < HW; i4 += gridDim.x * blockDim.x) {
+  // per-warp transpose buffer: a lane produces 48 contiguous bytes (4 points); staged so that
+  // every store instruction of the warp writes 512 contiguous bytes
+  __shared__ float4 sT[8][96];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_w = 1.f / (float)W;
+  for (int base4 = blockIdx.x * blockDim.x; base4 * 4 < HW; base4 += gridDim.x * blockDim.x) {
+    const int i4 = base4 + threadIdx.x;
     const int i = i4 * 4;
     float d[4];
     const bool full = (i + 3 < HW) && (HW & 3) == 0;  // image bases stay 16-byte aligned
@@ -159,9 +179,12 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
     }
     float o[12];
     uint8_t ok[4];
+    int r0, c0;
+    row_col(i < HW ? i : 0, W, inv_w, r0, c0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int r = (i + j) / W, c = (i + j) - r * W;
+      int r = r0, c = c0 + j;
+      if (c >= W) { c -= W; ++r; }
       ok[j] = use_clip ? (d[j] > lo && d[j] < hi) : 1;
       const float z = ok[j] ? d[j] : invalid;
       float x, y;
@@ -170,7 +193,20 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
       o[j * 3 + 1] = ok[j] ? y : invalid;
       o[j * 3 + 2] = z;
     }
-    if (full) {
+    // the whole warp inside the image and 16-byte aligned: coalesced path
+    const int w0 = (base4 + warp * 32) * 4;           // first pixel of this warp
+    const bool warp_full = (w0 + 127 < HW) && (HW & 3) == 0;
+    if (warp_full) {
+      sT[warp][lane * 3 + 0] = make_float4(o[0], o[1], o[2], o[3]);
+      sT[warp][lane * 3 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+      sT[warp][lane * 3 + 2] = make_float4(o[8], o[9], o[10], o[11]);
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(pimg + (size_t)w0 * 3);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) __stcs(dst + q * 32 + lane, sT[warp][q * 32 + lane]);
+      __syncwarp();
+      *reinterpret_cast<uchar4*>(vimg + i) = make_uchar4(ok[0], ok[1], ok[2], ok[3]);
+    } else if (full) {
       float4* dst = reinterpret_cast<float4*>(pimg + (size_t)i * 3);
       __stcs(dst + 0, make_float4(o[0], o[1], o[2], o[3]));
       __stcs(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
@@ -319,14 +355,23 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
   if (B == 0) return PRG_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int HW = H * W;
-  const size_t n = (size_t)B * HW;
-  PRG_CUDA_OK(cudaMemsetAsync(depth_out, 0xFF, n * sizeof(float), s));
-  dim3 g1(grid_for(HW, 256, 4), B);
-  k_reproject_splat<<<g1, 256, 0, s>>>(depth, K, pose, clip_lo, clip_hi, (unsigned*)depth_out, HW,
-                                      H, W);
-  PRG_LAUNCH_CHECK();
-  k_zbuf_finalize<<<grid_for((int64_t)n, 256, 4), 256, 0, s>>>((unsigned*)depth_out, mask_out, n);
-  PRG_LAUNCH_CHECK();
+  // The z-buffer is depth_out itself.  Maps are processed in groups whose z-buffers (<= 32 MB) stay
+  // in the 126 MB L2 between the fill, the atomicMin splat and the in-place finalisation, so HBM
+  // sees the 9 algorithmic bytes per pixel (depth read, depth + mask written back once).
+  int group = (int)((32u << 20) / ((size_t)HW * sizeof(float)));
+  if (group < 1) group = 1;
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int nb = std::min(group, B - b0);
+    const size_t n = (size_t)nb * HW;
+    float* out = depth_out + (size_t)b0 * HW;
+    PRG_CUDA_OK(cudaMemsetAsync(out, 0xFF, n * sizeof(float), s));
+    dim3 g1(grid_for(HW, 256, 4), nb);
+    k_reproject_splat<<<g1, 256, 0, s>>>(depth + (size_t)b0 * HW, K + (size_t)b0 * 9, pose + (size_t)b0 * 16,
+                                        clip_lo, clip_hi, (unsigned*)out, HW, H, W);
+    PRG_LAUNCH_CHECK();
+    k_zbuf_finalize<<<grid_for((int64_t)n, 256, 4), 256, 0, s>>>((unsigned*)out, mask_out + (size_t)b0 * HW, n);
+    PRG_LAUNCH_CHECK();
+  }
   return PRG_OK;
 }
 
