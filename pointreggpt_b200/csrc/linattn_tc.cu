@@ -366,6 +366,7 @@ k_linattn_fold(const float* __restrict__ partials, const float* __restrict__ wou
   __shared__ float sS[kMaxChunks][32];   // exp(m_k - m) per chunk and channel of this head
   __shared__ float sN[32];               // 1 / (z n)
   __shared__ float sC[32 * 33];          // combined context [d][e]
+  __shared__ float sW[256 * 33];         // W_out[:, h*32 .. h*32+31] (C <= 256 rows; larger C loops)
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const float* base = partials + (size_t)b * cpi * kPartialFloats;
   if (tid < 32) {
@@ -399,20 +400,24 @@ k_linattn_fold(const float* __restrict__ partials, const float* __restrict__ wou
     sC[dd * 33 + (i & 31)] = a;
   }
   __syncthreads();
+  // this head's slice of the to_out weight, staged (coalesced) in blocks of 256 output channels
+  // instead of being re-read from global memory by every warp in a latency-bound loop
   const int dd = tid & 31;
   const float norm = sN[dd];
-  for (int c = tid >> 5; c < C; c += 8) {
-    const float4* w4 = reinterpret_cast<const float4*>(wout + (size_t)c * 128 + h * 32);
-    float a = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 w = __ldg(w4 + q);
-      a = fmaf(w.x, sC[dd * 33 + q * 4 + 0], a);
-      a = fmaf(w.y, sC[dd * 33 + q * 4 + 1], a);
-      a = fmaf(w.z, sC[dd * 33 + q * 4 + 2], a);
-      a = fmaf(w.w, sC[dd * 33 + q * 4 + 3], a);
+  for (int cb = 0; cb < C; cb += 256) {
+    const int nc = min(256, C - cb);
+    __syncthreads();
+    for (int i = tid; i < nc * 32; i += 256) {
+      const int c = i >> 5, e = i & 31;
+      sW[c * 33 + e] = __ldg(wout + (size_t)(cb + c) * 128 + h * 32 + e);
     }
-    weff[((size_t)b * C + c) * 128 + h * 32 + dd] = __float2half_rn(a * norm);
+    __syncthreads();
+    for (int c = tid >> 5; c < nc; c += 8) {
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) a = fmaf(sW[c * 33 + e], sC[dd * 33 + e], a);
+      weff[((size_t)b * C + cb + c) * 128 + h * 32 + dd] = __float2half_rn(a * norm);
+    }
   }
 }
 
