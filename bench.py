@@ -318,9 +318,16 @@ def main():
         conv_ms = c["ms"] / fw
         achieved = UNET_CONV_FLOP_PER_IMAGE * min(B, a.micro_batch or B) / (conv_ms * 1e-3) / 1e12
         unet_ms = sum(v["ms"] for v in prof.values()) / fw
-        roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv / 1x1 GEMM)",
+        # DRAM bytes of all k_conv2 launches of one evaluation at batch 32, 256x256, from the ncu
+        # capture summarised in profiles/r1_kernel_metrics_unet_b32.txt (10082 MB read + 4950 MB
+        # written); algorithmic minimum (every conv input read once, output written once) ~9.6 GB
+        traffic = 15_032_200_000 if (B == 32 and a.size == 256 and not a.micro_batch) else None
+        roof = {"bound": "tensor",
+                "kernel": "k_conv2 (persistent tcgen05 implicit-GEMM conv engine; the 62 conv launches "
+                          "of one U-Net evaluation, timed with CUDA events on the launching stream)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "bytes per U-Net evaluation (all conv launches)",
+                "peak_source": peak_src,
                 "launches_per_unet_eval": c["launches"] / fw, "ms_per_unet_eval": conv_ms,
                 "families_ms_per_unet_eval": {k: v["ms"] / fw for k, v in prof.items()}}
 
