@@ -433,7 +433,7 @@ k_linattn_fold(const float* __restrict__ partials, const float* __restrict__ wou
 //   o-warps (thread = pixel): + bias, channel LayerNorm * g, + residual x -> fp16 -> per-warp
 //          staging slab -> TMA store.
 // ------------------------------------------------------------------------------------------
-struct alignas(8) QCtl {
+struct alignas(16) QCtl {
   uint64_t full[kMaxStages], empty[kMaxStages];
   uint64_t dq_full[2], dq_empty[2];
   uint64_t q_ready[2], q_free[2], do_full[2], do_empty[2];
@@ -470,7 +470,8 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
   uint8_t* sO = sE + kWeffBytes;
   QCtl* ctl = reinterpret_cast<QCtl*>(sO + 4 * kSlabBytes);
   // bias / gain: shared-memory copies when they fit (C <= 128), else read through L1
-  float* scoef = reinterpret_cast<float*>(ctl + 1);
+  float* sxch = reinterpret_cast<float*>(ctl + 1);    // LayerNorm partial sums: [4 quarters][192]
+  float* scoef = sxch + 768;
   const float* sbias = (C <= 128) ? scoef : P.bias;
   const float* sgain = (C <= 128) ? scoef + C : P.gain;
 
@@ -496,11 +497,11 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&ctl->dq_full[b], 1);
-      mbar_init(&ctl->dq_empty[b], 128);
-      mbar_init(&ctl->q_ready[b], 128);
+      mbar_init(&ctl->dq_empty[b], 256);
+      mbar_init(&ctl->q_ready[b], 256);
       mbar_init(&ctl->q_free[b], 1);
       mbar_init(&ctl->do_full[b], 1);
-      mbar_init(&ctl->do_empty[b], 128);
+      mbar_init(&ctl->do_empty[b], 256);
     }
     mbar_init(&ctl->weff_full, 1);
     mbar_init(&ctl->weff_free, 1);
@@ -621,171 +622,200 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
-    // =============================== q-warps: softmax_d ==========================
+  } else {
+    // =============================== epilogue warps ==============================
+    // Symmetric roles: warp (quarter, hh) owns the 32 pixels of its TMEM lane quarter and, of those,
+    //   S(i):   the softmax of heads 2hh, 2hh+1 (D_q columns [64 hh, 64 hh + 64)) -> K block hh of Q
+    //   O(i-1): the LayerNorm / residual / store of output channels [hh C/2, (hh+1) C/2)
+    // so every scheduler holds two warps whose MUFU- and FMA-bound phases overlap.  The two warps of
+    // a quarter exchange their LayerNorm partial sums through shared memory (named barrier 1+quarter).
     const int quarter = warp & 3;
+    const int hh = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int tyr = row >> P.tile_w_log2, txr = row & (tile_w - 1);
+    constexpr int CH = C / 2;                      // output channels per warp
+    uint8_t* slab = sO + (size_t)quarter * kSlabBytes;
+    float* xch = sxch + quarter * 192;             // [2 hh][sum, centred squares, shift][32 lanes]
     const float qs = P.q_scale;
-    for (int i = 0; i < ntiles; ++i) {
+    auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
+
+    auto softmax_tile = [&](int i) {
       const int b = i & 1;
       const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 48;
       if (tr) P.trace[i * 16 + 0] = clock64();
       mbar_wait(&ctl->dq_full[b], (uint32_t)(i >> 1) & 1u);
-      tc_fence_after();
       if (tr) P.trace[i * 16 + 1] = clock64();
-      uint32_t hq[4][16];
-      // one head per 32-column chunk; two heads per step with independent reduction trees, so a
-      // lone warp per scheduler still finds independent instructions to issue
-#pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        uint32_t va[32], vb[32];
-        tmem_ld32(taddr + (uint32_t)(b * 128 + c * 32) + lane_off, va);
-        tmem_ld32(taddr + (uint32_t)(b * 128 + c * 32 + 32) + lane_off, vb);
-        tmem_ld_wait();
-        float ma[4], mq[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { ma[r] = __uint_as_float(va[r]); mq[r] = __uint_as_float(vb[r]); }
-#pragma unroll
-        for (int jj = 4; jj < 32; ++jj) {
-          ma[jj & 3] = fmaxf(ma[jj & 3], __uint_as_float(va[jj]));
-          mq[jj & 3] = fmaxf(mq[jj & 3], __uint_as_float(vb[jj]));
-        }
-        const float mba = fmaxf(fmaxf(ma[0], ma[1]), fmaxf(ma[2], ma[3])) * kLog2e;
-        const float mbb = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])) * kLog2e;
-        float fa[32], fb[32];
-        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          fa[jj] = ex2_f(fmaf(__uint_as_float(va[jj]), kLog2e, -mba));
-          fb[jj] = ex2_f(fmaf(__uint_as_float(vb[jj]), kLog2e, -mbb));
-          sa[jj & 3] += fa[jj];
-          sb[jj & 3] += fb[jj];
-        }
-        const float inva = __fdividef(qs, (sa[0] + sa[1]) + (sa[2] + sa[3]));
-        const float invb = __fdividef(qs, (sb[0] + sb[1]) + (sb[2] + sb[3]));
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const __half2 xa = __floats2half2_rn(fa[2 * jj] * inva, fa[2 * jj + 1] * inva);
-          const __half2 xb = __floats2half2_rn(fb[2 * jj] * invb, fb[2 * jj + 1] * invb);
-          hq[c][jj] = *reinterpret_cast<const uint32_t*>(&xa);
-          hq[c + 1][jj] = *reinterpret_cast<const uint32_t*>(&xb);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&ctl->dq_empty[b]);
-      if (tr) P.trace[i * 16 + 2] = clock64();
       const int bq = ring_b(i);
       if (i >= NB) mbar_wait(&ctl->q_free[bq], ring_par(i - NB));   // MMA2(i - NB) has read this Q tile
-      if (tr) P.trace[i * 16 + 3] = clock64();
-      uint8_t* qrow = sQ + (size_t)bq * 32768 + (size_t)row * 128;
+      tc_fence_after();
+      if (tr) P.trace[i * 16 + 2] = clock64();
+      uint8_t* qrow = sQ + (size_t)bq * 32768 + (size_t)hh * 16384 + (size_t)row * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint8_t* blk = qrow + (size_t)(c >> 1) * 16384;
+      for (int c = 0; c < 2; ++c) {                // one head per 32-column chunk
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(b * 128 + hh * 64 + c * 32) + lane_off, v);
+        tmem_ld_wait();
+        if (c == 1) {
+          tc_fence_before();
+          mbar_arrive(&ctl->dq_empty[b]);
+        }
+        float m4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(blk + ((((c & 1) * 4 + q) ^ (row & 7)) << 4)) =
-              make_uint4(hq[c][q * 4], hq[c][q * 4 + 1], hq[c][q * 4 + 2], hq[c][q * 4 + 3]);
+        for (int r = 0; r < 4; ++r) m4[r] = __uint_as_float(v[r]);
+#pragma unroll
+        for (int jj = 4; jj < 32; ++jj) m4[jj & 3] = fmaxf(m4[jj & 3], __uint_as_float(v[jj]));
+        const float mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
+        float f[32];
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          f[jj] = ex2_f(fmaf(__uint_as_float(v[jj]), kLog2e, -mb));
+          s4[jj & 3] += f[jj];
+        }
+        const float inv = __fdividef(qs, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const __half2 x = __floats2half2_rn(f[q * 8 + 2 * jj] * inv, f[q * 8 + 2 * jj + 1] * inv);
+            o[jj] = *reinterpret_cast<const uint32_t*>(&x);
+          }
+          *reinterpret_cast<uint4*>(qrow + (((c * 4 + q) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
+      if (tr) P.trace[i * 16 + 3] = clock64();
       fence_proxy_async();
       mbar_arrive(&ctl->q_ready[bq]);
       if (tr) P.trace[i * 16 + 4] = clock64();
-    }
-  } else {
-    // =============================== o-warps: LayerNorm + residual + store =======
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int tyr = row >> P.tile_w_log2, txr = row & (tile_w - 1);
-    uint8_t* slab = sO + (size_t)quarter * kSlabBytes;
-    for (int i = 0; i < ntiles; ++i) {
-      int img, x0, y0;
-      tile_xy(t_begin + i, img, x0, y0);
-      const __half* rp = P.res + (((size_t)img * P.H + (y0 + tyr)) * P.W + (x0 + txr)) * C;
-      const int bo = ring_b(i);
-      const uint32_t dout = taddr + 256u + (uint32_t)(bo * C) + lane_off;
-      // residual of the first 64 channels: issued before the wait so its latency hides behind it
-      uint4 rv[8];
+    };
+
+    // residual row of tile i (this warp's channel half): fetched one softmax phase ahead of its use
+    uint4 rv[4];
+    int o_img = 0, o_x0 = 0, o_y0 = 0;         // coordinates of the tile whose output is pending
+    const __half* rp = nullptr;
+    auto prefetch_res = [&](int i) {
+      tile_xy(t_begin + i, o_img, o_x0, o_y0);
+      rp = P.res + (((size_t)o_img * P.H + (o_y0 + tyr)) * P.W + (o_x0 + txr)) * C + hh * CH;
+      const uint4* r4 = reinterpret_cast<const uint4*>(rp);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 6 && lane == 0 && i < 48;
+      for (int q = 0; q < 4; ++q) rv[q] = __ldg(r4 + q);
+    };
+
+    auto output_tile = [&](int i) {
+      const int img = o_img, x0 = o_x0, y0 = o_y0;
+      const int bo = ring_b(i);
+      const uint32_t dout = taddr + 256u + (uint32_t)(bo * C + hh * CH) + lane_off;
+      const float* cb = sbias + hh * CH;
+      const float* cg = sgain + hh * CH;
+      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 48;
       if (tr) P.trace[i * 16 + 8] = clock64();
       mbar_wait(&ctl->do_full[bo], ring_par(i));
       tc_fence_after();
       if (tr) P.trace[i * 16 + 9] = clock64();
-      // pass 1: mean and variance of (acc + bias) over the C channels of this pixel, shifted by
-      // the first channel's value (single sweep, no cancellation)
+      // one sweep: S = sum x and Q = sum (x - a)^2 over this warp's channels (x = acc + bias, a = its
+      // first value), exchanged with the partner warp and combined exactly:
+      //   sum_h (x - mean)^2 = Q_h - 2 (mean - a_h) (S_h - n a_h) + n (mean - a_h)^2
       float sh = 0.f;
-      float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+      float p4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c = 0; c < C; c += 64) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(dout + (uint32_t)c, v0);
-        tmem_ld32(dout + (uint32_t)c + 32, v1);
+      for (int c = 0; c < CH; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(dout + (uint32_t)c, v);
         tmem_ld_wait();
-        if (c == 0) sh = __uint_as_float(v0[0]) + sbias[0];
+        if (c == 0) sh = __uint_as_float(v[0]) + cb[0];
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const float d0 = __uint_as_float(v0[jj]) + sbias[c + jj] - sh;
-          const float d1 = __uint_as_float(v1[jj]) + sbias[c + 32 + jj] - sh;
-          p1[jj & 1] += d0;
-          p1[2 + (jj & 1)] += d1;
-          p2[jj & 1] = fmaf(d0, d0, p2[jj & 1]);
-          p2[2 + (jj & 1)] = fmaf(d1, d1, p2[2 + (jj & 1)]);
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(cb + c + q * 4);
+          const float x0 = __uint_as_float(v[q * 4 + 0]) + b4.x, x1 = __uint_as_float(v[q * 4 + 1]) + b4.y;
+          const float x2 = __uint_as_float(v[q * 4 + 2]) + b4.z, x3 = __uint_as_float(v[q * 4 + 3]) + b4.w;
+          p4[0] += x0; p4[1] += x1; p4[2] += x2; p4[3] += x3;
+          const float d0 = x0 - sh, d1 = x1 - sh, d2 = x2 - sh, d3 = x3 - sh;
+          q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]);
+          q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
         }
       }
-      const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
-      const float dm = s1 * (1.f / C);
-      const float mean = sh + dm;
-      const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - dm * dm, 0.f) + 1e-5f);
+      {
+        float* mine = xch + hh * 96;
+        mine[lane] = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+        mine[32 + lane] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        mine[64 + lane] = sh;
+      }
+      if (hh == 0 && lane == 0) bulk_wait_read0_();   // the slab's previous TMA store has read it
+      pair_bar();
       if (tr) P.trace[i * 16 + 10] = clock64();
-      if (lane == 0) bulk_wait_read0_();     // the slab's previous TMA store has read it
-      __syncwarp();
+      float mean, rstd;
+      {
+        const float s0 = xch[lane], q0 = xch[32 + lane], a0 = xch[64 + lane];
+        const float s1 = xch[96 + lane], q1 = xch[128 + lane], a1 = xch[160 + lane];
+        mean = (s0 + s1) * (1.f / C);
+        const float e0 = mean - a0, e1 = mean - a1;
+        const float m2 = (q0 - 2.f * e0 * (s0 - CH * a0) + CH * e0 * e0) +
+                         (q1 - 2.f * e1 * (s1 - CH * a1) + CH * e1 * e1);
+        rstd = rsqrtf(fmaxf(m2, 0.f) * (1.f / C) + 1e-5f);
+      }
       if (tr) P.trace[i * 16 + 11] = clock64();
+      // normalise + gain + residual -> slab (this warp's channel half of each pixel row)
 #pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 64) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(dout + (uint32_t)c0, v0);
-        tmem_ld32(dout + (uint32_t)c0 + 32, v1);
+      for (int c = 0; c < CH; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(dout + (uint32_t)c, v);
         tmem_ld_wait();
-        if (c0 + 64 >= C) {                  // last read of this accumulator
+        if (c + 32 >= CH) {                  // last read of this accumulator
           tc_fence_before();
           mbar_arrive(&ctl->do_empty[bo]);
         }
-        uint8_t* blk = slab + (size_t)(c0 >> 6) * (32 * 128) + (size_t)lane * 128;
+        const int cglob = hh * CH + c;       // first output channel of this chunk
+        uint8_t* blk = slab + (size_t)(cglob >> 6) * (32 * 128) + (size_t)lane * 128;
+        const int ch0 = (cglob & 63) >> 3;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           const __half2* rh = reinterpret_cast<const __half2*>(&rv[q]);
+          const float4 b0 = *reinterpret_cast<const float4*>(cb + c + q * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(cb + c + q * 8 + 4);
+          const float4 g0 = *reinterpret_cast<const float4*>(cg + c + q * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(cg + c + q * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
           uint32_t o[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const int ch = c0 + q * 8 + jj * 2;
             const float2 r2 = __half22float2(rh[jj]);
-            const float a0 = __uint_as_float(q < 4 ? v0[q * 8 + jj * 2] : v1[(q - 4) * 8 + jj * 2]);
-            const float a1 = __uint_as_float(q < 4 ? v0[q * 8 + jj * 2 + 1] : v1[(q - 4) * 8 + jj * 2 + 1]);
-            const float y0f = (a0 + sbias[ch] - mean) * rstd * sgain[ch] + r2.x;
-            const float y1f = (a1 + sbias[ch + 1] - mean) * rstd * sgain[ch + 1] + r2.y;
-            const __half2 hh = __floats2half2_rn(y0f, y1f);
-            o[jj] = *reinterpret_cast<const uint32_t*>(&hh);
+            const float u0 = (__uint_as_float(v[q * 8 + jj * 2]) + (bb[jj * 2] - mean)) * rstd;
+            const float u1 = (__uint_as_float(v[q * 8 + jj * 2 + 1]) + (bb[jj * 2 + 1] - mean)) * rstd;
+            const __half2 hv = __floats2half2_rn(fmaf(u0, gg[jj * 2], r2.x), fmaf(u1, gg[jj * 2 + 1], r2.y));
+            o[jj] = *reinterpret_cast<const uint32_t*>(&hv);
           }
-          *reinterpret_cast<uint4*>(blk + ((q ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(blk + (((ch0 + q) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        if (c0 + 64 < C) {                   // residual of the next 64 channels
+        if (c + 32 < CH) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rp + c0 + 64) + q);
+          for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rp + c + 32) + q);
         }
       }
+      if (tr) P.trace[i * 16 + 12] = clock64();
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
+      pair_bar();
+      if (tr) P.trace[i * 16 + 13] = clock64();
+      if (hh == 0 && lane == 0) {
         const int px = quarter * 32;
 #pragma unroll
-        for (int cb = 0; cb < C / 64; ++cb)
-          tma_store_4d_(&tmO, slab + (size_t)cb * (32 * 128), cb * 64, x0 + (px & (tile_w - 1)),
+        for (int cbx = 0; cbx < C / 64; ++cbx)
+          tma_store_4d_(&tmO, slab + (size_t)cbx * (32 * 128), cbx * 64, x0 + (px & (tile_w - 1)),
                         y0 + (px >> P.tile_w_log2), img);
         bulk_commit_();
       }
-      if (tr) P.trace[i * 16 + 12] = clock64();
+    };
+
+    for (int i = 0; i < ntiles; ++i) {
+      if (i > 0) prefetch_res(i - 1);
+      softmax_tile(i);
+      if (i > 0) output_tile(i - 1);
+    }
+    if (ntiles > 0) {
+      prefetch_res(ntiles - 1);
+      output_tile(ntiles - 1);
     }
     if (lane == 0) bulk_wait0_();
     tc_fence_before();
@@ -951,10 +981,10 @@ int qout_plan(QOutOp* op, int maxB, const __half* xn, int H, int W, int C, const
   P.gain = gain;
   P.res = res;
   P.q_scale = 0.17677669529663687f;   // 32^-0.5 (SDD:742)
-  const int fixed = (C <= 128 ? 2 : 1) * 32768 + 2 * C * 256 + 1024 + (int)sizeof(QCtl) + (C <= 128 ? 8 * C : 0) + 64;
+  const int fixed = (C <= 128 ? 2 : 1) * 32768 + 2 * C * 256 + 1024 + (int)sizeof(QCtl) + 3072 + (C <= 128 ? 8 * C : 0) + 64;
   int stages = (kSmemBudget - fixed) / kQStage;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) {
+  if (stages < 1) {   // C = 256 gets a single load stage (two small layers of the network)
     delete L;
     set_error("qout_plan: shared memory budget too small");
     return PRG_ERR_ARG;
@@ -1013,9 +1043,9 @@ int qout_run(QOutOp& op, int B, cudaStream_t s) {
   L.P.total_tiles = B * L.P.tpi;
   const int grid = std::min(L.P.total_tiles, num_sms());
   if (getenv("PRG_QOUT_TRACE") != nullptr && L.C == 64) {
-    // debug timeline of CTA 0 (synchronous): q-warp  0 loop top | 1 Dq ready | 2 softmax done |
-    // 3 Q tile free | 4 Q written;  MMA warp  5 MMA1 go | 6 MMA2 loop top | 7 MMA2 go;
-    // o-warp  8 loop top | 9 Do ready | 10 stats done | 11 slab free | 12 stored
+    // debug timeline of CTA 0, warp 2 (synchronous): S: 0 top | 1 Dq ready | 2 Q tile free |
+    // 3 softmax + Q written | 4 fenced + arrived;  MMA warp: 5 MMA1 go | 6 MMA2 loop top | 7 MMA2 go;
+    // O: 8 top | 9 Do ready | 10 mean exchanged | 11 var exchanged | 12 slab written | 13 pair ready
     long long* d = nullptr;
     PRG_CUDA_OK(cudaMalloc(&d, 48 * 16 * sizeof(long long)));
     PRG_CUDA_OK(cudaMemset(d, 0, 48 * 16 * sizeof(long long)));
@@ -1027,7 +1057,7 @@ int qout_run(QOutOp& op, int B, cudaStream_t s) {
     const long long t0 = h[1];
     for (int t = 0; t < 32; ++t) {
       fprintf(stderr, "tile %2d:", t);
-      for (int k = 0; k < 13; ++k) fprintf(stderr, " %6lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      for (int k = 0; k < 14; ++k) fprintf(stderr, " %6lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
       fprintf(stderr, "\n");
     }
     return rc;
