@@ -128,7 +128,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   // fp16 staging.  BN = 64: eight per-warp 4 KB slabs.  BN >= 128: ONE 64-channel box (16 KB) that
   // the epilogue fills and stores BN/64 times per tile -- the shared memory this frees buys a
   // fourth load stage, and these layers are bound by the bytes in flight, not by the epilogue.
-  constexpr int kStageOut = (BN == 64) ? 2 * kABytes : kABytes;
+  constexpr int kStageOut = (BN == 64) ? (EPI == EPI_GNRES ? 4 * kABytes : 2 * kABytes) : kABytes;
   constexpr int kOutBufs = 1;
   // TMEM: BN = 64 owns all 512 columns (eight accumulators, halo mode walks them as a ring),
   // the wider tiles two accumulators.
@@ -179,7 +179,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   if (EPI == EPI_QKV && threadIdx.x < 128) ctl->colmax[threadIdx.x] = INT_MIN;
   for (int i = threadIdx.x; i < BN * P.n_tiles; i += kThreads)
     ctl->bias[i] = (p.bias != nullptr) ? __ldg(p.bias + i) : 0.f;
-  if (EPI == EPI_LN_RES)
+  if (EPI == EPI_LN_RES || (EPI == EPI_GNRES && p.has_ln_out))
     for (int i = threadIdx.x; i < BN; i += kThreads) ctl->gain[i] = __ldg(p.ln_g + i);
   tc_fence_before();
   if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
@@ -625,6 +625,23 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = (f[j] - ln_mean) * ln_rstd * ctl->gain[c + j];
         }
+        if (EPI == EPI_GNRES) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + c);
+          const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + (size_t)img * (BN * P.n_tiles) + n0 + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = __ldg(rp + q);
+            const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 ab = __ldg(cf + q * 4 + j);
+              const float2 r2 = __half22float2(h[j]);
+              const float t0 = fmaf(r2.x, ab.x, ab.y), t1 = fmaf(r2.y, ab.z, ab.w);
+              f[q * 8 + j * 2 + 0] += __fdividef(t0, 1.f + __expf(-t0));
+              f[q * 8 + j * 2 + 1] += __fdividef(t1, 1.f + __expf(-t1));
+            }
+          }
+        }
         if (EPI == EPI_RES || EPI == EPI_LN_RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + c);
 #pragma unroll
@@ -707,7 +724,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       const int oy = (y0 + tyr) * p.out_scale + cpy, ox = (x0 + txr) * p.out_scale + cpx;
       const long long off = (long long)img * p.out_img_stride + (long long)oy * p.out_row_stride +
                             (long long)ox * p.out_pix_stride;
-      const bool has_res = (EPI == EPI_RES || EPI == EPI_LN_RES || (EPI == EPI_GN && p.res != nullptr));
+      const bool has_res = (EPI == EPI_RES || EPI == EPI_LN_RES || EPI == EPI_GNRES ||
+                            (EPI == EPI_GN && p.res != nullptr));
       uint4 rv[8];
       if (has_res) {   // this pixel's 64 residual channels = one 128-byte line; issued before the wait
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
@@ -824,6 +842,40 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           }
         }
       }
+      float ln_m = 0.f, ln_r = 0.f;
+      if (EPI == EPI_GNRES) {
+        // y = res_conv(x) + SiLU(GroupNorm(raw) [* (scale + 1) + shift]): rv holds this pixel's raw row
+        const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + (size_t)img * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __half2* h = reinterpret_cast<const __half2*>(&rv[q]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 ab = __ldg(cf + q * 4 + j);        // (A, B) of two consecutive channels
+            const float2 r2 = __half22float2(h[j]);
+            const float t0 = fmaf(r2.x, ab.x, ab.y), t1 = fmaf(r2.y, ab.z, ab.w);
+            f[q * 8 + j * 2 + 0] += __fdividef(t0, 1.f + __expf(-t0));
+            f[q * 8 + j * 2 + 1] += __fdividef(t1, 1.f + __expf(-t1));
+          }
+        }
+        if (p.has_ln_out) {
+          // LayerNorm of the fp16-rounded y (what the attention would otherwise re-read)
+          float sm4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            f[j] = __half2float(__float2half_rn(f[j]));
+            sm4[j & 3] += f[j];
+          }
+          ln_m = ((sm4[0] + sm4[1]) + (sm4[2] + sm4[3])) * (1.f / 64.f);
+          float ss4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const float d = f[j] - ln_m;
+            ss4[j & 3] = fmaf(d, d, ss4[j & 3]);
+          }
+          ln_r = rsqrtf(((ss4[0] + ss4[1]) + (ss4[2] + ss4[3])) * (1.f / 64.f) + 1e-5f);
+        }
+      }
       // the slab's previous TMA store must have finished reading it
       uint8_t* slab = sO + (size_t)(grp * 4 + quarter) * 4096;
       if (lane == 0) bulk_wait_read0();
@@ -842,12 +894,31 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         o.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(srow + ((q ^ (lane & 7)) << 4)) = o;
       }
+      if (EPI == EPI_GNRES && p.has_ln_out) {
+        // second slab (after the eight y slabs): LayerNorm_c(y) * g
+        uint8_t* lrow = slab + 8 * 4096 + (size_t)lane * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 o;
+          __half2 h0 = __floats2half2_rn((f[q * 8 + 0] - ln_m) * ln_r * ctl->gain[q * 8 + 0], (f[q * 8 + 1] - ln_m) * ln_r * ctl->gain[q * 8 + 1]);
+          __half2 h1 = __floats2half2_rn((f[q * 8 + 2] - ln_m) * ln_r * ctl->gain[q * 8 + 2], (f[q * 8 + 3] - ln_m) * ln_r * ctl->gain[q * 8 + 3]);
+          __half2 h2 = __floats2half2_rn((f[q * 8 + 4] - ln_m) * ln_r * ctl->gain[q * 8 + 4], (f[q * 8 + 5] - ln_m) * ln_r * ctl->gain[q * 8 + 5]);
+          __half2 h3 = __floats2half2_rn((f[q * 8 + 6] - ln_m) * ln_r * ctl->gain[q * 8 + 6], (f[q * 8 + 7] - ln_m) * ln_r * ctl->gain[q * 8 + 7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2);
+          o.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(lrow + ((q ^ (lane & 7)) << 4)) = o;
+        }
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0 && !(P.dbg_flags & 4)) {
         const CUtensorMap* tmo = cls == 0 ? &tmO0 : cls == 1 ? &tmO1 : cls == 2 ? &tmO2 : &tmO3;
         const int px = quarter * 32;
         tma_store_4d(tmo, slab, 0, x0 + (px & (tile_w - 1)), y0 + (px >> p.tile_w_log2), img);
+        if (EPI == EPI_GNRES && p.has_ln_out)
+          tma_store_4d(&tmO1, slab + 8 * 4096, 0, x0 + (px & (tile_w - 1)), y0 + (px >> p.tile_w_log2), img);
         bulk_commit();
       }
       if (tr) P.trace[tcount * 8 + 7] = clock64();       // tile done
@@ -1047,7 +1118,8 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   P.num_kb = ntaps * (cin / 64);
   P.m_tiles = p.tiles_x * p.tiles_y * B;
   const int b_bytes = bn * 128;
-  const int stage_out = (bn == 64) ? 2 * kABytes : kABytes;
+  // BN = 64: eight 4 KB slabs (+ eight more when EPI_GNRES also stores the LayerNorm output)
+  const int stage_out = (bn == 64) ? (epi == EPI_GNRES ? 4 * kABytes : 2 * kABytes) : kABytes;
   const int fixed = stage_out + kCtlBytes + 1024;
 
   // ---- mode selection
@@ -1208,6 +1280,7 @@ static int conv2_run(const Conv2Launch& L, cudaStream_t stream) {
   PRG_CASE(128, EPI_QKV)
   PRG_CASE(64, EPI_LN_RES) PRG_CASE(128, EPI_LN_RES) PRG_CASE(256, EPI_LN_RES)
   PRG_CASE(64, EPI_RES) PRG_CASE(128, EPI_RES) PRG_CASE(256, EPI_RES)
+  PRG_CASE(64, EPI_GNRES) PRG_CASE(128, EPI_GNRES) PRG_CASE(256, EPI_GNRES)
 #undef PRG_CASE
   set_error("conv_run: no kernel for N tile %d / epilogue %d", L.bn, L.epi);
   return PRG_ERR_ARG;
@@ -1239,6 +1312,25 @@ int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1,
   }
   delete reinterpret_cast<Conv2Launch*>(op->impl);
   op->impl = L;
+  return PRG_OK;
+}
+
+int conv_op_set_ln_out(ConvOp& op, const ActSrc& ln_out) {
+  Conv2Launch* L = reinterpret_cast<Conv2Launch*>(op.impl);
+  if (L->bn != 64 || L->epi != EPI_GNRES || L->P.c.classes != 1) {
+    set_error("conv_op_set_ln_out: only the N = 64 EPI_GNRES epilogue has a LayerNorm output");
+    return PRG_ERR_ARG;
+  }
+  const ConvParams& p = L->P.c;
+  const int tile_w = 1 << p.tile_w_log2;
+  const uint64_t ps = (uint64_t)ln_out.pix_stride * 2;
+  uint64_t dims[4] = {(uint64_t)ln_out.C, (uint64_t)ln_out.W, (uint64_t)ln_out.H, (uint64_t)p.B};
+  uint64_t str[3] = {ps, ps * ln_out.W, ps * ln_out.W * ln_out.H};
+  uint32_t box[4] = {64, (uint32_t)std::min(tile_w, 32), 0, 1};
+  box[2] = 32u / box[1];
+  int rc = tmap_encode_f16(&L->tmO[1], ln_out.ptr, 4, dims, str, box);
+  if (rc) return rc;
+  L->P.c.has_ln_out = 1;
   return PRG_OK;
 }
 

@@ -20,6 +20,8 @@ enum ConvEpi : int {
   EPI_QKV = 2,     // to_qkv: q softmax_d * scale | k (+ column max) | v -> fp16
   EPI_LN_RES = 3,  // y = LayerNorm_c(acc + bias) * g + residual       -> fp16
   EPI_RES = 4,     // y = acc + bias + residual                        -> fp16
+  EPI_GNRES = 5,   // y = acc + bias + SiLU(A[b][c] * raw + B[b][c])    -> fp16 (+ LayerNorm_c(y) * g, N = 64)
+                   // = res_conv fused with the block's second GroupNorm apply (SDD:734)
 };
 
 struct ConvParams {
@@ -45,6 +47,8 @@ struct ConvParams {
   int* colmax;           // EPI_QKV: [B][128] order-preserving int encoding of max_n k, or nullptr
   int q_softmax;         // EPI_QKV: 1 = softmax over each 32-channel head then * q_scale
   float q_scale;
+  const float2* gn_coef; // EPI_GNRES: [B][Cout] (A, B) of the GroupNorm (+ scale/shift) affine, see gn_coef()
+  int has_ln_out;        // EPI_GNRES, N = 64: also store LayerNorm_c(y) * ln_g through the second output map
 };
 
 // Description of one NHWC fp16 activation tensor (source or destination).
@@ -67,6 +71,8 @@ struct ConvOp {
 int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
                  int classes, const __half* w, int w_batched, int Cout, const ActSrc& out);
 int conv_op_run(ConvOp& op, int B, cudaStream_t stream);
+// EPI_GNRES with N = 64: second destination (same shape as the output) for LayerNorm_c(y) * ln_g.
+int conv_op_set_ln_out(ConvOp& op, const ActSrc& ln_out);
 const char* conv_op_describe(const ConvOp& op, char* buf, int n);
 void conv_op_set_trace(ConvOp& op, long long* buf);  // debug: clock64 stamps of CTA 0 (64 tiles x 8)
 

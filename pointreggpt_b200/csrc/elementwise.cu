@@ -468,6 +468,27 @@ __device__ __forceinline__ void gn_coeffs(const long long* stats, const float* g
 
 // LN: also emit LayerNorm_c(y) * g (the PreNorm of the attention that follows) from the same
 // registers -- the lanes holding one pixel (C/8 consecutive lanes) reduce with shuffles.
+// (A, B) per (image, channel) of y = SiLU(A * raw + B), for epilogues that apply the GroupNorm
+// on the fly (conv engine EPI_GNRES).  One CTA per image.
+__global__ void __launch_bounds__(256)
+k_gn_coef(const long long* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+          const float* __restrict__ ss, int ss_stride, int ss_off, int C, int HW, float2* __restrict__ coef) {
+  extern __shared__ float sm[];
+  float* sA = sm;
+  float* sB = sm + C;
+  const int b = blockIdx.x;
+  gn_coeffs(stats, gamma, beta, ss ? ss + (size_t)b * ss_stride + ss_off : nullptr, C, HW, b, sA, sB);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) coef[(size_t)b * C + c] = make_float2(sA[c], sB[c]);
+}
+
+int gn_coef(const GnApply& a, float2* coef, int B, cudaStream_t s) {
+  k_gn_coef<<<B, 256, 2 * a.C * sizeof(float), s>>>(a.stats, a.gamma, a.beta, a.ss, a.ss_stride, a.ss_off, a.C,
+                                                     a.HW, coef);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
 template <bool LN>
 __global__ void __launch_bounds__(256, LN ? 3 : 4)
 k_gn_apply(GnApply a, int total_blocks, int nblk) {

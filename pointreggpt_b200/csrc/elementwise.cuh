@@ -48,6 +48,8 @@ struct GnApply {
   __half* ln_out;     // ... and destination
 };
 int gn_apply(const GnApply& a, int B, cudaStream_t s);
+// coef[b][c] = (A, B) with y = SiLU(A * raw + B) (uses stats / gamma / beta / ss / HW / C of `a`).
+int gn_coef(const GnApply& a, float2* coef, int B, cudaStream_t s);
 
 // ---- channel LayerNorm with gain (SDD:619-628): y = LN_c(x) * g [+ res] -----------------------
 int ln_apply(const __half* x, const float* g, const __half* res, __half* y, int64_t npix, int C,

@@ -135,6 +135,7 @@ struct prg_net {
   __half *raw = nullptr, *h1 = nullptr, *resb = nullptr, *xn = nullptr, *qkv = nullptr,
          *ao = nullptr, *weff = nullptr;
   float* kv_partials = nullptr;   // LinearAttention context partials (shared by all attention layers)
+  float2* gn_coef_buf = nullptr;  // (A, B) per (image, channel) for the EPI_GNRES epilogue
   size_t unit = 0;  // maxB * S * S * 64 halves
 
   // tail (filled by the builder)
@@ -358,6 +359,47 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
   }));
   const __half* res_ptr;
   int res_stride;
+  // res_conv fused with the second GroupNorm apply (conv engine EPI_GNRES): y = res_conv(x) +
+  // SiLU(GN(raw2)); the shortcut tensor never reaches HBM.  With a PreNorm LayerNorm to emit this
+  // needs the whole channel row in one thread, i.e. Cout = 64.
+  // Measured on B200 (batch 32): parity green but NOT faster -- 277 us vs 147 + 150 us at 256x256,
+  // 192 vs 67 + 80 us at 128x128: the SiLU turns the conv epilogue (8 warps per SM) into the
+  // MUFU / issue bound part, while k_gn_apply hides the same work behind 32 resident warps.
+  // Opt-in (PRG_GNRES=1) until the epilogue has more warps to spread it over.
+  const bool fuse_res = !last && n->has(pfx + ".res_conv.weight") && cout <= 512 &&
+                        (fuse_ln_g == nullptr || cout == 64) && getenv("PRG_GNRES") != nullptr;
+  if (fuse_res) {
+    NET_PTR(wr, n->f16(pfx + ".res_conv.weight"));
+    NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
+    Act y = new_act(n, H, W, cout);
+    if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+    GnApply a{};
+    a.raw = raw.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr; a.HW = HW; a.C = cout;
+    float2* coef = n->gn_coef_buf;
+    n->add_op(CAT_GN, [a, coef](const Run& r) { return gn_coef(a, coef, r.B, r.s); },
+              "gn_coef c" + std::to_string(cout));
+    ConvOp op;
+    {
+      ActSrc a0 = src_of(x0), a1;
+      if (x1) a1 = src_of(*x1);
+      NET_TRY(conv_op_plan(&op, EPI_GNRES, n->maxB, a0, x1 ? &a1 : nullptr, 0, 1, 1, wr, 0, cout, src_of(y)));
+      ConvParams& p = op.params();
+      p.bias = br;
+      p.res = raw.p;
+      p.gn_coef = coef;
+      if (fuse_ln_g != nullptr) {
+        p.ln_g = fuse_ln_g;
+        Act xn{n->xn, H, W, cout, cout};
+        NET_TRY(conv_op_set_ln_out(op, src_of(xn)));
+      }
+      char buf[160], lab[256];
+      snprintf(lab, sizeof(lab), "conv+gn %dx%d %d->%d k1 [%s]", H, W, cin, cout, conv_op_describe(op, buf, sizeof(buf)));
+      n->add_op(CAT_CONV, [op](const Run& r) mutable { return conv_op_run(op, r.B, r.s); }, lab,
+                2.0 * H * W * (double)cout * cin);
+    }
+    bo->y = y;
+    return PRG_OK;
+  }
   if (n->has(pfx + ".res_conv.weight")) {
     NET_PTR(wr, n->f16(pfx + ".res_conv.weight"));
     NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
@@ -544,7 +586,8 @@ int build(prg_net* n) {
     for (int i = 0; i < L; ++i) pf = std::max(pf, kvctx_partial_floats(B, S >> i, S >> i));
     n->kv_partials = n->dalloc<float>(pf);
   }
-  if (!n->kv_partials || !n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
+  n->gn_coef_buf = n->dalloc<float2>((size_t)B * 1024);
+  if (!n->gn_coef_buf || !n->kv_partials || !n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
       !n->colmax_arena || !n->x_state) {
     set_error("out of device memory allocating the workspace");
     return PRG_ERR_CUDA;
