@@ -1,12 +1,6 @@
 // Attention cores of the U-Net (everything between to_qkv and to_out).
 //
-//  LinearAttention (SDD:748-769): q = softmax_d(q)*scale (done in the to_qkv epilogue),
-//      k = softmax_n(k), v = v/n, ctx = k v^T (32x32 per head), out = ctx^T q, to_out 1x1.
-//      Here: (1) k_linattn_context accumulates ctx~ = sum_n exp(k - max_n k) v^T and
-//      Z = sum_n exp(k - max) per (image, head) -- a reduction over up to 65 536 pixels with
-//      tiny 32x32 outputs, bandwidth-bound, run on mma.sync tiles; (2) k_linattn_weff folds
-//      ctx~/(Z n) into the to_out weight: W_eff[b] = W_out . blockdiag(ctx_b^T), so that the
-//      remaining per-pixel work is one tcgen05 GEMM (K = 128) with per-image weights.
+//  LinearAttention (SDD:748-769) lives in linattn_tc.cu (fused tcgen05 kernels).
 //  Attention (mid block, SDD:782-796): flash-style softmax(q k^T) v over n = (S/8)^2 keys.
 //
 // These reductions are < 1.5 % of the forward FLOPs; the dense
@@ -43,165 +37,6 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// ------------------------------------------------------------------------------------------
-// linear attention: context accumulation
-// ------------------------------------------------------------------------------------------
-constexpr int kCtxTile = 64;  // pixels per smem tile
-constexpr double kCtxScale = 16777216.0;  // 2^24 fixed point for the cross-CTA sums
-
-__global__ void __launch_bounds__(128)
-k_linattn_context(const __half* __restrict__ qkv, const int* __restrict__ colmax,
-                  long long* __restrict__ ctx, long long* __restrict__ zsum, int n, int chunk) {
-  // [row][16 chunks of 16 B], chunk index XOR (row & 7): conflict-free ldmatrix
-  __shared__ __align__(16) __half sK[kCtxTile * 128];
-  __shared__ __align__(16) __half sV[kCtxTile * 128];
-  __shared__ float sMax[128];
-  const int b = blockIdx.y;
-  const int p_begin = blockIdx.x * chunk;
-  const int p_end = min(n, p_begin + chunk);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  sMax[tid] = ordered_to_float(colmax[b * 128 + tid]);
-  __syncthreads();
-
-  float acc[2][4][4];
-  float zacc[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      zacc[i][j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-    }
-  }
-  const uint32_t ones = 0x3C003C00u;  // half2(1, 1)
-  const int h = warp;
-
-  for (int p0 = p_begin; p0 < p_end; p0 += kCtxTile) {
-    // ---- stage: global -> (exp for k) -> swizzled smem
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int id = i * 128 + tid;
-      const int row = id >> 4, ch = id & 15;
-      const __half* src = qkv + ((size_t)b * n + p0 + row) * 384 + ch * 8;
-      uint4 kv = __ldg(reinterpret_cast<const uint4*>(src + 128));
-      const uint4 vv = __ldg(reinterpret_cast<const uint4*>(src + 256));
-      __half2* kh = reinterpret_cast<__half2*>(&kv);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(kh[j]);
-        kh[j] = __floats2half2_rn(__expf(f.x - sMax[ch * 8 + 2 * j]),
-                                  __expf(f.y - sMax[ch * 8 + 2 * j + 1]));
-      }
-      const int sw = (row * 16 + (ch ^ (row & 7))) * 8;
-      *reinterpret_cast<uint4*>(sK + sw) = kv;
-      *reinterpret_cast<uint4*>(sV + sw) = vv;
-    }
-    __syncthreads();
-    // ---- ctx[d][e] += sum_n p[n][d] v[n][e] for this warp's head
-#pragma unroll
-    for (int ks = 0; ks < kCtxTile / 16; ++ks) {
-      const int n0 = ks * 16;
-      uint32_t a[2][4];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const int row = n0 + (lane & 7) + ((lane >> 4) << 3);
-        const int ch = h * 4 + mb * 2 + ((lane >> 3) & 1);
-        ldsm_x4_t(smem_addr(sK + (row * 16 + (ch ^ (row & 7))) * 8), a[mb][0], a[mb][1], a[mb][2],
-                  a[mb][3]);
-      }
-#pragma unroll
-      for (int ep = 0; ep < 2; ++ep) {
-        const int row = n0 + (lane & 7) + (((lane >> 3) & 1) << 3);
-        const int ch = h * 4 + ep * 2 + (lane >> 4);
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(smem_addr(sV + (row * 16 + (ch ^ (row & 7))) * 8), b0, b1, b2, b3);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          mma16816(acc[mb][ep * 2 + 0], a[mb], b0, b1);
-          mma16816(acc[mb][ep * 2 + 1], a[mb], b2, b3);
-        }
-      }
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) mma16816(zacc[mb], a[mb], ones, ones);
-    }
-    __syncthreads();
-  }
-  // ---- flush: ctx [b][h][d][e], zsum [b][h*32+d]; fixed-point integer atomics so the sum over
-  // pixel chunks does not depend on CTA arrival order
-  unsigned long long* cb = reinterpret_cast<unsigned long long*>(ctx) + ((size_t)b * 4 + h) * 1024;
-  unsigned long long* zb = reinterpret_cast<unsigned long long*>(zsum) + (size_t)b * 128 + h * 32;
-  auto fx = [](float v) { return (unsigned long long)__double2ll_rn((double)v * kCtxScale); };
-#pragma unroll
-  for (int mb = 0; mb < 2; ++mb) {
-    const int d = mb * 16 + (lane >> 2);
-#pragma unroll
-    for (int eb = 0; eb < 4; ++eb) {
-      const int e = eb * 8 + (lane & 3) * 2;
-      atomicAdd(cb + d * 32 + e, fx(acc[mb][eb][0]));
-      atomicAdd(cb + d * 32 + e + 1, fx(acc[mb][eb][1]));
-      atomicAdd(cb + (d + 8) * 32 + e, fx(acc[mb][eb][2]));
-      atomicAdd(cb + (d + 8) * 32 + e + 1, fx(acc[mb][eb][3]));
-    }
-    if ((lane & 3) == 0) {
-      atomicAdd(zb + d, fx(zacc[mb][0]));
-      atomicAdd(zb + d + 8, fx(zacc[mb][2]));
-    }
-  }
-}
-
-// note on the A-fragment ldmatrix above: the four 8x8 blocks are
-//   m0: pixels n0..+7,  channels d0..+7      m1: pixels n0..+7,  channels d0+8..+15
-//   m2: pixels n0+8..15, channels d0..+7     m3: pixels n0+8..15, channels d0+8..+15
-// and .trans hands thread (lane) the element [pixel = 2*(lane%4)+{0,1}][channel = lane/4],
-// i.e. A[row = channel][k = pixel]: exactly the m16n8k16 A fragment order a0a1|a2a3|a4a5|a6a7.
-
-int linattn_context(const __half* qkv, const int* colmax, long long* ctx, long long* zsum, int B, int n,
-                    cudaStream_t s) {
-  if (n % kCtxTile != 0) {
-    set_error("linattn_context: n=%d is not a multiple of %d", n, kCtxTile);
-    return PRG_ERR_ARG;
-  }
-  // enough CTAs per image to hide the load->mma latency chain, few enough to keep the
-  // cross-CTA atomics cheap
-  int chunk = n / 32;
-  if (chunk < 256) chunk = 256;
-  if (chunk > n) chunk = n;
-  chunk = (chunk + kCtxTile - 1) / kCtxTile * kCtxTile;
-  dim3 g((n + chunk - 1) / chunk, B);
-  k_linattn_context<<<g, 128, 0, s>>>(qkv, colmax, ctx, zsum, n, chunk);
-  PRG_LAUNCH_CHECK();
-  return PRG_OK;
-}
-
-// W_eff[b][c][h*32+d] = sum_e W_out[c][h*32+e] * ctx[b][h][d][e] / (Z[b][h*32+d] * n)
-__global__ void __launch_bounds__(128)
-k_linattn_weff(const float* __restrict__ wout, const long long* __restrict__ ctx,
-               const long long* __restrict__ zsum, __half* __restrict__ weff, int C, float inv_n) {
-  __shared__ float sC[4 * 32 * 33];
-  const int b = blockIdx.y, c = blockIdx.x, hd = threadIdx.x;
-  for (int i = threadIdx.x; i < 4096; i += 128) {
-    const int hh = i >> 10, d = (i >> 5) & 31, e = i & 31;
-    sC[(hh * 32 + d) * 33 + e] = (float)((double)ctx[(size_t)b * 4096 + i] * (1.0 / kCtxScale));
-  }
-  __syncthreads();
-  const int h = hd >> 5;
-  const float* w = wout + (size_t)c * 128 + h * 32;
-  float a = 0.f;
-#pragma unroll
-  for (int e = 0; e < 32; ++e) a = fmaf(__ldg(w + e), sC[hd * 33 + e], a);
-  a = a * inv_n / (float)((double)zsum[(size_t)b * 128 + hd] * (1.0 / kCtxScale));
-  weff[((size_t)b * C + c) * 128 + hd] = __float2half_rn(a);
-}
-
-int linattn_weff(const float* wout, const long long* ctx, const long long* zsum, __half* weff, int B, int C,
-                 int n, cudaStream_t s) {
-  dim3 g(C, B);
-  k_linattn_weff<<<g, 128, 0, s>>>(wout, ctx, zsum, weff, C, 1.f / (float)n);
-  PRG_LAUNCH_CHECK();
-  return PRG_OK;
 }
 
 // ------------------------------------------------------------------------------------------

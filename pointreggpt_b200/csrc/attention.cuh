@@ -5,14 +5,6 @@
 
 namespace prg {
 
-// qkv (B, n, 384) fp16: [0,128) q', [128,256) k, [256,384) v.  colmax (B,128): max_n k as
-// ordered ints.  ctx (B,4,32,32) and zsum (B,128) are 2^-24 fixed-point int64 sums (order-independent,
-// bit-reproducible), zero on entry.
-int linattn_context(const __half* qkv, const int* colmax, long long* ctx, long long* zsum, int B, int n,
-                    cudaStream_t s);
-// weff (B, C, 128) fp16 = W_out (C,128) fp32 folded with the normalised context.
-int linattn_weff(const float* wout, const long long* ctx, const long long* zsum, __half* weff, int B, int C,
-                 int n, cudaStream_t s);
 // ---- fused k/v projection + context on the tcgen05 engine (linattn_tc.cu)
 constexpr int kPartialFloats = 256 + 4096;   // per chunk of an image: m[128], z[128], ctx[128][32]
 struct KvCtxOp {

@@ -14,116 +14,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
 
-// ------------------------------------------------------------------------------------------
-// stems: direct 7x7 convolution on CUDA cores (K = 49 / 147: far too thin for the tensor pipe)
-// 16x16 output pixels per CTA, one pixel per thread, all 64 output channels in registers.
-// ------------------------------------------------------------------------------------------
-constexpr int kStemT = 16;
+constexpr int kStemT = 16;                 // stem patch: 16x16 output pixels per CTA iteration
 constexpr int kStemHalo = kStemT + 6;
-
-template <int CIN, bool AUG>
-__global__ void __launch_bounds__(256)
-k_stem(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-       __half* __restrict__ y, int S) {
-  // weights transposed to [cin][tap][64] so a tap's 64 output channels are contiguous
-  __shared__ __align__(16) float sw[CIN * 49 * 64];
-  __shared__ float sin_[CIN][kStemHalo][kStemHalo + 1];
-  __shared__ float sraw[AUG ? (kStemHalo + 2) : 1][AUG ? (kStemHalo + 2 + 1) : 1];
-  const int b = blockIdx.z;
-  const int x0 = blockIdx.x * kStemT, y0 = blockIdx.y * kStemT;
-  const float* img = x + (size_t)b * S * S;
-  for (int i = threadIdx.x; i < CIN * 49 * 64; i += 256) {
-    const int co = i & 63, rest = i >> 6;  // rest = cin*49 + tap
-    sw[i] = __ldg(w + (size_t)co * CIN * 49 + rest);
-  }
-  if (!AUG) {
-    for (int i = threadIdx.x; i < kStemHalo * kStemHalo; i += 256) {
-      const int r = i / kStemHalo, c = i - r * kStemHalo;
-      const int gy = y0 + r - 3, gx = x0 + c - 3;
-      sin_[0][r][c] = (gy >= 0 && gy < S && gx >= 0 && gx < S) ? __ldg(img + (size_t)gy * S + gx) : 0.f;
-    }
-  } else {
-    // DepthAugment (DC:582-604): ch0 = depth, ch1 = 3x3 min over valid (!=0) neighbours (max_pool
-    // pads with -inf, i.e. out-of-image neighbours are ignored), falling back to the plain 3x3
-    // min (zeros included) when no neighbour is valid; ch2 = ch1 - ch0.  Zero padding of the
-    // 7x7 conv applies to all three channels outside the image.
-    constexpr int R = kStemHalo + 2;
-    for (int i = threadIdx.x; i < R * R; i += 256) {
-      const int r = i / R, c = i - r * R;
-      const int gy = y0 + r - 4, gx = x0 + c - 4;
-      sraw[r][c] = (gy >= 0 && gy < S && gx >= 0 && gx < S) ? __ldg(img + (size_t)gy * S + gx)
-                                                           : __int_as_float(0x7fc00000);  // NaN = outside
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kStemHalo * kStemHalo; i += 256) {
-      const int r = i / kStemHalo, c = i - r * kStemHalo;
-      const float d = sraw[r + 1][c + 1];
-      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-      if (d == d) {  // inside the image
-        float mn_valid = INFINITY, mn_all = INFINITY;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const float v = sraw[r + dy][c + dx];
-            if (v == v) {
-              mn_all = fminf(mn_all, v);
-              if (v != 0.f) mn_valid = fminf(mn_valid, v);
-            }
-          }
-        const float mn = isinf(mn_valid) ? mn_all : mn_valid;
-        c0 = d;
-        c1 = mn;
-        c2 = mn - d;
-      }
-      sin_[0][r][c] = c0;
-      if (CIN > 1) {
-        sin_[CIN > 1 ? 1 : 0][r][c] = c1;
-        sin_[CIN > 2 ? 2 : 0][r][c] = c2;
-      }
-    }
-  }
-  __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[64];
-#pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = __ldg(bias + c);
-  for (int ci = 0; ci < CIN; ++ci) {
-#pragma unroll 1
-    for (int ky = 0; ky < 7; ++ky) {
-#pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float v = sin_[ci][ty + ky][tx + kx];
-        const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 49) + ky * 7 + kx) * 64);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 w4 = wp[q];
-          acc[q * 4 + 0] = fmaf(v, w4.x, acc[q * 4 + 0]);
-          acc[q * 4 + 1] = fmaf(v, w4.y, acc[q * 4 + 1]);
-          acc[q * 4 + 2] = fmaf(v, w4.z, acc[q * 4 + 2]);
-          acc[q * 4 + 3] = fmaf(v, w4.w, acc[q * 4 + 3]);
-        }
-      }
-    }
-  }
-  const int gy = y0 + ty, gx = x0 + tx;
-  if (gy < S && gx < S) {
-    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)b * S + gy) * S + gx) * 64);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      __half2 h0 = __floats2half2_rn(acc[q * 8 + 0], acc[q * 8 + 1]);
-      __half2 h1 = __floats2half2_rn(acc[q * 8 + 2], acc[q * 8 + 3]);
-      __half2 h2 = __floats2half2_rn(acc[q * 8 + 4], acc[q * 8 + 5]);
-      __half2 h3 = __floats2half2_rn(acc[q * 8 + 6], acc[q * 8 + 7]);
-      uint4 o;
-      o.x = *reinterpret_cast<uint32_t*>(&h0);
-      o.y = *reinterpret_cast<uint32_t*>(&h1);
-      o.z = *reinterpret_cast<uint32_t*>(&h2);
-      o.w = *reinterpret_cast<uint32_t*>(&h3);
-      dst[q] = o;
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // stems on the tensor pipe (mma.sync m16n8k16, fp16 operands, fp32 accumulate).

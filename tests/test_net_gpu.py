@@ -70,6 +70,40 @@ def test_unet_forward_256_batch_independent(unet):
     assert rel_l2(alone, got[2:]) < 1e-5
 
 
+def test_unet_forward_odd_batch(unet):
+    """Five images: LinearAttention chunk partials, pair-mode / CTA-pair tiles and the row-streaming
+    segments all see a batch that is not a power of two."""
+    net, sd = unet
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(5, 1, 128, 128, generator=g)
+    t = torch.tensor([0, 1, 250, 777, 999])
+    pc = _pcond(5)
+    ref = R.unet_forward(sd, x, t, pc)
+    got = net(x.cuda(), t.cuda(), pc.cuda()).cpu()
+    for i in range(5):
+        assert rel_l2(got[i], ref[i]) <= REL_TOL, i
+    # bit-reproducible: integer GroupNorm statistics, fixed-order attention partials
+    again = net(x.cuda(), t.cuda(), pc.cuda()).cpu()
+    assert torch.equal(got, again)
+
+
+def test_unet_forward_fused_shortcut_epilogue(monkeypatch):
+    """Opt-in conv-engine epilogue that fuses res_conv with the second GroupNorm apply (and the
+    PreNorm LayerNorm at 64 channels): same numbers as the default path within tolerance."""
+    monkeypatch.setenv("PRG_GNRES", "1")
+    torch.manual_seed(0)
+    net = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 1, 128, 128, generator=g)
+    t = torch.tensor([600, 40])
+    pc = _pcond(2)
+    got = net(x.cuda(), t.cuda(), pc.cuda()).cpu()      # the handle is built here, with the flag set
+    ref = R.unet_forward(sd, x, t, pc)
+    assert rel_l2(got, ref) <= REL_TOL
+
+
 def test_maskunet_forward(masknet):
     net, sd = masknet
     g = torch.Generator().manual_seed(7)
