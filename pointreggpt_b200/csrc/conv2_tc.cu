@@ -99,6 +99,8 @@ struct Conv2Params {
   ConvParams c;
   int halo, wres, n_tiles, stages;
   int pair;             // per-tap mode, BN = 128: an item is TWO adjacent M tiles sharing every B stage
+  int nsrc;             // halo mode: 1, or 2 = cat(x0, x1) of two 64-channel sources streamed row by row
+  int direct_store;     // BN = 64 epilogue writes global memory itself (no staging slabs / TMA store)
   int total_items;      // per-tap: m_tiles * n_tiles * classes ; halo: number of row segments
   int m_tiles;          // per-tap: tiles_x * tiles_y * B
   int rseg, segs_per_strip;
@@ -142,7 +144,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   uint8_t* sA = sW + P.w_bytes;                     // A ring
   uint8_t* sB = sA + P.stages * P.a_slot;           // streamed B ring (when !wres)
   uint8_t* sO = sB + (P.wres ? 0 : P.stages * kBBytes);
-  Ctl* ctl = reinterpret_cast<Ctl*>(sO + kOutBufs * kStageOut);
+  Ctl* ctl = reinterpret_cast<Ctl*>(sO + (P.direct_store ? 0 : kOutBufs * kStageOut));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_w = 1 << p.tile_w_log2;
@@ -225,7 +227,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           for (int kb = 0; kb < num_kb; ++kb) {
             // halo mode: tap (dy, dx) goes to block dx*3 + (2 - dy), so that for one dx the taps
             // dy = 2, 1, 0 are one contiguous N = 192 B operand
-            const int blk = P.halo ? (kb % 3) * 3 + (2 - kb / 3) : nt * num_kb + kb;
+            const int wtap = kb / chunks, wcc = kb - wtap * chunks;   // halo: per source, per dx, dy = 2, 1, 0
+            const int blk = P.halo ? wcc * 9 + (wtap % 3) * 3 + (2 - wtap / 3) : nt * num_kb + kb;
             tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)blk * kBBytes, kb * kBlockK, nt * BN, 0);
           }
       }
@@ -237,13 +240,15 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
           for (int r = 0; r < nr + 2; ++r) {
-            mbar_wait(&ctl->empty[stage], phase ^ 1);
-            if (P.trace != nullptr && blockIdx.x == 0 && dbg_row < 96) P.trace[512 + 2 * dbg_row] = clock64();
-            ++dbg_row;
-            mbar_arrive_expect_tx(&ctl->full[stage], kHaloBytes);
-            tma_load_4d(&tmA0, &ctl->full[stage], sA + (size_t)stage * P.a_slot, 0, x0 - 1,
-                        y0 - 1 + r, img);
-            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            for (int src = 0; src < P.nsrc; ++src) {
+              mbar_wait(&ctl->empty[stage], phase ^ 1);
+              if (P.trace != nullptr && blockIdx.x == 0 && dbg_row < 96) P.trace[512 + 2 * dbg_row] = clock64();
+              ++dbg_row;
+              mbar_arrive_expect_tx(&ctl->full[stage], kHaloBytes);
+              tma_load_4d(src == 0 ? &tmA0 : &tmA1, &ctl->full[stage], sA + (size_t)stage * P.a_slot, 0,
+                          x0 - 1, y0 - 1 + r, img);
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       } else {
@@ -339,18 +344,20 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         int img, x0, y0, nr;
         decode_seg(seg, img, x0, y0, nr);
         for (int ri = 0; ri < nr + 2; ++ri) {
+         for (int src = 0; src < P.nsrc; ++src) {
           mbar_wait(&ctl->full[stage], phase);
-          if (ri < nr) {   // slot of the new target must have been drained
+          if (ri < nr && src == 0) {   // slot of the new target must have been drained
             const uint32_t tn = tcount + (uint32_t)ri;
             mbar_wait(&ctl->tmem_empty[tn & 7u], ((tn >> 3) & 1u) ^ 1u);
           }
           tc_fence_after();
-          const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && ri >= 2 &&
+          const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && ri >= 2 && src == 0 &&
                           tcount + (uint32_t)ri - 2u < 64u;
           if (tr) P.trace[(tcount + ri - 2) * 8 + 0] = clock64();   // last input row + slot ready
           const int j_lo = max(ri - 2, 0), j_hi = min(ri, nr - 1);
           const uint32_t row_lo = (sA_u + (uint32_t)stage * P.a_slot) >> 4;
-          const uint32_t w_lo = sW_u >> 4;
+          const uint32_t w_lo = (sW_u >> 4) + (uint32_t)(src * 9) * (kBBytes >> 4);   // this source's taps
+          const bool last_src = (src == P.nsrc - 1);
           if (elect_one()) {
             // Descriptors of step s = dx*4 + k: A = row + 2*s (dx*128 B + k*32 B, in 16-byte
             // units), B = first target's block + dx*3 blocks + 2*k.  All twelve are the row's base
@@ -362,16 +369,16 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             const int c1 = min(cnt, 8 - (int)sa);                    // targets before the slot ring wraps
             const uint64_t db0 = desc_hi | (uint64_t)(w_lo + (uint32_t)(2 - ri + j_lo) * kBlk);
             const uint32_t d0 = taddr_u + sa * 64u;
-            // step 0: targets that already hold a partial sum accumulate, the new one (j = ri)
-            // overwrites its slot
-            const int n_old = (ri < nr) ? cnt - 1 : cnt;             // old targets come first
+            // step 0: targets that already hold a partial sum accumulate, the new one (j = ri, first
+            // source only) overwrites its slot
+            const int n_old = (ri < nr && src == 0) ? cnt - 1 : cnt;  // old targets come first
             {
               const int o1 = min(n_old, c1);                         // old targets before the wrap
               if (o1 > 0) umma_f16(d0, da0, db0, idesc0 | ((uint32_t)(o1 * 8) << 17), 1u);
               if (n_old > o1)
                 umma_f16(taddr_u, da0, db0 + (uint64_t)(o1 * kBlk),
                          idesc0 | ((uint32_t)((n_old - o1) * 8) << 17), 1u);
-              if (ri < nr) {
+              if (ri < nr && src == 0) {
                 const uint32_t sn = (tcount + (uint32_t)ri) & 7u;
                 umma_f16(taddr_u + sn * 64u, da0, db0 + (uint64_t)(n_old * kBlk), idesc0 | (8u << 17), 0u);
               }
@@ -394,11 +401,12 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               }
             }
             umma_commit(&ctl->empty[stage]);                       // input row consumed
-            if (ri >= 2) umma_commit(&ctl->tmem_full[(tcount + (uint32_t)(ri - 2)) & 7u]);
+            if (ri >= 2 && last_src) umma_commit(&ctl->tmem_full[(tcount + (uint32_t)(ri - 2)) & 7u]);
           }
           __syncwarp();
           if (tr) P.trace[(tcount + ri - 2) * 8 + 2] = clock64();   // row's MMAs issued
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
+         }
         }
         tcount += (uint32_t)nr;
       }
@@ -876,6 +884,27 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           ln_r = rsqrtf(((ss4[0] + ss4[1]) + (ss4[2] + ss4[3])) * (1.f / 64.f) + 1e-5f);
         }
       }
+      if (P.direct_store) {
+        // no staging: this thread writes its pixel's 64 channels (one 128-byte line) itself -- the
+        // shared memory goes to the 147 KB of resident weights of the two-source conv instead
+        uint4* gdst = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 o;
+          __half2 h0 = __floats2half2_rn(f[q * 8 + 0], f[q * 8 + 1]);
+          __half2 h1 = __floats2half2_rn(f[q * 8 + 2], f[q * 8 + 3]);
+          __half2 h2 = __floats2half2_rn(f[q * 8 + 4], f[q * 8 + 5]);
+          __half2 h3 = __floats2half2_rn(f[q * 8 + 6], f[q * 8 + 7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2);
+          o.w = *reinterpret_cast<uint32_t*>(&h3);
+          gdst[q] = o;
+        }
+        if (tr) P.trace[tcount * 8 + 7] = clock64();
+        ++tcount;
+        return;
+      }
       // the slab's previous TMA store must have finished reading it
       uint8_t* slab = sO + (size_t)(grp * 4 + quarter) * 4096;
       if (lane == 0) bulk_wait_read0();
@@ -1130,7 +1159,21 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
                        cin == 64 && bn == 64 && tile_w == kBlockM && P.n_tiles == 1 &&
                        !(conv_flags() & 1) &&
                        w_all + fixed + 5 * kHaloSlot <= kSmemBudget;
-  if (halo_ok) {
+  // cat(x0, x1) of two 64-channel sources -> 64: both weight halves (147 KB) stay resident, the
+  // rows of the two sources alternate through a four-slot ring, and the epilogue stores to global
+  // memory directly (no room for staging slabs)
+  const bool halo2_ok = !w_batched && classes == 1 && mode == 0 && ksize == 3 && s1 != nullptr &&
+                        s0.C == 64 && s1->C == 64 && bn == 64 && tile_w == kBlockM && P.n_tiles == 1 &&
+                        (epi == EPI_BIAS || epi == EPI_GN) && !(conv_flags() & 33) &&
+                        w_all + kCtlBytes + 1024 + 4 * kHaloSlot <= kSmemBudget;
+  P.nsrc = 1;
+  P.direct_store = 0;
+  if (halo2_ok) {
+    P.halo = 1;
+    P.wres = 1;
+    P.nsrc = 2;
+    P.direct_store = 1;
+  } else if (halo_ok) {
     P.halo = 1;
     P.wres = 1;
   } else if (!w_batched && classes == 1 && w_all + fixed + 8 * kABytes <= kSmemBudget) {
@@ -1149,14 +1192,15 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   L->cg = (bn == 256 && !P.halo && !P.wres && !P.pair && !w_batched && (epi == EPI_BIAS || epi == EPI_GN) &&
            (p.tiles_x * p.tiles_y) % 2 == 0 && !(conv_flags() & 16)) ? 2 : 1;
   const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes / L->cg);
-  int stages = (kSmemBudget - fixed - P.w_bytes) / per_stage;
+  const int fixed_used = P.direct_store ? kCtlBytes + 1024 : fixed;
+  int stages = (kSmemBudget - fixed_used - P.w_bytes) / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     set_error("conv_plan: shared memory budget too small (%d stages)", stages);
     return PRG_ERR_ARG;
   }
   P.stages = stages;
-  L->smem = P.w_bytes + stages * per_stage + fixed;
+  L->smem = P.w_bytes + stages * per_stage + fixed_used;
 
   const int sms = num_sms();
   if (P.halo) {

@@ -320,10 +320,11 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
   NET_PTR(g2, n->f32(pfx + ".block2.norm.weight"));
   NET_PTR(be2, n->f32(pfx + ".block2.norm.bias"));
 
-  if (x1 != nullptr && n->has(pfx + ".block1.proj.weight.a")) {
-    // 64 + 64 -> 64 at >= 128-pixel rows: neither the 147 KB weight matrix nor a 128-channel
-    // row ring fits beside the other in one SM, so the concat conv is split by source into two
-    // halo-ring convs; the second adds the first's fp16 partial before the GN statistics.
+  if (x1 != nullptr && n->has(pfx + ".block1.proj.weight.a") && getenv("PRG_SPLIT_CAT") != nullptr) {
+    // (fallback, PRG_SPLIT_CAT=1) 64 + 64 -> 64 at >= 128-pixel rows split by source into two
+    // row-streaming convs; the second adds the first's fp16 partial before the GN statistics.
+    // The default is the single-pass two-source row-streaming conv (both weight halves resident,
+    // rows of the two sources alternating through the ring, direct-store epilogue).
     NET_PTR(wa, n->f16(pfx + ".block1.proj.weight.a"));
     NET_PTR(wb, n->f16(pfx + ".block1.proj.weight.b"));
     NET_TRY(add_conv(n, EPI_BIAS, x0, nullptr, 0, 3, 1, wa, 0, nullptr, h1));
