@@ -336,17 +336,24 @@ int cond_mlp(const float* W, const float* bias, const float* cond_act, float* ss
 __device__ __forceinline__ void gn_coeffs(const long long* stats, const float* gamma, const float* beta,
                                           const float* ss_row, int C, int HW, int b, float* sA,
                                           float* sB) {
+  // the eight group statistics need the fp64 path (exact integer sums -> mean / variance without
+  // cancellation); everything per channel is fp32.  Must be called by the whole CTA (it syncs).
+  __shared__ float s_mean[8], s_rstd[8];
   const int gs = C >> 3;
-  const float inv_n = 1.f / ((float)gs * (float)HW);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / gs;
-    // exact integer sums -> double for the mean/variance (no cancellation issue), then fp32
+  if (threadIdx.x < 8) {
+    const int g = threadIdx.x;
+    const double inv_n = 1.0 / ((double)gs * (double)HW);
     const double sum = (double)stats[((size_t)b * 8 + g) * 2 + 0] * (double)kStatUnscale;
     const double sq = (double)stats[((size_t)b * 8 + g) * 2 + 1] * (double)kStatUnscale;
-    const double meand = sum * (double)inv_n;
-    const float mean = (float)meand;
-    const float var = fmaxf((float)(sq * (double)inv_n - meand * meand), 0.f);
-    const float rstd = rsqrtf(var + 1e-5f);
+    const double meand = sum * inv_n;
+    const float var = fmaxf((float)(sq * inv_n - meand * meand), 0.f);
+    s_mean[g] = (float)meand;
+    s_rstd[g] = rsqrtf(var + 1e-5f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gs;
+    const float mean = s_mean[g], rstd = s_rstd[g];
     float a = rstd * gamma[c], d = beta[c] - mean * rstd * gamma[c];
     if (ss_row != nullptr) {
       const float sc = ss_row[c] + 1.f, sh = ss_row[C + c];
@@ -358,8 +365,6 @@ __device__ __forceinline__ void gn_coeffs(const long long* stats, const float* g
   }
 }
 
-// LN: also emit LayerNorm_c(y) * g (the PreNorm of the attention that follows) from the same
-// registers -- the lanes holding one pixel (C/8 consecutive lanes) reduce with shuffles.
 // (A, B) per (image, channel) of y = SiLU(A * raw + B), for epilogues that apply the GroupNorm
 // on the fly (conv engine EPI_GNRES).  One CTA per image.
 __global__ void __launch_bounds__(256)
