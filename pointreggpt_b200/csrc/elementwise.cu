@@ -306,6 +306,96 @@ int cond_embed(const CondWeights& w, const int64_t* time, int time_scalar, const
   return PRG_OK;
 }
 
+// ---- sampler fast path: every image of the batch shares the timestep and param_cond is constant
+// over the steps, and Linear(SiLU(cat(t, p))) = W_t SiLU(t) + W_p SiLU(p) + b is separable:
+//   once per sample():  act_t[i] = SiLU(time_mlp(t_i)) for ALL steps i,  ss_p[b] = W_p SiLU(param_mlp(p_b))
+//   per step:           ss[b] = W_t act_t[i] + bias + ss_p[b]            (one small launch)
+__global__ void __launch_bounds__(256)
+k_cond_time_all(CondWeights w, const int* __restrict__ ts, float* __restrict__ act_t) {
+  extern __shared__ float sm[];
+  const int dim = w.dim, hid = 4 * w.dim;
+  float* emb = sm;        // [dim]
+  float* h1 = emb + dim;  // [hid]
+  const float t = (float)ts[blockIdx.x];
+  const int half = dim / 2;
+  const float step = logf(10000.f) / (float)(half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf((float)i * -step);
+    const float a = t * f;
+    emb[i] = sinf(a);
+    emb[i + half] = cosf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < hid; r += nwarps) {
+    const float* wr = w.t1w + (size_t)r * dim;
+    float a = 0.f;
+    for (int k = lane; k < dim; k += 32) a = fmaf(__ldg(wr + k), emb[k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) h1[r] = gelu_erf(a + w.t1b[r]);
+  }
+  __syncthreads();
+  for (int r = warp; r < hid; r += nwarps) {
+    const float* wr = w.t2w + (size_t)r * hid;
+    float a = 0.f;
+    for (int k = lane; k < hid; k += 32) a = fmaf(__ldg(wr + k), h1[k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) act_t[(size_t)blockIdx.x * hid + r] = silu(a + w.t2b[r]);
+  }
+}
+
+// ss_p[b][r] = W[r][k0 : k0 + K] . act[b][k0 : k0 + K]   (no bias): the param_cond half, once per sample()
+__global__ void __launch_bounds__(256)
+k_cond_mlp_part(const float* __restrict__ W, const float* __restrict__ act, float* __restrict__ out, int rows,
+                int Ktot, int k0, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= rows) return;
+  const float* wr = W + (size_t)warp * Ktot + k0;
+  const float* c = act + (size_t)b * Ktot + k0;
+  float a = 0.f;
+  for (int k = lane; k < K; k += 32) a = fmaf(__ldg(wr + k), c[k], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[(size_t)b * rows + warp] = a;
+}
+
+// per step: one warp per output row computes the time half once and adds every image's param half
+__global__ void __launch_bounds__(256)
+k_cond_mlp_step(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ act_t,
+                const float* __restrict__ ss_p, float* __restrict__ ss, int rows, int Ktot, int K, int B) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* wr = W + (size_t)warp * Ktot;
+  float a = 0.f;
+  for (int k = lane; k < K; k += 32) a = fmaf(__ldg(wr + k), act_t[k], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  a += __ldg(bias + warp);
+  for (int b = lane; b < B; b += 32) ss[(size_t)b * rows + warp] = a + ss_p[(size_t)b * rows + warp];
+}
+
+int cond_time_all(const CondWeights& w, const int* ts_dev, int nsteps, float* act_t, cudaStream_t s) {
+  k_cond_time_all<<<nsteps, 256, sizeof(float) * 5 * w.dim, s>>>(w, ts_dev, act_t);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+int cond_mlp_param(const float* W, const float* cond_act, float* ss_p, int rows, int Ktot, int B,
+                   cudaStream_t s) {
+  dim3 g((rows * 32 + 255) / 256, B);
+  k_cond_mlp_part<<<g, 256, 0, s>>>(W, cond_act, ss_p, rows, Ktot, Ktot / 2, Ktot / 2);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+int cond_mlp_step(const float* W, const float* bias, const float* act_t, const float* ss_p, float* ss,
+                  int rows, int Ktot, int B, cudaStream_t s) {
+  k_cond_mlp_step<<<(rows * 32 + 255) / 256, 256, 0, s>>>(W, bias, act_t, ss_p, ss, rows, Ktot, Ktot / 2, B);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
 // one warp per (image, output row)
 __global__ void __launch_bounds__(256)
 k_cond_mlp(const float* __restrict__ W, const float* __restrict__ bias,

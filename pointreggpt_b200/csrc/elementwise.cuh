@@ -25,6 +25,12 @@ struct CondWeights {
 // `time_scalar` broadcast (sampler).
 int cond_embed(const CondWeights& w, const int64_t* time, int time_scalar, const float* pcond,
                float* cond_act, int B, cudaStream_t s);
+// sampler fast path (shared timestep, constant param_cond): see elementwise.cu
+int cond_time_all(const CondWeights& w, const int* ts_dev, int nsteps, float* act_t, cudaStream_t s);
+int cond_mlp_param(const float* W, const float* cond_act, float* ss_p, int rows, int Ktot, int B,
+                   cudaStream_t s);
+int cond_mlp_step(const float* W, const float* bias, const float* act_t, const float* ss_p, float* ss,
+                  int rows, int Ktot, int B, cudaStream_t s);
 // ss[b][r] = W[r] . cond_act[b] + bias[r] for the concatenated rows of every block MLP.
 int cond_mlp(const float* W, const float* bias, const float* cond_act, float* ss, int rows, int K,
              int B, cudaStream_t s);

@@ -93,6 +93,7 @@ struct Run {
   const int64_t* time;     // per-image timesteps or nullptr
   int time_scalar;
   const float* pcond;
+  int cond_done;           // sampler fast path: ss is already in place, skip the conditioning ops
 };
 
 }  // namespace
@@ -123,6 +124,11 @@ struct prg_net {
   float* cond_act = nullptr;
   float* ss = nullptr;
   int ss_rows = 0;
+  float* ss_p = nullptr;       // sampler: param_cond half of every block MLP, per image
+  float* act_t_all = nullptr;  // sampler: SiLU(time_mlp(t)) of every step
+  int* ts_dev = nullptr;
+  int act_t_cap = 0;
+  const float *mlp_w = nullptr, *mlp_b = nullptr;
   CondWeights cw{};
 
   // per-forward zeroed arena (GroupNorm stats, ctx, zsum) and the colmax arena (0x80 fill)
@@ -618,10 +624,18 @@ int build(prg_net* n) {
     float* cond_act = n->cond_act;
     float* ss = n->ss;
     const int rows = n->ss_rows, K = 8 * n->dim;
+    n->mlp_w = mlp_w;
+    n->mlp_b = mlp_b;
+    n->ss_p = n->dalloc<float>((size_t)B * n->ss_rows);
+    if (!n->ss_p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
     n->add_op(CAT_COND, [=](const Run& r) {
+      if (r.cond_done) return (int)PRG_OK;
       return cond_embed(cw, r.time, r.time_scalar, r.pcond, cond_act, r.B, r.s);
     });
-    n->add_op(CAT_COND, [=](const Run& r) { return cond_mlp(mlp_w, mlp_b, cond_act, ss, rows, K, r.B, r.s); });
+    n->add_op(CAT_COND, [=](const Run& r) {
+      if (r.cond_done) return (int)PRG_OK;
+      return cond_mlp(mlp_w, mlp_b, cond_act, ss, rows, K, r.B, r.s);
+    });
   }
 
   // ---- stem
@@ -834,6 +848,8 @@ EXPORT void prg_net_destroy(prg_net* n) {
   DeviceGuard guard(n->dev);
   cudaDeviceSynchronize();
   for (void* p : n->allocs) cudaFree(p);
+  if (n->act_t_all) cudaFree(n->act_t_all);
+  if (n->ts_dev) cudaFree(n->ts_dev);
   delete n;
 }
 
@@ -845,7 +861,7 @@ EXPORT int prg_unet_forward(prg_net* n, const float* x, const int64_t* time, con
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(x && time && pcond && out, "null pointer");
   PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
-  Run r{B, (cudaStream_t)stream, x, time, 0, pcond};
+  Run r{B, (cudaStream_t)stream, x, time, 0, pcond, 0};
   NET_TRY(run_trunk(n, r));
   TailParams t = n->tail;
   t.mode = 0;
@@ -859,7 +875,7 @@ EXPORT int prg_maskunet_forward(prg_net* n, const float* depth01, float* prob, u
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth01 && (prob || keep), "null pointer");
   PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
-  Run r{B, (cudaStream_t)stream, depth01, nullptr, 0, nullptr};
+  Run r{B, (cudaStream_t)stream, depth01, nullptr, 0, nullptr, 0};
   NET_TRY(run_trunk(n, r));
   TailParams t = n->tail;
   t.mode = 1;
@@ -883,11 +899,35 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
     PRG_CUDA_OK(cudaMemcpyAsync(n->x_state, noise, npx * sizeof(float), cudaMemcpyDeviceToDevice, s));
   else
     NET_TRY(fill_normal(n->x_state, (int64_t)npx, seed, 0ull, s));
+  // conditioning, hoisted out of the step loop: the time embedding of every step in one launch,
+  // the param_cond half of every block MLP once (SDD:925, 932, 709-713 are separable per half)
+  {
+    if (nsteps > n->act_t_cap) {
+      if (n->act_t_all) { cudaFree(n->act_t_all); cudaFree(n->ts_dev); }
+      n->act_t_all = nullptr;
+      n->ts_dev = nullptr;
+      const int cap = nsteps + 16;
+      if (cudaMalloc(&n->act_t_all, (size_t)cap * 4 * n->dim * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&n->ts_dev, (size_t)cap * sizeof(int)) != cudaSuccess) {
+        set_error("out of device memory for the per-step time embeddings");
+        return PRG_ERR_CUDA;
+      }
+      n->act_t_cap = cap;
+    }
+    std::vector<int> ts(nsteps);
+    for (int i = 0; i < nsteps; ++i) ts[i] = steps[i].t;
+    PRG_CUDA_OK(cudaMemcpyAsync(n->ts_dev, ts.data(), nsteps * sizeof(int), cudaMemcpyHostToDevice, s));
+    NET_TRY(cond_time_all(n->cw, n->ts_dev, nsteps, n->act_t_all, s));
+    NET_TRY(cond_embed(n->cw, nullptr, steps[0].t, pcond, n->cond_act, B, s));   // param half -> cond_act
+    NET_TRY(cond_mlp_param(n->mlp_w, n->cond_act, n->ss_p, n->ss_rows, 8 * n->dim, B, s));
+  }
   size_t slab = 1;
   for (int i = 0; i < nsteps; ++i) {
     const prg_step& st = steps[i];
     PRG_CHECK_ARG(st.kind >= 0 && st.kind <= 4, "step kind");
-    Run r{B, s, n->x_state, nullptr, st.t, pcond};
+    NET_TRY(cond_mlp_step(n->mlp_w, n->mlp_b, n->act_t_all + (size_t)i * 4 * n->dim, n->ss_p, n->ss, n->ss_rows,
+                          8 * n->dim, B, s));
+    Run r{B, s, n->x_state, nullptr, st.t, pcond, 1};
     NET_TRY(run_trunk(n, r));
     TailParams t = n->tail;
     t.mode = 2;
