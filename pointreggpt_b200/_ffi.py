@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprg.so")
+# PRG_LIB_PATH: load another build of the library (A/B measurements of two builds on one box)
+LIB_PATH = os.environ.get("PRG_LIB_PATH") or os.path.join(_HERE, "libprg.so")
 
 c_void_p, c_int, c_float, c_int64, c_size_t, c_uint64 = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64, ctypes.c_size_t,

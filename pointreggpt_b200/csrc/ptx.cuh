@@ -61,6 +61,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    // (measured: a nanosleep back-off here changes neither the short-run nor the power-capped
+    // 1000-step throughput -- mbarrier.try_wait already suspends the thread in hardware)
     if (clock64() - t0 > 4000000000LL) {  // ~2 s
       printf("prg: mbarrier wait timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x);
