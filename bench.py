@@ -163,7 +163,10 @@ def run_reference_arm(a, rank, world):
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1000.0 * sum(t for _, t in vals) / len(vals),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_name(a)},
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "image_size": a.size,
+                   "timesteps": a.timesteps,
+                   "sample": "bounded sample of the workload on the host cores, extrapolated (BASELINE.md section 4)"},
         "cpu_baseline": info,
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
