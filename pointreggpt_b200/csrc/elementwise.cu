@@ -10,6 +10,24 @@ namespace prg {
 // x * sigmoid(x) with the hardware reciprocal (<= 2 ulp; an IEEE division costs ~10 instructions and
 // made the GroupNorm-apply pass issue-bound instead of HBM-bound)
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// Two SiLUs at once on the packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2 issue one instruction per
+// element PAIR; the 3-register scalar forms issue at half rate on this part, which made the
+// GroupNorm-apply pass co-limited by instruction issue).  Same approximations as silu().
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 silu2(float2 t) {
+  const float2 u = __fmul2_rn(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = __fadd2_rn(make_float2(ex2_approx(u.x), ex2_approx(u.y)), make_float2(1.f, 1.f));
+  return __fmul2_rn(t, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
@@ -549,20 +567,12 @@ k_gn_apply(GnApply a, int total_blocks, int nblk) {
       float f[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 t = __half22float2(h[j]);
-        f[2 * j] = t.x;
-        f[2 * j + 1] = t.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu(fmaf(f[j], cA[j], cB[j]));
-      if (a.res != nullptr) {
-        const __half2* rh = reinterpret_cast<const __half2*>(&rv[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = __half22float2(rh[j]);
-          f[2 * j] += t.x;
-          f[2 * j + 1] += t.y;
-        }
+        float2 y = silu2(__ffma2_rn(__half22float2(h[j]), make_float2(cA[2 * j], cA[2 * j + 1]),
+                                    make_float2(cB[2 * j], cB[2 * j + 1])));
+        if (a.res != nullptr)
+          y = __fadd2_rn(y, __half22float2(reinterpret_cast<const __half2*>(&rv[u])[j]));
+        f[2 * j] = y.x;
+        f[2 * j + 1] = y.y;
       }
       uint4 o;
       __half2 o0 = __floats2half2_rn(f[0], f[1]), o1 = __floats2half2_rn(f[2], f[3]),
