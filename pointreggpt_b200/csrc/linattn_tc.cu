@@ -666,20 +666,27 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
 #pragma unroll
         for (int jj = 4; jj < 32; ++jj) m4[jj & 3] = fmaxf(m4[jj & 3], __uint_as_float(v[jj]));
         const float mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
-        float f[32];
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        // packed fp32x2 math (FFMA2 / FADD2 / FMUL2): one instruction per element pair
+        const float2 l2 = make_float2(kLog2e, kLog2e), nmb = make_float2(-mb, -mb);
+        float2 f2[16];
+        float2 s2a = make_float2(0.f, 0.f), s2b = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          f[jj] = ex2_f(fmaf(__uint_as_float(v[jj]), kLog2e, -mb));
-          s4[jj & 3] += f[jj];
+        for (int jj = 0; jj < 16; ++jj) {
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1])), l2, nmb);
+          f2[jj] = make_float2(ex2_f(a.x), ex2_f(a.y));
+          if (jj & 1) s2b = __fadd2_rn(s2b, f2[jj]);
+          else s2a = __fadd2_rn(s2a, f2[jj]);
         }
-        const float inv = __fdividef(qs, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+        const float2 st = __fadd2_rn(s2a, s2b);
+        const float inv = __fdividef(qs, st.x + st.y);
+        const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t o[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const __half2 x = __floats2half2_rn(f[q * 8 + 2 * jj] * inv, f[q * 8 + 2 * jj + 1] * inv);
+            const float2 y = __fmul2_rn(f2[q * 4 + jj], inv2);
+            const __half2 x = __floats2half2_rn(y.x, y.y);
             o[jj] = *reinterpret_cast<const uint32_t*>(&x);
           }
           *reinterpret_cast<uint4*>(qrow + (((c * 4 + q) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -718,28 +725,33 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
       // first value), exchanged with the partner warp and combined exactly:
       //   sum_h (x - mean)^2 = Q_h - 2 (mean - a_h) (S_h - n a_h) + n (mean - a_h)^2
       float sh = 0.f;
-      float p4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 pa = make_float2(0.f, 0.f), pb = pa, qa = pa, qb = pa;
 #pragma unroll 1
       for (int c = 0; c < CH; c += 32) {
         uint32_t v[32];
         tmem_ld32(dout + (uint32_t)c, v);
         tmem_ld_wait();
         if (c == 0) sh = __uint_as_float(v[0]) + cb[0];
+        const float2 nsh = make_float2(-sh, -sh);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 b4 = *reinterpret_cast<const float4*>(cb + c + q * 4);
-          const float x0 = __uint_as_float(v[q * 4 + 0]) + b4.x, x1 = __uint_as_float(v[q * 4 + 1]) + b4.y;
-          const float x2 = __uint_as_float(v[q * 4 + 2]) + b4.z, x3 = __uint_as_float(v[q * 4 + 3]) + b4.w;
-          p4[0] += x0; p4[1] += x1; p4[2] += x2; p4[3] += x3;
-          const float d0 = x0 - sh, d1 = x1 - sh, d2 = x2 - sh, d3 = x3 - sh;
-          q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]);
-          q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
+          const float2 xa = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1])),
+                                       make_float2(b4.x, b4.y));
+          const float2 xb = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])),
+                                       make_float2(b4.z, b4.w));
+          pa = __fadd2_rn(pa, xa);
+          pb = __fadd2_rn(pb, xb);
+          const float2 da = __fadd2_rn(xa, nsh), db = __fadd2_rn(xb, nsh);
+          qa = __ffma2_rn(da, da, qa);
+          qb = __ffma2_rn(db, db, qb);
         }
       }
+      const float p4s = (pa.x + pa.y) + (pb.x + pb.y), q4s = (qa.x + qa.y) + (qb.x + qb.y);
       {
         float* mine = xch + hh * 96;
-        mine[lane] = (p4[0] + p4[1]) + (p4[2] + p4[3]);
-        mine[32 + lane] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        mine[lane] = p4s;
+        mine[32 + lane] = q4s;
         mine[64 + lane] = sh;
       }
       if (hh == 0 && lane == 0) bulk_wait_read0_();   // the slab's previous TMA store has read it
@@ -782,9 +794,11 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const float2 r2 = __half22float2(rh[jj]);
-            const float u0 = (__uint_as_float(v[q * 8 + jj * 2]) + (bb[jj * 2] - mean)) * rstd;
-            const float u1 = (__uint_as_float(v[q * 8 + jj * 2 + 1]) + (bb[jj * 2 + 1] - mean)) * rstd;
-            const __half2 hv = __floats2half2_rn(fmaf(u0, gg[jj * 2], r2.x), fmaf(u1, gg[jj * 2 + 1], r2.y));
+            const float2 bm = __fadd2_rn(make_float2(bb[jj * 2], bb[jj * 2 + 1]), make_float2(-mean, -mean));
+            const float2 x2 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + jj * 2]), __uint_as_float(v[q * 8 + jj * 2 + 1])), bm);
+            const float2 u2 = __fmul2_rn(x2, make_float2(rstd, rstd));
+            const float2 y2 = __ffma2_rn(u2, make_float2(gg[jj * 2], gg[jj * 2 + 1]), r2);
+            const __half2 hv = __floats2half2_rn(y2.x, y2.y);
             o[jj] = *reinterpret_cast<const uint32_t*>(&hv);
           }
           *reinterpret_cast<uint4*>(blk + (((ch0 + q) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
