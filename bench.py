@@ -326,7 +326,7 @@ def main():
         # written); algorithmic minimum (every conv input read once, output written once) ~9.6 GB
         traffic = 15_032_200_000 if (B == 32 and a.size == 256 and not a.micro_batch) else None
         roof = {"bound": "tensor",
-                "kernel": "k_conv2 (persistent tcgen05 implicit-GEMM conv engine; the 62 conv launches "
+                "kernel": "k_conv2 (persistent tcgen05 implicit-GEMM conv engine; the conv launches "
                           "of one U-Net evaluation, timed with CUDA events on the launching stream)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_unit": "bytes per U-Net evaluation (all conv launches)",
