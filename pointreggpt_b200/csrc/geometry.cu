@@ -19,7 +19,33 @@ constexpr unsigned kEmpty = 0xFFFFFFFFu;
 
 struct Intr {
   float fx, fy, cx, cy;
+  float rfx, rfy;   // correctly rounded reciprocals of fx, fy
+  bool fast;        // intrinsics inside the range the three-instruction division is validated for
 };
+
+// Correctly rounded a / b in three instructions, given y = RN(1 / b) (Markstein's correction step):
+//   q0 = RN(a y);  r = a - q0 b (exact, one FMA);  q = RN(q0 + r y).
+// tools/check_division.py: 0 mismatches against the IEEE quotient on 16 M emulated trials over the
+// operand ranges of these kernels; the parity tests compare every pixel with the C oracle, which
+// divides.  __fdiv_rn costs ~12 instructions and made the kernels issue-bound (profiles/
+// r1_geometry_summary.txt).  Only valid while nothing under- or overflows: callers check the operand
+// ranges (Intr::fast, depth_in_range) and take the IEEE division otherwise.  A zero numerator
+// yields +0 whatever its sign; div_exact_signed() restores the sign the division gives (b > 0).
+__device__ __forceinline__ float div_exact(float a, float b, float y) {
+  const float q0 = __fmul_rn(a, y);
+  return __fmaf_rn(__fmaf_rn(-q0, b, a), y, q0);
+}
+__device__ __forceinline__ float div_exact_signed(float a, float b, float y) {
+  const unsigned q = __float_as_uint(div_exact(a, b, y));
+  return __uint_as_float((q & 0x7fffffffu) | (__float_as_uint(a) & 0x80000000u));
+}
+
+// |z| in [1e-9, 1e9] or exactly zero: with Intr::fast the numerators (c - cx) z are zero or in
+// [1e-19, 1e16] and the quotients zero or in [1e-25, 1e16] -- no underflow in q0 or in the residual
+__device__ __forceinline__ bool depth_in_range(float z) {
+  const float az = fabsf(z);
+  return (az > 1e-9f && az < 1e9f) || z == 0.f;
+}
 
 __device__ __forceinline__ Intr load_intr(const float* __restrict__ K, int b) {
   const float* k = K + b * 9;
@@ -28,10 +54,17 @@ __device__ __forceinline__ Intr load_intr(const float* __restrict__ K, int b) {
   i.fy = __ldg(k + 4);
   i.cx = __ldg(k + 2);
   i.cy = __ldg(k + 5);
+  i.rfx = __frcp_rn(i.fx);
+  i.rfy = __frcp_rn(i.fy);
+  // focal lengths in [1, 1e6]; principal point zero or in [1e-3, 1e6] in magnitude, so that c - cx is
+  // zero or at least 1e-10 in magnitude
+  const float acx = fabsf(i.cx), acy = fabsf(i.cy);
+  i.fast = i.fx >= 1.f && i.fx <= 1e6f && i.fy >= 1.f && i.fy <= 1e6f &&
+           (i.cx == 0.f || (acx >= 1e-3f && acx <= 1e6f)) &&
+           (i.cy == 0.f || (acy >= 1e-3f && acy <= 1e6f));
   return i;
 }
 
-// row / column of pixel i (i < 2^23) without an integer division: float estimate + fix-up
 __device__ __forceinline__ void row_col(int i, int W, float inv_w, int& r, int& c) {
   r = __float2int_rz(__fmul_rn((float)i, inv_w));
   c = i - r * W;
@@ -39,9 +72,20 @@ __device__ __forceinline__ void row_col(int i, int W, float inv_w, int& r, int& 
   if (c >= W) { c -= W; ++r; }
 }
 
-__device__ __forceinline__ void unproject(int r, int c, float z, const Intr& k, float& x, float& y) {
+__device__ __forceinline__ void unproject_ieee(int r, int c, float z, const Intr& k, float& x, float& y) {
   x = __fdiv_rn(__fmul_rn(__fsub_rn((float)c, k.cx), z), k.fx);
   y = __fdiv_rn(__fmul_rn(__fsub_rn((float)r, k.cy), z), k.fy);
+}
+
+// requires k.fast && depth_in_range(z)
+__device__ __forceinline__ void unproject_fast(int r, int c, float z, const Intr& k, float& x, float& y) {
+  x = div_exact_signed(__fmul_rn(__fsub_rn((float)c, k.cx), z), k.fx, k.rfx);
+  y = div_exact_signed(__fmul_rn(__fsub_rn((float)r, k.cy), z), k.fy, k.rfy);
+}
+
+__device__ __forceinline__ void unproject(int r, int c, float z, const Intr& k, float& x, float& y) {
+  if (k.fast && depth_in_range(z)) unproject_fast(r, c, z, k, x, y);
+  else unproject_ieee(r, c, z, k, x, y);
 }
 
 __device__ __forceinline__ void rigid(const float* __restrict__ P, float& x, float& y, float& z) {
@@ -55,8 +99,20 @@ __device__ __forceinline__ void rigid(const float* __restrict__ P, float& x, flo
 
 __device__ __forceinline__ void splat(float x, float y, float z, const Intr& k, int H, int W,
                                       unsigned* __restrict__ zimg) {
-  float cf = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(x, k.fx), z), k.cx));
-  float rf = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(y, k.fy), z), k.cy));
+  float qx, qy;
+  if (k.fast && z > 1e-6f && z < 1e12f) {
+    // one IEEE reciprocal shared by both divisions by z.  Quotients too small for the residual to be
+    // exact vanish in the sum with cx / cy (zero or >= 1e-3); an overflowing one gives NaN instead of
+    // +-inf and both fail the bounds test below.
+    const float rz = __frcp_rn(z);
+    qx = div_exact(__fmul_rn(x, k.fx), z, rz);
+    qy = div_exact(__fmul_rn(y, k.fy), z, rz);
+  } else {                                 // non-positive / extreme depths: plain divisions
+    qx = __fdiv_rn(__fmul_rn(x, k.fx), z);
+    qy = __fdiv_rn(__fmul_rn(y, k.fy), z);
+  }
+  float cf = rintf(__fadd_rn(qx, k.cx));
+  float rf = rintf(__fadd_rn(qy, k.cy));
   bool ok = (cf >= 0.f) && (cf < (float)W) && (rf >= 0.f) && (rf < (float)H) && (z > 0.f);
   if (ok) atomicMin(zimg + (int)rf * W + (int)cf, __float_as_uint(z));
 }
@@ -181,17 +237,26 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
     uint8_t ok[4];
     int r0, c0;
     row_col(i < HW ? i : 0, W, inv_w, r0, c0);
+    bool safe = k.fast;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int r = r0, c = c0 + j;
       if (c >= W) { c -= W; ++r; }
       ok[j] = use_clip ? (d[j] > lo && d[j] < hi) : 1;
       const float z = ok[j] ? d[j] : invalid;
+      safe = safe && (!ok[j] || depth_in_range(z));
       float x, y;
-      unproject(r, c, z, k, x, y);
+      unproject_fast(r, c, z, k, x, y);
       o[j * 3 + 0] = ok[j] ? x : invalid;
       o[j * 3 + 1] = ok[j] ? y : invalid;
       o[j * 3 + 2] = z;
+    }
+    if (!safe) {   // extreme depths or intrinsics somewhere in these four pixels: IEEE divisions
+      for (int j = 0; j < 4; ++j) {
+        int r = r0, c = c0 + j;
+        if (c >= W) { c -= W; ++r; }
+        if (ok[j]) unproject_ieee(r, c, o[j * 3 + 2], k, o[j * 3 + 0], o[j * 3 + 1]);
+      }
     }
     // the whole warp inside the image and 16-byte aligned: coalesced path
     const int w0 = (base4 + warp * 32) * 4;           // first pixel of this warp

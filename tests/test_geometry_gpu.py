@@ -62,6 +62,32 @@ def test_depth2pc_bit_exact(shape):
         assert np.array_equal(gv.cpu().numpy(), ov)
 
 
+def _same_bits_or_nan(a, b):
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+def test_extreme_depths_bit_exact():
+    """Signed zeros, negatives, denormals, huge values, inf and NaN: the fast exact division in the
+    kernels must hand these to the IEEE division and agree with the oracle bit for bit."""
+    B, H, W = 2, 64, 96
+    d01, K, P = _inputs(B, H, W, 13)
+    dm = (d01 * 10).numpy().copy()
+    special = np.array([0.0, -0.0, -1.5, 1e-42, 1e-30, 1e-12, 1e12, 1e30, 3e38, np.inf, -np.inf, np.nan,
+                        1.0, 2.5e-7, 7.7e19, 65504.0], np.float32)
+    flat = dm.reshape(B, -1)
+    flat[:, ::3] = special[np.arange(flat[:, ::3].shape[1]) % special.size]
+    dm_t = torch.tensor(dm)
+    with np.errstate(all="ignore"):
+        opc, ov = G.depth2pc(dm, K, clip=None, invalid=float("nan"))
+        od, om = G.reproject(dm, K, P)
+    gpc, gv = pg.depth2pc_tensor(dm_t.cuda(), torch.tensor(K).cuda(), clip=None, invalid_num=None)
+    assert _same_bits_or_nan(gpc.cpu().numpy(), opc)
+    assert np.array_equal(gv.cpu().numpy(), ov)
+    gd, gm = pg.reproject_tensor(dm_t.cuda(), torch.tensor(K).cuda(), torch.tensor(P).cuda())
+    assert _same_bits_or_nan(gd.cpu().numpy(), od)
+    assert np.array_equal(gm.cpu().numpy(), om)
+
+
 def test_pc2depth_ragged_bit_exact():
     B, H, W = 4, 256, 256
     d01, K, P = _inputs(B, H, W, 11)
