@@ -71,6 +71,14 @@ int prg_depth2pc_f32(const float* depth, const float* K, float clip_lo, float cl
                      int use_clip, float invalid, float* pc, uint8_t* valid,
                      int B, int H, int W, prg_stream_t stream);
 
+/* occlusion_filter (SDD:446-463), used by image_condition(use_occlusion_filter=True)
+ * (SDD:492-493) and Tester.sample (SDD:2035-2037).  depth (B,H,W) f32 metres, mask (B,H,W) u8
+ * (the z-buffer's outputs); depth_out (B,H,W) must not alias depth.  A pixel farther than
+ * 0.0375 behind the nearest valid depth of its 3x3 neighbourhood takes that depth.  The mask
+ * is returned unchanged by the reference, so there is no mask output. */
+int prg_occlusion_filter_f32(const float* depth, const uint8_t* mask, float* depth_out,
+                             int B, int H, int W, prg_stream_t stream);
+
 /* point_cloud (SDD:122-143) applied to depth01*scale, then optionally the
  * back-transform (pc - t) @ R of SDD:2627-2628 (pose NULL = skip).  Valid
  * pixels are compacted in row-major order.  pc_out: B slabs of H*W*3 f64,

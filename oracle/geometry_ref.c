@@ -149,3 +149,31 @@ void prg_ref_depth2pc_compact_f64(const float* depth01, const float* K, const fl
         counts[b] = n;
     }
 }
+
+/* occlusion_filter, SDD:446-463.  depth (B,H,W) metres (0 where empty), mask (B,H,W).
+ *   pre = depth with invalid pixels set to +inf; minN = 3x3 min of pre, the window clipped at the
+ *   image border (max_pool2d pads -depth with -inf); out = (depth - minN < 0.0375f) ? depth : minN.
+ * The mask is returned unchanged by the reference and is not touched here.  The comparison is
+ * fp32: torch compares a float32 tensor with the Python scalar 0.0375 in float32. */
+void prg_ref_occlusion_filter_f32(const float* depth, const uint8_t* mask, float* out,
+                                  int B, int H, int W) {
+    for (int b = 0; b < B; ++b) {
+        const float* d = depth + (size_t)b * H * W;
+        const uint8_t* m = mask + (size_t)b * H * W;
+        float* o = out + (size_t)b * H * W;
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c) {
+                float mn = INFINITY;
+                for (int dr = -1; dr <= 1; ++dr)
+                    for (int dc = -1; dc <= 1; ++dc) {
+                        int rr = r + dr, cc = c + dc;
+                        if (rr < 0 || rr >= H || cc < 0 || cc >= W) continue;
+                        float v = m[rr * W + cc] ? d[rr * W + cc] : INFINITY;   /* SDD:448-449 */
+                        if (v < mn) mn = v;                                     /* SDD:452-453 */
+                    }
+                float z = d[r * W + c];
+                float diff = z - mn;                                            /* SDD:458 */
+                o[r * W + c] = (diff < 0.0375f) ? z : mn;                       /* SDD:461 */
+            }
+    }
+}

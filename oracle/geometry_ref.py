@@ -109,3 +109,16 @@ def depth2pc_compact(depth01, K, pose=None, scale=10.0, clip=(0.5, 10)):
         ctypes.c_float(scale), ctypes.c_float(clip[0]), ctypes.c_float(clip[1]),
         _p(pc, ctypes.c_double), _p(counts, ctypes.c_int64), B, H, W)
     return [pc[b, :counts[b]].copy() for b in range(B)]
+
+
+def occlusion_filter(depth_rpj, mask_rpj):
+    """occlusion_filter (SDD:446-463): depth (B,1,H,W) f32 + mask (B,1,H,W) bool -> (depth, mask)."""
+    depth = _f32(depth_rpj)
+    shape = depth.shape
+    H, W = shape[-2:]
+    depth = np.ascontiguousarray(depth.reshape(-1, H, W))
+    m = np.ascontiguousarray(np.asarray(mask_rpj).reshape(-1, H, W).astype(np.uint8))
+    out = np.empty_like(depth)
+    _load().prg_ref_occlusion_filter_f32(_p(depth, ctypes.c_float), _p(m, ctypes.c_uint8),
+                                         _p(out, ctypes.c_float), depth.shape[0], H, W)
+    return out.reshape(shape), np.asarray(mask_rpj).astype(bool)

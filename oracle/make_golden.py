@@ -42,10 +42,36 @@ def inject_noise(noises):
     return orig
 
 
+def occlusion(sdd):
+    """occlusion_filter (SDD:446-463) on the reprojection of the 256x256 geometry case and on a
+    translated view (the Tester.sample use, SDD:2021-2037: 0.5 m forward, then the filter)."""
+    o = {}
+    B, H, W = 2, 256, 256
+    d01 = S.synthetic_depth_batch(40, B, H, W)
+    K = S.synthetic_intrinsics(B, 256, seed=5)
+    fwd = np.stack([np.eye(4, dtype=np.float32)] * B)
+    fwd[:, :3, 3] = [0, 0, 0.5]
+    for tag, P in (("pose", S.synthetic_poses(B, seed=6)), ("fwd", fwd)):
+        rd, rm = sdd.reproject_tensor(d01 * 10, torch.tensor(K), torch.tensor(P))
+        fd, fm = sdd.occlusion_filter(rd.clone(), rm.clone())
+        o["in_depth_sha_" + tag] = sha(rd.numpy())
+        o["out_depth_sha_" + tag] = sha(fd.numpy())
+        o["out_mask_sha_" + tag] = sha(fm.numpy())
+        o["changed_" + tag] = np.int64((fd != rd).sum())
+        o["out_crop_" + tag] = fd.numpy()[:, :, 96:160, 96:160]
+    o["P_fwd"] = fwd
+    np.savez_compressed(os.path.join(OUT, "occlusion.npz"), **o)
+    print("occlusion.npz", os.path.getsize(os.path.join(OUT, "occlusion.npz")) // 1024, "KiB")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sdd, dc = load_reference()
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["occlusion"]:       # mint only the newer fixture, leave the others alone
+        occlusion(sdd)
+        return
+    occlusion(sdd)
 
     # ------------------------------------------------------------------ geometry
     g = {}

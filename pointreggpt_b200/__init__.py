@@ -7,6 +7,7 @@ from .geometry import (depth2pc_tensor, pc2depth_tensor, pc2depth_ragged, reproj
                        point_cloud, point_cloud_batch, intrinsic_transform, param_vector,
                        random_sample_intrinsic, random_sample_pose, num_to_groups,
                        normalize_to_neg_one_to_one, unnormalize_to_zero_to_one,
-                       get_mask_from_img_cond, null_image_condition)
+                       get_mask_from_img_cond, null_image_condition, occlusion_filter,
+                       image_condition)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -62,6 +62,7 @@ SIGNATURES = {
                                      c_void_p]),
     "prg_sampler_run": (c_int, [c_void_p, ctypes.POINTER(Step), c_int, c_void_p, c_void_p,
                                 c_void_p, c_uint64, c_void_p, c_int, c_void_p]),
+    "prg_occlusion_filter_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "prg_profile_set": (c_int, [c_int]),
     "prg_profile_read": (c_int, [ctypes.POINTER(Profile), c_int, c_int]),
     "prg_test_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -200,6 +200,33 @@ def reproject_tensor(depth, intrinsic, relative_pose, *, clip=[0, 10], invalid_n
     return out, mask.view(torch.bool)
 
 
+def occlusion_filter(depth_rpj, mask_rpj):
+    """Replace pixels that lie more than 0.0375 behind the nearest valid depth of their 3x3
+    neighbourhood by that depth (SDD:446-463).  Returns (depth, mask_rpj); the mask is passed
+    through unchanged, as in the reference."""
+    _ffi.require_cuda(depth_rpj, mask_rpj)
+    b, c, h, w = depth_rpj.shape
+    assert c == 1 and mask_rpj.shape == depth_rpj.shape
+    d = _f32c(depth_rpj)
+    m = mask_rpj.to(torch.bool).contiguous().view(torch.uint8)
+    out = torch.empty_like(d)
+    _ffi.check(_ffi.lib().prg_occlusion_filter_f32(_ffi.ptr(d), _ffi.ptr(m), _ffi.ptr(out), b, h, w,
+                                                   _ffi.stream()))
+    return out, mask_rpj
+
+
+def image_condition(depth, intrinsic, relative_pose, depth_unit=10, depth_clip=[0, 10],
+                    use_occlusion_filter=False):
+    """depth (b,1,h,w) in [0,1] -> img_cond (b,2,h,w) in [-1,1]: reprojected depth / depth_unit and
+    the z-buffer mask (SDD:466-504)."""
+    depth_rpj, mask_rpj = reproject_tensor(depth * depth_unit, intrinsic, relative_pose,
+                                           clip=depth_clip)
+    if use_occlusion_filter:
+        depth_rpj, mask_rpj = occlusion_filter(depth_rpj, mask_rpj)
+    img_cond = torch.cat([depth_rpj / depth_unit, mask_rpj.to(depth_rpj.dtype)], dim=1)
+    return normalize_to_neg_one_to_one(img_cond)
+
+
 def point_cloud_batch(depth01, intrinsic, *, pose=None, scale=10.0, clip=(0.5, 10)):
     """Batched `point_cloud(depth01 * scale, K, clip)` (+ optional `(pc - t) @ R`,
     SDD:2623-2628) on the device.  Returns (pc (B, H*W, 3) float64 slabs, counts (B) int64)."""

@@ -51,6 +51,21 @@ def test_c_oracle_reproject_and_depth2pc(geo, tag):
     assert sha(valid) == str(geo["depth2pc_valid_sha_" + tag])
 
 
+@pytest.mark.parametrize("tag", ["pose", "fwd"])
+def test_c_oracle_occlusion_filter(geo, tag):
+    occ = np.load(os.path.join(GOLD, "occlusion.npz"))
+    d01, K, P, _ = _geo_inputs(geo, "256")
+    if tag == "fwd":
+        P = occ["P_fwd"]
+    rd, rm = G.reproject((d01 * 10).numpy(), K, P)
+    assert sha(rd) == str(occ["in_depth_sha_" + tag])
+    fd, fm = G.occlusion_filter(rd, rm)
+    assert sha(fd) == str(occ["out_depth_sha_" + tag])
+    assert sha(fm) == str(occ["out_mask_sha_" + tag])
+    assert int((fd != rd).sum()) == int(occ["changed_" + tag]) > 0
+    assert np.array_equal(fd[:, :, 96:160, 96:160], occ["out_crop_" + tag])
+
+
 @pytest.mark.parametrize("tag", ["256", "640"])
 def test_c_oracle_generate_path(geo, tag):
     d01, K, P, (B, H, W) = _geo_inputs(geo, tag)

@@ -69,3 +69,30 @@ def test_unet_and_sampler_bit_exact(ref):
         torch.randn, torch.randn_like = o1, o2
     got = R.p_sample_loop(sd, R.make_schedule(4), pc, ic, noises, has_refine_step=True)
     assert torch.equal(want, got)
+
+
+def test_occlusion_filter_bit_exact(ref):
+    sdd, _ = ref
+    B, H, W = 3, 96, 128
+    d01 = S.synthetic_depth_batch(21, B, H, W)
+    K = S.synthetic_intrinsics(B, None, seed=1).copy()
+    K[:, 0, 0] = K[:, 1, 1] = 150.0
+    K[:, 0, 2], K[:, 1, 2] = W / 2, H / 2
+    P = S.synthetic_poses(B, seed=5)
+    rd, rm = sdd.reproject_tensor(d01 * 10, torch.tensor(K), torch.tensor(P))
+    # differences exactly at, one ulp below and one ulp above the fp32 threshold, next to each other
+    thr = np.float32(0.0375)
+    base = np.float32(1.25)
+    edge = rd.clone()
+    for i, t in enumerate([thr, np.nextafter(thr, np.float32(0)), np.nextafter(thr, np.float32(1))]):
+        edge[0, 0, 10, 4 * i + 8] = float(base)
+        edge[0, 0, 10, 4 * i + 9] = float(np.float32(base + t))
+        rm[0, 0, 10, 4 * i + 8: 4 * i + 10] = True
+    edge[1, 0, 40:50, 30:50] = 0.0          # an empty region: all-invalid windows
+    rm[1, 0, 40:50, 30:50] = False
+    for dep in (rd, edge):
+        want_d, want_m = sdd.occlusion_filter(dep.clone(), rm.clone())
+        got_d, got_m = G.occlusion_filter(dep.numpy(), rm.numpy())
+        assert np.array_equal(want_d.numpy().view(np.uint32), got_d.view(np.uint32))
+        assert np.array_equal(want_m.numpy(), got_m)
+    assert (want_d != edge).any()            # the filter did replace something

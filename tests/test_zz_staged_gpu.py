@@ -1,0 +1,86 @@
+"""GPU parity tests of kernels written after the round's GPU budget was spent.
+
+Everything here has been checked on CPU as far as that goes (the oracle side is pinned to the
+reference in tests/test_oracle_vs_reference.py / test_oracle_golden.py, the library builds and
+exports the symbols), but the kernels have not run on hardware yet.  The tests are therefore
+non-strict xfail: a pass shows up as XPASS, a failure as XFAIL, and neither hides the verdict of the
+validated suite.  The file sorts last so that a faulting kernel cannot disturb other tests.
+Remove the marker once a GPU run shows XPASS.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry_ref as G
+from pointreggpt_b200 import geometry as pg
+from pointreggpt_b200 import synthetic as S
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="staged: not yet run on hardware", strict=False)]
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _reprojected(B, H, W, seed):
+    d01 = S.synthetic_depth_batch(300 + seed, B, H, W)
+    K = S.synthetic_intrinsics(B, 256 if H == 256 else None, seed=seed)
+    if (H, W) not in ((256, 256), (480, 640)):
+        K = K.copy()
+        K[:, 0, 0] = K[:, 1, 1] = 1.2 * W
+        K[:, 0, 2], K[:, 1, 2] = W / 2, H / 2
+    P = S.synthetic_poses(B, seed=seed + 1)
+    rd, rm = G.reproject((d01 * 10).numpy(), K, P)
+    return d01, K, P, rd, rm
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 256), (1, 480, 640), (2, 33, 47), (1, 5, 7), (1, 40, 260)])
+def test_occlusion_filter_bit_exact(shape):
+    B, H, W = shape
+    _, _, _, rd, rm = _reprojected(B, H, W, 17)
+    # threshold neighbours: exactly at, just below and just above 0.0375f behind the neighbour
+    thr = np.float32(0.0375)
+    if W >= 16 and H >= 4:
+        for i, t in enumerate([thr, np.nextafter(thr, np.float32(0)), np.nextafter(thr, np.float32(1))]):
+            rd[0, 0, 2, 4 * i + 1] = np.float32(1.25)
+            rd[0, 0, 2, 4 * i + 2] = np.float32(1.25) + t
+            rm[0, 0, 2, 4 * i + 1: 4 * i + 3] = True
+    od, om = G.occlusion_filter(rd, rm)
+    gd, gm = pg.occlusion_filter(torch.tensor(rd).cuda(), torch.tensor(rm).cuda())
+    assert gd.dtype == torch.float32 and gm.dtype == torch.bool
+    assert np.array_equal(gd.cpu().numpy().view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(gm.cpu().numpy(), om)
+
+
+def test_occlusion_filter_golden_and_empty():
+    occ = np.load(os.path.join(GOLD, "occlusion.npz"))
+    geo = np.load(os.path.join(GOLD, "geometry.npz"))
+    d01 = S.synthetic_depth_batch(40, 2, 256, 256)
+    K = torch.tensor(geo["K_256"]).cuda()
+    for tag, P in (("pose", geo["P_256"]), ("fwd", occ["P_fwd"])):
+        rd, rm = pg.reproject_tensor((d01 * 10).cuda(), K, torch.tensor(P).cuda())
+        fd, fm = pg.occlusion_filter(rd, rm)
+        assert np.array_equal(fd.cpu().numpy()[:, :, 96:160, 96:160], occ["out_crop_" + tag])
+        assert int((fd != rd).sum()) == int(occ["changed_" + tag])
+        assert torch.equal(fm, rm)
+    # nothing valid: output equals input (zeros); B = 0 is a no-op
+    z = torch.zeros(1, 1, 64, 64, device="cuda")
+    fd, _ = pg.occlusion_filter(z, torch.zeros_like(z, dtype=torch.bool))
+    assert (fd == 0).all()
+    fd, _ = pg.occlusion_filter(z[:0], torch.zeros_like(z[:0], dtype=torch.bool))
+    assert fd.shape == (0, 1, 64, 64)
+
+
+def test_image_condition_matches_composition():
+    B, H, W = 2, 256, 256
+    d01, K, P, _, _ = _reprojected(B, H, W, 23)
+    Kt, Pt = torch.tensor(K).cuda(), torch.tensor(P).cuda()
+    for occl in (False, True):
+        ic = pg.image_condition(d01.cuda(), Kt, Pt, use_occlusion_filter=occl)
+        rd, rm = G.reproject((d01 * 10).numpy(), K, P)
+        if occl:
+            rd, rm = G.occlusion_filter(rd, rm)
+        want = np.concatenate([rd / np.float32(10), rm.astype(np.float32)], 1) * np.float32(2) - np.float32(1)
+        assert ic.shape == (B, 2, H, W)
+        assert np.array_equal(ic.cpu().numpy(), want)
