@@ -1,11 +1,19 @@
-"""Offline evidence for next round's geometry kernels: is  q1 = fma(fma(-q0, b, a), y, q0)  with
-q0 = RN(a * y), y = RN(1 / b)  (3 instructions once y is known) the correctly rounded fp32 quotient
-a / b for the operand ranges of the reprojection?  Emulated exactly (float64 products of float32
-values are exact; mismatches are re-checked with Fractions).  Result on 16 M trials: 0 mismatches
-(see DESIGN.md section 5).  CPU only.
+"""Evidence for the three-instruction division of the geometry kernels (csrc/geometry.cu,
+div_exact):  is  q1 = fma(fma(-q0, b, a), y, q0)  with q0 = RN(a * y), y = RN(1 / b)  the correctly
+rounded fp32 quotient a / b?  Emulated exactly (float64 products of float32 values are exact; sums
+that land within two float64 ulps of a float32 rounding boundary, and all mismatches, are re-checked
+with Fractions).  CPU only.
 
-    python tools/check_division.py
+    python tools/check_division.py               # 16 M sampled trials over the kernels' operand ranges
+    python tools/check_division.py --exhaustive  # every fp32 significand of a, for each 3DMatch focal
+                                                 # length (raw and after Resize(256)+CenterCrop(256))
+
+A fixed divisor only needs one binade of numerators: scaling a by a power of two scales q0, r and q1
+exactly (no under/overflow inside the range the kernels guard), and the sign is symmetric.
+Results: sampled 0 mismatches in 16 M; exhaustive 0 mismatches in 18 x 2^23 (profiles/
+r1_division_exhaustive.txt).
 """
+import sys
 import numpy as np
 from fractions import Fraction
 rng = np.random.default_rng(0)
@@ -47,8 +55,51 @@ def run(name, a, b):
     print("%-28s n=%9d  residual exact: %s  mismatches (double emu) %d, confirmed exactly %d, q0 already correct %.4f"
           % (name, a.size, bool(exact_r.all()), bad.size, real_bad, float((q0 == truth).mean())))
 
-N = 4_000_000
+def exhaustive(b):
+    """All 2^23 significands a in [1, 2) against the fixed divisor b.  Returns (mismatches, rechecked)."""
+    b32 = f32(b)
+    y32 = f32(f32(1.0) / b32)
+    bad_total = recheck_total = 0
+    for lo in range(1 << 23, 1 << 24, 1 << 21):
+        a = (np.arange(lo, lo + (1 << 21), dtype=np.uint32)).astype(np.float64)
+        a = (a / float(1 << 23)).astype(f32)                      # 1.xxx, every significand once
+        bb = np.full(a.shape, b32, f32)
+        yy = np.full(a.shape, y32, f32)
+        truth = (a / bb).astype(f32)
+        q0, q1, exact_r, s64 = markstein_div(a, bb, yy)
+        assert exact_r.all(), "residual not exactly representable"
+        # sums whose float64 rounding could have moved them across a float32 rounding boundary
+        up = np.nextafter(q1, f32(np.inf)).astype(np.float64)
+        dn = np.nextafter(q1, f32(-np.inf)).astype(np.float64)
+        q64 = q1.astype(np.float64)
+        ulp64 = np.spacing(np.abs(s64))
+        risky = (np.abs(s64 - (q64 + up) * 0.5) <= 2 * ulp64) | (np.abs(s64 - (q64 + dn) * 0.5) <= 2 * ulp64)
+        idx = np.nonzero(risky | (q1 != truth))[0]
+        recheck_total += idx.size
+        for i in idx:
+            r = Fraction(float(a[i])) - Fraction(float(q0[i])) * Fraction(float(b32))
+            q1x = rn32_from_fraction(Fraction(float(q0[i])) + r * Fraction(float(y32)))
+            tx = rn32_from_fraction(Fraction(float(a[i])) / Fraction(float(b32)))
+            if q1x != tx:
+                bad_total += 1
+                print("  MISMATCH a=%r b=%r fast=%r ieee=%r" % (float(a[i]), float(b32), float(q1x), float(tx)))
+    return bad_total, recheck_total
+
+
 fxs = np.array([585, 572, 583, 540.02, 570.34, 533.07], dtype=np.float64)
+if "--exhaustive" in sys.argv:
+    consts = [("raw 640x480", v) for v in fxs.astype(f32)]
+    consts += [("fx*341/640", v) for v in (fxs * 341.0 / 640.0).astype(f32)]      # intrinsic_transform, SDD:47-119
+    consts += [("fy*256/480", v) for v in (fxs * 256.0 / 480.0).astype(f32)]
+    total = 0
+    for nm, v in consts:
+        bad, re = exhaustive(v)
+        total += bad
+        print("%-12s b=%-12.6f  2^23 numerators: mismatches %d  (exact re-checks %d)" % (nm, float(v), bad, re))
+    print("exhaustive: %d mismatches over %d divisors x 2^23 numerators" % (total, len(consts)))
+    sys.exit(1 if total else 0)
+
+N = 4_000_000
 fx256 = (fxs * 341.0 / 640.0)
 # unproject: a = (c - cx) * z ; divide by fx
 for nm, F, cx, Wd in (("unproject /fx 640x480", fxs, 320.0, 640), ("unproject /fx 256", fx256, 128.5, 256)):
