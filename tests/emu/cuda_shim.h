@@ -1,8 +1,12 @@
 /* TEST INFRASTRUCTURE ONLY.  Just enough of the CUDA device vocabulary to compile the body of a
- * simple, barrier-free kernel with g++ and run its threads one after another on the host
+ * simple kernel with g++ and run its threads one after another on the host
  * (tests/test_kernel_emulation.py).  It checks a kernel's index arithmetic, border handling and
- * rounding order against the oracle without a GPU; it says nothing about performance or about
- * kernels that use shared memory, shuffles or atomics.  Never part of the product library. */
+ * rounding order against the oracle without a GPU; it says nothing about performance, races or
+ * memory ordering.  Barriers are no-ops and __shared__ becomes a function-local static: a kernel
+ * that stages data through shared memory is run twice per block (the first pass fills the staging
+ * buffers, the second produces the output), which is valid when every thread makes one trip through
+ * its loop.  Compile with -ffp-contract=off so that only the explicit fmaf() calls fuse.  Never part
+ * of the product library. */
 #pragma once
 #include <cmath>
 #include <cstddef>
@@ -20,4 +24,22 @@ static dim3 blockIdx, threadIdx, blockDim, gridDim;
 static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+struct uint4 { unsigned x, y, z, w; };
+#define __shared__ static
+static inline void __syncthreads() {}
+static inline void __syncwarp() {}
+static inline uchar4 make_uchar4(unsigned char a, unsigned char b, unsigned char c, unsigned char d) { return {a, b, c, d}; }
+template <class T> static inline T __ldcs(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+/* x86-64 SSE arithmetic rounds every operation to nearest even in its own precision */
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline int __float2int_rz(float f) { return (int)f; }
+static inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }

@@ -31,20 +31,91 @@ extern "C" void emu_occlusion(const float* d, const uint8_t* m, float* o, int B,
 '''
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+GEOM_DRIVER = '''
+static void run_block(unsigned x, unsigned y, unsigned first, unsigned last, void (*fn)(void*), void* arg) {
+  for (unsigned t = first; t < last; ++t) {
+    blockIdx = {x, y, 0};
+    threadIdx = {t, 0, 0};
+    fn(arg);
+  }
+}
+struct RArgs { const float *depth, *K, *pose; float lo, hi; unsigned* z; int HW, H, W; };
+static void call_splat(void* p) {
+  RArgs& a = *(RArgs*)p;
+  k_reproject_splat(a.depth, a.K, a.pose, a.lo, a.hi, a.z, a.HW, a.H, a.W);
+}
+// prg_reproject_f32 without the L2 grouping: fill 0xFF, splat, finalise.  gx = grid_for(HW, 256, 4).
+extern "C" void emu_reproject(const float* depth, const float* K, const float* pose, float lo, float hi,
+                              float* out, uint8_t* mask, unsigned* scratch, int B, int H, int W, int gx) {
+  const int HW = H * W;
+  const size_t n = (size_t)B * HW;
+  memset(out, 0xFF, n * 4);
+  blockDim = {256, 1, 1};
+  gridDim = {(unsigned)gx, (unsigned)B, 1};
+  for (unsigned y = 0; y < (unsigned)B; ++y)
+    for (unsigned x = 0; x < (unsigned)gx; ++x) {
+      RArgs a{depth, K, pose, lo, hi, scratch, HW, H, W};
+      run_block(x, y, 0, 12, call_splat, &a);      // the threads that fill the pose in shared memory
+      a.z = (unsigned*)out;
+      run_block(x, y, 0, 256, call_splat, &a);
+    }
+  gridDim = {(unsigned)((n + 1023) / 1024), 1, 1};
+  for (unsigned x = 0; x < gridDim.x; ++x)
+    for (unsigned t = 0; t < 256; ++t) {
+      blockIdx = {x, 0, 0};
+      threadIdx = {t, 0, 0};
+      k_zbuf_finalize((unsigned*)out, mask, n);
+    }
+}
+struct DArgs { const float *depth, *K; float lo, hi; int use_clip; float invalid; float* pc; uint8_t* valid; int HW, W; };
+static void call_d2pc(void* p) {
+  DArgs& a = *(DArgs*)p;
+  k_depth2pc(a.depth, a.K, a.lo, a.hi, a.use_clip, a.invalid, a.pc, a.valid, a.HW, a.W);
+}
+extern "C" void emu_depth2pc(const float* depth, const float* K, float lo, float hi, int use_clip, float invalid,
+                             float* pc, uint8_t* valid, int B, int H, int W, int gx) {
+  const int HW = H * W;
+  blockDim = {256, 1, 1};
+  gridDim = {(unsigned)gx, (unsigned)B, 1};
+  DArgs a{depth, K, lo, hi, use_clip, invalid, pc, valid, HW, W};
+  for (unsigned y = 0; y < (unsigned)B; ++y)
+    for (unsigned x = 0; x < (unsigned)gx; ++x) {
+      run_block(x, y, 0, 256, call_d2pc, &a);      // fills the per-warp transpose buffers
+      run_block(x, y, 0, 256, call_d2pc, &a);      // reads them: the real output
+    }
+}
+'''
+
+
+def _compile(tmp, name, text):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    src = open(CU).read()
-    a = src.index("constexpr int kOccRows")
-    b = src.index("// ------------------------------------------------------------------ point_cloud")
-    d = tmp_path_factory.mktemp("emu")
-    cpp = d / "occ.cpp"
-    cpp.write_text('#include "cuda_shim.h"\n' + src[a:b] + DRIVER)
-    so = d / "occ.so"
+    cpp = tmp / (name + ".cpp")
+    cpp.write_text('#include "cuda_shim.h"\n' + text)
+    so = tmp / (name + ".so")
     subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC",
                            "-I", os.path.join(ROOT, "tests", "emu"), "-o", str(so), str(cpp)])
     return ctypes.CDLL(str(so))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    src = open(CU).read()
+    a = src.index("constexpr int kOccRows")
+    b = src.index("// ------------------------------------------------------------------ point_cloud")
+    return _compile(tmp_path_factory.mktemp("emu"), "occ", src[a:b] + DRIVER)
+
+
+@pytest.fixture(scope="module")
+def geom(tmp_path_factory):
+    """Device helpers (division, unproject, rigid, splat) + k_reproject_splat, k_zbuf_finalize and
+    k_depth2pc, exactly as they stand in geometry.cu."""
+    src = open(CU).read()
+    a = src.index("constexpr unsigned kEmpty")
+    b = src.index("// ------------------------------------------------------------------ pc2depth (ragged)")
+    c = src.index("// ------------------------------------------------------------------ depth2pc (dense)")
+    d = src.index("// ------------------------------------------------------------------ occlusion_filter")
+    return _compile(tmp_path_factory.mktemp("emu"), "geom", src[a:b] + src[c:d] + GEOM_DRIVER)
 
 
 @pytest.mark.parametrize("shape", [(2, 256, 256), (1, 480, 640), (2, 33, 47), (1, 5, 7), (1, 40, 260),
@@ -64,3 +135,63 @@ def test_occlusion_filter_kernel_logic(emu, shape):
     vp = ctypes.c_void_p
     emu.emu_occlusion(d.ctypes.data_as(vp), m.ctypes.data_as(vp), got.ctypes.data_as(vp), B, H, W)
     assert np.array_equal(got.reshape(rd.shape).view(np.uint32), want.view(np.uint32))
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _geo_inputs(B, H, W, seed, extreme=False):
+    d01 = S.synthetic_depth_batch(400 + seed, B, H, W)
+    K = S.synthetic_intrinsics(B, 256 if H == 256 else None, seed=seed).copy()
+    if (H, W) not in ((256, 256), (480, 640)):
+        K[:, 0, 0] = K[:, 1, 1] = 1.2 * W
+        K[:, 0, 2], K[:, 1, 2] = W / 2, H / 2
+    dm = (d01 * 10).numpy().reshape(B, H, W).copy()
+    if extreme:
+        special = np.array([0.0, -0.0, -1.5, 1e-42, 1e-30, 1e-12, 1e12, 1e30, 3e38, np.inf, -np.inf,
+                            np.nan, 1.0, 2.5e-7, 7.7e19, 65504.0], np.float32)
+        flat = dm.reshape(B, -1)
+        flat[:, ::3] = special[np.arange(flat[:, ::3].shape[1]) % special.size]
+    return dm, np.ascontiguousarray(K, np.float32), np.ascontiguousarray(S.synthetic_poses(B, seed=seed + 1), np.float32)
+
+
+def _same_bits_or_nan(a, b):
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+@pytest.mark.parametrize("shape,extreme", [((2, 256, 256), False), ((1, 480, 640), False),
+                                           ((2, 33, 47), False), ((2, 64, 96), True)])
+def test_reproject_kernel_numerics(geom, shape, extreme):
+    """The fast exact division, the rigid transform and the z-buffer of the CUDA source, compiled for
+    the host, against the oracle: bit-exact, including signed zeros / denormals / inf / NaN depths."""
+    B, H, W = shape
+    dm, K, P = _geo_inputs(B, H, W, 3, extreme)
+    with np.errstate(all="ignore"):
+        want_d, want_m = G.reproject(dm, K, P)
+    out = np.empty((B, H, W), np.float32)
+    mask = np.empty((B, H, W), np.uint8)
+    scratch = np.full((B, H, W), 0xFFFFFFFF, np.uint32)
+    gx = (H * W + 1023) // 1024
+    geom.emu_reproject(_vp(dm), _vp(K), _vp(P), ctypes.c_float(0.0), ctypes.c_float(10.0), _vp(out), _vp(mask),
+                       _vp(scratch), B, H, W, gx)
+    assert _same_bits_or_nan(out.reshape(want_d.shape), want_d)
+    assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m) and want_m.any()
+
+
+@pytest.mark.parametrize("shape,extreme", [((2, 256, 256), False), ((1, 480, 640), False),
+                                           ((1, 5, 7), False), ((2, 64, 96), True)])
+def test_depth2pc_kernel_numerics(geom, shape, extreme):
+    B, H, W = shape
+    dm, K, _ = _geo_inputs(B, H, W, 7, extreme)
+    gx = (H * W + 1023) // 1024
+    for clip, inv in [((0.0, 10.0), float("nan")), ((0.5, 10.0), 0.0), (None, float("nan"))]:
+        with np.errstate(all="ignore"):
+            want_pc, want_v = G.depth2pc(dm, K, clip=clip, invalid=inv)
+        pc = np.full((B, H * W, 3), -777.0, np.float32)
+        valid = np.full((B, H * W), 7, np.uint8)
+        lo, hi = clip if clip is not None else (0.0, 0.0)
+        geom.emu_depth2pc(_vp(dm), _vp(K), ctypes.c_float(lo), ctypes.c_float(hi), int(clip is not None),
+                          ctypes.c_float(inv), _vp(pc), _vp(valid), B, H, W, gx)
+        assert _same_bits_or_nan(pc, want_pc)
+        assert np.array_equal(valid.astype(bool), want_v)
