@@ -177,3 +177,51 @@ void prg_ref_occlusion_filter_f32(const float* depth, const uint8_t* mask, float
             }
     }
 }
+
+/* PointCloud.voxel_down_sample as the reference uses it (SDD:2486-2500, 2640-2680).  open3d is not
+ * under /root/reference and not installed: this restates Open3D 0.17's published behaviour
+ * (PointCloud::VoxelDownSample) -- PARITY UNPINNED against open3d itself; cross-checked against the
+ * independent torch formulation in pointreggpt_b200/cloud.py.
+ *   origin = min_bound - voxel/2;  index = floor((p - origin) / voxel) per axis (float64);
+ *   output = sum of the voxel's points in input order / their number.
+ * Output is ordered by the packed index (ix << 42 | iy << 21 | iz); open3d's order is unspecified.
+ * Returns the number of voxels, or -1 if an index does not fit 21 bits. */
+#include <stdlib.h>
+typedef struct { int64_t key; int64_t idx; } prg_ref_ki;
+static int prg_ref_cmp_ki(const void* a, const void* b) {
+    const prg_ref_ki* x = (const prg_ref_ki*)a; const prg_ref_ki* y = (const prg_ref_ki*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+int64_t prg_ref_voxel_downsample_f64(const double* pts, int64_t n, double voxel, double* out,
+                                     int64_t* keys_out) {
+    if (n <= 0) return 0;
+    double mn[3] = {pts[0], pts[1], pts[2]};
+    for (int64_t i = 1; i < n; ++i)
+        for (int a = 0; a < 3; ++a) if (pts[i * 3 + a] < mn[a]) mn[a] = pts[i * 3 + a];
+    double origin[3];
+    for (int a = 0; a < 3; ++a) origin[a] = mn[a] - voxel * 0.5;
+    prg_ref_ki* ki = (prg_ref_ki*)malloc((size_t)n * sizeof(prg_ref_ki));
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t key = 0;
+        for (int a = 0; a < 3; ++a) {
+            double f = floor((pts[i * 3 + a] - origin[a]) / voxel);
+            if (!(f >= 0.0 && f < 2097152.0)) { free(ki); return -1; }
+            key = (key << 21) | (int64_t)f;
+        }
+        ki[i].key = key; ki[i].idx = i;
+    }
+    qsort(ki, (size_t)n, sizeof(prg_ref_ki), prg_ref_cmp_ki);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n;) {
+        double s[3] = {0, 0, 0};
+        int64_t j = i;
+        for (; j < n && ki[j].key == ki[i].key; ++j)
+            for (int a = 0; a < 3; ++a) s[a] += pts[ki[j].idx * 3 + a];
+        for (int a = 0; a < 3; ++a) out[m * 3 + a] = s[a] / (double)(j - i);
+        keys_out[m++] = ki[i].key;
+        i = j;
+    }
+    free(ki);
+    return m;
+}

@@ -122,3 +122,19 @@ def occlusion_filter(depth_rpj, mask_rpj):
     _load().prg_ref_occlusion_filter_f32(_p(depth, ctypes.c_float), _p(m, ctypes.c_uint8),
                                          _p(out, ctypes.c_float), depth.shape[0], H, W)
     return out.reshape(shape), np.asarray(mask_rpj).astype(bool)
+
+
+def voxel_down_sample(points, voxel_size):
+    """Open3D-style voxel-grid centroids of points (N,3) f64, ordered by packed voxel index.
+    Returns (centroids (M,3) f64, keys (M,) i64)."""
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 3))
+    n = pts.shape[0]
+    out = np.empty((max(n, 1), 3), np.float64)
+    keys = np.empty((max(n, 1),), np.int64)
+    fn = _load().prg_ref_voxel_downsample_f64
+    fn.restype = ctypes.c_int64
+    m = fn(_p(pts, ctypes.c_double), ctypes.c_int64(n), ctypes.c_double(voxel_size),
+           _p(out, ctypes.c_double), _p(keys, ctypes.c_int64))
+    if m < 0:
+        raise ValueError("voxel index does not fit 21 bits per axis")
+    return out[:m].copy(), keys[:m].copy()

@@ -63,6 +63,9 @@ SIGNATURES = {
     "prg_sampler_run": (c_int, [c_void_p, ctypes.POINTER(Step), c_int, c_void_p, c_void_p,
                                 c_void_p, c_uint64, c_void_p, c_int, c_void_p]),
     "prg_occlusion_filter_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "prg_voxel_downsample_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
+    "prg_voxel_downsample_f64": (c_int, [c_void_p, ctypes.c_int64, ctypes.c_double, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "prg_profile_set": (c_int, [c_int]),
     "prg_profile_read": (c_int, [ctypes.POINTER(Profile), c_int, c_int]),
     "prg_test_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -33,6 +33,34 @@ def voxel_down_sample(points, voxel_size):
     return out / cnt[:, None]
 
 
+def voxel_down_sample_native(points, voxel_size):
+    """voxel_down_sample through the hand-written kernels (csrc/cloud.cu, prg_voxel_downsample_f64):
+    one hash-grid pass with order-independent fixed-point sums instead of unique + index_add.
+    Same semantics and output order (sorted voxel index) as voxel_down_sample above; centroids agree
+    to 2e-11 m.  STAGED: written after the round's GPU budget was spent -- the generator keeps using
+    voxel_down_sample until tests/test_zz_staged_gpu.py has passed on hardware."""
+    from . import _ffi
+    _ffi.require_cuda(points)
+    n = points.shape[0]
+    if n == 0:
+        return points.to(torch.float64)
+    p = points.to(torch.float64).contiguous()
+    dev = p.device
+    ws_bytes = int(_ffi.lib().prg_voxel_downsample_workspace_bytes(n))
+    ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
+    cent = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    keys = torch.empty((n,), dtype=torch.int64, device=dev)
+    ce = torch.empty((2,), dtype=torch.int32, device=dev)
+    _ffi.check(_ffi.lib().prg_voxel_downsample_f64(_ffi.ptr(p), n, float(voxel_size), _ffi.ptr(cent),
+                                                   _ffi.ptr(keys), _ffi.ptr(ce), _ffi.ptr(ws), ws_bytes,
+                                                   _ffi.stream()))
+    m, err = ce.tolist()
+    if err:
+        raise _ffi.PrgError("voxel_down_sample: non-finite point or more than 2^21 voxels along an axis")
+    order = torch.argsort(keys[:m])
+    return cent[:m][order]
+
+
 def transform(points, T):
     T = torch.as_tensor(T, dtype=torch.float64, device=points.device)
     return points.to(torch.float64) @ T[:3, :3].T + T[:3, 3]

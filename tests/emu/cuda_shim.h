@@ -43,3 +43,16 @@ static inline float __frcp_rn(float a) { volatile float r = 1.0f / a; return r; 
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline int __float2int_rz(float f) { return (int)f; }
 static inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
+typedef unsigned long long prg_emu_ull;
+static inline prg_emu_ull atomicMin(prg_emu_ull* p, prg_emu_ull v) { prg_emu_ull o = *p; if (v < o) *p = v; return o; }
+static inline prg_emu_ull atomicCAS(prg_emu_ull* p, prg_emu_ull cmp, prg_emu_ull v) { prg_emu_ull o = *p; if (o == cmp) *p = v; return o; }
+static inline prg_emu_ull atomicAdd(prg_emu_ull* p, prg_emu_ull v) { prg_emu_ull o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
+static inline long long __double_as_longlong(double d) { long long u; memcpy(&u, &d, 8); return u; }
+static inline double __longlong_as_double(long long u) { double d; memcpy(&d, &u, 8); return d; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline long long __double2ll_rn(double a) { return llrint(a); }

@@ -87,6 +87,37 @@ extern "C" void emu_depth2pc(const float* depth, const float* K, float lo, float
 '''
 
 
+VOX_DRIVER = '''
+template <class F> static void run_grid(unsigned blocks, F f) {
+  blockDim = {256, 1, 1};
+  gridDim = {blocks, 1, 1};
+  for (unsigned x = 0; x < blocks; ++x)
+    for (unsigned t = 0; t < 256; ++t) {
+      blockIdx = {x, 0, 0};
+      threadIdx = {t, 0, 0};
+      f();
+    }
+}
+// the body of prg_voxel_downsample_f64 on host memory; thread order reversed on request to show that
+// the result does not depend on the order of arrival
+extern "C" long long emu_voxel(const double* pts, long long n, double voxel, double* cent, long long* keys_out,
+                               int* count_err, unsigned char* ws, int blocks) {
+  const unsigned long long cap = vox_capacity(n);
+  unsigned long long* minb = (unsigned long long*)ws;
+  unsigned long long* keys = minb + 4;
+  unsigned long long* sums = keys + cap;
+  int* counts = (int*)(sums + 3 * cap);
+  memset(minb, 0xFF, 32 + cap * 8);
+  memset(sums, 0, cap * 28);
+  count_err[0] = count_err[1] = 0;
+  run_grid(blocks, [&] { k_vox_bounds(pts, n, minb); });
+  run_grid(blocks, [&] { k_vox_insert(pts, n, voxel, minb, keys, sums, counts, cap - 1, count_err); });
+  run_grid((unsigned)((cap + 1023) / 1024), [&] { k_vox_emit(minb, keys, sums, counts, cap, voxel, cent, keys_out, count_err); });
+  return (long long)cap;
+}
+'''
+
+
 def _compile(tmp, name, text):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
@@ -104,6 +135,14 @@ def emu(tmp_path_factory):
     a = src.index("constexpr int kOccRows")
     b = src.index("// ------------------------------------------------------------------ point_cloud")
     return _compile(tmp_path_factory.mktemp("emu"), "occ", src[a:b] + DRIVER)
+
+
+@pytest.fixture(scope="module")
+def vox(tmp_path_factory):
+    src = open(os.path.join(ROOT, "pointreggpt_b200", "csrc", "cloud.cu")).read()
+    a = src.index("constexpr unsigned long long kVoxEmpty")
+    b = src.index("}  // namespace prg")
+    return _compile(tmp_path_factory.mktemp("emu"), "vox", src[a:b] + VOX_DRIVER)
 
 
 @pytest.fixture(scope="module")
@@ -195,3 +234,48 @@ def test_depth2pc_kernel_numerics(geom, shape, extreme):
                           ctypes.c_float(inv), _vp(pc), _vp(valid), B, H, W, gx)
         assert _same_bits_or_nan(pc, want_pc)
         assert np.array_equal(valid.astype(bool), want_v)
+
+
+def _cloud(n, seed, extent=1.0):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-extent, extent, (n, 3)) + np.array([0.3, -1.1, 2.5])
+    pts[: n // 5] = np.round(pts[: n // 5] / 0.025) * 0.025        # points on voxel faces
+    pts[n // 5: n // 4] = pts[0]                                    # duplicates
+    return np.ascontiguousarray(pts)
+
+
+@pytest.mark.parametrize("n,voxel,blocks", [(20000, 0.025, 20), (20000, 0.1, 7), (5000, 0.002, 5), (3, 0.5, 1),
+                                            (1, 0.1, 1), (4097, 0.05, 64)])
+def test_voxel_downsample_kernel_logic(vox, n, voxel, blocks):
+    pts = _cloud(n, n)
+    want_c, want_k = G.voxel_down_sample(pts, voxel)
+    cap = 1024
+    while cap < 2 * n:
+        cap *= 2
+    ws = np.zeros(32 + cap * 36, np.uint8)
+    cent = np.zeros((n, 3), np.float64)
+    keys = np.zeros((n,), np.int64)
+    ce = np.zeros((2,), np.int32)
+    got_cap = vox.emu_voxel(_vp(pts), ctypes.c_longlong(n), ctypes.c_double(voxel), _vp(cent), _vp(keys), _vp(ce),
+                            _vp(ws), blocks)
+    assert got_cap == cap
+    m, err = int(ce[0]), int(ce[1])
+    assert err == 0 and m == want_k.shape[0]
+    if n > 100:
+        assert m < n                                               # several points per voxel somewhere
+    order = np.argsort(keys[:m])
+    assert np.array_equal(keys[:m][order], want_k)
+    assert np.abs(cent[:m][order] - want_c).max() < 1e-10          # fixed-point sums: < 2e-11 m
+
+
+def test_voxel_downsample_kernel_flags_bad_points(vox):
+    pts = _cloud(100, 1)
+    pts[17, 1] = np.nan
+    ws = np.zeros(32 + 1024 * 36, np.uint8)
+    cent, keys, ce = np.zeros((100, 3)), np.zeros((100,), np.int64), np.zeros((2,), np.int32)
+    vox.emu_voxel(_vp(pts), ctypes.c_longlong(100), ctypes.c_double(0.05), _vp(cent), _vp(keys), _vp(ce), _vp(ws), 1)
+    assert ce[1] == 1
+    pts = _cloud(100, 2)
+    pts[3, 0] += 1e6                                                  # 1e6 / 1e-3 voxels > 2^21
+    vox.emu_voxel(_vp(pts), ctypes.c_longlong(100), ctypes.c_double(1e-3), _vp(cent), _vp(keys), _vp(ce), _vp(ws), 1)
+    assert ce[1] == 1

@@ -14,6 +14,7 @@ import pytest
 import torch
 
 from oracle import geometry_ref as G
+from pointreggpt_b200 import cloud
 from pointreggpt_b200 import geometry as pg
 from pointreggpt_b200 import synthetic as S
 
@@ -84,3 +85,29 @@ def test_image_condition_matches_composition():
         want = np.concatenate([rd / np.float32(10), rm.astype(np.float32)], 1) * np.float32(2) - np.float32(1)
         assert ic.shape == (B, 2, H, W)
         assert np.array_equal(ic.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n,voxel", [(200000, 0.025), (200000, 0.002), (5000, 0.1), (3, 0.5), (1, 0.1)])
+def test_voxel_down_sample_native(n, voxel):
+    rng = np.random.default_rng(n)
+    pts = rng.uniform(-1.0, 1.0, (n, 3)) + np.array([0.3, -1.1, 2.5])
+    pts[: n // 5] = np.round(pts[: n // 5] / 0.025) * 0.025        # points on voxel faces
+    pts[n // 5: n // 4] = pts[0]                                    # duplicates
+    want_c, _ = G.voxel_down_sample(pts, voxel)
+    t = torch.tensor(pts).cuda()
+    got = cloud.voxel_down_sample_native(t, voxel)
+    assert got.dtype == torch.float64 and got.shape == want_c.shape
+    assert np.abs(got.cpu().numpy() - want_c).max() < 1e-10         # fixed-point sums: < 2e-11 m
+    again = cloud.voxel_down_sample_native(t.flip(0), voxel)        # order of arrival does not matter
+    assert torch.equal(got, again)
+    lib = cloud.voxel_down_sample(t, voxel)                         # the torch-op formulation in use today
+    assert np.abs(lib.cpu().numpy() - want_c).max() < 1e-10
+
+
+def test_voxel_down_sample_native_rejects_bad_points():
+    from pointreggpt_b200._ffi import PrgError
+    pts = torch.rand(100, 3, dtype=torch.float64).cuda()
+    assert cloud.voxel_down_sample_native(pts[:0], 0.1).shape == (0, 3)
+    pts[7, 2] = float("nan")
+    with pytest.raises(PrgError):
+        cloud.voxel_down_sample_native(pts, 0.1)
