@@ -92,6 +92,15 @@ int prg_voxel_downsample_f64(const double* points, int64_t n_points, double voxe
                              double* centroids, int64_t* keys_out, int32_t* count_err,
                              void* workspace, size_t workspace_bytes, prg_stream_t stream);
 
+/* Inner loop of compute_overlap_ratio (generate_gt.py:84-101): count_err[0] receives the
+ * number of query points (Nq,3 f64) that have a target point (Nt,3 f64) at squared distance
+ * < radius^2; count_err[1] = 1 if a point was skipped (non-finite, or beyond +-2^20 cells of size
+ * radius).  workspace: prg_overlap_workspace_bytes(Nt) bytes, 16-byte aligned. */
+size_t prg_overlap_workspace_bytes(int64_t n_target);
+int prg_overlap_count_f64(const double* query, int64_t n_query, const double* target,
+                          int64_t n_target, double radius, int32_t* count_err, void* workspace,
+                          size_t workspace_bytes, prg_stream_t stream);
+
 /* point_cloud (SDD:122-143) applied to depth01*scale, then optionally the
  * back-transform (pc - t) @ R of SDD:2627-2628 (pose NULL = skip).  Valid
  * pixels are compacted in row-major order.  pc_out: B slabs of H*W*3 f64,

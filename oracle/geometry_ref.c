@@ -225,3 +225,24 @@ int64_t prg_ref_voxel_downsample_f64(const double* pts, int64_t n, double voxel,
     free(ki);
     return m;
 }
+
+/* compute_overlap_ratio's inner loop (generate_gt.py:84-101): how many query points have a target
+ * point at squared distance < radius^2 (the strict test of the nanoflann radius search open3d's
+ * KDTreeFlann wraps -- open3d is not installed here: PARITY UNPINNED against open3d, cross-checked
+ * against scipy's cKDTree in tests/test_oracle_golden.py).  Brute force. */
+int64_t prg_ref_overlap_count_f64(const double* q, int64_t nq, const double* t, int64_t nt, double radius) {
+    const double r2 = radius * radius;
+    int64_t hits = 0;
+    for (int64_t i = 0; i < nq; ++i) {
+        int found = 0;
+        for (int64_t j = 0; j < nt && !found; ++j) {
+            double dx = t[j * 3 + 0] - q[i * 3 + 0];
+            double dy = t[j * 3 + 1] - q[i * 3 + 1];
+            double dz = t[j * 3 + 2] - q[i * 3 + 2];
+            double d2 = (dx * dx + dy * dy) + dz * dz;
+            found = d2 < r2;
+        }
+        hits += found;
+    }
+    return hits;
+}

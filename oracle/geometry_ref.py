@@ -138,3 +138,22 @@ def voxel_down_sample(points, voxel_size):
     if m < 0:
         raise ValueError("voxel index does not fit 21 bits per axis")
     return out[:m].copy(), keys[:m].copy()
+
+
+def overlap_count(query, target, radius):
+    """Number of query points (Nq,3) f64 with a target point (Nt,3) closer than radius."""
+    q = np.ascontiguousarray(np.asarray(query, dtype=np.float64).reshape(-1, 3))
+    t = np.ascontiguousarray(np.asarray(target, dtype=np.float64).reshape(-1, 3))
+    fn = _load().prg_ref_overlap_count_f64
+    fn.restype = ctypes.c_int64
+    return int(fn(_p(q, ctypes.c_double), ctypes.c_int64(q.shape[0]), _p(t, ctypes.c_double),
+                  ctypes.c_int64(t.shape[0]), ctypes.c_double(radius)))
+
+
+def compute_overlap_ratio(pc1, pc2, voxel_size=0.025, overlap_factor=1.5, is_down_sample=True):
+    """generate_gt.py:68-102 on (N,3) arrays."""
+    r = voxel_size * overlap_factor
+    if is_down_sample:
+        pc1, _ = voxel_down_sample(pc1, voxel_size)
+        pc2, _ = voxel_down_sample(pc2, voxel_size)
+    return overlap_count(pc1, pc2, r) / pc1.shape[0], overlap_count(pc2, pc1, r) / pc2.shape[0]

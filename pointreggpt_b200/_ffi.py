@@ -66,6 +66,9 @@ SIGNATURES = {
     "prg_voxel_downsample_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
     "prg_voxel_downsample_f64": (c_int, [c_void_p, ctypes.c_int64, ctypes.c_double, c_void_p, c_void_p,
                                          c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
+    "prg_overlap_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
+    "prg_overlap_count_f64": (c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_double,
+                                      c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "prg_profile_set": (c_int, [c_int]),
     "prg_profile_read": (c_int, [ctypes.POINTER(Profile), c_int, c_int]),
     "prg_test_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

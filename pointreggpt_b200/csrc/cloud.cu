@@ -8,7 +8,7 @@
 // atomicCAS, and every point adds (p - origin) as 2^-36 m fixed point to its voxel's three 64-bit sums,
 // so the result does not depend on the order in which threads arrive (float64 atomics would).  The
 // centroid differs from a sequential float64 mean by < 2e-11 m.  HBM: 24 B/point read; the table
-// (40 B/slot, 2 slots per point at most) lives in L2 for the clouds of this pipeline (<= 1 M points).
+// (36 B/slot, 2 to 4 slots per point) lives in L2 for the clouds of this pipeline (<= 1 M points).
 #include "common.cuh"
 
 namespace prg {
@@ -111,6 +111,91 @@ k_vox_emit(const unsigned long long* __restrict__ minb, const unsigned long long
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Overlap ratio of two clouds (generate_gt.py:68-102): the fraction of query points that
+// have a target point closer than `radius` (squared distance < radius^2, the strict test of the
+// nanoflann radius search behind open3d's KDTreeFlann.search_radius_vector_3d).  The targets go into a
+// hash grid of cell size `radius` (one singly linked list per cell, built with atomicExch), a query
+// looks at its 27 neighbouring cells and stops at the first hit.  The count is exact and does not
+// depend on the order of arrival.
+// ------------------------------------------------------------------------------------------------
+constexpr double kOvlBias = 1048576.0;          // 2^20: cell indices are offset to be positive
+
+__device__ __forceinline__ bool ovl_cell(const double* __restrict__ p, double radius, long long c[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double f = __dadd_rn(floor(__ddiv_rn(p[a], radius)), kOvlBias);
+    if (!(f >= 1.0 && f < kVoxMaxIndex - 1.0)) return false;   // non-finite or outside +-2^20 cells
+    c[a] = (long long)f;
+  }
+  return true;
+}
+__device__ __forceinline__ unsigned long long ovl_key(long long x, long long y, long long z) {
+  return ((unsigned long long)x << 42) | ((unsigned long long)y << 21) | (unsigned long long)z;
+}
+
+__global__ void __launch_bounds__(256)
+k_ovl_build(const double* __restrict__ tgt, long long n, double radius,
+            unsigned long long* __restrict__ keys, int* __restrict__ head, int* __restrict__ next,
+            unsigned long long mask, int* __restrict__ count_err) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long c[3];
+    if (!ovl_cell(tgt + i * 3, radius, c)) {
+      next[i] = -1;
+      atomicExch(count_err + 1, 1);
+      continue;
+    }
+    const unsigned long long key = ovl_key(c[0], c[1], c[2]);
+    unsigned long long slot = vox_mix(key) & mask;
+    for (;;) {
+      const unsigned long long prev = atomicCAS(keys + slot, kVoxEmpty, key);
+      if (prev == kVoxEmpty || prev == key) break;
+      slot = (slot + 1) & mask;
+    }
+    next[i] = atomicExch(head + slot, (int)i);      // push front
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_ovl_query(const double* __restrict__ qry, long long nq, const double* __restrict__ tgt, double radius,
+            const unsigned long long* __restrict__ keys, const int* __restrict__ head,
+            const int* __restrict__ next, unsigned long long mask, int* __restrict__ count_err) {
+  const double r2 = __dmul_rn(radius, radius);
+  int hits = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nq;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double q0 = qry[i * 3 + 0], q1 = qry[i * 3 + 1], q2 = qry[i * 3 + 2];
+    long long c[3];
+    if (!ovl_cell(qry + i * 3, radius, c)) {
+      atomicExch(count_err + 1, 1);
+      continue;
+    }
+    bool found = false;
+    for (int d = 0; d < 27 && !found; ++d) {
+      const unsigned long long key = ovl_key(c[0] + d / 9 - 1, c[1] + (d / 3) % 3 - 1, c[2] + d % 3 - 1);
+      unsigned long long slot = vox_mix(key) & mask;
+      for (;;) {
+        const unsigned long long k = keys[slot];
+        if (k == kVoxEmpty) break;
+        if (k == key) {
+          for (int j = head[slot]; j >= 0 && !found; j = next[j]) {
+            const double dx = __dsub_rn(tgt[(size_t)j * 3 + 0], q0);
+            const double dy = __dsub_rn(tgt[(size_t)j * 3 + 1], q1);
+            const double dz = __dsub_rn(tgt[(size_t)j * 3 + 2], q2);
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            found = d2 < r2;
+          }
+          break;
+        }
+        slot = (slot + 1) & mask;
+      }
+    }
+    hits += found ? 1 : 0;
+  }
+  if (hits) atomicAdd(count_err, hits);
+}
+
 static unsigned long long vox_capacity(long long n) {
   unsigned long long cap = 1024;
   while (cap < 2ull * (unsigned long long)n) cap <<= 1;
@@ -158,6 +243,41 @@ extern "C" __attribute__((visibility("default"))) int prg_voxel_downsample_f64(
   if (eblocks > num_sms() * 8) eblocks = num_sms() * 8;
   k_vox_emit<<<eblocks, 256, 0, s>>>(minb, keys, sums, counts, cap, voxel_size, centroids,
                                      reinterpret_cast<long long*>(keys_out), count_err);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t prg_overlap_workspace_bytes(int64_t n_target) {
+  if (n_target < 0) return 0;
+  return vox_capacity(n_target) * 12 + (size_t)n_target * 4;
+}
+
+extern "C" __attribute__((visibility("default"))) int prg_overlap_count_f64(
+    const double* query, int64_t n_query, const double* target, int64_t n_target, double radius,
+    int32_t* count_err, void* workspace, size_t workspace_bytes, prg_stream_t stream) {
+  PRG_CHECK_ARG(count_err != nullptr, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  PRG_CUDA_OK(cudaMemsetAsync(count_err, 0, 2 * sizeof(int32_t), s));
+  if (n_query == 0 || n_target == 0) return PRG_OK;
+  PRG_CHECK_ARG(query && target && workspace, "null pointer");
+  PRG_CHECK_ARG(n_query > 0 && n_target > 0 && n_query <= (1ll << 30) && n_target <= (1ll << 30), "point count");
+  PRG_CHECK_ARG(radius > 0.0, "radius must be positive");
+  const unsigned long long cap = vox_capacity(n_target);
+  PRG_CHECK_ARG(workspace_bytes >= cap * 12 + (size_t)n_target * 4, "workspace too small");
+  PRG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  // [keys cap x u64 | head cap x i32] filled with 0xFF (empty key, head = -1); [next n_target x i32]
+  unsigned long long* keys = static_cast<unsigned long long*>(workspace);
+  int* head = reinterpret_cast<int*>(keys + cap);
+  int* next = head + cap;
+  PRG_CUDA_OK(cudaMemsetAsync(keys, 0xFF, cap * 12, s));
+  int blocks = ceil_div(n_target, 256 * 4);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  k_ovl_build<<<blocks, 256, 0, s>>>(target, (long long)n_target, radius, keys, head, next, cap - 1, count_err);
+  PRG_LAUNCH_CHECK();
+  blocks = ceil_div(n_query, 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  k_ovl_query<<<blocks, 256, 0, s>>>(query, (long long)n_query, target, radius, keys, head, next, cap - 1,
+                                     count_err);
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }

@@ -171,3 +171,33 @@ def test_two_rank_weight_broadcast_and_sharding_gloo():
     assert fp0 == fp1 and nb0 == nb1 > 0
     assert (lo0, hi0, lo1, hi1) == (0, 3, 3, 5)
     assert tot0 == tot1 == [5.0, 2.0]
+
+
+def test_generate_gt_file_logic(tmp_path, monkeypatch):
+    """generate_gt.py:105-199: pair enumeration, the < 1000 points and < 0.1 / < 0.1 filters, the TSV
+    format, skip-if-exists and gather.  The GPU ratio is replaced by the oracle's (CPU)."""
+    import numpy as np
+    import torch
+    from oracle import geometry_ref as G
+    from pointreggpt_b200 import cloud, overlap
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(overlap, "compute_overlap_ratio",
+                        lambda a, b: G.compute_overlap_ratio(a.cpu().numpy(), b.cpu().numpy()))
+    rng = np.random.default_rng(0)
+    base = rng.uniform(0, 1, (3000, 3))
+    clouds = {0: base, 1: base + [0.3, 0, 0], 2: base + [5.0, 0, 0], 3: base[:500]}
+    sdir = tmp_path / "ds" / "data" / "scene-000004"
+    sdir.mkdir(parents=True)
+    for i, c in clouds.items():
+        cloud.write_ply(str(sdir / "sample-{:0>6d}.cloud.ply".format(i)), torch.tensor(c))
+    (tmp_path / "ds" / "data" / "scene-000005").mkdir()
+    assert overlap.generate_gt("ds", 4, 6, 4, device="cpu") == 2
+    lines = (sdir / "gt.log").read_text().splitlines()
+    assert len(lines) == 1                                  # only (0, 1): 2 is far away, 3 is too small
+    name, s, t, o1, o2 = lines[0].split("\t")
+    r1, r2 = G.compute_overlap_ratio(clouds[0], clouds[1])
+    assert (name, s, t) == ("scene-000004", "0", "1") and o1 == "%.4f" % r1 and o2 == "%.4f" % r2
+    assert (tmp_path / "ds" / "data" / "scene-000005" / "gt.log").read_text() == ""
+    assert overlap.generate_gt("ds", 4, 6, 4, device="cpu") == 0       # both exist now
+    final = overlap.gather_gt("ds", 4, 6)
+    assert open(final).read().splitlines() == lines

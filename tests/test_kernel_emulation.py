@@ -115,6 +115,18 @@ extern "C" long long emu_voxel(const double* pts, long long n, double voxel, dou
   run_grid((unsigned)((cap + 1023) / 1024), [&] { k_vox_emit(minb, keys, sums, counts, cap, voxel, cent, keys_out, count_err); });
   return (long long)cap;
 }
+// the body of prg_overlap_count_f64
+extern "C" void emu_overlap(const double* q, long long nq, const double* t, long long nt, double radius,
+                            int* count_err, unsigned char* ws, int blocks) {
+  const unsigned long long cap = vox_capacity(nt);
+  unsigned long long* keys = (unsigned long long*)ws;
+  int* head = (int*)(keys + cap);
+  int* next = head + cap;
+  memset(keys, 0xFF, cap * 12);
+  count_err[0] = count_err[1] = 0;
+  run_grid(blocks, [&] { k_ovl_build(t, nt, radius, keys, head, next, cap - 1, count_err); });
+  run_grid(blocks, [&] { k_ovl_query(q, nq, t, radius, keys, head, next, cap - 1, count_err); });
+}
 '''
 
 
@@ -278,4 +290,29 @@ def test_voxel_downsample_kernel_flags_bad_points(vox):
     pts = _cloud(100, 2)
     pts[3, 0] += 1e6                                                  # 1e6 / 1e-3 voxels > 2^21
     vox.emu_voxel(_vp(pts), ctypes.c_longlong(100), ctypes.c_double(1e-3), _vp(cent), _vp(keys), _vp(ce), _vp(ws), 1)
+    assert ce[1] == 1
+
+
+@pytest.mark.parametrize("nq,nt,radius,blocks", [(4000, 3000, 0.075, 9), (3000, 4000, 0.0375, 3), (500, 1, 0.5, 1),
+                                                 (1, 500, 0.2, 2), (2000, 2000, 1.5, 4)])
+def test_overlap_kernel_logic(vox, nq, nt, radius, blocks):
+    rng = np.random.default_rng(nq + nt)
+    q = np.ascontiguousarray(rng.uniform(-1, 1, (nq, 3)))
+    t = np.ascontiguousarray(rng.uniform(-0.5, 1.5, (nt, 3)))
+    if nt > 10 and nq > 10:
+        t[:5] = q[:5] + np.array([radius, 0, 0])          # exactly at the radius: not a neighbour (strict <)
+        t[5:10] = q[5:10]                                 # coincident points
+    want = G.overlap_count(q, t, radius)
+    cap = 1024
+    while cap < 2 * nt:
+        cap *= 2
+    ws = np.zeros(cap * 12 + nt * 4, np.uint8)
+    ce = np.zeros((2,), np.int32)
+    vox.emu_overlap(_vp(q), ctypes.c_longlong(nq), _vp(t), ctypes.c_longlong(nt), ctypes.c_double(radius), _vp(ce),
+                    _vp(ws), blocks)
+    assert ce[1] == 0 and int(ce[0]) == want
+    assert 0 < want or nt == 1
+    q[0, 0] = np.inf
+    vox.emu_overlap(_vp(q), ctypes.c_longlong(nq), _vp(t), ctypes.c_longlong(nt), ctypes.c_double(radius), _vp(ce),
+                    _vp(ws), blocks)
     assert ce[1] == 1

@@ -141,3 +141,22 @@ def test_schedule_buffers(net):
     for k, v in sch.items():
         assert np.array_equal(v.numpy(), net["sched_" + k]), k
     assert [t for t, _ in R.ddim_times(1000, 250)] + [-1] == list(net["ddim_times_1000_250"])
+
+
+def test_c_oracle_overlap_and_voxel_against_independent_formulations():
+    """open3d is not installed, so these two restatements have no reference pin; they are checked
+    against independent implementations instead: scipy's KD-tree and the torch-op voxel grid."""
+    from scipy.spatial import cKDTree
+    from pointreggpt_b200 import cloud
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1, 1, (6000, 3))
+    b = rng.uniform(-0.6, 1.4, (5000, 3))
+    for r in (0.0375, 0.1):
+        want = sum(1 for x in cKDTree(b).query_ball_point(a, r) if len(x) > 0)
+        assert G.overlap_count(a, b, r) == want
+    for v in (0.025, 0.2):
+        c, k = G.voxel_down_sample(a, v)
+        t = cloud.voxel_down_sample(torch.tensor(a), v).numpy()
+        assert c.shape == t.shape and np.abs(c - t).max() < 1e-12 and np.all(np.diff(k) > 0)
+    r1, r2 = G.compute_overlap_ratio(a, b)
+    assert 0 < r1 < 1 and 0 < r2 < 1

@@ -111,3 +111,29 @@ def test_voxel_down_sample_native_rejects_bad_points():
     pts[7, 2] = float("nan")
     with pytest.raises(PrgError):
         cloud.voxel_down_sample_native(pts, 0.1)
+
+
+@pytest.mark.parametrize("nq,nt,radius", [(60000, 50000, 0.0375), (5000, 70000, 0.1), (300, 1, 0.5)])
+def test_overlap_count_exact(nq, nt, radius):
+    from scipy.spatial import cKDTree
+    from pointreggpt_b200 import overlap
+    rng = np.random.default_rng(nq)
+    q = rng.uniform(-1, 1, (nq, 3))
+    t = rng.uniform(-0.5, 1.5, (nt, 3))
+    want = sum(1 for x in cKDTree(t).query_ball_point(q, radius) if len(x) > 0)
+    got = overlap.overlap_count(torch.tensor(q).cuda(), torch.tensor(t).cuda(), radius)
+    assert got == want
+
+
+def test_compute_overlap_ratio_matches_oracle():
+    from pointreggpt_b200 import overlap
+    d01 = S.synthetic_depth_batch(77, 2, 256, 256)
+    K = S.synthetic_intrinsics(2, 256, seed=3)
+    P = S.synthetic_poses(2, seed=4)
+    a = G.depth2pc_compact(d01[:1].numpy(), K[:1], None)[0]
+    b = G.depth2pc_compact(d01[:1].numpy(), K[:1], P[:1])[0]      # the same surface seen from a moved camera
+    want = G.compute_overlap_ratio(a, b)
+    got = overlap.compute_overlap_ratio(torch.tensor(a).cuda(), torch.tensor(b).cuda())
+    # the voxel centroids come from torch index_add here (last-bit differences in the means are
+    # possible), so a point exactly at the search radius may flip: allow a handful of points
+    assert got == pytest.approx(want, abs=1e-3) and 0.05 < got[0] < 1.0
