@@ -8,7 +8,6 @@ The radius search runs on the GPU (csrc/cloud.cu, prg_overlap_count_f64: hash gr
 STAGED: written after the round's GPU budget was spent; the parity tests are in
 tests/test_zz_staged_gpu.py and have not run on hardware yet.
 """
-import os
 from itertools import combinations
 from pathlib import Path
 
@@ -50,53 +49,54 @@ def compute_overlap_ratio(pc1, pc2, voxel_size=0.025, overlap_factor=1.5, is_dow
     return r1, r2
 
 
+MIN_POINTS = 1000        # generate_gt.py:143-145: pairs with a smaller cloud are not rated
+MIN_OVERLAP = 0.1        # generate_gt.py:154: dropped when both ratios are below
+
+
+def _scene_dir(dataset_name, scene_idx):
+    return Path(".") / dataset_name / "data" / "scene-{:0>6d}".format(scene_idx)
+
+
+def _rate_pair(scene_dir, i, j, device):
+    """TSV line for clouds i, j of a scene, or None when the pair is skipped (generate_gt.py:131-163)."""
+    files = [scene_dir / "sample-{:0>6d}.cloud.ply".format(k) for k in (i, j)]
+    if not all(f.exists() for f in files):
+        return None
+    pts = [cloud.read_ply(str(f)) for f in files]
+    if min(p.shape[0] for p in pts) < MIN_POINTS:
+        return None
+    ra, rb = compute_overlap_ratio(*(torch.tensor(p, device=device) for p in pts))
+    if np.isnan(ra) or np.isnan(rb) or (ra < MIN_OVERLAP and rb < MIN_OVERLAP):
+        return None
+    return "\t".join([scene_dir.name, str(i), str(j), "%.4f" % ra, "%.4f" % rb]) + "\n"
+
+
 def generate_gt(dataset_name, start_scene_index, stop_scene_index, num_samples, device="cuda"):
-    """generate_gt.py:105-176: one `gt.log` per scene with a TSV line per kept pair."""
-    root_path = Path("./{}/data".format(dataset_name))
+    """One `gt.log` per scene, a TSV line per kept pair (generate_gt.py:105-176); scenes that already
+    have one are left alone.  Returns the number of logs written."""
     written = 0
     for scene_idx in range(start_scene_index, stop_scene_index):
-        scene_name = "scene-{:0>6d}".format(scene_idx)
-        scene_path = root_path.joinpath(scene_name)
-        gt_path = scene_path.joinpath("gt.log")
-        if gt_path.exists():
+        sdir = _scene_dir(dataset_name, scene_idx)
+        log = sdir / "gt.log"
+        if log.exists():
             print("scene gt log has existed, skip over it")
             continue
-        lines = []
-        for src_idx, tgt_idx in combinations(range(num_samples), 2):
-            src_path = scene_path.joinpath("sample-{:0>6d}.cloud.ply".format(src_idx))
-            tgt_path = scene_path.joinpath("sample-{:0>6d}.cloud.ply".format(tgt_idx))
-            if (not src_path.exists()) or (not tgt_path.exists()):
-                continue
-            src = cloud.read_ply(str(src_path))
-            tgt = cloud.read_ply(str(tgt_path))
-            if src.shape[0] < 1000 or tgt.shape[0] < 1000:
-                continue
-            overlap_src, overlap_tgt = compute_overlap_ratio(
-                torch.tensor(src, device=device), torch.tensor(tgt, device=device))
-            if np.isnan(overlap_src) or np.isnan(overlap_tgt):
-                continue
-            if overlap_src < 0.1 and overlap_tgt < 0.1:
-                continue
-            lines.append("{}\t{}\t{}\t{:.4f}\t{:.4f}\n".format(scene_name, src_idx, tgt_idx,
-                                                             overlap_src, overlap_tgt))
-        gt_path.parent.mkdir(parents=True, exist_ok=True)
-        with open(gt_path, "w") as f:
-            f.writelines(lines)
+        rated = (_rate_pair(sdir, i, j, device) for i, j in combinations(range(num_samples), 2))
+        sdir.mkdir(parents=True, exist_ok=True)
+        log.write_text("".join(line for line in rated if line is not None))
         written += 1
     return written
 
 
 def gather_gt(dataset_name, start_index, stop_index):
-    """generate_gt.py:178-190: concatenate the per-scene logs into metadata/gt.log."""
-    final_gt_path = Path("./{}/metadata/gt.log".format(dataset_name))
-    final_gt_path.parent.mkdir(parents=True, exist_ok=True)
-    if final_gt_path.exists():
-        print("gt log exists, delete it")
-        os.remove(str(final_gt_path))
-    with open(final_gt_path, "ab") as out:
-        for scene_idx in range(start_index, stop_index):
-            scene_gt_path = "./{}/data/scene-{:0>6d}/gt.log".format(dataset_name, scene_idx)
-            if os.path.isfile(scene_gt_path):
-                with open(scene_gt_path, "rb") as f:
-                    out.write(f.read())
-    return str(final_gt_path)
+    """Concatenate the per-scene logs into metadata/gt.log, replacing an older one
+    (generate_gt.py:178-190, which shells out to `cat`)."""
+    target = Path(".") / dataset_name / "metadata" / "gt.log"
+    target.parent.mkdir(parents=True, exist_ok=True)
+    parts = []
+    for scene_idx in range(start_index, stop_index):
+        log = _scene_dir(dataset_name, scene_idx) / "gt.log"
+        if log.is_file():
+            parts.append(log.read_bytes())
+    target.write_bytes(b"".join(parts))
+    return str(target)
