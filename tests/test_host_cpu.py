@@ -201,3 +201,44 @@ def test_generate_gt_file_logic(tmp_path, monkeypatch):
     assert overlap.generate_gt("ds", 4, 6, 4, device="cpu") == 0       # both exist now
     final = overlap.gather_gt("ds", 4, 6)
     assert open(final).read().splitlines() == lines
+
+
+def test_tester_sample_host_logic(tmp_path, monkeypatch):
+    """Tester.sample's orchestration (SDD:1961-2065) with the device operations stubbed: views are
+    chained, the occlusion filter only runs once the camera has moved, files follow the reference's
+    names."""
+    import numpy as np
+    import torch
+    from pointreggpt_b200 import geometry, tester
+    S = 32
+    calls = {"occ": 0, "cond": []}
+
+    class FakeModel:
+        channels, image_size = 1, S
+
+        def to(self, d):
+            return self
+
+        def sample(self, *, param_cond, img_cond=None, disable_tqdm=False):
+            calls["cond"].append(None if img_cond is None else tuple(img_cond.shape))
+            return torch.rand(param_cond.shape[0], 1, S, S)
+
+    def occ(d, m):
+        calls["occ"] += 1
+        return d, m
+
+    monkeypatch.setattr(geometry, "reproject_tensor", lambda d, K, P, **k: (d.clone(), d > 3))
+    monkeypatch.setattr(geometry, "occlusion_filter", occ)
+    monkeypatch.setattr(geometry, "point_cloud_batch",
+                        lambda d, K, pose=None, scale=10.0, clip=(0.5, 10):
+                        (torch.rand(d.shape[0], S * S, 3, dtype=torch.float64), torch.full((d.shape[0],), 17)))
+    np.random.seed(0)
+    t = tester.Tester(FakeModel(), batch_size=2, results_folder=str(tmp_path / "r"),
+                      samples_folder=str(tmp_path / "o"), device="cpu")
+    out = t.sample(3, 3)
+    assert out.shape == (3, 1, S, 3 * S)
+    assert calls["cond"] == [None, (2, 2, S, S), (2, 2, S, S), None, (1, 2, S, S), (1, 2, S, S)]
+    assert calls["occ"] == 4                                  # every conditional view: the pose is never zero
+    names = sorted(p.name for p in (tmp_path / "o").iterdir())
+    assert len(names) == 3 * (1 + 2 * 3) + 1 and "overview.png" in names and "scene-2-sample-2.ply" in names
+    assert t.sample_uncondition(4).shape == (4, 1, S, S)

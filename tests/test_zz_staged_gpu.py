@@ -137,3 +137,27 @@ def test_compute_overlap_ratio_matches_oracle():
     # the voxel centroids come from torch index_add here (last-bit differences in the means are
     # possible), so a point exactly at the search radius may flip: allow a handful of points
     assert got == pytest.approx(want, abs=1e-3) and 0.05 < got[0] < 1.0
+
+
+def test_tester_sample_successive_views(tmp_path):
+    """Tester.sample (SDD:1961-2065): unconditional view, then views conditioned on the previous one
+    reprojected 0.5 m forward through the occlusion filter; files as the reference names them."""
+    from pointreggpt_b200 import nets
+    from pointreggpt_b200.diffusion import GaussianDiffusion
+    from pointreggpt_b200.tester import Tester
+    torch.manual_seed(0)
+    np.random.seed(0)
+    unet = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
+    diff = GaussianDiffusion(unet, image_size=128, timesteps=8, sampling_timesteps=2, objective="pred_x0",
+                             beta_schedule="sigmoid", ddim_sampling_eta=1.0)
+    t = Tester(diff, batch_size=2, results_folder=str(tmp_path / "res"), samples_folder=str(tmp_path / "out"))
+    strip = t.sample(num_scenes=3, num_samples=3)
+    assert strip.shape == (3, 1, 128, 3 * 128) and torch.isfinite(strip).all()
+    assert 0.0 <= float(strip.min()) and float(strip.max()) <= 1.0
+    for scene in range(3):
+        assert (tmp_path / "out" / f"scene-{scene}-camera-intrinsics.txt").is_file()
+        for k in range(3):
+            assert (tmp_path / "out" / f"scene-{scene}-sample-{k}.png").is_file()
+            pts = cloud.read_ply(str(tmp_path / "out" / f"scene-{scene}-sample-{k}.ply"))
+            assert pts.shape[1] == 3 and np.isfinite(pts).all()
+    assert (tmp_path / "out" / "overview.png").is_file()
