@@ -96,3 +96,69 @@ def test_occlusion_filter_bit_exact(ref):
         assert np.array_equal(want_d.numpy().view(np.uint32), got_d.view(np.uint32))
         assert np.array_equal(want_m.numpy(), got_m)
     assert (want_d != edge).any()            # the filter did replace something
+
+
+def test_generate_batch_composition_bit_exact(ref):
+    """oracle/pipeline_ref.generate_batch against the same sequence of reference calls as
+    Generator.generate's per-batch body (SDD:2479-2628; open3d's crop restated as an inclusive box)."""
+    from oracle import pipeline_ref
+    sdd, dc = ref
+    B, SZ, T = 2, 64, 3
+    torch.manual_seed(5)
+    net = sdd.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1).eval()
+    mnet = dc.MaskUnet(dim=64, dim_mults=(1, 2, 4, 8)).eval()
+    with torch.no_grad():
+        mnet.final_conv[0].bias.fill_(4.6)          # logits straddle the 0.99 threshold (4.595)
+    diff = sdd.GaussianDiffusion(net, image_size=SZ, timesteps=T, objective='pred_x0',
+                                 beta_schedule='sigmoid', is_ddnm_sampling=True)
+    d01 = S.synthetic_depth_batch(55, B, SZ, SZ)
+    K = S.synthetic_intrinsics(B, None, seed=3).copy()
+    K[:, 0, 0] = K[:, 1, 1] = 1.2 * SZ
+    K[:, 0, 2], K[:, 1, 2] = SZ / 2, SZ / 2
+    P = S.synthetic_poses(B, seed=4)
+    g = torch.Generator().manual_seed(6)
+    noises = [torch.randn(B, 1, SZ, SZ, generator=g) for _ in range(T + 1)]
+    # ---- the reference's own sequence
+    lo, hi = np.array([-1.5, -1.5, 0.5]), np.array([1.5, 1.5, 3.5])
+    rpj, msk = [], []
+    for b in range(B):
+        pc = sdd.point_cloud(d01[b, 0].numpy() * 10, K[b], clip=[0.5, 10]).astype(np.float32)
+        pc = pc[np.all((pc >= lo) & (pc <= hi), axis=1)]
+        moved = pc @ P[b, :3, :3].T + P[b, :3, 3]
+        d, m = sdd.pc2depth_tensor(torch.tensor(moved[None]), torch.ones((1, moved.shape[0]), dtype=torch.bool),
+                                   torch.tensor(K[b][None]), image_size=[SZ, SZ])
+        rpj.append(d)
+        msk.append(m)
+    with torch.no_grad():
+        images_rpj = torch.cat(rpj) * 0.1
+        mask_rpj = torch.cat(msk)
+        mask_crt = mnet(images_rpj) > 0.99
+        images_rpj[~mask_crt] = 0
+        mask_rpj = mask_rpj & mask_crt
+        img_cond = sdd.normalize_to_neg_one_to_one(torch.cat([images_rpj, mask_rpj], dim=1))
+        it = iter(noises)
+        o1, o2 = torch.randn, torch.randn_like
+        torch.randn = lambda *a, **k: next(it).clone()
+        torch.randn_like = lambda *a, **k: next(it).clone()
+        try:
+            images = diff.sample(param_cond=sdd.param_vector(torch.tensor(K)), img_cond=img_cond,
+                                 disable_tqdm=True, has_refine_step=True)
+        finally:
+            torch.randn, torch.randn_like = o1, o2
+        mask_crt2 = mnet(images) > 0.99
+        images[~mask_crt2] = 0
+    clouds = []
+    for b in range(B):
+        pc = sdd.point_cloud(images[b, 0].numpy() * 10, K[b], clip=[0.5, 10])
+        clouds.append((pc - P[b, :3, 3]) @ P[b, :3, :3])
+    # ---- the oracle composition
+    got = pipeline_ref.generate_batch({k: v.detach() for k, v in net.state_dict().items()},
+                                      {k: v.detach() for k, v in mnet.state_dict().items()},
+                                      d01, K, P, noises, timesteps=T, has_refine_step=True)
+    assert torch.equal(got["images_rpj"], images_rpj) and torch.equal(got["mask_rpj"], mask_rpj)
+    assert torch.equal(got["img_cond"], img_cond)
+    assert torch.equal(got["images"], images)
+    assert 0 < int(mask_crt.sum()) < mask_crt.numel()
+    for a, b_ in zip(got["clouds"], clouds):
+        assert np.array_equal(a, b_)
+
