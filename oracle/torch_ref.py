@@ -291,8 +291,32 @@ def make_schedule(timesteps, beta_schedule="sigmoid"):
     )
 
 
-def _predictions(sd, sch, x, t, param_cond, img_cond, clip_x_start, ban_ddnm, emu):
-    """model_predictions for objective='pred_x0', ddnm dropout 0 -- SDD:1182-1232."""
+def dropout_tables(timesteps, ddnm_sampling_dropout=0., ddnm_dropout_schedule='none'):
+    """(ddnm_dropouts, denoise_dropouts), float64 -- SDD:1076-1094."""
+    end = ddnm_sampling_dropout if ddnm_dropout_schedule == 'none' else 0.
+    ddnm = torch.linspace(ddnm_sampling_dropout, end, timesteps, dtype=torch.float64)
+    denoise = torch.linspace(1., 0., timesteps, dtype=torch.float64) ** 100
+    return ddnm, denoise
+
+
+class KeepMask:
+    """The Bernoulli keep-mask of model_predictions (SDD:1213-1216 DDNM dropout, SDD:1220-1225
+    denoise): `uniform_(0, 1) > table[t]`, with the uniform draws injected (`draws` is consumed in
+    step order).  mode 'ddnm' draws only where table[t] > 0; mode 'denoise' always."""
+
+    def __init__(self, mode, table, draws):
+        assert mode in ('ddnm', 'denoise')
+        self.mode, self.table, self.draws = mode, table, iter(draws)
+
+    def __call__(self, t, mask):
+        if self.mode == 'ddnm' and not (self.table[t] > 0):
+            return mask
+        return (next(self.draws) > self.table[t]) & mask
+
+
+def _predictions(sd, sch, x, t, param_cond, img_cond, clip_x_start, ban_ddnm, emu, keep=None):
+    """model_predictions for objective='pred_x0' -- SDD:1182-1232.  `keep` (a KeepMask) adds the
+    keep-mask dropout of the DDNM / denoise branches."""
     b = x.shape[0]
     tt = torch.full((b,), t, dtype=torch.long)
     x0 = unet_forward(sd, x, tt, param_cond, emu)
@@ -303,20 +327,22 @@ def _predictions(sd, sch, x, t, param_cond, img_cond, clip_x_start, ban_ddnm, em
     if img_cond is not None and not ban_ddnm:
         rpj = img_cond[:, 0:1]
         mask = ((img_cond[:, 1:2] + 1) * 0.5) > 0.5
+        if keep is not None:
+            mask = keep(t, mask)
         x0 = torch.where(mask, rpj, x0)
     return pred_noise, x0
 
 
 @torch.no_grad()
 def p_sample_loop(sd, sch, param_cond, img_cond, noises, has_refine_step=False,
-                  emu=None, trajectory=None):
+                  emu=None, trajectory=None, keep=None):
     """SDD:1283-1317 with torch.randn replaced by the injected `noises`
     (noises[0] = x_T, noises[1 + i] = the i-th randn_like draw)."""
     T = sch["betas"].shape[0]
     img = noises[0].clone()
     k = 1
     for t in reversed(range(T)):
-        _, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, False, False, emu)
+        _, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, False, False, emu, keep)
         x0 = x0.clamp(-1., 1.)
         mean = sch["posterior_mean_coef1"][t] * x0 + sch["posterior_mean_coef2"][t] * img
         logvar = sch["posterior_log_variance_clipped"][t]
@@ -346,14 +372,14 @@ def ddim_times(total_timesteps, sampling_timesteps):
 
 @torch.no_grad()
 def ddim_sample(sd, sch, param_cond, img_cond, noises, sampling_timesteps, eta=1.0,
-                has_refine_step=False, emu=None, trajectory=None):
+                has_refine_step=False, emu=None, trajectory=None, keep=None):
     """SDD:1319-1392 with injected noise (same convention as p_sample_loop)."""
     T = sch["betas"].shape[0]
     img = noises[0].clone()
     k = 1
     ac = sch["alphas_cumprod"]
     for t, t_next in ddim_times(T, sampling_timesteps):
-        pred_noise, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, True, False, emu)
+        pred_noise, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, True, False, emu, keep)
         if t_next < 0:
             img = x0
         else:

@@ -81,9 +81,11 @@ class GaussianDiffusion(nn.Module):
         self.ddnm_sampling_dropout = ddnm_sampling_dropout
         if ddnm_dropout_schedule not in ('none', 'linear'):
             raise ValueError(f'unknown ddnm dropout schedule {ddnm_dropout_schedule}')
-        if ddnm_sampling_dropout != 0.:
-            raise NotImplementedError("DDNM keep-mask dropout (SDD:1213-1216) is off on the "
-                                      "data-generation path and not implemented natively")
+        # SDD:1076-1094: plain float64 tensors, not buffers (they are not part of the state dict)
+        self.ddnm_dropouts = torch.linspace(
+            ddnm_sampling_dropout, ddnm_sampling_dropout if ddnm_dropout_schedule == 'none' else 0.,
+            timesteps, dtype=torch.float64)
+        self.denoise_dropouts = torch.linspace(1., 0., timesteps, dtype=torch.float64) ** 100
 
         def reg(name, val):
             self.register_buffer(name, val.to(torch.float32))
@@ -151,25 +153,50 @@ class GaussianDiffusion(nn.Module):
         """1 (x_T) + the number of `randn_like` draws of one `sample()` call."""
         return 1 + sum(s.add_noise for s in self.sampling_steps(has_refine_step))
 
+    def keep_probabilities(self, steps, is_denoise=False):
+        """Per step, the dropout probability of the Bernoulli keep-mask in model_predictions, or None
+        where the condition mask is used as it is: DDNM sampling draws `uniform > ddnm_dropouts[t]`
+        only where that entry is positive (SDD:1213-1216); `denoise()` on a model built with
+        is_ddnm_sampling=False draws `uniform > denoise_dropouts[t]` at every step (SDD:1220-1225).
+        Refine steps never draw (they ban the replacement, SDD:1308-1312)."""
+        main = (_ffi.STEP_P_SAMPLE, _ffi.STEP_DDIM, _ffi.STEP_DDIM_LAST)
+        out = []
+        for st in steps:
+            p = None
+            if st.kind in main:
+                if self.is_ddnm_sampling:
+                    if self.ddnm_dropouts[st.t] > 0:
+                        p = self.ddnm_dropouts[st.t]
+                elif is_denoise:
+                    p = self.denoise_dropouts[st.t]
+            out.append(p)
+        return out
+
     # ------------------------------------------------------------------ sampling
     @torch.no_grad()
     def sample(self, *, param_cond, img_cond=None, disable_tqdm=False, has_refine_step=False,
-               noise=None, seed=None):
+               noise=None, seed=None, keep_uniform=None, _is_denoise=False):
         """(b,4) intrinsics vector [+ (b,2,s,s) DDNM image condition] -> (b,1,s,s) in [0,1].
 
         `noise` (optional, (num_noise_draws, b,1,s,s)) injects the Gaussian draws (parity tests);
         otherwise the device Philox generator is seeded from `seed` or torch's global RNG.
+        `keep_uniform` (optional, (number of keep-mask draws, b,1,s,s)) injects the uniform draws
+        of the keep-mask dropout in step order.
         """
-        _ffi.require_cuda(param_cond, img_cond, noise)
+        _ffi.require_cuda(param_cond, img_cond, noise, keep_uniform)
         b, s = param_cond.shape[0], self.image_size
         dev = param_cond.device
         steps = self.sampling_steps(has_refine_step)
         arr = (_ffi.Step * len(steps))(*steps)
         p = param_cond.float().contiguous()
         ic = None
-        if img_cond is not None and self.is_ddnm_sampling:
+        replace_in_loop = self.is_ddnm_sampling or _is_denoise
+        if img_cond is not None and (replace_in_loop or has_refine_step):
             ic = img_cond.float().contiguous()
             assert ic.shape == (b, 2, s, s)
+        probs = self.keep_probabilities(steps, _is_denoise) if ic is not None else [None] * len(steps)
+        if any(q is not None for q in probs) or (ic is not None and not replace_in_loop):
+            return self._sample_stepwise(steps, probs, p, ic, replace_in_loop, noise, seed, keep_uniform)
         if has_refine_step and ic is None:
             raise NotImplementedError("has_refine_step needs DDNM sampling with an image "
                                       "condition (SDD:1313)")
@@ -189,6 +216,70 @@ class GaussianDiffusion(nn.Module):
                 h, arr, len(steps), _ffi.ptr(p[i:j]),
                 _ffi.ptr(ic[i:j]) if ic is not None else None,
                 _ffi.ptr(nz), ctypes.c_uint64(seed + i), _ffi.ptr(out[i:j]), j - i, _ffi.stream()))
+        return out
+
+    @torch.no_grad()
+    def denoise(self, *, param_cond, img_cond=None, disable_tqdm=False, has_refine_step=False,
+                noise=None, seed=None, keep_uniform=None):
+        """SDD:1411-1427: `sample` with is_denoise=True -- on a model built with
+        is_ddnm_sampling=False the condition is imposed through a keep-mask that lets almost
+        nothing through at large t and everything at t = 0 (denoise_dropouts = linspace(1,0,T)^100)."""
+        return self.sample(param_cond=param_cond, img_cond=img_cond, disable_tqdm=disable_tqdm,
+                           has_refine_step=has_refine_step, noise=noise, seed=seed,
+                           keep_uniform=keep_uniform, _is_denoise=True)
+
+    def _sample_stepwise(self, steps, probs, p, ic, replace_in_loop, noise, seed, keep_uniform):
+        """The sampling loop driven step by step from the host, for the configurations whose image
+        condition changes per step (keep-mask dropout) or is only used by the refine step: every step
+        is one `prg_sampler_run` call of a single step whose `noise` argument carries the current
+        sample (slab 0) and that step's Gaussian draw (slab 1).  Same kernels and arithmetic as the
+        fused loop; the Gaussian / uniform draws come from torch's device generator."""
+        b, s = p.shape[0], self.image_size
+        dev = p.device
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed))
+        shape = (b, 1, s, s)
+        main = (_ffi.STEP_P_SAMPLE, _ffi.STEP_DDIM, _ffi.STEP_DDIM_LAST)
+        mask = None if ic is None else (((ic[:, 1:2] + 1) * 0.5) > 0.5)          # SDD:507-508
+        k = 1
+        ku = 0
+        x = noise[0].float().contiguous() if noise is not None else \
+            torch.randn(shape, device=dev, generator=gen)
+        h, cap = self.model.native_handle(b, s, dev)
+        for st, q in zip(steps, probs):
+            ic_step = ic
+            if st.kind in main:
+                if not replace_in_loop:
+                    ic_step = None                     # is_ddnm_sampling=False: no replacement here
+                elif q is not None:
+                    if keep_uniform is not None:
+                        u = keep_uniform[ku].float()
+                    else:
+                        u = torch.rand(shape, device=dev, generator=gen)
+                    ku += 1
+                    keep = (u > q.to(torch.float32).to(dev)) & mask
+                    ic_step = ic.clone()
+                    ic_step[:, 1:2] = torch.where(keep, 1.0, -1.0)
+            slabs = [x]
+            if st.add_noise:
+                slabs.append(noise[k].float() if noise is not None else
+                             torch.randn(shape, device=dev, generator=gen))
+                k += 1
+            x = self._run_single_step(h, cap, st, p, ic_step, torch.stack(slabs).contiguous())
+        return x
+
+    def _run_single_step(self, h, cap, st, p, ic_step, buf):
+        """One sampler step on the device: buf[0] = x_t, buf[1] = the step's Gaussian draw (if any)."""
+        b = p.shape[0]
+        out = torch.empty_like(buf[0])
+        one = (_ffi.Step * 1)(st)
+        for i in range(0, b, cap):
+            j = min(b, i + cap)
+            _ffi.check(_ffi.lib().prg_sampler_run(
+                h, one, 1, _ffi.ptr(p[i:j]),
+                _ffi.ptr(ic_step[i:j].contiguous()) if ic_step is not None else None,
+                _ffi.ptr(buf[:, i:j].contiguous()), ctypes.c_uint64(0), _ffi.ptr(out[i:j]), j - i,
+                _ffi.stream()))
         return out
 
     def forward(self, *args, **kwargs):

@@ -125,8 +125,13 @@ def test_unsupported_configurations_fail_loudly():
     u = nets.Unet(dim=64, param_cond_dim=4)
     with pytest.raises(NotImplementedError):
         GaussianDiffusion(u, image_size=256, objective="pred_noise")
-    with pytest.raises(NotImplementedError):
-        GaussianDiffusion(u, image_size=256, objective="pred_x0", ddnm_sampling_dropout=0.1)
+    with pytest.raises(ValueError):
+        GaussianDiffusion(u, image_size=256, objective="pred_x0", ddnm_dropout_schedule="cosine")
+    d = GaussianDiffusion(u, image_size=256, objective="pred_x0", timesteps=10, ddnm_sampling_dropout=0.1,
+                          ddnm_dropout_schedule="linear")
+    assert d.ddnm_dropouts.dtype == torch.float64 and float(d.ddnm_dropouts[0]) == 0.1 and float(d.ddnm_dropouts[-1]) == 0.0
+    assert float(d.denoise_dropouts[0]) == 1.0 and float(d.denoise_dropouts[-1]) == 0.0
+    assert "ddnm_dropouts" not in d.state_dict()            # plain tensors, not buffers (SDD:1076-1094)
 
 
 def test_shard_range_covers_everything_once():
@@ -242,3 +247,81 @@ def test_tester_sample_host_logic(tmp_path, monkeypatch):
     names = sorted(p.name for p in (tmp_path / "o").iterdir())
     assert len(names) == 3 * (1 + 2 * 3) + 1 and "overview.png" in names and "scene-2-sample-2.ply" in names
     assert t.sample_uncondition(4).shape == (4, 1, S, S)
+
+
+@pytest.mark.parametrize("mode", ["ddnm_none", "ddnm_linear_ddim", "denoise", "no_ddnm_refine_only"])
+def test_stepwise_sampler_host_logic(monkeypatch, mode):
+    """Keep-mask dropout / denoise / refine-only conditioning drive the sampler step by step from the
+    host (diffusion._sample_stepwise).  With the single device step replaced by the oracle's arithmetic
+    for that step, the host loop must reproduce the oracle's full loop bit for bit: order of the
+    Gaussian and uniform draws, per-step masks, which steps replace."""
+    import torch
+    from oracle import torch_ref as R
+    from pointreggpt_b200 import _ffi, nets
+    from pointreggpt_b200.diffusion import GaussianDiffusion
+    torch.manual_seed(9)
+    net = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    SZ, B = 32, 2
+    cfg = dict(ddnm_none=dict(timesteps=4, ddnm_sampling_dropout=0.3),
+               ddnm_linear_ddim=dict(timesteps=8, sampling_timesteps=3, ddnm_sampling_dropout=0.5,
+                                     ddnm_dropout_schedule='linear', ddim_sampling_eta=1.0),
+               denoise=dict(timesteps=4, is_ddnm_sampling=False),
+               no_ddnm_refine_only=dict(timesteps=3, is_ddnm_sampling=False))[mode]
+    diff = GaussianDiffusion(net, image_size=SZ, objective='pred_x0', beta_schedule='sigmoid', **cfg)
+    T = cfg["timesteps"]
+    sch = R.make_schedule(T)
+    g = torch.Generator().manual_seed(10)
+    noises = torch.stack([torch.randn(B, 1, SZ, SZ, generator=g) for _ in range(9)])
+    uniforms = torch.stack([torch.rand(B, 1, SZ, SZ, generator=g) for _ in range(9)])
+    d = torch.rand(B, 1, SZ, SZ, generator=g)
+    d[d < 0.3] = 0
+    ic = torch.cat([d, (d > 0).float()], 1) * 2 - 1
+    pc = torch.tensor([[304., 304., 16.5, 16.], [290., 291., 16.5, 16.]])
+
+    def fake_step(h, cap, st, p, ic_step, buf):
+        """The arithmetic of one prg_step, from the oracle's pieces (SDD:1234-1281, 1343-1389)."""
+        x, t = buf[0], st.t
+        ddim = st.kind in (_ffi.STEP_DDIM, _ffi.STEP_DDIM_LAST, _ffi.STEP_REFINE_DDIM)
+        refine = st.kind in (_ffi.STEP_REFINE_P, _ffi.STEP_REFINE_DDIM)
+        pred_noise, x0 = R._predictions(sd, sch, x, t, p, ic_step, ddim, refine, None)
+        mask = None if ic_step is None else ((ic_step[:, 1:2] + 1) * 0.5) > 0.5
+        if st.kind in (_ffi.STEP_P_SAMPLE, _ffi.STEP_REFINE_P):
+            x0 = x0.clamp(-1., 1.)
+            mean = sch["posterior_mean_coef1"][t] * x0 + sch["posterior_mean_coef2"][t] * x
+            sig = (0.5 * sch["posterior_log_variance_clipped"][t]).exp()
+            out = mean + sig * (buf[1] if st.add_noise else 0.)
+            if refine:
+                out = torch.where(mask, out, x)
+        elif st.kind == _ffi.STEP_DDIM:
+            out = x0 * st.c2 + st.c3 * pred_noise + st.c4 * buf[1]
+        elif st.kind == _ffi.STEP_DDIM_LAST:
+            out = x0
+        else:
+            out = torch.where(mask, x0, x)
+        return (out + 1) * 0.5 if st.unnormalize else out
+
+    monkeypatch.setattr(_ffi, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(GaussianDiffusion, "_run_single_step", lambda self, *a: fake_step(*a))
+    monkeypatch.setattr(type(net), "native_handle", lambda self, b, s, dev: (None, 1 << 30), raising=False)
+    fn = diff.denoise if mode == "denoise" else diff.sample
+    got = fn(param_cond=pc, img_cond=ic, has_refine_step=True, noise=noises, keep_uniform=uniforms)
+    ddnm, denoise = R.dropout_tables(T, cfg.get("ddnm_sampling_dropout", 0.), cfg.get("ddnm_dropout_schedule", "none"))
+    keep = {"denoise": R.KeepMask("denoise", denoise, list(uniforms)),
+            "no_ddnm_refine_only": None}.get(mode, R.KeepMask("ddnm", ddnm, list(uniforms)))
+    if mode == "no_ddnm_refine_only":
+        # no replacement in the loop; the refine step still uses the mask (SDD:1307-1314)
+        img = R.p_sample_loop(sd, sch, pc, None, list(noises))          # unnormalised at the end
+        x = img * 2 - 1
+        _, x0 = R._predictions(sd, sch, x, 0, pc, ic, False, True, None)
+        x0 = x0.clamp(-1., 1.)
+        mean = sch["posterior_mean_coef1"][0] * x0 + sch["posterior_mean_coef2"][0] * x
+        want = (torch.where(((ic[:, 1:2] + 1) * 0.5) > 0.5, mean, x) + 1) * 0.5
+        assert torch.allclose(got, want, atol=1e-6)
+        return
+    if "sampling_timesteps" in cfg:
+        want = R.ddim_sample(sd, sch, pc, ic, list(noises), cfg["sampling_timesteps"], 1.0, has_refine_step=True, keep=keep)
+    else:
+        want = R.p_sample_loop(sd, sch, pc, ic, list(noises), has_refine_step=True, keep=keep)
+    assert torch.allclose(got, want, atol=1e-6)
+    assert torch.equal(got, want) or mode == "ddnm_linear_ddim"     # ddim coefficients pass through float()

@@ -162,3 +162,47 @@ def test_generate_batch_composition_bit_exact(ref):
     for a, b_ in zip(got["clouds"], clouds):
         assert np.array_equal(a, b_)
 
+
+
+@pytest.mark.parametrize("mode", ["ddnm_none", "ddnm_linear_ddim", "denoise"])
+def test_keep_mask_dropout_bit_exact(ref, mode):
+    """The Bernoulli keep-mask of model_predictions (SDD:1213-1225) with injected uniform draws."""
+    sdd, _ = ref
+    torch.manual_seed(9)
+    net = sdd.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1).eval()
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    SZ, B = 32, 2
+    cfg = dict(ddnm_none=dict(timesteps=4, ddnm_sampling_dropout=0.3),
+               ddnm_linear_ddim=dict(timesteps=8, sampling_timesteps=3, ddnm_sampling_dropout=0.5,
+                                     ddnm_dropout_schedule='linear', ddim_sampling_eta=1.0),
+               denoise=dict(timesteps=4, is_ddnm_sampling=False))[mode]
+    diff = sdd.GaussianDiffusion(net, image_size=SZ, objective='pred_x0', beta_schedule='sigmoid', **cfg)
+    g = torch.Generator().manual_seed(10)
+    noises = [torch.randn(B, 1, SZ, SZ, generator=g) for _ in range(9)]
+    uniforms = [torch.rand(B, 1, SZ, SZ, generator=g) for _ in range(9)]
+    d = torch.rand(B, 1, SZ, SZ, generator=g)
+    d[d < 0.3] = 0
+    ic = torch.cat([d, (d > 0).float()], 1) * 2 - 1
+    pc = torch.tensor([[304., 304., 16.5, 16.], [290., 291., 16.5, 16.]])
+    it, iu = iter(noises), iter(uniforms)
+    o1, o2, o3 = torch.randn, torch.randn_like, torch.Tensor.uniform_
+    torch.randn = lambda *a, **k: next(it).clone()
+    torch.randn_like = lambda *a, **k: next(it).clone()
+    torch.Tensor.uniform_ = lambda self, a=0, b=1: self.copy_(next(iu))
+    try:
+        fn = diff.denoise if mode == "denoise" else diff.sample
+        want = fn(param_cond=pc, img_cond=ic, disable_tqdm=True, has_refine_step=True)
+    finally:
+        torch.randn, torch.randn_like, torch.Tensor.uniform_ = o1, o2, o3
+    T = cfg["timesteps"]
+    ddnm, denoise = R.dropout_tables(T, cfg.get("ddnm_sampling_dropout", 0.), cfg.get("ddnm_dropout_schedule", "none"))
+    keep = R.KeepMask("denoise", denoise, uniforms) if mode == "denoise" else R.KeepMask("ddnm", ddnm, uniforms)
+    sch = R.make_schedule(T)
+    if "sampling_timesteps" in cfg:
+        got = R.ddim_sample(sd, sch, pc, ic, noises, cfg["sampling_timesteps"], 1.0, has_refine_step=True, keep=keep)
+    else:
+        got = R.p_sample_loop(sd, sch, pc, ic, noises, has_refine_step=True, keep=keep)
+    assert torch.equal(want, got)
+    plain = R.p_sample_loop(sd, sch, pc, ic, noises, has_refine_step=True) if "sampling_timesteps" not in cfg else None
+    if plain is not None:
+        assert not torch.equal(plain, got)          # the dropout did change the result
