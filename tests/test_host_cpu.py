@@ -325,3 +325,40 @@ def test_stepwise_sampler_host_logic(monkeypatch, mode):
         want = R.p_sample_loop(sd, sch, pc, ic, list(noises), has_refine_step=True, keep=keep)
     assert torch.allclose(got, want, atol=1e-6)
     assert torch.equal(got, want) or mode == "ddnm_linear_ddim"     # ddim coefficients pass through float()
+
+
+def test_default_sampling_stays_on_the_fused_device_loop(monkeypatch):
+    """The shipped configuration (DDNM, dropout 0) must issue ONE prg_sampler_run covering every
+    step; only keep-mask dropout / denoise / refine-only conditioning may take the step-wise loop."""
+    import torch
+    from pointreggpt_b200 import _ffi, nets
+    from pointreggpt_b200.diffusion import GaussianDiffusion
+    calls = []
+
+    class FakeLib:
+        def prg_sampler_run(self, h, arr, nsteps, p, ic, noise, seed, out, b, stream):
+            calls.append((nsteps, ic is not None, noise is not None, b))
+            return 0
+
+    monkeypatch.setattr(_ffi, "lib", lambda: FakeLib())
+    monkeypatch.setattr(_ffi, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_ffi, "stream", lambda: None)
+    torch.manual_seed(0)
+    net = nets.Unet(dim=64, param_cond_dim=4)
+    monkeypatch.setattr(type(net), "native_handle", lambda self, b, s, dev: (None, 1 << 30), raising=False)
+    monkeypatch.setattr(GaussianDiffusion, "_sample_stepwise",
+                        lambda self, *a, **k: (_ for _ in ()).throw(AssertionError("step-wise loop used")))
+    pc = torch.zeros(3, 4)
+    ic = torch.zeros(3, 2, 32, 32)
+    for kw, nsteps in ((dict(timesteps=20), 20), (dict(timesteps=20, sampling_timesteps=5), 5)):
+        d = GaussianDiffusion(net, image_size=32, objective="pred_x0", beta_schedule="sigmoid", **kw)
+        calls.clear()
+        d.sample(param_cond=pc, img_cond=ic)
+        d.sample(param_cond=pc, img_cond=ic, has_refine_step=True)
+        d.sample(param_cond=pc)
+        assert calls == [(nsteps, True, False, 3), (nsteps + 1, True, False, 3), (nsteps, False, False, 3)]
+    # a model built without DDNM ignores the condition in the loop: still the fused path
+    d = GaussianDiffusion(net, image_size=32, objective="pred_x0", timesteps=6, is_ddnm_sampling=False)
+    calls.clear()
+    d.sample(param_cond=pc, img_cond=ic)
+    assert calls == [(6, False, False, 3)]
