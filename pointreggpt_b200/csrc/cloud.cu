@@ -77,10 +77,15 @@ k_vox_insert(const double* __restrict__ pts, long long n, double voxel,
     const unsigned long long key = ((unsigned long long)f0 << 42) | ((unsigned long long)f1 << 21) |
                                    (unsigned long long)f2;
     unsigned long long slot = vox_mix(key) & mask;
-    for (;;) {
+    bool placed = false;                  // the table has >= 2 slots per point, so a free slot exists;
+    for (unsigned long long probe = 0; probe <= mask; ++probe) {   // the bound only guards against hangs
       const unsigned long long prev = atomicCAS(keys + slot, kVoxEmpty, key);
-      if (prev == kVoxEmpty || prev == key) break;
-      slot = (slot + 1) & mask;           // the table has >= 2 slots per point: a free slot exists
+      if (prev == kVoxEmpty || prev == key) { placed = true; break; }
+      slot = (slot + 1) & mask;
+    }
+    if (!placed) {
+      atomicExch(count_err + 1, 1);
+      continue;
     }
     atomicAdd(sums + slot * 3 + 0, (unsigned long long)__double2ll_rn(__dmul_rn(r0, kVoxFix)));
     atomicAdd(sums + slot * 3 + 1, (unsigned long long)__double2ll_rn(__dmul_rn(r1, kVoxFix)));
@@ -148,10 +153,16 @@ k_ovl_build(const double* __restrict__ tgt, long long n, double radius,
     }
     const unsigned long long key = ovl_key(c[0], c[1], c[2]);
     unsigned long long slot = vox_mix(key) & mask;
-    for (;;) {
+    bool placed = false;
+    for (unsigned long long probe = 0; probe <= mask; ++probe) {   // bounded: never spins on a full table
       const unsigned long long prev = atomicCAS(keys + slot, kVoxEmpty, key);
-      if (prev == kVoxEmpty || prev == key) break;
+      if (prev == kVoxEmpty || prev == key) { placed = true; break; }
       slot = (slot + 1) & mask;
+    }
+    if (!placed) {
+      next[i] = -1;
+      atomicExch(count_err + 1, 1);
+      continue;
     }
     next[i] = atomicExch(head + slot, (int)i);      // push front
   }
@@ -175,11 +186,12 @@ k_ovl_query(const double* __restrict__ qry, long long nq, const double* __restri
     for (int d = 0; d < 27 && !found; ++d) {
       const unsigned long long key = ovl_key(c[0] + d / 9 - 1, c[1] + (d / 3) % 3 - 1, c[2] + d % 3 - 1);
       unsigned long long slot = vox_mix(key) & mask;
-      for (;;) {
+      for (unsigned long long probe = 0; probe <= mask; ++probe) {
         const unsigned long long k = keys[slot];
         if (k == kVoxEmpty) break;
         if (k == key) {
-          for (int j = head[slot]; j >= 0 && !found; j = next[j]) {
+          int walked = 0;                 // a list cannot be longer than the table; guards against cycles
+          for (int j = head[slot]; j >= 0 && !found && walked <= (int)mask; j = next[j], ++walked) {
             const double dx = __dsub_rn(tgt[(size_t)j * 3 + 0], q0);
             const double dy = __dsub_rn(tgt[(size_t)j * 3 + 1], q1);
             const double dz = __dsub_rn(tgt[(size_t)j * 3 + 2], q2);
