@@ -149,7 +149,7 @@ k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
       const float z0 = d[j];
       if (i + j < HW && z0 > lo && z0 < hi) {
         int r = r0, c = c0 + j;
-        if (c >= W) { c -= W; ++r; }
+        if (c >= W) { c -= W; ++r; while (c >= W) { c -= W; ++r; } }   // a second wrap only when W < 4
         float x, y, z = z0;
         unproject(r, c, z, k, x, y);
         rigid(sP, x, y, z);
@@ -241,7 +241,7 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int r = r0, c = c0 + j;
-      if (c >= W) { c -= W; ++r; }
+      if (c >= W) { c -= W; ++r; while (c >= W) { c -= W; ++r; } }     // a second wrap only when W < 4
       ok[j] = use_clip ? (d[j] > lo && d[j] < hi) : 1;
       const float z = ok[j] ? d[j] : invalid;
       safe = safe && (!ok[j] || depth_in_range(z));
@@ -254,7 +254,7 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
     if (!safe) {   // extreme depths or intrinsics somewhere in these four pixels: IEEE divisions
       for (int j = 0; j < 4; ++j) {
         int r = r0, c = c0 + j;
-        if (c >= W) { c -= W; ++r; }
+        if (c >= W) { c -= W; ++r; while (c >= W) { c -= W; ++r; } }   // a second wrap only when W < 4
         if (ok[j]) unproject_ieee(r, c, o[j * 3 + 2], k, o[j * 3 + 0], o[j * 3 + 1]);
       }
     }

@@ -316,3 +316,62 @@ def test_overlap_kernel_logic(vox, nq, nt, radius, blocks):
     vox.emu_overlap(_vp(q), ctypes.c_longlong(nq), _vp(t), ctypes.c_longlong(nt), ctypes.c_double(radius), _vp(ce),
                     _vp(ws), blocks)
     assert ce[1] == 1
+
+
+_FX = [0.5, 0.999, 1.0, 1.5, 300.0, 585.0, 1e6, 1.0000001e6, 2e6, 1e-3, 1e9, 3e38, 1e-30, -300.0, 0.0, np.inf, np.nan,
+       511.99997]
+_CX = [0.0, -0.0, 1e-4, 1e-3, 0.999e-3, 128.5, 320.0, 1e6, 1.1e6, -5.0, 1e-30, -1e-3, np.nan, np.inf, 5.0000005]
+_Z = np.array([0.0, -0.0, -1.5, 1e-42, 1e-30, 1e-12, 0.9e-9, 1.1e-9, 1e-9, 1e9, 0.9e9, 1.1e9, 1e12, 1e30, 3e38, np.inf,
+               -np.inf, np.nan, 1.0, 2.5e-7, 7.7e19, 65504.0, 1e-20, 1e-6, 0.99e-6], np.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_geometry_kernels_differential_fuzz(geom, seed):
+    """Random small images (including widths below four, where four consecutive pixels span several
+    rows), intrinsics on and beyond the borders of the fast-division range, depths from the list of
+    special values, random clips and poses: the emulated kernels must match the oracle bit for bit.
+    (This is the test that found the W < 4 row-wrap bug.)"""
+    rng = np.random.default_rng(seed)
+    for trial in range(120):
+        B, H, W = int(rng.integers(1, 3)), int(rng.integers(1, 40)), int(rng.integers(1, 70))
+        if rng.random() < 0.3:
+            W = (W // 4 + 1) * 4
+        dm = (rng.random((B, H, W)) * 10).astype(np.float32)
+        m = rng.random((B, H, W)) < 0.3
+        dm[m] = _Z[rng.integers(0, _Z.size, int(m.sum()))]
+        K = np.zeros((B, 3, 3), np.float32)
+        K[:, 2, 2] = 1
+        for b in range(B):
+            if rng.random() < 0.5:
+                K[b, 0, 0], K[b, 1, 1] = rng.choice(_FX), rng.choice(_FX)
+                K[b, 0, 2], K[b, 1, 2] = rng.choice(_CX), rng.choice(_CX)
+            else:
+                K[b, 0, 0], K[b, 1, 1] = 1.2 * W * rng.uniform(0.5, 2), 1.2 * W * rng.uniform(0.5, 2)
+                K[b, 0, 2], K[b, 1, 2] = W / 2 + rng.uniform(-1, 1), H / 2
+        P = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+        ang = rng.uniform(-0.3, 0.3, B)
+        P[:, 0, 0], P[:, 0, 2], P[:, 2, 0], P[:, 2, 2] = np.cos(ang), np.sin(ang), -np.sin(ang), np.cos(ang)
+        P[:, :3, 3] = rng.normal(0, 0.3, (B, 3))
+        if rng.random() < 0.1:
+            P[0, 0, 3] = np.float32(rng.choice([np.inf, np.nan, 1e30]))
+        gx = (H * W + 1023) // 1024
+        clip = [(0.0, 10.0), (0.5, 10.0), None, (-1.0, 1e30)][int(rng.integers(0, 4))]
+        inv = [float("nan"), 0.0][int(rng.integers(0, 2))]
+        rclip = [(0.0, 10.0), (0.5, 3.5), (-1.0, 3e38)][int(rng.integers(0, 3))]
+        with np.errstate(all="ignore"):
+            want_pc, want_v = G.depth2pc(dm, K, clip=clip, invalid=inv)
+            want_d, want_m = G.reproject(dm, K, P, clip=rclip)
+        pc = np.full((B, H * W, 3), -777.0, np.float32)
+        valid = np.full((B, H * W), 7, np.uint8)
+        lo, hi = clip if clip is not None else (0.0, 0.0)
+        geom.emu_depth2pc(_vp(dm), _vp(K), ctypes.c_float(lo), ctypes.c_float(hi), int(clip is not None),
+                          ctypes.c_float(inv), _vp(pc), _vp(valid), B, H, W, gx)
+        ctx = "trial %d shape %s K %s clip %s %s" % (trial, (B, H, W), K[:, [0, 1, 0, 1], [0, 1, 2, 2]].tolist(), clip, rclip)
+        assert _same_bits_or_nan(pc, want_pc) and np.array_equal(valid.astype(bool), want_v), ctx
+        out = np.empty((B, H, W), np.float32)
+        mask = np.empty((B, H, W), np.uint8)
+        scratch = np.full((B, H, W), 0xFFFFFFFF, np.uint32)
+        geom.emu_reproject(_vp(dm), _vp(K), _vp(P), ctypes.c_float(rclip[0]), ctypes.c_float(rclip[1]), _vp(out),
+                           _vp(mask), _vp(scratch), B, H, W, gx)
+        assert _same_bits_or_nan(out.reshape(want_d.shape), want_d), ctx
+        assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m), ctx
