@@ -375,3 +375,29 @@ def test_geometry_kernels_differential_fuzz(geom, seed):
                            _vp(mask), _vp(scratch), B, H, W, gx)
         assert _same_bits_or_nan(out.reshape(want_d.shape), want_d), ctx
         assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m), ctx
+
+
+def _occlusion_case(rng):
+    B, H, W = int(rng.integers(1, 3)), int(rng.integers(1, 70)), int(rng.integers(1, 300))
+    if rng.random() < 0.4:
+        W = (W // 4 + 1) * 4
+    d = (rng.random((B, 1, H, W)) * 3).astype(np.float32)
+    d = np.round(d / 0.0125).astype(np.float32) * np.float32(0.0125)     # plateaus: differences hit 0.0375 exactly
+    m = rng.random((B, 1, H, W)) < 0.7
+    d[~m] = 0
+    if rng.random() < 0.2:
+        d[rng.random(d.shape) < 0.02] = np.float32(np.inf)
+    return d, m
+
+
+def test_occlusion_filter_kernel_fuzz(emu):
+    rng = np.random.default_rng(0)
+    for trial in range(150):
+        d, m = _occlusion_case(rng)
+        B, _, H, W = d.shape
+        want, _ = G.occlusion_filter(d, m)
+        got = np.full((B, H, W), -7.0, np.float32)
+        dd = np.ascontiguousarray(d.reshape(B, H, W))
+        mm = np.ascontiguousarray(m.reshape(B, H, W).astype(np.uint8))
+        emu.emu_occlusion(_vp(dd), _vp(mm), _vp(got), B, H, W)
+        assert _same_bits_or_nan(got.reshape(want.shape), want), (trial, d.shape)

@@ -206,3 +206,18 @@ def test_keep_mask_dropout_bit_exact(ref, mode):
     plain = R.p_sample_loop(sd, sch, pc, ic, noises, has_refine_step=True) if "sampling_timesteps" not in cfg else None
     if plain is not None:
         assert not torch.equal(plain, got)          # the dropout did change the result
+
+
+def test_occlusion_filter_fuzz_bit_exact(ref):
+    """Random shapes (down to 1x1), quantised depths whose differences land exactly on the 0.0375
+    threshold, infinities: oracle == reference bit for bit.  (NaN depths are outside the contract:
+    the inputs are z-buffer outputs, and torch's max_pool2d would propagate NaN where the oracle
+    skips it.)"""
+    from test_kernel_emulation import _occlusion_case, _same_bits_or_nan     # tests/ is on sys.path (rootdir conftest)
+    sdd, _ = ref
+    rng = np.random.default_rng(1)
+    for trial in range(100):
+        d, m = _occlusion_case(rng)
+        want, _ = sdd.occlusion_filter(torch.tensor(d), torch.tensor(m))
+        got, _ = G.occlusion_filter(d, m)
+        assert _same_bits_or_nan(got, want.numpy()), (trial, d.shape)
