@@ -88,10 +88,22 @@ __device__ __forceinline__ void unproject(int r, int c, float z, const Intr& k, 
   else unproject_ieee(r, c, z, k, x, y);
 }
 
+// torch.matmul(pc, R^T) + t (SDD:279).  For every realistic size ATen's bmm accumulates like
+// fma(z, r2, fma(y, r1, x * r0)); for maps of at most 44 pixels (N * 9 < 400) it runs a scalar loop
+// that rounds every product and sum on its own.  kScalarBmm selects that form so that even tiny test
+// maps match the reference bit for bit; it is a separate kernel instantiation, the real one is untouched.
+template <bool kScalarBmm = false>
 __device__ __forceinline__ void rigid(const float* __restrict__ P, float& x, float& y, float& z) {
-  float xn = __fadd_rn(__fmaf_rn(z, P[2], __fmaf_rn(y, P[1], __fmul_rn(x, P[0]))), P[3]);
-  float yn = __fadd_rn(__fmaf_rn(z, P[6], __fmaf_rn(y, P[5], __fmul_rn(x, P[4]))), P[7]);
-  float zn = __fadd_rn(__fmaf_rn(z, P[10], __fmaf_rn(y, P[9], __fmul_rn(x, P[8]))), P[11]);
+  float xn, yn, zn;
+  if (kScalarBmm) {
+    xn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, P[0]), __fmul_rn(y, P[1])), __fmul_rn(z, P[2])), P[3]);
+    yn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, P[4]), __fmul_rn(y, P[5])), __fmul_rn(z, P[6])), P[7]);
+    zn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, P[8]), __fmul_rn(y, P[9])), __fmul_rn(z, P[10])), P[11]);
+  } else {
+    xn = __fadd_rn(__fmaf_rn(z, P[2], __fmaf_rn(y, P[1], __fmul_rn(x, P[0]))), P[3]);
+    yn = __fadd_rn(__fmaf_rn(z, P[6], __fmaf_rn(y, P[5], __fmul_rn(x, P[4]))), P[7]);
+    zn = __fadd_rn(__fmaf_rn(z, P[10], __fmaf_rn(y, P[9], __fmul_rn(x, P[8]))), P[11]);
+  }
   x = xn;
   y = yn;
   z = zn;
@@ -120,6 +132,7 @@ __device__ __forceinline__ void splat(float x, float y, float z, const Intr& k, 
 // ------------------------------------------------------------------ reproject
 // One thread = 4 consecutive pixels (16-byte load).  The z-buffer lives in
 // depth_out itself (pre-filled with 0xFFFFFFFF), finalised in place.
+template <bool kScalarBmm>
 __global__ void __launch_bounds__(256)
 k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
                   const float* __restrict__ pose, float lo, float hi,
@@ -152,7 +165,7 @@ k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
         if (c >= W) { c -= W; ++r; while (c >= W) { c -= W; ++r; } }   // a second wrap only when W < 4
         float x, y, z = z0;
         unproject(r, c, z, k, x, y);
-        rigid(sP, x, y, z);
+        rigid<kScalarBmm>(sP, x, y, z);
         splat(x, y, z, k, H, W, zimg);
       }
     }
@@ -508,8 +521,12 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
     float* out = depth_out + (size_t)b0 * HW;
     PRG_CUDA_OK(cudaMemsetAsync(out, 0xFF, n * sizeof(float), s));
     dim3 g1(grid_for(HW, 256, 4), nb);
-    k_reproject_splat<<<g1, 256, 0, s>>>(depth + (size_t)b0 * HW, K + (size_t)b0 * 9, pose + (size_t)b0 * 16,
-                                        clip_lo, clip_hi, (unsigned*)out, HW, H, W);
+    if ((long long)HW * 9 < 400)      // maps of at most 44 pixels: ATen's scalar bmm rounding (see rigid())
+      k_reproject_splat<true><<<g1, 256, 0, s>>>(depth + (size_t)b0 * HW, K + (size_t)b0 * 9, pose + (size_t)b0 * 16,
+                                                clip_lo, clip_hi, (unsigned*)out, HW, H, W);
+    else
+      k_reproject_splat<false><<<g1, 256, 0, s>>>(depth + (size_t)b0 * HW, K + (size_t)b0 * 9, pose + (size_t)b0 * 16,
+                                                 clip_lo, clip_hi, (unsigned*)out, HW, H, W);
     PRG_LAUNCH_CHECK();
     k_zbuf_finalize<<<grid_for((int64_t)n, 256, 4), 256, 0, s>>>((unsigned*)out, mask_out + (size_t)b0 * HW, n);
     PRG_LAUNCH_CHECK();

@@ -42,7 +42,8 @@ static void run_block(unsigned x, unsigned y, unsigned first, unsigned last, voi
 struct RArgs { const float *depth, *K, *pose; float lo, hi; unsigned* z; int HW, H, W; };
 static void call_splat(void* p) {
   RArgs& a = *(RArgs*)p;
-  k_reproject_splat(a.depth, a.K, a.pose, a.lo, a.hi, a.z, a.HW, a.H, a.W);
+  if ((long long)a.HW * 9 < 400) k_reproject_splat<true>(a.depth, a.K, a.pose, a.lo, a.hi, a.z, a.HW, a.H, a.W);
+  else k_reproject_splat<false>(a.depth, a.K, a.pose, a.lo, a.hi, a.z, a.HW, a.H, a.W);      // as prg_reproject_f32
 }
 // prg_reproject_f32 without the L2 grouping: fill 0xFF, splat, finalise.  gx = grid_for(HW, 256, 4).
 extern "C" void emu_reproject(const float* depth, const float* K, const float* pose, float lo, float hi,
