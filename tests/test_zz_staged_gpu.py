@@ -255,3 +255,25 @@ def test_keep_mask_dropout_sampling(mode):
     a = fn(param_cond=pc.cuda(), img_cond=ic.cuda(), seed=5)
     b_ = fn(param_cond=pc.cuda(), img_cond=ic.cuda(), seed=5)
     assert torch.equal(a, b_) and torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 7), (2, 9, 3), (1, 44, 1), (1, 1, 1), (2, 3, 15)])
+def test_reproject_tiny_and_narrow_maps(shape):
+    """Maps of at most 44 pixels (ATen's scalar bmm rounding, a separate kernel instantiation) and
+    maps narrower than four pixels (several row wraps per thread)."""
+    B, H, W = shape
+    d01 = S.synthetic_depth_batch(500, B, H, W)
+    K = S.synthetic_intrinsics(B, None, seed=2).copy()
+    K[:, 0, 0] = K[:, 1, 1] = 1.2 * max(W, 4)
+    K[:, 0, 2], K[:, 1, 2] = W / 2, H / 2
+    P = S.synthetic_poses(B, seed=3)
+    dm = d01 * 10
+    od, om = G.reproject(dm.numpy(), K, P)
+    gd, gm = pg.reproject_tensor(dm.cuda(), torch.tensor(K).cuda(), torch.tensor(P).cuda())
+    assert np.array_equal(gd.cpu().numpy().view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(gm.cpu().numpy(), om)
+    opc, ov = G.depth2pc(dm.numpy(), K, clip=[0, 10])
+    gpc, gv = pg.depth2pc_tensor(dm.cuda(), torch.tensor(K).cuda(), clip=[0, 10])
+    a, b = gpc.cpu().numpy(), opc
+    assert np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))
+    assert np.array_equal(gv.cpu().numpy(), ov)
