@@ -68,6 +68,33 @@ extern "C" void emu_reproject(const float* depth, const float* K, const float* p
       k_zbuf_finalize((unsigned*)out, mask, n);
     }
 }
+struct PArgs { const float* pc; const uint8_t* valid; const int64_t* off; int64_t total; const float *K, *pose; unsigned* z; int B, H, W; };
+static void call_pc2d(void* p) {
+  PArgs& a = *(PArgs*)p;
+  k_pc2depth_splat(a.pc, a.valid, a.off, a.total, a.K, a.pose, a.z, a.B, a.H, a.W);
+}
+// prg_pc2depth_f32: fill 0xFF, splat the ragged clouds (offsets staged in shared memory), finalise
+extern "C" void emu_pc2depth(const float* pc, const uint8_t* valid, const int64_t* off, long long total,
+                             const float* K, const float* pose, float* out, uint8_t* mask, unsigned* scratch,
+                             int B, int H, int W, int gx) {
+  const size_t n = (size_t)B * H * W;
+  memset(out, 0xFF, n * 4);
+  blockDim = {256, 1, 1};
+  gridDim = {(unsigned)gx, 1, 1};
+  for (unsigned x = 0; x < (unsigned)gx; ++x) {
+    PArgs a{pc, valid, off, total, K, pose, scratch, B, H, W};
+    run_block(x, 0, 0, 256, call_pc2d, &a);        // fills the staged offsets
+    a.z = (unsigned*)out;
+    run_block(x, 0, 0, 256, call_pc2d, &a);
+  }
+  gridDim = {(unsigned)((n + 1023) / 1024), 1, 1};
+  for (unsigned x = 0; x < gridDim.x; ++x)
+    for (unsigned t = 0; t < 256; ++t) {
+      blockIdx = {x, 0, 0};
+      threadIdx = {t, 0, 0};
+      k_zbuf_finalize((unsigned*)out, mask, n);
+    }
+}
 struct DArgs { const float *depth, *K; float lo, hi; int use_clip; float invalid; float* pc; uint8_t* valid; int HW, W; };
 static void call_d2pc(void* p) {
   DArgs& a = *(DArgs*)p;
@@ -167,7 +194,11 @@ def geom(tmp_path_factory):
     b = src.index("// ------------------------------------------------------------------ pc2depth (ragged)")
     c = src.index("// ------------------------------------------------------------------ depth2pc (dense)")
     d = src.index("// ------------------------------------------------------------------ occlusion_filter")
-    return _compile(tmp_path_factory.mktemp("emu"), "geom", src[a:b] + src[c:d] + GEOM_DRIVER)
+    text = src[a:c] + src[c:d]
+    # dynamic shared memory has no host counterpart: a fixed array of the ABI's maximum (B <= 4096)
+    assert "extern __shared__ int64_t s_off[];" in text
+    text = text.replace("extern __shared__ int64_t s_off[];", "static int64_t s_off[4097];")
+    return _compile(tmp_path_factory.mktemp("emu"), "geom", text + GEOM_DRIVER)
 
 
 @pytest.mark.parametrize("shape", [(2, 256, 256), (1, 480, 640), (2, 33, 47), (1, 5, 7), (1, 40, 260),
@@ -402,3 +433,45 @@ def test_occlusion_filter_kernel_fuzz(emu):
         mm = np.ascontiguousarray(m.reshape(B, H, W).astype(np.uint8))
         emu.emu_occlusion(_vp(dd), _vp(mm), _vp(got), B, H, W)
         assert _same_bits_or_nan(got.reshape(want.shape), want), (trial, d.shape)
+
+
+def test_pc2depth_kernel_fuzz(geom):
+    """Ragged z-buffer (the Generator path: pose applied in the kernel) against the oracle: random
+    clouds with awkward coordinates, validity masks, empty clouds in the batch."""
+    rng = np.random.default_rng(3)
+    V = np.array([0.0, -0.0, -1.5, 1e-42, 1e-30, 1e-12, 1e9, 1e12, 1e30, 3e38, np.inf, -np.inf, np.nan, 1.0, 0.5, 2.5],
+                 np.float32)
+    for trial in range(120):
+        B, H, W = int(rng.integers(1, 4)), int(rng.integers(1, 40)), int(rng.integers(1, 70))
+        sizes = rng.integers(0, 300, B)
+        if trial % 7 == 0:
+            sizes[int(rng.integers(0, B))] = 0
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        N = int(offs[-1])
+        pc = (rng.normal(0, 1, (max(N, 1), 3)) * np.array([1, 1, 0.5]) + np.array([0, 0, 2.0])).astype(np.float32)
+        m = rng.random(pc.shape) < 0.1
+        pc[m] = V[rng.integers(0, V.size, int(m.sum()))]
+        valid = (rng.random(max(N, 1)) < 0.8) if trial % 3 else None
+        K = np.zeros((B, 3, 3), np.float32)
+        K[:, 2, 2] = 1
+        K[:, 0, 0], K[:, 1, 1] = 1.2 * W * rng.uniform(0.5, 2, B), 1.2 * W * rng.uniform(0.5, 2, B)
+        K[:, 0, 2], K[:, 1, 2] = W / 2 + rng.uniform(-1, 1, B), H / 2
+        if trial % 5 == 0:
+            K[0, 0, 0], K[0, 0, 2] = rng.choice(_FX), rng.choice(_CX)
+        P = None
+        if trial % 2:
+            P = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+            ang = rng.uniform(-0.3, 0.3, B)
+            P[:, 0, 0], P[:, 0, 2], P[:, 2, 0], P[:, 2, 2] = np.cos(ang), np.sin(ang), -np.sin(ang), np.cos(ang)
+            P[:, :3, 3] = rng.normal(0, 0.3, (B, 3))
+        with np.errstate(all="ignore"):
+            want_d, want_m = G.pc2depth(pc[:N], None if valid is None else valid[:N], offs, K, (H, W), pose=P)
+        out = np.empty((B, H, W), np.float32)
+        mask = np.empty((B, H, W), np.uint8)
+        scratch = np.full((B, H, W), 0xFFFFFFFF, np.uint32)
+        v8 = None if valid is None else np.ascontiguousarray(valid.astype(np.uint8))
+        gx = max(1, (N + 255) // 256)
+        geom.emu_pc2depth(_vp(pc), None if v8 is None else _vp(v8), _vp(offs), ctypes.c_longlong(N), _vp(K),
+                          None if P is None else _vp(np.ascontiguousarray(P)), _vp(out), _vp(mask), _vp(scratch), B, H, W, gx)
+        assert _same_bits_or_nan(out.reshape(want_d.shape), want_d), (trial, B, H, W, N)
+        assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m), (trial, B, H, W, N)
