@@ -267,3 +267,21 @@ def test_geometry_fuzz_bit_exact(ref):
         ctx = (trial, H, W, K[0, [0, 1, 0, 1], [0, 1, 2, 2]].tolist(), clip, rclip)
         assert same(rpc.numpy(), opc) and np.array_equal(rv.numpy(), ov), ctx
         assert same(rd.numpy(), od) and np.array_equal(rm.numpy(), om), ctx
+
+
+@pytest.mark.parametrize("dim,mults,size,batch", [(32, (1, 2, 4, 8), 32, 3), (48, (1, 2, 4), 48, 2), (64, (1, 2), 32, 1)])
+def test_network_oracle_other_architectures_bit_exact(ref, dim, mults, size, batch):
+    """The functional restatement is generic in width, depth, image size and batch: bit-exact against
+    the reference modules for configurations other than the shipped one."""
+    sdd, dc = ref
+    torch.manual_seed(dim + size)
+    net = sdd.Unet(dim=dim, param_cond_dim=4, dim_mults=mults, channels=1).eval()
+    m = dc.MaskUnet(dim=dim, dim_mults=mults).eval()
+    x = torch.randn(batch, 1, size, size)
+    t = torch.randint(0, 1000, (batch,))
+    pc = torch.rand(batch, 4) * 300
+    d = torch.rand(batch, 1, size, size)
+    d[d < 0.3] = 0
+    with torch.no_grad():
+        assert torch.equal(net(x, t, pc), R.unet_forward({k: v.detach() for k, v in net.state_dict().items()}, x, t, pc))
+        assert torch.equal(m(d), R.maskunet_forward({k: v.detach() for k, v in m.state_dict().items()}, d))
