@@ -234,6 +234,7 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
   __shared__ float4 sT[8][96];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_w = 1.f / (float)W;
+  const bool clip_bounds = use_clip && lo >= 0.f && hi <= 1e9f;
   for (int base4 = blockIdx.x * blockDim.x; base4 * 4 < HW; base4 += gridDim.x * blockDim.x) {
     const int i4 = base4 + threadIdx.x;
     const int i = i4 * 4;
@@ -257,7 +258,9 @@ k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float l
       if (c >= W) { c -= W; ++r; while (c >= W) { c -= W; ++r; } }     // a second wrap only when W < 4
       ok[j] = use_clip ? (d[j] > lo && d[j] < hi) : 1;
       const float z = ok[j] ? d[j] : invalid;
-      safe = safe && (!ok[j] || depth_in_range(z));
+      // a clip inside [0, 1e9] already bounds the valid depths from above and keeps them positive:
+      // one comparison is left of depth_in_range (clip_bounds is uniform over the launch)
+      safe = safe && (!ok[j] || (clip_bounds ? z > 1e-9f : depth_in_range(z)));
       float x, y;
       unproject_fast(r, c, z, k, x, y);
       o[j * 3 + 0] = ok[j] ? x : invalid;
