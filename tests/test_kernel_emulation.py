@@ -475,3 +475,96 @@ def test_pc2depth_kernel_fuzz(geom):
                           None if P is None else _vp(np.ascontiguousarray(P)), _vp(out), _vp(mask), _vp(scratch), B, H, W, gx)
         assert _same_bits_or_nan(out.reshape(want_d.shape), want_d), (trial, B, H, W, N)
         assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m), (trial, B, H, W, N)
+
+
+TAIL_DRIVER_HEAD = '''
+struct TailParams {
+  const float* x_t; const float* img_cond; const float* noise; float* out;
+  int HW, clip_x_start, use_ddnm, sampler, add_noise, unnormalize;
+  float c0, c1, c2, c3, c4;
+  unsigned long long seed, noise_offset;
+};
+static float philox_normal(unsigned long long, unsigned long long) { return 0.f; }   // noise is always injected here
+static void tail_pixel(const TailParams& t, float net, int b, long long p, size_t o) {
+'''
+TAIL_DRIVER_TAIL = '''
+}
+extern "C" void emu_tail(const float* x_t, const float* img_cond, const float* noise, const float* net, float* out,
+                         int B, int HW, int kind, int add_noise, int unnormalize, int has_cond,
+                         float c0, float c1, float c2, float c3, float c4) {
+  // the host side of prg_sampler_run for one step (net.cu): which kinds clamp before pred_noise, which replace
+  TailParams t{x_t, has_cond ? img_cond : nullptr, noise, out, HW, 0, 0, kind, add_noise, unnormalize, c0, c1, c2, c3, c4, 0, 0};
+  t.clip_x_start = (kind == 1 || kind == 2 || kind == 4);
+  t.use_ddnm = has_cond && (kind == 0 || kind == 1 || kind == 2);
+  for (int b = 0; b < B; ++b)
+    for (long long p = 0; p < HW; ++p) {
+      const size_t o = (size_t)b * HW + p;
+      tail_pixel(t, net[o], b, p, o);
+    }
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def tail(tmp_path_factory):
+    """The sampler-step arithmetic of k_net_tail (mode 2), cut out of elementwise.cu verbatim."""
+    src = open(os.path.join(ROOT, "pointreggpt_b200", "csrc", "elementwise.cu")).read()
+    a = src.index("      const float xt = t.x_t[o];")
+    b = src.index("      t.out[o] = xn;") + len("      t.out[o] = xn;")
+    return _compile(tmp_path_factory.mktemp("emu"), "tail", TAIL_DRIVER_HEAD + src[a:b] + TAIL_DRIVER_TAIL)
+
+
+@pytest.mark.parametrize("mode", ["p_sample", "p_sample_refine", "ddim", "ddim_refine", "ddim_eta0", "uncond"])
+def test_sampler_step_arithmetic_bit_exact(tail, monkeypatch, mode):
+    """Host step tables (diffusion.sampling_steps) + the device's per-pixel sampler arithmetic, run on
+    the host with a stand-in network, must reproduce the oracle's sampling loops BIT FOR BIT (the
+    oracle is pinned bit-exactly to the reference): given the same network output, the DDNM
+    replacement, clamps, posterior / DDIM updates, refine step and unnormalisation are identical."""
+    import torch
+    from oracle import torch_ref as R
+    from pointreggpt_b200 import _ffi, nets
+    from pointreggpt_b200.diffusion import GaussianDiffusion
+    B, SZ = 2, 24
+    cfg = dict(p_sample=dict(timesteps=12), p_sample_refine=dict(timesteps=12),
+               ddim=dict(timesteps=50, sampling_timesteps=7, ddim_sampling_eta=1.0),
+               ddim_refine=dict(timesteps=50, sampling_timesteps=7, ddim_sampling_eta=1.0),
+               ddim_eta0=dict(timesteps=40, sampling_timesteps=5, ddim_sampling_eta=0.0),
+               uncond=dict(timesteps=9))[mode]
+    refine = mode.endswith("refine")
+    T = cfg["timesteps"]
+
+    def fake_net(x, t):          # exceeds [-1, 1] so that every clamp is exercised
+        return torch.tanh(x * 0.7 + 0.013 * float(t)) * 1.3 - 0.05
+
+    monkeypatch.setattr(R, "unet_forward", lambda sd, x, tt, pc, emu=None: fake_net(x, int(tt[0])))
+    g = torch.Generator().manual_seed(4)
+    noises = [torch.randn(B, 1, SZ, SZ, generator=g) for _ in range(T + 2)]
+    d = torch.rand(B, 1, SZ, SZ, generator=g)
+    d[d < 0.4] = 0
+    ic = None if mode == "uncond" else torch.cat([d, (d > 0).float()], 1) * 2 - 1
+    pc = torch.zeros(B, 4)
+    sch = R.make_schedule(T)
+    if "sampling_timesteps" in cfg:
+        want = R.ddim_sample(None, sch, pc, ic, noises, cfg["sampling_timesteps"], cfg["ddim_sampling_eta"],
+                             has_refine_step=refine)
+    else:
+        want = R.p_sample_loop(None, sch, pc, ic, noises, has_refine_step=refine)
+    torch.manual_seed(0)
+    diff = GaussianDiffusion(nets.Unet(dim=64, param_cond_dim=4), image_size=SZ, objective="pred_x0",
+                             beta_schedule="sigmoid", **cfg)
+    x = noises[0].clone().numpy()
+    k = 1
+    icn = None if ic is None else np.ascontiguousarray(ic.numpy())
+    for st in diff.sampling_steps(refine):
+        net = np.ascontiguousarray(fake_net(torch.tensor(x), st.t).numpy())
+        nz = None
+        if st.add_noise:
+            nz = np.ascontiguousarray(noises[k].numpy())
+            k += 1
+        out = np.empty_like(x)
+        f = ctypes.c_float
+        tail.emu_tail(_vp(x), None if icn is None else _vp(icn), None if nz is None else _vp(nz), _vp(net), _vp(out),
+                      B, SZ * SZ, st.kind, st.add_noise, st.unnormalize, int(icn is not None),
+                      f(st.c0), f(st.c1), f(st.c2), f(st.c3), f(st.c4))
+        x = out
+    assert np.array_equal(x.view(np.uint32), want.numpy().view(np.uint32))
