@@ -4,9 +4,10 @@ model / sampler hyper-parameters, same output layout -- running on the B200-nati
     python generate_dataset.py --resume official [-start 0 -stop 10 --num_samples 1]
     torchrun --nproc-per-node 8 generate_dataset.py --resume official -start 0 -stop 10000
 
-Extra (optional) flags for the offline environment: --data_root (3DMatch RGB-D train tree;
-when it does not exist the seeded synthetic source frames are used), --random_init (skip
-checkpoint loading), --sampling_timesteps / --batch_size overrides.
+Extra (optional) flags: --data_root (3DMatch RGB-D train tree; it must exist) or --synthetic (seeded
+synthetic source frames -- no dataset can be downloaded offline), --random_init (skip checkpoint
+loading), --seed (base seed: scene k's pose and noise depend on (seed, k) only, so the dataset is the
+same for any world size / batch size / -start -stop split), --sampling_timesteps / --batch_size.
 """
 import argparse
 import os
@@ -25,7 +26,9 @@ parser.add_argument('--start_scene_index', '-start', default=0, type=int, help='
 parser.add_argument('--stop_scene_index', '-stop', default=1, type=int, help='scenes index to stop')
 parser.add_argument('--num_samples', default=1, type=int, help='sample numbers for each scene')
 parser.add_argument('--data_root', default='/path/to/3DMatch-RGBD/train', type=str)
+parser.add_argument('--synthetic', action='store_true', help='seeded synthetic source frames instead of 3DMatch')
 parser.add_argument('--random_init', action='store_true', help='seeded random weights, no checkpoint')
+parser.add_argument('--seed', default=0, type=int, help='base seed of the per-scene pose / noise streams')
 parser.add_argument('--sampling_timesteps', default=250, type=int)
 parser.add_argument('--batch_size', default=4, type=int)
 args = parser.parse_args()
@@ -34,13 +37,20 @@ if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not torch.distributed.is_initi
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     torch.distributed.init_process_group("nccl")
 
-torch.manual_seed(0)
+if args.random_init:
+    torch.manual_seed(0)          # weight construction only; sampling noise is keyed per scene (--seed)
 model = Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
 diffusion = GaussianDiffusion(model, image_size=256, timesteps=1000,
                               sampling_timesteps=args.sampling_timesteps, loss_type='l1',
                               objective='pred_x0', beta_schedule='sigmoid', ddim_sampling_eta=1.0,
                               is_ddnm_sampling=True)
-folder = args.data_root if os.path.isdir(args.data_root) else "synthetic"
+if args.synthetic:
+    folder = "synthetic"
+elif os.path.isdir(args.data_root):
+    folder = args.data_root
+else:
+    raise FileNotFoundError("--data_root %r does not exist (use --synthetic for the synthetic source "
+                            "frames)" % args.data_root)
 generator = Generator(diffusion, folder, batch_size=args.batch_size, ema_decay=0.995,
                       results_folder='./successive_ddnm_diffusion_results',
                       samples_folder='./{}/data'.format(args.dataset_name), amp=False)
@@ -54,6 +64,6 @@ if torch.distributed.is_initialized():
     pdist.broadcast_weights([generator.ema.ema_model, depth_correction.to(generator.device)], src=0)
 n = generator.generate(start_scene_index=args.start_scene_index, stop_scene_index=args.stop_scene_index,
                        num_samples=args.num_samples, has_refine_step=False,
-                       depth_correction=depth_correction)
+                       depth_correction=depth_correction, base_seed=args.seed)
 if generator.rank == 0:
     print("generated %d scenes into ./%s/data" % (n, args.dataset_name))

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PRG_ABI_VERSION 1
+#define PRG_ABI_VERSION 2
 
 #define PRG_OK 0
 #define PRG_ERR_ARG (-1)
@@ -168,12 +168,20 @@ typedef struct prg_step {
 
 /* GaussianDiffusion.sample (SDD:1394-1409) for objective pred_x0 with the DDNM null-space
  * replacement (SDD:1210-1218) when img_cond != NULL.
- *  steps: host array.  noise: NULL => device Philox(seed); else (1 + #noisy steps, B,1,S,S)
- *  f32: slab 0 = x_T, slab 1+i = the i-th randn_like draw (parity runs inject the reference's
- *  draws).  out (B,1,S,S) f32 (in [0,1] when the last step unnormalizes).  B <= max_batch. */
+ *  steps: host array.  noise: NULL => device Philox, one stream per image keyed by
+ *  philox_seeds[b] (HOST array of B entries; the draws of an image depend on its seed only, not
+ *  on batch composition, rank or world size); else (1 + #noisy steps, B,1,S,S) f32: slab 0 =
+ *  x_T, slab 1+i = the i-th randn_like draw (parity runs inject the reference's draws; seeds may
+ *  then be NULL).  out (B,1,S,S) f32 (in [0,1] when the last step unnormalizes).  B <= max_batch. */
 int prg_sampler_run(prg_net* unet, const prg_step* steps, int nsteps, const float* param_cond,
-                    const float* img_cond, const float* noise, uint64_t philox_seed, float* out,
-                    int B, prg_stream_t stream);
+                    const float* img_cond, const float* noise, const uint64_t* philox_seeds,
+                    float* out, int B, prg_stream_t stream);
+
+/* The sampler's Gaussian generator on its own (replaces torch.randn / randn_like, SDD:1279, 1293,
+ * 1339, 1369): out (B, per_image) f32, image b filled from Philox4x32-10 keyed by seeds[b] (HOST
+ * array) at counters offset .. offset + per_image - 1, Box-Muller on the first two words. */
+int prg_fill_normal_f32(float* out, int B, int64_t per_image, const uint64_t* seeds,
+                        uint64_t offset, prg_stream_t stream);
 
 /* Sampled kernel timing for bench.py's roofline: every n-th network evaluation (0 = off) each
  * launch is bracketed by CUDA events on the launching stream.  prg_profile_read synchronises

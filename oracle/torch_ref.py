@@ -334,6 +334,19 @@ def _predictions(sd, sch, x, t, param_cond, img_cond, clip_x_start, ban_ddnm, em
 
 
 @torch.no_grad()
+def p_sample_step(sd, sch, img, t, param_cond, img_cond, noise, emu=None, keep=None):
+    """One iteration of the p_sample_loop body (p_sample -> p_mean_variance -> q_posterior,
+    SDD:1257-1281, 1234-1255, 1173-1180): x_t -> x_{t-1}; `noise` is the randn_like draw (unused at t = 0)."""
+    _, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, False, False, emu, keep)
+    x0 = x0.clamp(-1., 1.)
+    mean = sch["posterior_mean_coef1"][t] * x0 + sch["posterior_mean_coef2"][t] * img
+    logvar = sch["posterior_log_variance_clipped"][t]
+    if t > 0:
+        return mean + (0.5 * logvar).exp() * noise
+    return mean + (0.5 * logvar).exp() * 0.
+
+
+@torch.no_grad()
 def p_sample_loop(sd, sch, param_cond, img_cond, noises, has_refine_step=False,
                   emu=None, trajectory=None, keep=None):
     """SDD:1283-1317 with torch.randn replaced by the injected `noises`
@@ -342,16 +355,11 @@ def p_sample_loop(sd, sch, param_cond, img_cond, noises, has_refine_step=False,
     img = noises[0].clone()
     k = 1
     for t in reversed(range(T)):
-        _, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, False, False, emu, keep)
-        x0 = x0.clamp(-1., 1.)
-        mean = sch["posterior_mean_coef1"][t] * x0 + sch["posterior_mean_coef2"][t] * img
-        logvar = sch["posterior_log_variance_clipped"][t]
+        noise = None
         if t > 0:
             noise = noises[k]
             k += 1
-            img = mean + (0.5 * logvar).exp() * noise
-        else:
-            img = mean + (0.5 * logvar).exp() * 0.
+        img = p_sample_step(sd, sch, img, t, param_cond, img_cond, noise, emu, keep)
         if trajectory is not None:
             trajectory.append(img.clone())
     if has_refine_step:
@@ -371,24 +379,31 @@ def ddim_times(total_timesteps, sampling_timesteps):
 
 
 @torch.no_grad()
+def ddim_step(sd, sch, img, t, t_next, param_cond, img_cond, noise, eta=1.0, emu=None, keep=None):
+    """One iteration of the ddim_sample body (SDD:1343-1373): x_t -> x_{t_next}."""
+    ac = sch["alphas_cumprod"]
+    pred_noise, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, True, False, emu, keep)
+    if t_next < 0:
+        return x0
+    alpha, alpha_next = ac[t], ac[t_next]
+    sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+    c = (1 - alpha_next - sigma ** 2).sqrt()
+    return x0 * alpha_next.sqrt() + c * pred_noise + sigma * noise
+
+
+@torch.no_grad()
 def ddim_sample(sd, sch, param_cond, img_cond, noises, sampling_timesteps, eta=1.0,
                 has_refine_step=False, emu=None, trajectory=None, keep=None):
     """SDD:1319-1392 with injected noise (same convention as p_sample_loop)."""
     T = sch["betas"].shape[0]
     img = noises[0].clone()
     k = 1
-    ac = sch["alphas_cumprod"]
     for t, t_next in ddim_times(T, sampling_timesteps):
-        pred_noise, x0 = _predictions(sd, sch, img, t, param_cond, img_cond, True, False, emu, keep)
-        if t_next < 0:
-            img = x0
-        else:
-            alpha, alpha_next = ac[t], ac[t_next]
-            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
-            c = (1 - alpha_next - sigma ** 2).sqrt()
+        noise = None
+        if t_next >= 0:
             noise = noises[k]
             k += 1
-            img = x0 * alpha_next.sqrt() + c * pred_noise + sigma * noise
+        img = ddim_step(sd, sch, img, t, t_next, param_cond, img_cond, noise, eta, emu, keep)
         if trajectory is not None:
             trajectory.append(img.clone())
     if has_refine_step:

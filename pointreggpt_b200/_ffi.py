@@ -61,7 +61,9 @@ SIGNATURES = {
     "prg_maskunet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int,
                                      c_void_p]),
     "prg_sampler_run": (c_int, [c_void_p, ctypes.POINTER(Step), c_int, c_void_p, c_void_p,
-                                c_void_p, c_uint64, c_void_p, c_int, c_void_p]),
+                                c_void_p, ctypes.POINTER(c_uint64), c_void_p, c_int, c_void_p]),
+    "prg_fill_normal_f32": (c_int, [c_void_p, c_int, c_int64, ctypes.POINTER(c_uint64), c_uint64,
+                                    c_void_p]),
     "prg_occlusion_filter_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "prg_voxel_downsample_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
     "prg_voxel_downsample_f64": (c_int, [c_void_p, ctypes.c_int64, ctypes.c_double, c_void_p, c_void_p,
@@ -93,7 +95,7 @@ def lib():
             fn = getattr(l, name)   # AttributeError if the ABI is incomplete
             fn.restype = res
             fn.argtypes = args
-        if l.prg_abi_version() != 1:
+        if l.prg_abi_version() != 2:
             raise PrgError("libprg.so ABI version mismatch")
         _lib = l
     return _lib
@@ -111,8 +113,12 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
-def stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(ref=None):
+    """The current CUDA stream of the device `ref` (a tensor or a device) lives on -- not of whatever
+    device happens to be current; the library's entry points select the device of their buffers
+    themselves (csrc/common.cuh PtrDeviceGuard / net.cu DeviceGuard)."""
+    dev = ref.device if torch.is_tensor(ref) else ref
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def require_cuda(*tensors):
@@ -120,6 +126,12 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             raise PrgError("pointreggpt_b200 runs on CUDA tensors only (got a %s tensor); "
                            "there is no CPU fallback" % t.device)
+
+
+def seed_array(seeds):
+    """Host uint64 array for the per-image Philox keys."""
+    vals = [int(v) & 0xFFFFFFFFFFFFFFFF for v in seeds]
+    return (c_uint64 * len(vals))(*vals)
 
 
 def launch_count():

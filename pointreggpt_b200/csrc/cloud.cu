@@ -228,6 +228,7 @@ extern "C" __attribute__((visibility("default"))) int prg_voxel_downsample_f64(
     const double* points, int64_t n_points, double voxel_size, double* centroids, int64_t* keys_out,
     int32_t* count_err, void* workspace, size_t workspace_bytes, prg_stream_t stream) {
   PRG_CHECK_ARG(count_err != nullptr, "null pointer");
+  PtrDeviceGuard guard(count_err);
   cudaStream_t s = (cudaStream_t)stream;
   PRG_CUDA_OK(cudaMemsetAsync(count_err, 0, 2 * sizeof(int32_t), s));
   if (n_points == 0) return PRG_OK;
@@ -268,6 +269,7 @@ extern "C" __attribute__((visibility("default"))) int prg_overlap_count_f64(
     const double* query, int64_t n_query, const double* target, int64_t n_target, double radius,
     int32_t* count_err, void* workspace, size_t workspace_bytes, prg_stream_t stream) {
   PRG_CHECK_ARG(count_err != nullptr, "null pointer");
+  PtrDeviceGuard guard(count_err);
   cudaStream_t s = (cudaStream_t)stream;
   PRG_CUDA_OK(cudaMemsetAsync(count_err, 0, 2 * sizeof(int32_t), s));
   if (n_query == 0 || n_target == 0) return PRG_OK;

@@ -57,6 +57,23 @@ inline int num_sms() {
   return n;
 }
 
+// Selects the device that owns `ptr` for the lifetime of the guard (entry points take raw device
+// pointers and a stream of that device; the caller's current device may be another GPU).
+struct PtrDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit PtrDeviceGuard(const void* ptr) {
+    cudaPointerAttributes a;
+    if (ptr == nullptr || cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    if (prev != a.device && cudaSetDevice(a.device) == cudaSuccess) switched = true;
+  }
+  ~PtrDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace prg

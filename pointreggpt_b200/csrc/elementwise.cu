@@ -749,18 +749,26 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
   return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
+// One Philox stream per image: key = seeds[b], counter = offset + index inside the image.  The draws of
+// an image therefore depend only on its own seed -- not on the batch it travels in, its position in
+// the batch, the rank or the world size.
 __global__ void __launch_bounds__(256)
-k_fill_normal(float* __restrict__ x, int64_t n, unsigned long long seed, unsigned long long offset) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+k_fill_normal(float* __restrict__ x, int64_t per_image, const unsigned long long* __restrict__ seeds,
+              unsigned long long offset) {
+  const int b = blockIdx.y;
+  const unsigned long long seed = seeds[b];
+  float* xi = x + (size_t)b * per_image;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image;
        i += (int64_t)gridDim.x * blockDim.x)
-    x[i] = philox_normal(seed, offset + (unsigned long long)i);
+    xi[i] = philox_normal(seed, offset + (unsigned long long)i);
 }
 
-int fill_normal(float* x, int64_t n, unsigned long long seed, unsigned long long offset,
-                cudaStream_t s) {
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  k_fill_normal<<<blocks, 256, 0, s>>>(x, n, seed, offset);
+int fill_normal(float* x, int B, int64_t per_image, const unsigned long long* seeds_dev,
+                unsigned long long offset, cudaStream_t s) {
+  int blocks = (int)((per_image + 255) / 256);
+  const int cap = std::max(1, num_sms() * 8 / std::max(1, B));
+  if (blocks > cap) blocks = cap;
+  k_fill_normal<<<dim3(blocks, B), 256, 0, s>>>(x, per_image, seeds_dev, offset);
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -823,7 +831,7 @@ k_net_tail(TailParams t) {
       }
       float nz = 0.f;
       if (t.add_noise)
-        nz = (t.noise != nullptr) ? t.noise[o] : philox_normal(t.seed, t.noise_offset + o);
+        nz = (t.noise != nullptr) ? t.noise[o] : philox_normal(t.seeds[b], t.noise_offset + (unsigned long long)p);
       float xn;
       if (t.sampler == 0 || t.sampler == 3) {
         x0 = fminf(fmaxf(x0, -1.f), 1.f);                                       // SDD:1250-1251

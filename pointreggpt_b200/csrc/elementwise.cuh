@@ -83,7 +83,8 @@ struct TailParams {
   const float* x_t;       // current sample (B,HW)
   const float* img_cond;  // (B,2,HW) or nullptr
   const float* noise;     // (B,HW) or nullptr (=> Philox)
-  unsigned long long seed, noise_offset;
+  const unsigned long long* seeds;  // per-image Philox keys (device, B entries)
+  unsigned long long noise_offset;  // counter offset of this draw inside an image's stream
   int clip_x_start;       // ddim: clamp the network output before pred_noise
   int use_ddnm;
   int sampler;            // 0 = p_sample, 1 = ddim, 2 = ddim last step (x = x0), 3 = refine
@@ -95,8 +96,8 @@ struct TailParams {
 };
 int net_tail(const TailParams& t, int B, cudaStream_t s);
 
-// x_T ~ N(0,1) from Philox (throughput runs)
-int fill_normal(float* x, int64_t n, unsigned long long seed, unsigned long long offset,
-                cudaStream_t s);
+// N(0,1) draws from one Philox stream per image (key = seeds_dev[b], counter = offset + index)
+int fill_normal(float* x, int B, int64_t per_image, const unsigned long long* seeds_dev,
+                unsigned long long offset, cudaStream_t s);
 
 }  // namespace prg

@@ -509,6 +509,7 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
                                  uint8_t* mask_out, int B, int H, int W, prg_stream_t stream) {
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth && K && pose && depth_out && mask_out, "null pointer");
+  PtrDeviceGuard guard(depth_out);
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
   if (B == 0) return PRG_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -543,6 +544,7 @@ extern "C" __attribute__((visibility("default"))) int prg_pc2depth_f32(const flo
                                 prg_stream_t stream) {
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(offsets && K && depth_out && mask_out, "null pointer");
+  PtrDeviceGuard guard(depth_out);
   PRG_CHECK_ARG(pc || total_points == 0, "null point cloud");
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && total_points >= 0 && B <= 4096, "bad shape");
   if (B == 0) return PRG_OK;
@@ -564,6 +566,7 @@ extern "C" __attribute__((visibility("default"))) int prg_depth2pc_f32(const flo
                                 int H, int W, prg_stream_t stream) {
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth && K && pc && valid, "null pointer");
+  PtrDeviceGuard guard(pc);
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
   if (B == 0) return PRG_OK;
   const int HW = H * W;
@@ -578,6 +581,7 @@ extern "C" __attribute__((visibility("default"))) int prg_occlusion_filter_f32(c
                                         int B, int H, int W, prg_stream_t stream) {
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth && mask && depth_out, "null pointer");
+  PtrDeviceGuard guard(depth_out);
   PRG_CHECK_ARG(depth != depth_out, "occlusion filter cannot run in place");
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
   dim3 g((W + 255) / 256, (H + 4 * kOccRows - 1) / (4 * kOccRows), B);
@@ -593,6 +597,7 @@ extern "C" __attribute__((visibility("default"))) int prg_depth2pc_compact_f64(c
                                         prg_stream_t stream) {
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth01 && K && pc_out && counts && scratch, "null pointer");
+  PtrDeviceGuard guard(pc_out);
   PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
   if (B == 0) return PRG_OK;
   cudaStream_t s = (cudaStream_t)stream;

@@ -148,6 +148,7 @@ struct prg_net {
   TailParams tail{};
   __half* stem_out = nullptr;
   float* x_state = nullptr;  // sampler state (maxB, S*S) f32
+  unsigned long long* seeds_dev = nullptr;  // sampler: per-image Philox keys (maxB)
 
   template <typename T>
   T* dalloc(size_t count) {
@@ -588,6 +589,7 @@ int build(prg_net* n) {
   n->colmax_cap = (size_t)B * 128 * 16;
   n->colmax_arena = n->dalloc<int>(n->colmax_cap);
   n->x_state = n->dalloc<float>((size_t)B * S * S);
+  n->seeds_dev = n->dalloc<unsigned long long>((size_t)B);
   {
     size_t pf = 0;   // the largest level decides (chunks per image <= 32)
     for (int i = 0; i < L; ++i) pf = std::max(pf, kvctx_partial_floats(B, S >> i, S >> i));
@@ -595,7 +597,7 @@ int build(prg_net* n) {
   }
   n->gn_coef_buf = n->dalloc<float2>((size_t)B * 1024);
   if (!n->gn_coef_buf || !n->kv_partials || !n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
-      !n->colmax_arena || !n->x_state) {
+      !n->colmax_arena || !n->x_state || !n->seeds_dev) {
     set_error("out of device memory allocating the workspace");
     return PRG_ERR_CUDA;
   }
@@ -861,6 +863,8 @@ EXPORT int prg_unet_forward(prg_net* n, const float* x, const int64_t* time, con
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(x && time && pcond && out, "null pointer");
   PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
+  DeviceGuard guard(n->dev);
+  PRG_CHECK_ARG(guard.ok, "cannot select the handle's device");
   Run r{B, (cudaStream_t)stream, x, time, 0, pcond, 0};
   NET_TRY(run_trunk(n, r));
   TailParams t = n->tail;
@@ -875,6 +879,8 @@ EXPORT int prg_maskunet_forward(prg_net* n, const float* depth01, float* prob, u
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth01 && (prob || keep), "null pointer");
   PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
+  DeviceGuard guard(n->dev);
+  PRG_CHECK_ARG(guard.ok, "cannot select the handle's device");
   Run r{B, (cudaStream_t)stream, depth01, nullptr, 0, nullptr, 0};
   NET_TRY(run_trunk(n, r));
   TailParams t = n->tail;
@@ -886,19 +892,25 @@ EXPORT int prg_maskunet_forward(prg_net* n, const float* depth01, float* prob, u
 }
 
 EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const float* pcond,
-                           const float* img_cond, const float* noise, uint64_t seed, float* out,
-                           int B, prg_stream_t stream) {
+                           const float* img_cond, const float* noise, const uint64_t* seeds,
+                           float* out, int B, prg_stream_t stream) {
   PRG_CHECK_ARG(n && n->kind == PRG_NET_UNET, "not a Unet handle");
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(steps && pcond && out && nsteps >= 1, "null pointer / no steps");
+  PRG_CHECK_ARG(noise != nullptr || seeds != nullptr, "either injected noise or per-image seeds");
   PRG_CHECK_ARG(B > 0 && B <= n->maxB, "batch exceeds max_batch");
+  DeviceGuard guard(n->dev);
+  PRG_CHECK_ARG(guard.ok, "cannot select the handle's device");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t npx = (size_t)B * n->S * n->S;
   // x_T
-  if (noise != nullptr)
+  const unsigned long long hw = (unsigned long long)n->S * n->S;
+  if (noise != nullptr) {
     PRG_CUDA_OK(cudaMemcpyAsync(n->x_state, noise, npx * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  else
-    NET_TRY(fill_normal(n->x_state, (int64_t)npx, seed, 0ull, s));
+  } else {
+    PRG_CUDA_OK(cudaMemcpyAsync(n->seeds_dev, seeds, (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    NET_TRY(fill_normal(n->x_state, B, (int64_t)hw, n->seeds_dev, 0ull, s));
+  }
   // conditioning, hoisted out of the step loop: the time embedding of every step in one launch,
   // the param_cond half of every block MLP once (SDD:925, 932, 709-713 are separable per half)
   {
@@ -945,8 +957,8 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
     t.noise = nullptr;
     if (st.add_noise) {
       if (noise != nullptr) t.noise = noise + slab * npx;
-      t.seed = seed;
-      t.noise_offset = (unsigned long long)slab * npx;
+      t.seeds = n->seeds_dev;
+      t.noise_offset = (unsigned long long)slab * hw;
       ++slab;
     }
     t.c0 = st.c0; t.c1 = st.c1; t.c2 = st.c2; t.c3 = st.c3; t.c4 = st.c4;
@@ -958,6 +970,22 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
     NET_TRY(run_tail(n, t, B, s));
   }
   return PRG_OK;
+}
+
+EXPORT int prg_fill_normal_f32(float* out, int B, int64_t per_image, const uint64_t* seeds,
+                               uint64_t offset, prg_stream_t stream) {
+  if (B == 0 || per_image == 0) return PRG_OK;
+  PRG_CHECK_ARG(out && seeds && B > 0 && B <= 65535 && per_image > 0, "null pointer / bad shape");
+  PtrDeviceGuard guard(out);
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* sd = nullptr;
+  PRG_CUDA_OK(cudaMallocAsync(&sd, (size_t)B * sizeof(uint64_t), s));
+  cudaError_t e = cudaMemcpyAsync(sd, seeds, (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, s);
+  int rc = PRG_OK;
+  if (e == cudaSuccess) rc = fill_normal(out, B, per_image, sd, offset, s);
+  cudaFreeAsync(sd, s);
+  PRG_CUDA_OK(e);
+  return rc;
 }
 
 EXPORT int prg_profile_set(int every_n_forwards) {

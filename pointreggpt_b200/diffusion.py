@@ -14,7 +14,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import _ffi
+from . import _ffi, rng
 from .geometry import get_mask_from_img_cond  # noqa: F401  (re-exported like the reference)
 
 
@@ -179,7 +179,10 @@ class GaussianDiffusion(nn.Module):
         """(b,4) intrinsics vector [+ (b,2,s,s) DDNM image condition] -> (b,1,s,s) in [0,1].
 
         `noise` (optional, (num_noise_draws, b,1,s,s)) injects the Gaussian draws (parity tests);
-        otherwise the device Philox generator is seeded from `seed` or torch's global RNG.
+        otherwise every image draws from its own device Philox stream: `seed` is either a sequence of
+        b integers (one key per image -- `rng.scene_seed` in the generator, so an image's draws do
+        not depend on its batch, rank or world size) or one integer (image i gets mix(seed, i)), or
+        None (a fresh key from torch's global RNG, like the unseeded reference).
         `keep_uniform` (optional, (number of keep-mask draws, b,1,s,s)) injects the uniform draws
         of the keep-mask dropout in step order.
         """
@@ -205,8 +208,7 @@ class GaussianDiffusion(nn.Module):
             need = 1 + sum(st.add_noise for st in steps)
             assert noise.shape[0] >= need and tuple(noise.shape[1:]) == (b, 1, s, s), \
                 "noise must be (num_noise_draws, b, 1, s, s)"
-        if seed is None:
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        seeds = self._image_seeds(seed, b)
         out = torch.empty((b, self.channels, s, s), dtype=torch.float32, device=dev)
         h, cap = self.model.native_handle(b, s, dev)
         for i in range(0, b, cap):
@@ -215,8 +217,18 @@ class GaussianDiffusion(nn.Module):
             _ffi.check(_ffi.lib().prg_sampler_run(
                 h, arr, len(steps), _ffi.ptr(p[i:j]),
                 _ffi.ptr(ic[i:j]) if ic is not None else None,
-                _ffi.ptr(nz), ctypes.c_uint64(seed + i), _ffi.ptr(out[i:j]), j - i, _ffi.stream()))
+                _ffi.ptr(nz), _ffi.seed_array(seeds[i:j]), _ffi.ptr(out[i:j]), j - i, _ffi.stream(p)))
         return out
+
+    @staticmethod
+    def _image_seeds(seed, b):
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if isinstance(seed, int):
+            return rng.image_seeds(seed, b)
+        seeds = [int(v) for v in (seed.tolist() if torch.is_tensor(seed) else seed)]
+        assert len(seeds) == b, "one Philox key per image"
+        return seeds
 
     @torch.no_grad()
     def denoise(self, *, param_cond, img_cond=None, disable_tqdm=False, has_refine_step=False,
@@ -237,7 +249,7 @@ class GaussianDiffusion(nn.Module):
         b, s = p.shape[0], self.image_size
         dev = p.device
         gen = torch.Generator(device=dev)
-        gen.manual_seed(int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed))
+        gen.manual_seed(rng.mix(*self._image_seeds(seed, b)) >> 1)
         shape = (b, 1, s, s)
         main = (_ffi.STEP_P_SAMPLE, _ffi.STEP_DDIM, _ffi.STEP_DDIM_LAST)
         mask = None if ic is None else (((ic[:, 1:2] + 1) * 0.5) > 0.5)          # SDD:507-508
@@ -270,17 +282,42 @@ class GaussianDiffusion(nn.Module):
 
     def _run_single_step(self, h, cap, st, p, ic_step, buf):
         """One sampler step on the device: buf[0] = x_t, buf[1] = the step's Gaussian draw (if any)."""
+        return self._run_steps(h, cap, [st], p, ic_step, buf)
+
+    def _run_steps(self, h, cap, steps, p, ic, buf):
+        """A contiguous slice of the step list, started from a given state: buf[0] = x at the entry of
+        steps[0], buf[1 + i] = the i-th Gaussian draw the slice consumes."""
         b = p.shape[0]
         out = torch.empty_like(buf[0])
-        one = (_ffi.Step * 1)(st)
+        arr = (_ffi.Step * len(steps))(*steps)
         for i in range(0, b, cap):
             j = min(b, i + cap)
             _ffi.check(_ffi.lib().prg_sampler_run(
-                h, one, 1, _ffi.ptr(p[i:j]),
-                _ffi.ptr(ic_step[i:j].contiguous()) if ic_step is not None else None,
-                _ffi.ptr(buf[:, i:j].contiguous()), ctypes.c_uint64(0), _ffi.ptr(out[i:j]), j - i,
-                _ffi.stream()))
+                h, arr, len(steps), _ffi.ptr(p[i:j]),
+                _ffi.ptr(ic[i:j].contiguous()) if ic is not None else None,
+                _ffi.ptr(buf[:, i:j].contiguous()), None, _ffi.ptr(out[i:j]), j - i,
+                _ffi.stream(p)))
         return out
+
+    @torch.no_grad()
+    def run_steps(self, x, first, count, *, param_cond, img_cond=None, noise, has_refine_step=False):
+        """Steps [first, first + count) of `sample()`'s step list applied to the state `x` (b,1,s,s)
+        with injected draws `noise` (one (b,1,s,s) slab per noisy step of the slice, in order).
+        `run_steps(x_T, 0, len(steps))` equals `sample(noise=...)`: the same device loop, entered in the
+        middle -- used to compare trajectories with the reference state by state."""
+        _ffi.require_cuda(x, param_cond, img_cond, noise)
+        steps = self.sampling_steps(has_refine_step)[first:first + count]
+        need = sum(st.add_noise for st in steps)
+        b, s = param_cond.shape[0], self.image_size
+        assert tuple(x.shape) == (b, 1, s, s)
+        assert (noise.shape[0] if noise is not None else 0) >= need, "one draw per noisy step"
+        slabs = [x.float()] + ([noise[i].float() for i in range(need)] if need else [])
+        ic = None
+        if img_cond is not None and (self.is_ddnm_sampling or has_refine_step):
+            ic = img_cond.float().contiguous()
+        h, cap = self.model.native_handle(b, s, x.device)
+        return self._run_steps(h, cap, steps, param_cond.float().contiguous(), ic,
+                               torch.stack(slabs).contiguous())
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError("training (p_losses, SDD:1464-1510) is outside the native "

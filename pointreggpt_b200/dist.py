@@ -31,25 +31,32 @@ def shard_range(start, stop, rank, world_size):
 
 def broadcast_weights(modules, src=0):
     """Broadcast every parameter and buffer of `modules` from rank `src` as ONE flat message
-    per dtype (the packed blob is rebuilt from the received parameters on first use)."""
+    per dtype; every native network inside `modules` drops its packed blob and device handle, so the
+    next call packs the received parameters."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
     tensors = []
     for m in modules:
-        tensors += [p.data for p in m.parameters()] + [b.data for b in m.buffers()]
+        tensors += list(m.parameters()) + list(m.buffers())
     total = 0
     by_dtype = {}
     for t in tensors:
         by_dtype.setdefault((t.dtype, t.device), []).append(t)
     for (dtype, device), ts in by_dtype.items():
-        flat = torch.cat([t.reshape(-1) for t in ts])
-        dist.broadcast(flat, src=src)
-        off = 0
-        for t in ts:
-            n = t.numel()
-            t.copy_(flat[off:off + n].view_as(t))
-            off += n
+        with torch.no_grad():
+            flat = torch.cat([t.detach().reshape(-1) for t in ts])
+            dist.broadcast(flat, src=src)
+            off = 0
+            for t in ts:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t))      # in-place on the parameter: bumps _version
+                off += n
         total += flat.numel() * flat.element_size()
+    # a network that was already packed (any forward / sample before the broadcast) must re-pack
+    for m in modules:
+        for sub in m.modules():
+            if hasattr(sub, "invalidate"):
+                sub.invalidate()
     return total
 
 

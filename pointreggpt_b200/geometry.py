@@ -82,19 +82,22 @@ def random_sample_intrinsic(batch_size) -> np.ndarray:
     return cand[idx]
 
 
-def random_sample_pose(batch_size, center=(0, 0, 3)):
+def random_sample_pose(batch_size, center=(0, 0, 3), rng=None):
     """Random camera motion about a pivot 3 m ahead (SDD:417-443): pitch in +-pi/24, yaw in
     +-pi/12, no roll, x/y translation jitter N(0, 1/9).  Same numpy RNG call order as the
-    reference (rand, rand, randn)."""
+    reference (rand, rand, randn) on numpy's global RNG; with `rng` (a numpy Generator, see
+    pointreggpt_b200.rng.scene_rng) the same three draws come from that generator instead."""
     from scipy.spatial.transform import Rotation
     tmin, tmax = -np.pi / 24, np.pi / 24
     pmin, pmax = -np.pi / 12, np.pi / 12
-    theta = np.random.rand(batch_size) * (tmax - tmin) + tmin
-    phi = np.random.rand(batch_size) * (pmax - pmin) + pmin
+    rand = np.random.rand if rng is None else (lambda n: rng.random(n))
+    randn = np.random.randn if rng is None else (lambda n, m: rng.standard_normal((n, m)))
+    theta = rand(batch_size) * (tmax - tmin) + tmin
+    phi = rand(batch_size) * (pmax - pmin) + pmin
     euler = np.stack((theta, phi, np.zeros(batch_size)), axis=-1)
     rot = Rotation.from_euler("XYZ", euler, degrees=False).as_matrix()
     c = np.array(center)
-    jitter = np.random.randn(batch_size, 3) / 3
+    jitter = randn(batch_size, 3) / 3
     jitter[:, -1] = 0
     trans = c - rot @ c + jitter
     T = np.stack([np.eye(4) for _ in range(batch_size)])
@@ -150,7 +153,7 @@ def depth2pc_tensor(depth, intrinsic, *, clip=[0, 10], invalid_num=None):
     use_clip = clip is not None
     lo, hi = (float(clip[0]), float(clip[1])) if use_clip else (0.0, 0.0)
     _ffi.check(_ffi.lib().prg_depth2pc_f32(_ffi.ptr(d), _ffi.ptr(K), lo, hi, int(use_clip), inv,
-                                           _ffi.ptr(pc), _ffi.ptr(valid), b, h, w, _ffi.stream()))
+                                           _ffi.ptr(pc), _ffi.ptr(valid), b, h, w, _ffi.stream(d)))
     return pc, valid.view(torch.bool)
 
 
@@ -170,7 +173,7 @@ def pc2depth_ragged(pc, offsets, intrinsic, *, image_size, valid=None, pose=None
     mask = torch.empty((B, 1, rows, cols), dtype=torch.uint8, device=dev)
     _ffi.check(_ffi.lib().prg_pc2depth_f32(_ffi.ptr(pcs), _ffi.ptr(v), _ffi.ptr(off),
                                            pcs.shape[0], _ffi.ptr(K), _ffi.ptr(P), _ffi.ptr(depth),
-                                           _ffi.ptr(mask), B, rows, cols, _ffi.stream()))
+                                           _ffi.ptr(mask), B, rows, cols, _ffi.stream(pcs)))
     return depth, mask.view(torch.bool)
 
 
@@ -196,7 +199,7 @@ def reproject_tensor(depth, intrinsic, relative_pose, *, clip=[0, 10], invalid_n
     mask = torch.empty((b, 1, h, w), dtype=torch.uint8, device=d.device)
     _ffi.check(_ffi.lib().prg_reproject_f32(_ffi.ptr(d), _ffi.ptr(K), _ffi.ptr(P), float(clip[0]),
                                             float(clip[1]), _ffi.ptr(out), _ffi.ptr(mask), b, h, w,
-                                            _ffi.stream()))
+                                            _ffi.stream(d)))
     return out, mask.view(torch.bool)
 
 
@@ -211,7 +214,7 @@ def occlusion_filter(depth_rpj, mask_rpj):
     m = mask_rpj.to(torch.bool).contiguous().view(torch.uint8)
     out = torch.empty_like(d)
     _ffi.check(_ffi.lib().prg_occlusion_filter_f32(_ffi.ptr(d), _ffi.ptr(m), _ffi.ptr(out), b, h, w,
-                                                   _ffi.stream()))
+                                                   _ffi.stream(d)))
     return out, mask_rpj
 
 
@@ -223,7 +226,10 @@ def image_condition(depth, intrinsic, relative_pose, depth_unit=10, depth_clip=[
                                            clip=depth_clip)
     if use_occlusion_filter:
         depth_rpj, mask_rpj = occlusion_filter(depth_rpj, mask_rpj)
-    img_cond = torch.cat([depth_rpj / depth_unit, mask_rpj.to(depth_rpj.dtype)], dim=1)
+    # a TENSOR divisor: CUDA evaluates `tensor / python_scalar` as tensor * (1 / scalar), which is not
+    # the correctly rounded quotient the reference's CPU path produces (SDD:495)
+    unit = torch.tensor(depth_unit, dtype=depth_rpj.dtype, device=depth_rpj.device)
+    img_cond = torch.cat([depth_rpj / unit, mask_rpj.to(depth_rpj.dtype)], dim=1)
     return normalize_to_neg_one_to_one(img_cond)
 
 
@@ -243,7 +249,7 @@ def point_cloud_batch(depth01, intrinsic, *, pose=None, scale=10.0, clip=(0.5, 1
     scratch = torch.empty((B * (nblk + 1),), dtype=torch.int64, device=d.device)
     _ffi.check(_ffi.lib().prg_depth2pc_compact_f64(
         _ffi.ptr(d), _ffi.ptr(K), _ffi.ptr(P), float(scale), float(clip[0]), float(clip[1]),
-        _ffi.ptr(pc), _ffi.ptr(counts), _ffi.ptr(scratch), B, H, W, _ffi.stream()))
+        _ffi.ptr(pc), _ffi.ptr(counts), _ffi.ptr(scratch), B, H, W, _ffi.stream(d)))
     return pc, counts
 
 

@@ -7,6 +7,7 @@ reference checkpoints `load_state_dict` unchanged) and its default initialisatio
 torch op takes part in `forward`: parameters are packed once (re-packed when they change) and
 handed to `prg_net_create`; `forward` forwards device pointers.
 """
+import copy
 import ctypes
 
 import torch
@@ -126,6 +127,30 @@ class _NativeNet(nn.Module):
         self._handle_key = (self._kind, int(batch), int(size), dev)
         return h
 
+    _NATIVE_STATE = ("_handle", "_handle_key", "_blob", "_blob_sig")
+
+    def invalidate(self):
+        """Forget the packed blob and the device handle (they are rebuilt from the parameters on the
+        next call).  Needed after parameters were written through `.data` (no version bump)."""
+        self._release()
+        self._blob = None
+        self._blob_sig = None
+
+    def __deepcopy__(self, memo):
+        """A copy owns its parameters but not the native handle (a ctypes pointer cannot be copied
+        or pickled): it packs and creates its own on first use (ema_pytorch-style `deepcopy(model)`)."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in self._NATIVE_STATE else copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        for k in self._NATIVE_STATE:
+            d[k] = None
+        return d
+
     def _release(self):
         if getattr(self, "_handle", None) is not None:
             _ffi.lib().prg_net_destroy(self._handle)
@@ -200,7 +225,7 @@ class Unet(_NativeNet):
             j = min(b, i + cap)
             _ffi.check(_ffi.lib().prg_unet_forward(h, _ffi.ptr(x[i:j]), _ffi.ptr(t[i:j]),
                                                    _ffi.ptr(p[i:j]), _ffi.ptr(out[i:j]), j - i,
-                                                   _ffi.stream()))
+                                                   _ffi.stream(x)))
         return out
 
 
@@ -238,7 +263,7 @@ class MaskUnet(_NativeNet):
             _ffi.check(_ffi.lib().prg_maskunet_forward(
                 h, _ffi.ptr(x[i:j]), _ffi.ptr(prob[i:j]) if want_prob else None,
                 _ffi.ptr(keep[i:j]) if keep is not None else None,
-                float(thresh if thresh is not None else 0.0), j - i, _ffi.stream()))
+                float(thresh if thresh is not None else 0.0), j - i, _ffi.stream(x)))
         return prob, keep
 
     @torch.no_grad()

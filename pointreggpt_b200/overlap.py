@@ -29,7 +29,7 @@ def overlap_count(query, target, radius):
     ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=q.device)
     ce = torch.empty((2,), dtype=torch.int32, device=q.device)
     _ffi.check(_ffi.lib().prg_overlap_count_f64(_ffi.ptr(q), nq, _ffi.ptr(t), nt, float(radius),
-                                                _ffi.ptr(ce), _ffi.ptr(ws), ws_bytes, _ffi.stream()))
+                                                _ffi.ptr(ce), _ffi.ptr(ws), ws_bytes, _ffi.stream(q)))
     hits, err = ce.tolist()
     if err:
         raise _ffi.PrgError("overlap_count: non-finite point or coordinates beyond 2^20 search cells")

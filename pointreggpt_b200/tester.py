@@ -40,6 +40,8 @@ class Tester(object):
         if device is None:
             device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
         self._device = torch.device(device)
+        if self._device.type == "cuda":
+            torch.cuda.set_device(self._device)
         self.model = diffusion_model.to(self._device)
         self.channels = diffusion_model.channels
         self.batch_size = batch_size

@@ -27,7 +27,7 @@ def test_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "libprg.so does not export " + name
     assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
-    assert _ffi.lib().prg_abi_version() == 1
+    assert _ffi.lib().prg_abi_version() == 2
 
 
 @pytest.mark.skipif(not NO_GPU, reason="checks the no-GPU behaviour")
@@ -342,7 +342,7 @@ def test_default_sampling_stays_on_the_fused_device_loop(monkeypatch):
 
     monkeypatch.setattr(_ffi, "lib", lambda: FakeLib())
     monkeypatch.setattr(_ffi, "require_cuda", lambda *a: None)
-    monkeypatch.setattr(_ffi, "stream", lambda: None)
+    monkeypatch.setattr(_ffi, "stream", lambda ref=None: None)
     torch.manual_seed(0)
     net = nets.Unet(dim=64, param_cond_dim=4)
     monkeypatch.setattr(type(net), "native_handle", lambda self, b, s, dev: (None, 1 << 30), raising=False)

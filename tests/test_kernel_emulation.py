@@ -482,7 +482,7 @@ struct TailParams {
   const float* x_t; const float* img_cond; const float* noise; float* out;
   int HW, clip_x_start, use_ddnm, sampler, add_noise, unnormalize;
   float c0, c1, c2, c3, c4;
-  unsigned long long seed, noise_offset;
+  const unsigned long long* seeds; unsigned long long noise_offset;
 };
 static float philox_normal(unsigned long long, unsigned long long) { return 0.f; }   // noise is always injected here
 static void tail_pixel(const TailParams& t, float net, int b, long long p, size_t o) {
@@ -493,7 +493,7 @@ extern "C" void emu_tail(const float* x_t, const float* img_cond, const float* n
                          int B, int HW, int kind, int add_noise, int unnormalize, int has_cond,
                          float c0, float c1, float c2, float c3, float c4) {
   // the host side of prg_sampler_run for one step (net.cu): which kinds clamp before pred_noise, which replace
-  TailParams t{x_t, has_cond ? img_cond : nullptr, noise, out, HW, 0, 0, kind, add_noise, unnormalize, c0, c1, c2, c3, c4, 0, 0};
+  TailParams t{x_t, has_cond ? img_cond : nullptr, noise, out, HW, 0, 0, kind, add_noise, unnormalize, c0, c1, c2, c3, c4, nullptr, 0};
   t.clip_x_start = (kind == 1 || kind == 2 || kind == 4);
   t.use_ddnm = has_cond && (kind == 0 || kind == 1 || kind == 2);
   for (int b = 0; b < B; ++b)

@@ -156,7 +156,7 @@ def test_c_oracle_overlap_and_voxel_against_independent_formulations():
         assert G.overlap_count(a, b, r) == want
     for v in (0.025, 0.2):
         c, k = G.voxel_down_sample(a, v)
-        t = cloud.voxel_down_sample(torch.tensor(a), v).numpy()
+        t = cloud.voxel_down_sample_torch(torch.tensor(a), v).numpy()   # the torch-op cross-check (CPU)
         assert c.shape == t.shape and np.abs(c - t).max() < 1e-12 and np.all(np.diff(k) > 0)
     r1, r2 = G.compute_overlap_ratio(a, b)
     assert 0 < r1 < 1 and 0 < r2 < 1
