@@ -206,6 +206,11 @@ int prg_profile_ops(char* buf, int cap, int reset);
 int prg_test_conv_f16(const void* x, const void* w, const float* bias, void* y, int B,
                       int H, int W, int Cin, int Cout, int mode, prg_stream_t stream);
 
+/* Test hook: exhaustive check of the reprojection kernel's range-restricted reciprocal against the
+ * IEEE one: *mismatches_dev (device u64) = number of floats z with lo <= |z| <= hi (both signs) whose
+ * results differ. */
+int prg_test_frcp_exhaustive(float lo, float hi, uint64_t* mismatches_dev, prg_stream_t stream);
+
 /* Test hook: tensor-pipe rate probe (tools/mma_rate.py).  `grid` CTAs each issue `iters`
  * tcgen05.mma (M=128, N=n, K=16) back to back; out (grid) i64 device = SM cycles taken. */
 int prg_test_mma_rate(int grid, int n, int iters, int a_shift, int same_ab, int64_t* out,

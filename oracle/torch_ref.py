@@ -151,7 +151,7 @@ def sinusoidal_pos_emb(t, dim):
     """SDD:650-657."""
     half = dim // 2
     e = math.log(10000) / (half - 1)
-    e = torch.exp(torch.arange(half) * -e)
+    e = torch.exp(torch.arange(half, device=t.device) * -e)
     e = t[:, None] * e[None, :]
     return torch.cat((e.sin(), e.cos()), dim=-1)
 

@@ -73,6 +73,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "prg_profile_set": (c_int, [c_int]),
     "prg_profile_read": (c_int, [ctypes.POINTER(Profile), c_int, c_int]),
+    "prg_test_frcp_exhaustive": (c_int, [c_float, c_float, c_void_p, c_void_p]),
     "prg_test_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "prg_profile_ops": (c_int, [ctypes.c_char_p, c_int, c_int]),
     "prg_test_conv_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -383,9 +383,11 @@ k_cond_mlp_part(const float* __restrict__ W, const float* __restrict__ act, floa
 // per step: one warp per output row computes the time half once and adds every image's param half
 __global__ void __launch_bounds__(256)
 k_cond_mlp_step(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ act_t,
-                const float* __restrict__ ss_p, float* __restrict__ ss, int rows, int Ktot, int K, int B) {
+                const float* __restrict__ ss_p, float* __restrict__ ss, int rows, int Ktot, int K, int B,
+                const int* __restrict__ step_idx, int act_stride) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
+  if (step_idx != nullptr) act_t += (size_t)(*step_idx) * act_stride;   // this step's time embedding
   const float* wr = W + (size_t)warp * Ktot;
   float a = 0.f;
   for (int k = lane; k < K; k += 32) a = fmaf(__ldg(wr + k), act_t[k], a);
@@ -408,8 +410,9 @@ int cond_mlp_param(const float* W, const float* cond_act, float* ss_p, int rows,
   return PRG_OK;
 }
 int cond_mlp_step(const float* W, const float* bias, const float* act_t, const float* ss_p, float* ss,
-                  int rows, int Ktot, int B, cudaStream_t s) {
-  k_cond_mlp_step<<<(rows * 32 + 255) / 256, 256, 0, s>>>(W, bias, act_t, ss_p, ss, rows, Ktot, Ktot / 2, B);
+                  int rows, int Ktot, int B, cudaStream_t s, const int* step_idx, int act_stride) {
+  k_cond_mlp_step<<<(rows * 32 + 255) / 256, 256, 0, s>>>(W, bias, act_t, ss_p, ss, rows, Ktot, Ktot / 2, B,
+                                                         step_idx, act_stride);
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -777,10 +780,33 @@ int fill_normal(float* x, int B, int64_t per_image, const unsigned long long* se
 // network tail: GN+SiLU(block2) + res, final 1x1 (64 -> 1), then forward / sigmoid / sampler step
 // 8 lanes per pixel (8 channels each), 4 pixels per warp -> 512 contiguous bytes per warp load.
 // ------------------------------------------------------------------------------------------
+__global__ void k_step_advance(int* step_idx) { *step_idx += 1; }
+
+int step_advance(int* step_idx, cudaStream_t s) {
+  k_step_advance<<<1, 1, 0, s>>>(step_idx);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
 __global__ void __launch_bounds__(256)
 k_net_tail(TailParams t) {
   __shared__ float sA[64], sB[64], sW[64];
   const int b = blockIdx.y;
+  if (t.mode == 2 && t.steps != nullptr) {
+    // sampler loop: this step's parameters come from the device-resident list (same launch for every step)
+    const StepDev st = t.steps[*t.step_idx];
+    const SamplerCtx cx = *t.ctx;
+    t.sampler = st.kind;
+    t.add_noise = st.add_noise;
+    t.unnormalize = st.unnormalize;
+    t.c0 = st.c0; t.c1 = st.c1; t.c2 = st.c2; t.c3 = st.c3; t.c4 = st.c4;
+    t.img_cond = cx.img_cond;
+    t.noise = (cx.noise != nullptr && st.add_noise) ? cx.noise + (size_t)st.noise_slab * t.slab_stride : nullptr;
+    t.noise_offset = (unsigned long long)st.noise_slab * (unsigned long long)t.HW;
+    t.clip_x_start = (st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST || st.kind == PRG_STEP_REFINE_DDIM);
+    t.use_ddnm = (cx.img_cond != nullptr) &&
+                 (st.kind == PRG_STEP_P_SAMPLE || st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST);
+  }
   gn_coeffs(t.stats, t.gamma, t.beta, nullptr, 64, t.HW, b, sA, sB);
   if (threadIdx.x < 64) sW[threadIdx.x] = t.fw[threadIdx.x];
   __syncthreads();

@@ -30,7 +30,7 @@ int cond_time_all(const CondWeights& w, const int* ts_dev, int nsteps, float* ac
 int cond_mlp_param(const float* W, const float* cond_act, float* ss_p, int rows, int Ktot, int B,
                    cudaStream_t s);
 int cond_mlp_step(const float* W, const float* bias, const float* act_t, const float* ss_p, float* ss,
-                  int rows, int Ktot, int B, cudaStream_t s);
+                  int rows, int Ktot, int B, cudaStream_t s, const int* step_idx = nullptr, int act_stride = 0);
 // ss[b][r] = W[r] . cond_act[b] + bias[r] for the concatenated rows of every block MLP.
 int cond_mlp(const float* W, const float* bias, const float* cond_act, float* ss, int rows, int K,
              int B, cudaStream_t s);
@@ -67,6 +67,20 @@ int ln_apply(const __half* x, const float* g, const __half* res, __half* y, int6
 //   mode 1: out = sigmoid(conv), keep = out > thresh         (MaskUnet tail, DC:868-869)
 //   mode 2: one sampler update x_t -> x_{t-1}                 (SDD:1199-1218, 1250-1251,
 //                                                              1173-1180, 1279-1280 / 1358-1373)
+// One sampler step as the device sees it (prg_sampler_run uploads the whole list once per call; the
+// kernels of a step index it with a device-resident counter, so a step's launches are identical for
+// every step and can be replayed as ONE CUDA graph).
+struct StepDev {
+  int kind, add_noise, unnormalize, noise_slab;   // noise_slab: index of this step's Gaussian draw (slab 0 = x_T)
+  float c0, c1, c2, c3, c4;
+  int pad[3];
+};
+// per-call pointers of the sampler, device resident for the same reason
+struct SamplerCtx {
+  const float* img_cond;   // (B,2,HW) or nullptr
+  const float* noise;      // injected draws (slabs of B*HW) or nullptr (=> Philox)
+};
+
 struct TailParams {
   const __half* raw;
   const long long* stats;
@@ -93,7 +107,15 @@ struct TailParams {
   float c4;
   int add_noise;
   int unnormalize;        // write (x+1)/2 (last step)
+  // mode 2, device-resident step list (sampler loop): when `steps` is set the fields above from
+  // img_cond to unnormalize are filled inside the kernel from steps[*step_idx] and *ctx
+  const StepDev* steps;
+  const int* step_idx;
+  const SamplerCtx* ctx;
+  size_t slab_stride;     // B * HW: distance between two injected-noise slabs
 };
+// step_idx += 1 (last node of the per-step graph)
+int step_advance(int* step_idx, cudaStream_t s);
 int net_tail(const TailParams& t, int B, cudaStream_t s);
 
 // N(0,1) draws from one Philox stream per image (key = seeds_dev[b], counter = offset + index)

@@ -9,7 +9,10 @@
 // All fp32 arithmetic uses the _rn intrinsics so nvcc can neither contract nor
 // reorder it; the z-buffer is an order-independent atomicMin on the bit pattern of
 // the (strictly positive) depth, so the result is deterministic and bit-exact.
+#include <string.h>
+
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -130,46 +133,252 @@ __device__ __forceinline__ void splat(float x, float y, float z, const Intr& k, 
 }
 
 // ------------------------------------------------------------------ reproject
-// One thread = 4 consecutive pixels (16-byte load).  The z-buffer lives in
-// depth_out itself (pre-filled with 0xFFFFFFFF), finalised in place.
+// One persistent kernel, 9 bytes of DRAM traffic per pixel (4 read, 4 + 1 written):
+//   * the z-buffer of a map lives in a small ring of scratch slots (R maps, <= 24 MB) that stays in
+//     the 126 MB L2 for the whole call: atomicMin (RED) goes to L2, depth_out / mask_out are written
+//     exactly once by the finalisation, which also hands the slot back filled with 0xFFFFFFFF -- no
+//     fill pass, no read-modify-write of the output;
+//   * work items (4096 pixels) are dealt round-robin to the resident CTAs in this order: round k =
+//     [splat items of map k] then [finalise items of map k - D]; finalise(m) waits until all splat
+//     items of map m have signalled, splat(m) waits until finalise(m - R) has freed its slot.  Every
+//     wait targets an item EARLIER in the order, so with all CTAs resident the smallest unfinished
+//     item can always run: no deadlock, no grid-wide barrier, no launch gaps between maps;
+//   * lanes own CONSECUTIVE pixels: neighbouring pixels land on neighbouring targets, so a warp's 32
+//     RED operations fall into a few 32-byte sectors (measured 3.6 RED/clk/SM against 1.4 when a lane
+//     owns four consecutive pixels -- tools/microbench/zbuf_atomics.cu);
+//   * the arithmetic of two pixels runs on the packed fp32x2 pipe (FADD2 / FMUL2 / FFMA2 round each
+//     lane to nearest like the scalar instructions: bit-identical), rounding + bounds test is one
+//     F2I.RN (round-half-even, saturating) and one unsigned compare per coordinate.
+constexpr int kRpThreads = 256;
+constexpr int kRpItemPx = 4096;
+constexpr float kPoseMax = 1e4f;
+
+struct RpMap {
+  Intr k;
+  float P[12];
+  bool fast;      // k.fast, |pose entries| <= 1e4 and the clip inside [0, 1e9]: the fast path cannot overflow
+};
+
+__device__ __forceinline__ RpMap rp_load_map(const float* __restrict__ K, const float* __restrict__ pose, int b,
+                                             float lo, float hi) {
+  RpMap m;
+  m.k = load_intr(K, b);
+  bool ok = m.k.fast && lo >= 0.f && hi <= 1e9f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    m.P[i] = __ldg(pose + b * 16 + i);
+    ok = ok && (fabsf(m.P[i]) <= kPoseMax);     // false for NaN / inf
+  }
+  m.fast = ok;
+  return m;
+}
+
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+// two correctly rounded quotients a / b given y = RN(1 / b) and nb = -b (see div_exact)
+__device__ __forceinline__ float2 div_exact2(float2 a, float2 nb, float2 y) {
+  const float2 q0 = __fmul2_rn(a, y);
+  return __ffma2_rn(__ffma2_rn(q0, nb, a), y, q0);
+}
+// RN(1 / z) for a normal z with a normal reciprocal (no zero / denormal / inf / NaN handling): the fast
+// path of __frcp_rn without its range checks -- MUFU.RCP and one Newton step on the FMA pipe.  Checked
+// against __frcp_rn for every float in [2^-100, 2^100] by prg_test_frcp_exhaustive (tests/test_geometry_gpu.py).
+__device__ __forceinline__ float frcp_rn_normal(float z) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
+  return __fmaf_rn(r, __fmaf_rn(-z, r, 1.f), r);
+#else
+  return __frcp_rn(z);
+#endif
+}
+
+// One pixel through the validated scalar helpers (any intrinsics / pose / depth).
 template <bool kScalarBmm>
-__global__ void __launch_bounds__(256)
-k_reproject_splat(const float* __restrict__ depth, const float* __restrict__ K,
-                  const float* __restrict__ pose, float lo, float hi,
-                  unsigned* __restrict__ zbuf, int HW, int H, int W) {
-  __shared__ float sP[12];
-  const int b = blockIdx.y;
-  if (threadIdx.x < 12) sP[threadIdx.x] = __ldg(pose + b * 16 + threadIdx.x);
-  __syncthreads();
-  const Intr k = load_intr(K, b);
-  unsigned* zimg = zbuf + (size_t)b * HW;
-  const float* dimg = depth + (size_t)b * HW;
-  const float inv_w = 1.f / (float)W;
-  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < HW; i4 += gridDim.x * blockDim.x) {
-    const int i = i4 * 4;
-    float d[4];
-    if (i + 3 < HW && (HW & 3) == 0) {
-      float4 v = __ldcs(reinterpret_cast<const float4*>(dimg + i));
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) d[j] = (i + j < HW) ? dimg[i + j] : 0.f;
+__device__ __forceinline__ void rp_pixel_generic(float z0, int r, int c, const RpMap& m, int H, int W,
+                                                 unsigned* __restrict__ zslot) {
+  float x, y, z = z0;
+  unproject(r, c, z, m.k, x, y);
+  rigid<kScalarBmm>(m.P, x, y, z);
+  splat(x, y, z, m.k, H, W, zslot);
+}
+
+// Splat item: pixels [px0, px0 + kRpItemPx) of one map.  Thread t takes pixels px0 + t + 256 j.
+template <bool kScalarBmm>
+__device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, unsigned* __restrict__ zslot,
+                                              int px0, int HW, int H, int W, float lo, float hi,
+                                              const RpMap& m) {
+  const int t = threadIdx.x;
+  int i = px0 + t;
+  if (i >= HW) return;
+  int r = i / W, c = i - r * W;                  // one division per item and thread; then incremental
+  if (kScalarBmm || !m.fast) {
+    for (int j = 0; j < kRpItemPx / kRpThreads && i < HW; ++j, i += kRpThreads) {
+      const float z0 = __ldcs(dimg + i);
+      if (z0 > lo && z0 < hi) rp_pixel_generic<kScalarBmm>(z0, r, c, m, H, W, zslot);
+      c += kRpThreads;
+      while (c >= W) { c -= W; ++r; }
     }
-    int r0, c0;
-    row_col(i, W, inv_w, r0, c0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float z0 = d[j];
-      if (i + j < HW && z0 > lo && z0 < hi) {
-        int r = r0, c = c0 + j;
-        if (c >= W) { c -= W; ++r; while (c >= W) { c -= W; ++r; } }   // a second wrap only when W < 4
-        float x, y, z = z0;
-        unproject(r, c, z, k, x, y);
-        rigid<kScalarBmm>(sP, x, y, z);
-        splat(x, y, z, k, H, W, zimg);
-      }
+    return;
+  }
+  const Intr& k = m.k;
+  const float2 ncx = f2(-k.cx), ncy = f2(-k.cy), rfx = f2(k.rfx), rfy = f2(k.rfy), nfx = f2(-k.fx), nfy = f2(-k.fy);
+  const float2 fx2 = f2(k.fx), fy2 = f2(k.fy), cx2 = f2(k.cx), cy2 = f2(k.cy);
+  const float nan = __int_as_float(0x7fc00000);
+  const float Wf = (float)W, step = (float)kRpThreads;   // rows / columns are carried as floats (exact below 2^24)
+  float ra = (float)r, ca = (float)c;
+#pragma unroll 2
+  for (int j = 0; j < kRpItemPx / (2 * kRpThreads); ++j) {
+    if (i >= HW) break;
+    // pixel A = i, pixel B = i + 256
+    float rb = ra, cb = ca + step;
+    while (cb >= Wf) { cb -= Wf; rb += 1.f; }
+    const int ib = i + kRpThreads;
+    const float da = __ldcs(dimg + i);
+    const float db = (ib < HW) ? __ldcs(dimg + ib) : nan;
+    // valid <=> inside the clip; the clip is inside [0, 1e9], so d > 1e-9 completes depth_in_range
+    const bool va = da > lo && da < hi, vb = db > lo && db < hi;
+    const float2 d = make_float2(da, db);
+    // x = ((c - cx) * z) / fx, y = ((r - cy) * z) / fy   (SDD:196-197).  No sign fix-up as in
+    // div_exact_signed: with d > 1e-9 a numerator is zero only as the exact +0 of c - cx.
+    const float2 x = div_exact2(__fmul2_rn(__fadd2_rn(make_float2(ca, cb), ncx), d), nfx, rfx);
+    const float2 y = div_exact2(__fmul2_rn(__fadd2_rn(make_float2(ra, rb), ncy), d), nfy, rfy);
+    // matmul(pc, R^T) + t  (SDD:279): fma(z, r2, fma(y, r1, x * r0)) + t
+    const float2 X = __fadd2_rn(__ffma2_rn(d, f2(m.P[2]), __ffma2_rn(y, f2(m.P[1]), __fmul2_rn(x, f2(m.P[0])))), f2(m.P[3]));
+    const float2 Y = __fadd2_rn(__ffma2_rn(d, f2(m.P[6]), __ffma2_rn(y, f2(m.P[5]), __fmul2_rn(x, f2(m.P[4])))), f2(m.P[7]));
+    const float2 Z = __fadd2_rn(__ffma2_rn(d, f2(m.P[10]), __ffma2_rn(y, f2(m.P[9]), __fmul2_rn(x, f2(m.P[8])))), f2(m.P[11]));
+    // c' = round(((x * fx) / z) + cx)  (SDD:225-226).  For z in (1e-6, 1e12) nothing over- or
+    // underflows (|x * fx / z| < 1e33 with the bounds of RpMap::fast): no NaN can reach the F2I, whose
+    // round-half-even + saturation then IS torch.round + the bounds test on the integer index.
+    const bool sa = va && da > 1e-9f && Z.x > 1e-6f && Z.x < 1e12f;
+    const bool sb = vb && db > 1e-9f && Z.y > 1e-6f && Z.y < 1e12f;
+    const float2 rz = make_float2(frcp_rn_normal(sa ? Z.x : 1.f), frcp_rn_normal(sb ? Z.y : 1.f));
+    const float2 nZ = make_float2(-Z.x, -Z.y);
+    const float2 u = __fadd2_rn(div_exact2(__fmul2_rn(X, fx2), nZ, rz), cx2);
+    const float2 v = __fadd2_rn(div_exact2(__fmul2_rn(Y, fy2), nZ, rz), cy2);
+    const int cia = __float2int_rn(u.x), ria = __float2int_rn(v.x);
+    const int cib = __float2int_rn(u.y), rib = __float2int_rn(v.y);
+    if (sa && (unsigned)cia < (unsigned)W && (unsigned)ria < (unsigned)H)
+      atomicMin(zslot + (unsigned)(ria * W + cia), __float_as_uint(Z.x));
+    if (sb && (unsigned)cib < (unsigned)W && (unsigned)rib < (unsigned)H)
+      atomicMin(zslot + (unsigned)(rib * W + cib), __float_as_uint(Z.y));
+    // valid pixels outside the validated ranges (tiny depths, extreme depth after the transform):
+    // the scalar path (rare)
+    if ((va && !sa) || (vb && !sb)) {
+      if (va && !sa) rp_pixel_generic<false>(da, (int)ra, (int)ca, m, H, W, zslot);
+      if (vb && !sb) rp_pixel_generic<false>(db, (int)rb, (int)cb, m, H, W, zslot);
+    }
+    i += 2 * kRpThreads;
+    ca = cb + step; ra = rb;
+    while (ca >= Wf) { ca -= Wf; ra += 1.f; }
+  }
+}
+
+// Finalise item: pixels [px0, px0 + kRpItemPx) of one map: depth (0 where empty) and mask out, slot reset.
+__device__ __forceinline__ void rp_finalize_item(unsigned* __restrict__ zslot, float* __restrict__ dout,
+                                                 uint8_t* __restrict__ mout, int px0, int HW) {
+  const int end = min(px0 + kRpItemPx, HW);
+  if ((HW & 3) == 0) {
+    for (int i = px0 + (int)threadIdx.x * 4; i < end; i += kRpThreads * 4) {
+      uint4 v = __ldcg(reinterpret_cast<const uint4*>(zslot + i));
+      uchar4 mk;
+      mk.x = v.x != kEmpty; mk.y = v.y != kEmpty; mk.z = v.z != kEmpty; mk.w = v.w != kEmpty;
+      v.x = mk.x ? v.x : 0u; v.y = mk.y ? v.y : 0u; v.z = mk.z ? v.z : 0u; v.w = mk.w ? v.w : 0u;
+      __stcs(reinterpret_cast<uint4*>(dout + i), v);
+      *reinterpret_cast<uchar4*>(mout + i) = mk;
+      *reinterpret_cast<uint4*>(zslot + i) = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+    }
+  } else {
+    for (int i = px0 + (int)threadIdx.x; i < end; i += kRpThreads) {
+      const unsigned v = __ldcg(zslot + i);
+      mout[i] = v != kEmpty;
+      reinterpret_cast<unsigned*>(dout)[i] = v != kEmpty ? v : 0u;
+      zslot[i] = kEmpty;
     }
   }
+}
+
+struct RpPlan {
+  int B, H, W, HW;
+  int items;        // work items per map and phase
+  int R, D;         // ring slots, finalisation lag (D < R, D <= B)
+  long long total;  // work items of the call
+};
+
+// Item counters: release / acquire at device scope.  (The host emulation of the tests runs the items
+// one after another, where every dependency is already satisfied.)
+__device__ __forceinline__ void rp_wait(const int* cnt, int need) {
+#ifdef __CUDA_ARCH__
+  if (threadIdx.x == 0) {
+    while (true) {
+      int v;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+      if (v >= need) break;
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+#endif
+}
+__device__ __forceinline__ void rp_signal(int* cnt) {
+#ifdef __CUDA_ARCH__
+  __syncthreads();                 // the item's REDs / stores of every thread ...
+  if (threadIdx.x == 0) {
+    __threadfence();               // ... are ordered before the counter (cumulative fence)
+    atomicAdd(cnt, 1);
+  }
+#endif
+}
+
+// Work item p of the call (see the order described above).
+template <bool kScalarBmm>
+__device__ __forceinline__ void rp_run_item(long long p, const float* __restrict__ depth, const float* __restrict__ K,
+                                            const float* __restrict__ pose, float lo, float hi,
+                                            unsigned* __restrict__ scratch, float* __restrict__ depth_out,
+                                            uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat,
+                                            int* __restrict__ cnt_fin, const RpPlan& pl) {
+  const long long I = pl.items;
+  const long long head = (long long)pl.D * I, mid = (long long)(pl.B - pl.D) * 2 * I;
+  int map, j;
+  bool fin;
+  if (p < head) {
+    map = (int)(p / I); j = (int)(p - map * I); fin = false;
+  } else if (p < head + mid) {
+    const long long q = p - head;
+    const int k = (int)(q / (2 * I));
+    const int w = (int)(q - (long long)k * 2 * I);
+    fin = w >= I;
+    map = fin ? k : pl.D + k;
+    j = fin ? w - (int)I : w;
+  } else {
+    const long long q = p - head - mid;
+    const int k = (int)(q / I);
+    map = pl.B - pl.D + k; j = (int)(q - k * I); fin = true;
+  }
+  unsigned* zslot = scratch + (size_t)(map % pl.R) * pl.HW;
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+l"(zslot));   // keep the slot base in one register pair (index arithmetic stays 32-bit)
+#endif
+  if (!fin) {
+    if (map >= pl.R) rp_wait(cnt_fin + (map - pl.R), (int)I);      // the slot's previous map is out
+    const RpMap m = rp_load_map(K, pose, map, lo, hi);
+    rp_splat_item<kScalarBmm>(depth + (size_t)map * pl.HW, zslot, j * kRpItemPx, pl.HW, pl.H, pl.W, lo, hi, m);
+    rp_signal(cnt_splat + map);
+  } else {
+    rp_wait(cnt_splat + map, (int)I);                               // every pixel of the map has been splatted
+    rp_finalize_item(zslot, depth_out + (size_t)map * pl.HW, mask_out + (size_t)map * pl.HW, j * kRpItemPx, pl.HW);
+    rp_signal(cnt_fin + map);
+  }
+}
+
+template <bool kScalarBmm>
+__global__ void __launch_bounds__(kRpThreads)
+k_reproject_fused(const float* __restrict__ depth, const float* __restrict__ K, const float* __restrict__ pose,
+                  float lo, float hi, unsigned* __restrict__ scratch, float* __restrict__ depth_out,
+                  uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat, int* __restrict__ cnt_fin,
+                  const RpPlan pl) {
+  for (long long p = blockIdx.x; p < pl.total; p += gridDim.x)
+    rp_run_item<kScalarBmm>(p, depth, K, pose, lo, hi, scratch, depth_out, mask_out, cnt_splat, cnt_fin, pl);
 }
 
 __global__ void __launch_bounds__(256)
@@ -492,9 +701,35 @@ k_compact_write(const float* __restrict__ depth01, const float* __restrict__ K,
   o[2] = z;
 }
 
+// test hook: counts the floats in [lo_bits, hi_bits] (bit patterns, both signs) whose frcp_rn_normal differs from __frcp_rn
+__global__ void __launch_bounds__(256)
+k_frcp_check(unsigned lo_bits, unsigned hi_bits, unsigned long long* __restrict__ mismatches) {
+  unsigned long long bad = 0;
+  for (unsigned long long b = lo_bits + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= hi_bits;
+       b += (unsigned long long)gridDim.x * blockDim.x) {
+    const float z = __uint_as_float((unsigned)b);
+    bad += __float_as_uint(frcp_rn_normal(z)) != __float_as_uint(__frcp_rn(z));
+    bad += __float_as_uint(frcp_rn_normal(-z)) != __float_as_uint(__frcp_rn(-z));
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace prg
 
 using namespace prg;
+
+extern "C" __attribute__((visibility("default"))) int prg_test_frcp_exhaustive(float lo, float hi, uint64_t* mismatches_dev,
+                                                                               prg_stream_t stream) {
+  PRG_CHECK_ARG(mismatches_dev && lo > 0.f && hi >= lo, "bad range");
+  PtrDeviceGuard guard(mismatches_dev);
+  unsigned lb, hb;
+  memcpy(&lb, &lo, 4);
+  memcpy(&hb, &hi, 4);
+  PRG_CUDA_OK(cudaMemsetAsync(mismatches_dev, 0, sizeof(uint64_t), (cudaStream_t)stream));
+  k_frcp_check<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(lb, hb, reinterpret_cast<unsigned long long*>(mismatches_dev));
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
 
 static int grid_for(int64_t work_items, int threads, int per_thread) {
   int64_t blocks = (work_items + (int64_t)threads * per_thread - 1) / ((int64_t)threads * per_thread);
@@ -504,37 +739,89 @@ static int grid_for(int64_t work_items, int threads, int per_thread) {
   return (int)blocks;
 }
 
+// Library-owned z-buffer ring + item counters of prg_reproject_f32, one per device.  Calls are
+// serialised on the ring: a call on another stream waits (device side) for the previous one.
+namespace {
+struct ZScratch {
+  std::mutex mu;
+  unsigned* ring = nullptr;
+  size_t ring_words = 0;
+  int* counters = nullptr;
+  size_t ncounters = 0;
+  cudaEvent_t done = nullptr;
+  cudaStream_t last = nullptr;
+  bool used = false;
+  int grid = 0;
+};
+ZScratch g_zscratch[64];
+}  // namespace
+
 extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const float* depth, const float* K, const float* pose,
                                  float clip_lo, float clip_hi, float* depth_out,
                                  uint8_t* mask_out, int B, int H, int W, prg_stream_t stream) {
   if (B == 0) return PRG_OK;
   PRG_CHECK_ARG(depth && K && pose && depth_out && mask_out, "null pointer");
   PtrDeviceGuard guard(depth_out);
-  PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
-  if (B == 0) return PRG_OK;
+  PRG_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "bad shape");
   cudaStream_t s = (cudaStream_t)stream;
-  const int HW = H * W;
-  // The z-buffer is depth_out itself.  Maps are processed in groups whose z-buffers (<= 32 MB) stay
-  // in the 126 MB L2 between the fill, the atomicMin splat and the in-place finalisation, so HBM
-  // sees the 9 algorithmic bytes per pixel (depth read, depth + mask written back once).
-  int group = (int)((32u << 20) / ((size_t)HW * sizeof(float)));
-  if (group < 1) group = 1;
-  for (int b0 = 0; b0 < B; b0 += group) {
-    const int nb = std::min(group, B - b0);
-    const size_t n = (size_t)nb * HW;
-    float* out = depth_out + (size_t)b0 * HW;
-    PRG_CUDA_OK(cudaMemsetAsync(out, 0xFF, n * sizeof(float), s));
-    dim3 g1(grid_for(HW, 256, 4), nb);
-    if ((long long)HW * 9 < 400)      // maps of at most 44 pixels: ATen's scalar bmm rounding (see rigid())
-      k_reproject_splat<true><<<g1, 256, 0, s>>>(depth + (size_t)b0 * HW, K + (size_t)b0 * 9, pose + (size_t)b0 * 16,
-                                                clip_lo, clip_hi, (unsigned*)out, HW, H, W);
-    else
-      k_reproject_splat<false><<<g1, 256, 0, s>>>(depth + (size_t)b0 * HW, K + (size_t)b0 * 9, pose + (size_t)b0 * 16,
-                                                 clip_lo, clip_hi, (unsigned*)out, HW, H, W);
-    PRG_LAUNCH_CHECK();
-    k_zbuf_finalize<<<grid_for((int64_t)n, 256, 4), 256, 0, s>>>((unsigned*)out, mask_out + (size_t)b0 * HW, n);
-    PRG_LAUNCH_CHECK();
+  int dev = 0;
+  PRG_CUDA_OK(cudaGetDevice(&dev));
+  PRG_CHECK_ARG(dev >= 0 && dev < 64, "device index");
+  ZScratch& z = g_zscratch[dev];
+  std::lock_guard<std::mutex> lock(z.mu);
+
+  RpPlan pl;
+  pl.B = B; pl.H = H; pl.W = W; pl.HW = H * W;
+  pl.items = (pl.HW + kRpItemPx - 1) / kRpItemPx;
+  // ring: as many maps as fit 24 MB (L2-resident next to the streaming traffic), at least 2, at most 64
+  {
+    const size_t per_map = (size_t)pl.HW * sizeof(unsigned);
+    long long r = (long long)((24u << 20) / per_map);
+    r = std::max(2ll, std::min(64ll, r));
+    pl.R = (int)std::min<long long>(r, std::max(2, B));
+    pl.D = std::max(1, std::min(pl.R / 2, B));
+    if (pl.D >= pl.R) pl.D = pl.R - 1;
   }
+  pl.total = 2ll * B * pl.items;
+  const size_t need_words = (size_t)pl.R * pl.HW;
+  const size_t need_cnt = 2 * (size_t)B;
+  if (z.ring_words < need_words || z.ncounters < need_cnt) {
+    PRG_CUDA_OK(cudaDeviceSynchronize());          // nobody is using the old buffers
+    if (z.ring_words < need_words) {
+      if (z.ring) cudaFree(z.ring);
+      z.ring = nullptr; z.ring_words = 0;
+      PRG_CUDA_OK(cudaMalloc(&z.ring, need_words * sizeof(unsigned)));
+      PRG_CUDA_OK(cudaMemset(z.ring, 0xFF, need_words * sizeof(unsigned)));   // empty; every call leaves it so
+      z.ring_words = need_words;
+    }
+    if (z.ncounters < need_cnt) {
+      if (z.counters) cudaFree(z.counters);
+      z.counters = nullptr; z.ncounters = 0;
+      PRG_CUDA_OK(cudaMalloc(&z.counters, need_cnt * sizeof(int)));
+      z.ncounters = need_cnt;
+    }
+  }
+  if (z.done == nullptr) PRG_CUDA_OK(cudaEventCreateWithFlags(&z.done, cudaEventDisableTiming));
+  if (z.grid == 0) {
+    int occ = 0;
+    PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_reproject_fused<false>, kRpThreads, 0));
+    int occ2 = 0;
+    PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_reproject_fused<true>, kRpThreads, 0));
+    z.grid = num_sms() * std::max(1, std::min(occ, occ2));   // every CTA resident: the item order relies on it
+  }
+  if (z.used && z.last != s) PRG_CUDA_OK(cudaStreamWaitEvent(s, z.done, 0));
+  PRG_CUDA_OK(cudaMemsetAsync(z.counters, 0, need_cnt * sizeof(int), s));
+  const int grid = (int)std::min<long long>(z.grid, pl.total);
+  if ((long long)pl.HW * 9 < 400)     // maps of at most 44 pixels: ATen's scalar bmm rounding (see rigid())
+    k_reproject_fused<true><<<grid, kRpThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
+                                                       z.counters, z.counters + B, pl);
+  else
+    k_reproject_fused<false><<<grid, kRpThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
+                                                        z.counters, z.counters + B, pl);
+  PRG_LAUNCH_CHECK();
+  PRG_CUDA_OK(cudaEventRecord(z.done, s));
+  z.last = s;
+  z.used = true;
   return PRG_OK;
 }
 

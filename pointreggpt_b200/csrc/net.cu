@@ -149,6 +149,14 @@ struct prg_net {
   __half* stem_out = nullptr;
   float* x_state = nullptr;  // sampler state (maxB, S*S) f32
   unsigned long long* seeds_dev = nullptr;  // sampler: per-image Philox keys (maxB)
+  // sampler loop state on the device: the step list, the step counter and the per-call pointers, so
+  // that the launches of a step do not depend on the step and replay as one CUDA graph per batch size
+  StepDev* steps_dev = nullptr;
+  int steps_cap = 0;
+  int* step_idx = nullptr;
+  SamplerCtx* ctx_dev = nullptr;
+  std::map<int, cudaGraphExec_t> step_graphs;   // batch size -> instantiated graph of one step
+  std::map<int, int> step_graph_launches;       // batch size -> kernel launches inside that graph
 
   template <typename T>
   T* dalloc(size_t count) {
@@ -590,6 +598,8 @@ int build(prg_net* n) {
   n->colmax_arena = n->dalloc<int>(n->colmax_cap);
   n->x_state = n->dalloc<float>((size_t)B * S * S);
   n->seeds_dev = n->dalloc<unsigned long long>((size_t)B);
+  n->step_idx = n->dalloc<int>(4);
+  n->ctx_dev = n->dalloc<SamplerCtx>(1);
   {
     size_t pf = 0;   // the largest level decides (chunks per image <= 32)
     for (int i = 0; i < L; ++i) pf = std::max(pf, kvctx_partial_floats(B, S >> i, S >> i));
@@ -597,7 +607,7 @@ int build(prg_net* n) {
   }
   n->gn_coef_buf = n->dalloc<float2>((size_t)B * 1024);
   if (!n->gn_coef_buf || !n->kv_partials || !n->raw || !n->h1 || !n->resb || !n->xn || !n->qkv || !n->ao || !n->weff || !n->zero_arena ||
-      !n->colmax_arena || !n->x_state || !n->seeds_dev) {
+      !n->colmax_arena || !n->x_state || !n->seeds_dev || !n->step_idx || !n->ctx_dev) {
     set_error("out of device memory allocating the workspace");
     return PRG_ERR_CUDA;
   }
@@ -852,6 +862,8 @@ EXPORT void prg_net_destroy(prg_net* n) {
   for (void* p : n->allocs) cudaFree(p);
   if (n->act_t_all) cudaFree(n->act_t_all);
   if (n->ts_dev) cudaFree(n->ts_dev);
+  if (n->steps_dev) cudaFree(n->steps_dev);
+  for (auto& g : n->step_graphs) cudaGraphExecDestroy(g.second);
   delete n;
 }
 
@@ -933,42 +945,102 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
     NET_TRY(cond_embed(n->cw, nullptr, steps[0].t, pcond, n->cond_act, B, s));   // param half -> cond_act
     NET_TRY(cond_mlp_param(n->mlp_w, n->cond_act, n->ss_p, n->ss_rows, 8 * n->dim, B, s));
   }
-  size_t slab = 1;
-  for (int i = 0; i < nsteps; ++i) {
-    const prg_step& st = steps[i];
-    PRG_CHECK_ARG(st.kind >= 0 && st.kind <= 4, "step kind");
-    NET_TRY(cond_mlp_step(n->mlp_w, n->mlp_b, n->act_t_all + (size_t)i * 4 * n->dim, n->ss_p, n->ss, n->ss_rows,
-                          8 * n->dim, B, s));
-    Run r{B, s, n->x_state, nullptr, st.t, pcond, 1};
+  // the step list, the step counter and this call's pointers go to the device
+  {
+    if (nsteps > n->steps_cap) {
+      if (n->steps_dev) cudaFree(n->steps_dev);
+      n->steps_dev = nullptr;
+      if (cudaMalloc(&n->steps_dev, (size_t)(nsteps + 16) * sizeof(StepDev)) != cudaSuccess) {
+        set_error("out of device memory for the step list");
+        return PRG_ERR_CUDA;
+      }
+      n->steps_cap = nsteps + 16;
+    }
+    std::vector<StepDev> sd(nsteps);
+    int slab = 1;
+    for (int i = 0; i < nsteps; ++i) {
+      const prg_step& st = steps[i];
+      PRG_CHECK_ARG(st.kind >= 0 && st.kind <= 4, "step kind");
+      if (st.unnormalize && i != nsteps - 1) {
+        set_error("only the last step may unnormalize");
+        return PRG_ERR_ARG;
+      }
+      StepDev& d = sd[i];
+      memset(&d, 0, sizeof(d));
+      d.kind = st.kind; d.add_noise = st.add_noise; d.unnormalize = st.unnormalize;
+      d.noise_slab = st.add_noise ? slab++ : 0;
+      d.c0 = st.c0; d.c1 = st.c1; d.c2 = st.c2; d.c3 = st.c3; d.c4 = st.c4;
+    }
+    const SamplerCtx cx{img_cond, noise};
+    PRG_CUDA_OK(cudaMemcpyAsync(n->steps_dev, sd.data(), (size_t)nsteps * sizeof(StepDev), cudaMemcpyHostToDevice, s));
+    PRG_CUDA_OK(cudaMemcpyAsync(n->ctx_dev, &cx, sizeof(cx), cudaMemcpyHostToDevice, s));
+    PRG_CUDA_OK(cudaMemsetAsync(n->step_idx, 0, sizeof(int), s));
+  }
+  // One step = the same launch sequence whatever the step: conditioning row of step *step_idx, the
+  // U-Net trunk on x_state, the tail (final 1x1 + DDNM + posterior / DDIM update, in place on
+  // x_state), step_idx += 1.
+  auto issue_step = [&]() -> int {
+    NET_TRY(cond_mlp_step(n->mlp_w, n->mlp_b, n->act_t_all, n->ss_p, n->ss, n->ss_rows, 8 * n->dim, B, s,
+                          n->step_idx, 4 * n->dim));
+    Run r{B, s, n->x_state, nullptr, 0, pcond, 1};
     NET_TRY(run_trunk(n, r));
     TailParams t = n->tail;
     t.mode = 2;
     t.x_t = n->x_state;
-    const bool last = (i == nsteps - 1);
-    t.out = last ? out : n->x_state;
-    t.img_cond = img_cond;
-    t.sampler = st.kind;
-    t.clip_x_start = (st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST ||
-                      st.kind == PRG_STEP_REFINE_DDIM);
-    t.use_ddnm = (img_cond != nullptr) &&
-                 (st.kind == PRG_STEP_P_SAMPLE || st.kind == PRG_STEP_DDIM ||
-                  st.kind == PRG_STEP_DDIM_LAST);
-    t.add_noise = st.add_noise;
-    t.noise = nullptr;
-    if (st.add_noise) {
-      if (noise != nullptr) t.noise = noise + slab * npx;
-      t.seeds = n->seeds_dev;
-      t.noise_offset = (unsigned long long)slab * hw;
-      ++slab;
-    }
-    t.c0 = st.c0; t.c1 = st.c1; t.c2 = st.c2; t.c3 = st.c3; t.c4 = st.c4;
-    t.unnormalize = st.unnormalize;
-    if (st.unnormalize && !last) {
-      set_error("only the last step may unnormalize");
-      return PRG_ERR_ARG;
-    }
+    t.out = n->x_state;
+    t.seeds = n->seeds_dev;
+    t.steps = n->steps_dev;
+    t.step_idx = n->step_idx;
+    t.ctx = n->ctx_dev;
+    t.slab_stride = npx;
     NET_TRY(run_tail(n, t, B, s));
+    return step_advance(n->step_idx, s);
+  };
+  // Replayed as ONE CUDA graph per step (captured once per batch size); steps sampled by the
+  // profiler (per-launch events) and PRG_NO_GRAPH=1 runs issue the same launches directly.
+  static const bool no_graph = getenv("PRG_NO_GRAPH") != nullptr;
+  cudaGraphExec_t exec = nullptr;
+  {
+    auto it = n->step_graphs.find(B);
+    if (it != n->step_graphs.end()) exec = it->second;
   }
+  for (int i = 0; i < nsteps; ++i) {
+    if (exec == nullptr && !no_graph && i == 1 && nsteps >= 4) {
+      // first long call at this batch size: step 0 ran directly (every kernel is configured and
+      // loaded), now record the same launches once.  Nothing executes during the capture.
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &cs);
+      if (cs == cudaStreamCaptureStatusNone) {
+        const int every = g_prof.every;
+        g_prof.every = 0;              // no event records inside the capture
+        const uint64_t fw = n->forwards, lc = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        PRG_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = issue_step();
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        g_prof.every = every;
+        n->forwards = fw;
+        const uint64_t recorded = g_launches.load() - lc;   // kernel launches of one step
+        g_launches.fetch_sub(recorded);
+        if (rc != PRG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        PRG_CUDA_OK(ce);
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        PRG_CUDA_OK(ie);
+        n->step_graphs[B] = exec;
+        n->step_graph_launches[B] = (int)recorded;
+      }
+    }
+    const bool sampled = g_prof.every > 0 && (n->forwards % (uint64_t)g_prof.every) == 0;
+    if (exec != nullptr && !sampled) {
+      PRG_CUDA_OK(cudaGraphLaunch(exec, s));
+      n->forwards++;
+      count_launch(n->step_graph_launches[B]);
+    } else {
+      NET_TRY(issue_step());
+    }
+  }
+  PRG_CUDA_OK(cudaMemcpyAsync(out, n->x_state, npx * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return PRG_OK;
 }
 

@@ -56,3 +56,20 @@ static inline double __dadd_rn(double a, double b) { volatile double r = a + b; 
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline long long __double2ll_rn(double a) { return llrint(a); }
+
+/* round 2: packed fp32x2 arithmetic (each lane rounded like the scalar op), F2I.RN with saturation */
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { return {a, b}; }
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return {__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return {__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)}; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+static inline int __float2int_rn(float f) {
+  if (f != f) return 0;
+  if (f >= 2147483648.0f) return 2147483647;
+  if (f <= -2147483648.0f) return (-2147483647 - 1);
+  return (int)nearbyintf(f);            /* default rounding mode: half to even */
+}
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) {}

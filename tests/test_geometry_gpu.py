@@ -152,3 +152,60 @@ def test_reproject_full_size_properties():
     assert torch.equal(d1[:4], d1[4:8])
     od, om = G.reproject(dm[:4].cpu().numpy(), K[:4].cpu().numpy(), P[:4].cpu().numpy())
     assert np.array_equal(d1[:4].cpu().numpy(), od)
+
+
+def test_reproject_ring_reuse_many_maps_and_streams():
+    """The fused reprojection keeps its z-buffers in a ring of scratch slots that a call reuses many
+    times (300 maps of 256x256 through 64 slots; 70 maps of 640x480 through 20) and hands back empty:
+    every map bit-exact against the oracle, repeated calls identical, and a call issued on another
+    stream waits for the ring."""
+    for (B, H, W, nref) in ((300, 256, 256, 24), (70, 480, 640, 6)):
+        base, K, P = _inputs(nref, H, W, 29)
+        rep = (B + nref - 1) // nref
+        dm = (base * 10).repeat(rep, 1, 1, 1)[:B].cuda()
+        Kt = torch.tensor(K).repeat(rep, 1, 1)[:B].cuda()
+        Pt = torch.tensor(P).repeat(rep, 1, 1)[:B].cuda()
+        d1, m1 = pg.reproject_tensor(dm, Kt, Pt)
+        od, om = G.reproject((base * 10).numpy(), K, P)
+        for s in range(0, B, nref):
+            n = min(nref, B - s)
+            assert np.array_equal(d1[s:s + n].cpu().numpy().view(np.uint32), od[:n].view(np.uint32)), (B, s)
+            assert np.array_equal(m1[s:s + n].cpu().numpy(), om[:n]), (B, s)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            d2, m2 = pg.reproject_tensor(dm, Kt, Pt)          # other stream: ordered behind the first call
+        d3, m3 = pg.reproject_tensor(dm[:1], Kt[:1], Pt[:1])  # B = 1 right behind it, on the first stream
+        torch.cuda.synchronize()
+        assert torch.equal(d1, d2) and torch.equal(m1, m2)
+        assert torch.equal(d3, d1[:1]) and torch.equal(m3, m1[:1])
+
+
+def test_reproject_unusual_maps_take_the_scalar_path():
+    """Maps whose intrinsics / pose / clip fall outside the validated fast range (huge pose entries, a
+    clip that admits negative or enormous depths) mixed with ordinary ones in one batch."""
+    B, H, W = 6, 96, 128
+    d01, K, P = _inputs(B, H, W, 31)
+    dm = (d01 * 10).numpy()
+    P = P.copy()
+    P[1, 0, 3] = 2.5e4            # |t| beyond the fast-path bound
+    P[2, :3, :3] *= 3e4           # absurd scale
+    P[3, 2, 3] = -2.9             # pushes part of the map behind the camera (z <= 0)
+    K = K.copy()
+    K[4, 0, 2] = 3e6              # principal point outside the validated range
+    dm[5, 0, ::7, ::5] = 1e-12    # tiny depths inside a clip that admits them
+    for clip in ([0, 10], [-1.0, 3e38]):
+        with np.errstate(all="ignore"):
+            od, om = G.reproject(dm, K, P, clip=tuple(clip))
+        gd, gm = pg.reproject_tensor(torch.tensor(dm).cuda(), torch.tensor(K).cuda(), torch.tensor(P).cuda(), clip=clip)
+        a, b = gd.cpu().numpy(), od
+        assert bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))), clip
+        assert np.array_equal(gm.cpu().numpy(), om), clip
+
+
+def test_range_restricted_reciprocal_is_the_ieee_one():
+    """frcp_rn_normal (MUFU.RCP + one Newton step, no range checks) == __frcp_rn for EVERY float with
+    2^-100 <= |z| <= 2^100 -- a superset of the (1e-6, 1e12) the reprojection kernel feeds it."""
+    from pointreggpt_b200 import _ffi
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _ffi.check(_ffi.lib().prg_test_frcp_exhaustive(2.0 ** -100, 2.0 ** 100, _ffi.ptr(bad), _ffi.stream(bad)))
+    assert int(bad.item()) == 0

@@ -39,34 +39,33 @@ static void run_block(unsigned x, unsigned y, unsigned first, unsigned last, voi
     fn(arg);
   }
 }
-struct RArgs { const float *depth, *K, *pose; float lo, hi; unsigned* z; int HW, H, W; };
-static void call_splat(void* p) {
-  RArgs& a = *(RArgs*)p;
-  if ((long long)a.HW * 9 < 400) k_reproject_splat<true>(a.depth, a.K, a.pose, a.lo, a.hi, a.z, a.HW, a.H, a.W);
-  else k_reproject_splat<false>(a.depth, a.K, a.pose, a.lo, a.hi, a.z, a.HW, a.H, a.W);      // as prg_reproject_f32
-}
-// prg_reproject_f32 without the L2 grouping: fill 0xFF, splat, finalise.  gx = grid_for(HW, 256, 4).
+// prg_reproject_f32: the work items of the fused persistent kernel, run one after another in the order
+// the kernel deals them (every dependency of an item is an earlier item); ring of R slots, lag D as
+// the ABI entry plans them, but with a ring small enough that slots are reused even in tiny batches.
 extern "C" void emu_reproject(const float* depth, const float* K, const float* pose, float lo, float hi,
-                              float* out, uint8_t* mask, unsigned* scratch, int B, int H, int W, int gx) {
-  const int HW = H * W;
-  const size_t n = (size_t)B * HW;
-  memset(out, 0xFF, n * 4);
+                              float* out, uint8_t* mask, unsigned* scratch, int B, int H, int W, int R) {
+  RpPlan pl;
+  pl.B = B; pl.H = H; pl.W = W; pl.HW = H * W;
+  pl.items = (pl.HW + kRpItemPx - 1) / kRpItemPx;
+  pl.R = R < 2 ? 2 : R;
+  pl.D = pl.R / 2 < 1 ? 1 : pl.R / 2;
+  if (pl.D > B) pl.D = B;
+  if (pl.D >= pl.R) pl.D = pl.R - 1;
+  pl.total = 2ll * B * pl.items;
+  memset(scratch, 0xFF, (size_t)pl.R * pl.HW * 4);
   blockDim = {256, 1, 1};
-  gridDim = {(unsigned)gx, (unsigned)B, 1};
-  for (unsigned y = 0; y < (unsigned)B; ++y)
-    for (unsigned x = 0; x < (unsigned)gx; ++x) {
-      RArgs a{depth, K, pose, lo, hi, scratch, HW, H, W};
-      run_block(x, y, 0, 12, call_splat, &a);      // the threads that fill the pose in shared memory
-      a.z = (unsigned*)out;
-      run_block(x, y, 0, 256, call_splat, &a);
-    }
-  gridDim = {(unsigned)((n + 1023) / 1024), 1, 1};
-  for (unsigned x = 0; x < gridDim.x; ++x)
+  gridDim = {1, 1, 1};
+  blockIdx = {0, 0, 0};
+  int dummy[2] = {0, 0};
+  for (long long p = 0; p < pl.total; ++p)
     for (unsigned t = 0; t < 256; ++t) {
-      blockIdx = {x, 0, 0};
       threadIdx = {t, 0, 0};
-      k_zbuf_finalize((unsigned*)out, mask, n);
+      if ((long long)pl.HW * 9 < 400) rp_run_item<true>(p, depth, K, pose, lo, hi, scratch, out, mask, dummy, dummy, pl);
+      else rp_run_item<false>(p, depth, K, pose, lo, hi, scratch, out, mask, dummy, dummy, pl);
     }
+  // the call must hand the ring back empty
+  for (size_t i = 0; i < (size_t)pl.R * pl.HW; ++i)
+    if (scratch[i] != 0xFFFFFFFFu) { out[0] = -12345.f; break; }
 }
 struct PArgs { const float* pc; const uint8_t* valid; const int64_t* off; int64_t total; const float *K, *pose; unsigned* z; int B, H, W; };
 static void call_pc2d(void* p) {
@@ -187,8 +186,8 @@ def vox(tmp_path_factory):
 
 @pytest.fixture(scope="module")
 def geom(tmp_path_factory):
-    """Device helpers (division, unproject, rigid, splat) + k_reproject_splat, k_zbuf_finalize and
-    k_depth2pc, exactly as they stand in geometry.cu."""
+    """Device helpers (division, unproject, rigid, splat) + the work items of k_reproject_fused,
+    k_pc2depth_splat / k_zbuf_finalize and k_depth2pc, exactly as they stand in geometry.cu."""
     src = open(CU).read()
     a = src.index("constexpr unsigned kEmpty")
     b = src.index("// ------------------------------------------------------------------ pc2depth (ragged)")
@@ -254,10 +253,9 @@ def test_reproject_kernel_numerics(geom, shape, extreme):
         want_d, want_m = G.reproject(dm, K, P)
     out = np.empty((B, H, W), np.float32)
     mask = np.empty((B, H, W), np.uint8)
-    scratch = np.full((B, H, W), 0xFFFFFFFF, np.uint32)
-    gx = (H * W + 1023) // 1024
+    scratch = np.full((2, H, W), 0, np.uint32)            # ring of two slots: reused within the batch
     geom.emu_reproject(_vp(dm), _vp(K), _vp(P), ctypes.c_float(0.0), ctypes.c_float(10.0), _vp(out), _vp(mask),
-                       _vp(scratch), B, H, W, gx)
+                       _vp(scratch), B, H, W, 2)
     assert _same_bits_or_nan(out.reshape(want_d.shape), want_d)
     assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m) and want_m.any()
 
@@ -402,9 +400,10 @@ def test_geometry_kernels_differential_fuzz(geom, seed):
         assert _same_bits_or_nan(pc, want_pc) and np.array_equal(valid.astype(bool), want_v), ctx
         out = np.empty((B, H, W), np.float32)
         mask = np.empty((B, H, W), np.uint8)
-        scratch = np.full((B, H, W), 0xFFFFFFFF, np.uint32)
+        ring = 2 + trial % 3
+        scratch = np.full((ring, H, W), 0, np.uint32)
         geom.emu_reproject(_vp(dm), _vp(K), _vp(P), ctypes.c_float(rclip[0]), ctypes.c_float(rclip[1]), _vp(out),
-                           _vp(mask), _vp(scratch), B, H, W, gx)
+                           _vp(mask), _vp(scratch), B, H, W, ring)
         assert _same_bits_or_nan(out.reshape(want_d.shape), want_d), ctx
         assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m), ctx
 

@@ -52,22 +52,28 @@ def test_maskunet_forward_256_and_keep_threshold():
     """MaskUnet at the shipped size (DC:871-906) and the caller's `> 0.99` (SDD:2565, 2580)."""
     torch.manual_seed(0)
     net = nets.MaskUnet(dim=64, dim_mults=(1, 2, 4, 8))
+    d = S.synthetic_depth_batch(60, 1, 256, 256)
+    # place the final bias so that the probabilities straddle 0.99 (logit 4.595): the bias is additive
+    # in front of the sigmoid, so the median logit of a first oracle pass tells where to put it
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    p0 = R.maskunet_forward(sd, d).double().clamp(1e-12, 1 - 1e-12)
+    shift = math.log(0.99 / 0.01) - torch.log(p0 / (1 - p0)).median().item()
     with torch.no_grad():
-        net.final_conv[0].bias.fill_(4.6)            # logit(0.99) = 4.595: probabilities straddle the threshold
+        net.final_conv[0].bias.add_(shift)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.cuda()
-    d = S.synthetic_depth_batch(60, 1, 256, 256)
     ref = R.maskunet_forward(sd, d)
     got = net(d.cuda()).cpu()
     e = ((got - ref).norm() / ref.norm()).item()
     frac = (ref > 0.99).float().mean().item()
     print("maskunet 256 rel-l2 %.2e; %.1f %% of the pixels above 0.99" % (e, 100 * frac))
-    assert e <= 1e-3 and 0.02 < frac < 0.98
+    assert e <= 1e-3 and 0.2 < frac < 0.8
     keep = net.keep_mask(d.cuda(), 0.99).cpu()
     same = keep == (ref > 0.99)
     # a pixel may only differ when the reference probability is within the fp tolerance of 0.99
-    assert ((ref[~same] - 0.99).abs() < 1e-3).all()
-    assert same.float().mean().item() > 0.99
+    print("keep-mask agreement at 0.99: %.4f" % same.float().mean().item())
+    assert ((ref[~same] - 0.99).abs() < 1e-4).all()
+    assert same.float().mean().item() > 0.9
     assert torch.equal(keep, got > 0.99)             # the fused threshold is the kernel's own comparison
 
 
