@@ -44,6 +44,7 @@ constexpr int kHaloPix = kBlockM + 2;              // 130 pixels per ring row
 constexpr int kHaloBytes = kHaloPix * 128;         // 16640 B written by TMA
 constexpr int kHaloSlot = 17 * 1024;               // slot pitch (1024-aligned)
 constexpr int kThreads = 320;                     // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kXfThreads = 128;                   // XF: + 4 transform warps (GroupNorm apply on the ring slot)
 constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 227 * 1024;
@@ -54,6 +55,7 @@ struct alignas(8) Ctl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t wfull;
+  uint64_t xfull[kMaxStages];   // XF: ring slot transformed in place, ready for the MMA warp
   uint64_t tmem_full[8];
   uint64_t tmem_empty[8];
   uint32_t tmem_addr;
@@ -116,8 +118,31 @@ struct Conv2Params {
 // issues tcgen05.mma.cta_group::2, and each CTA drains its own 128 accumulator rows.  Per SM a
 // K block costs 32 KB of loads instead of 48 KB -- these layers sit at the ~64 B/clk/SM the TMA
 // path sustains, not at the tensor-pipe limit.
-template <int BN, int EPI, int CG = 1>
-__global__ void __launch_bounds__(kThreads, 1)
+// XF = 1 (row-streaming mode, one source): the input of the convolution is SiLU(A[b][c] * raw + B[b][c])
+// -- the GroupNorm apply (+ scale / shift) of the producing Block (SDD:690-696) -- and is never
+// materialised: four extra warps apply it IN PLACE to every ring slot between the TMA load and the MMAs
+// (same arithmetic as k_gn_apply: fp32 affine on the packed pipe, ex2 + rcp SiLU, round to fp16), leave
+// the zero padding (halo pixels and rows outside the image) untouched, then `fence.proxy.async` and
+// hand the slot to the MMA warp through its own barrier.  A thread keeps one 8-channel group of
+// coefficients in registers (the slot is 128B-swizzled: logical chunk g of pixel p sits at g ^ (p & 7)).
+__device__ __forceinline__ float xf_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float xf_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 xf_silu2(float2 t) {
+  const float2 u = __fmul2_rn(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = __fadd2_rn(make_float2(xf_ex2(u.x), xf_ex2(u.y)), make_float2(1.f, 1.f));
+  return __fmul2_rn(t, make_float2(xf_rcp(d.x), xf_rcp(d.y)));
+}
+
+template <int BN, int EPI, int CG = 1, int XF = 0>
+__global__ void __launch_bounds__(kThreads + XF * kXfThreads, 1)
 k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
         const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -163,6 +188,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       mbar_init(&ctl->empty[s], 1);
     }
     mbar_init(&ctl->wfull, 1);
+    if (XF)
+      for (int s = 0; s < P.stages; ++s) mbar_init(&ctl->xfull[s], kXfThreads);
     for (int a = 0; a < 8; ++a) {
       mbar_init(&ctl->tmem_full[a], 1);
       mbar_init(&ctl->tmem_empty[a], (BN == 64 ? kEpiThreads / 2 : kEpiThreads) * CG);
@@ -179,10 +206,10 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     }
   }
   if (EPI == EPI_QKV && threadIdx.x < 128) ctl->colmax[threadIdx.x] = INT_MIN;
-  for (int i = threadIdx.x; i < BN * P.n_tiles; i += kThreads)
+  for (int i = threadIdx.x; i < BN * P.n_tiles; i += blockDim.x)
     ctl->bias[i] = (p.bias != nullptr) ? __ldg(p.bias + i) : 0.f;
   if (EPI == EPI_LN_RES || (EPI == EPI_GNRES && p.has_ln_out))
-    for (int i = threadIdx.x; i < BN; i += kThreads) ctl->gain[i] = __ldg(p.ln_g + i);
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) ctl->gain[i] = __ldg(p.ln_g + i);
   tc_fence_before();
   if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   else __syncthreads();
@@ -345,7 +372,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         decode_seg(seg, img, x0, y0, nr);
         for (int ri = 0; ri < nr + 2; ++ri) {
          for (int src = 0; src < P.nsrc; ++src) {
-          mbar_wait(&ctl->full[stage], phase);
+          mbar_wait(XF ? &ctl->xfull[stage] : &ctl->full[stage], phase);
           if (ri < nr && src == 0) {   // slot of the new target must have been drained
             const uint32_t tn = tcount + (uint32_t)ri;
             mbar_wait(&ctl->tmem_empty[tn & 7u], ((tn >> 3) & 1u) ^ 1u);
@@ -456,6 +483,54 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         ++tcount;
+      }
+    }
+  } else if (XF && warp >= kThreads / 32) {
+    // =============================== input transform (XF) ========================
+    const int xt = (int)threadIdx.x - kThreads;      // 0..127
+    const int grp = xt & 7;                          // logical 16-byte chunk = channels 8 grp .. 8 grp + 7
+    const int p0 = xt >> 3;                          // first pixel of the slot this thread touches (then + 16)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+      int img, x0, y0, nr;
+      decode_seg(seg, img, x0, y0, nr);
+      // (A, B) of this thread's eight channels for this image (k_gn_coef wrote them; L2 hits)
+      float2 cA[4], cB[4];
+      {
+        const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + (size_t)img * 64 + grp * 8);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ab = __ldg(cf + q);             // (A0, B0, A1, B1)
+          cA[q] = make_float2(ab.x, ab.z);
+          cB[q] = make_float2(ab.y, ab.w);
+        }
+      }
+      // columns of the slot that lie inside the image: pixel pp <-> x = x0 - 1 + pp
+      const int pp_lo = (x0 == 0) ? 1 : 0;
+      const int pp_hi = min(kHaloPix, p.Wo - x0 + 1);   // exclusive
+      for (int r = 0; r < nr + 2; ++r) {
+        mbar_wait(&ctl->full[stage], phase);
+        const int y = y0 - 1 + r;
+        if (y >= 0 && y < p.Ho) {
+          uint8_t* slot = sA + (size_t)stage * P.a_slot;
+#pragma unroll 3
+          for (int pp = p0; pp < kHaloPix; pp += kXfThreads / 8) {
+            if (pp < pp_lo || pp >= pp_hi) continue;
+            uint4* cell = reinterpret_cast<uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4));
+            uint4 v = *cell;
+            __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 yv = xf_silu2(__ffma2_rn(__half22float2(h[q]), cA[q], cB[q]));
+              h[q] = __floats2half2_rn(yv.x, yv.y);
+            }
+            *cell = v;
+          }
+        }
+        fence_proxy_async();                 // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(&ctl->xfull[stage]);
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -1062,6 +1137,7 @@ struct Conv2Launch {
   int bn, epi, smem;
   int grid;
   int cg;   // 2 = CTA-pair kernel (cluster of two, tcgen05 cta_group::2)
+  int xf;   // 1 = input transform warps (GroupNorm apply of the producing Block on the ring slot)
 };
 
 static int g_conv_flags = -1;  // PRG_CONV_FLAGS bit0: disable the halo-ring mode (A/B measurements)
@@ -1284,6 +1360,20 @@ static int launch2(const Conv2Launch& L, cudaStream_t stream) {
 }
 
 template <int BN, int EPI>
+static int launch2_xf(const Conv2Launch& L, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < L.smem) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_conv2<BN, EPI, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemBudget));
+    configured = kSmemBudget;
+  }
+  k_conv2<BN, EPI, 1, 1><<<L.grid, kThreads + kXfThreads, L.smem, stream>>>(L.tmA0, L.tmA1, L.tmB, L.tmO[0], L.tmO[1],
+                                                                           L.tmO[2], L.tmO[3], L.P);
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+template <int BN, int EPI>
 static int launch2_pair(const Conv2Launch& L, cudaStream_t stream) {
   static int configured = 0;
   if (configured < L.smem) {
@@ -1311,6 +1401,11 @@ static int launch2_pair(const Conv2Launch& L, cudaStream_t stream) {
 }
 
 static int conv2_run(const Conv2Launch& L, cudaStream_t stream) {
+  if (L.xf) {
+    if (L.bn == 64 && L.epi == EPI_GN && L.P.halo && L.P.nsrc == 1) return launch2_xf<64, EPI_GN>(L, stream);
+    set_error("conv_run: the input transform exists for the row-streaming N = 64 EPI_GN kernel only");
+    return PRG_ERR_ARG;
+  }
   if (L.cg == 2) {
     if (L.bn == 256 && L.epi == EPI_BIAS) return launch2_pair<256, EPI_BIAS>(L, stream);
     if (L.bn == 256 && L.epi == EPI_GN) return launch2_pair<256, EPI_GN>(L, stream);
@@ -1359,6 +1454,22 @@ int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1,
   return PRG_OK;
 }
 
+bool conv_op_can_transform_input(const ConvOp& op) {
+  const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
+  return L->P.halo && L->P.nsrc == 1 && L->bn == 64 && L->epi == EPI_GN && L->cg == 1 && !(conv_flags() & 64);
+}
+
+int conv_op_set_input_transform(ConvOp& op, const float2* coef) {
+  Conv2Launch* L = reinterpret_cast<Conv2Launch*>(op.impl);
+  if (!conv_op_can_transform_input(op) || coef == nullptr) {
+    set_error("conv_op_set_input_transform: not a single-source row-streaming N = 64 EPI_GN plan");
+    return PRG_ERR_ARG;
+  }
+  L->xf = 1;
+  L->P.c.gn_coef = coef;
+  return PRG_OK;
+}
+
 int conv_op_set_ln_out(ConvOp& op, const ActSrc& ln_out) {
   Conv2Launch* L = reinterpret_cast<Conv2Launch*>(op.impl);
   if (L->bn != 64 || L->epi != EPI_GNRES || L->P.c.classes != 1) {
@@ -1394,8 +1505,8 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
 
 const char* conv_op_describe(const ConvOp& op, char* buf, int n) {
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
-  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d cg=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
-           L->P.halo, L->P.wres, L->P.pair, L->cg, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
+  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d cg=%d xf=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
+           L->P.halo, L->P.wres, L->P.pair, L->cg, L->xf, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
   return buf;
 }
 

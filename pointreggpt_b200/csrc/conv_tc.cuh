@@ -47,7 +47,8 @@ struct ConvParams {
   int* colmax;           // EPI_QKV: [B][128] order-preserving int encoding of max_n k, or nullptr
   int q_softmax;         // EPI_QKV: 1 = softmax over each 32-channel head then * q_scale
   float q_scale;
-  const float2* gn_coef; // EPI_GNRES: [B][Cout] (A, B) of the GroupNorm (+ scale/shift) affine, see gn_coef()
+  const float2* gn_coef; // EPI_GNRES: [B][Cout] (A, B) of the GroupNorm (+ scale/shift) affine, see gn_coef();
+                         // input transform (XF): [B][64] (A, B) applied to the INPUT
   int has_ln_out;        // EPI_GNRES, N = 64: also store LayerNorm_c(y) * ln_g through the second output map
 };
 
@@ -71,6 +72,11 @@ struct ConvOp {
 int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
                  int classes, const __half* w, int w_batched, int Cout, const ActSrc& out);
 int conv_op_run(ConvOp& op, int B, cudaStream_t stream);
+// Row-streaming N = 64 EPI_GN plans with one source can apply y = SiLU(A[b][c] * x + B[b][c]) to their
+// INPUT on the fly (the GroupNorm apply of the producing Block; coef = [B][64] (A, B) from gn_coef()),
+// so that the activated tensor is never written to or read from HBM.
+bool conv_op_can_transform_input(const ConvOp& op);
+int conv_op_set_input_transform(ConvOp& op, const float2* coef);
 // EPI_GNRES with N = 64: second destination (same shape as the output) for LayerNorm_c(y) * ln_g.
 int conv_op_set_ln_out(ConvOp& op, const ActSrc& ln_out);
 const char* conv_op_describe(const ConvOp& op, char* buf, int n);

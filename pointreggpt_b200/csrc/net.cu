@@ -314,6 +314,7 @@ struct BlockOut {
   Act y;                 // output (unused for the final block)
   const long long* stats2;  // final block: statistics of block2
   const float *g2, *b2;
+  const __half* raw2;    // final block: where block2's raw conv output lives
 };
 
 // ResnetBlock (SDD:720-734 / DC:734-740).  `last` = final_res_block: stop before the second
@@ -355,24 +356,47 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
       p.gs_log2 = gs_log2;
     }));
   }
-  {
-    GnApply a{};
-    a.raw = raw.p; a.stats = st1; a.gamma = g1; a.beta = be1;
-    if (n->kind == PRG_NET_UNET) {
-      a.ss = n->ss;
-      a.ss_stride = n->ss_rows;
-      a.ss_off = *ss_cursor;
-      *ss_cursor += 2 * cout;
-    }
-    a.res = nullptr; a.y = h1.p; a.HW = HW; a.C = cout;
-    n->add_op(CAT_GN, [a](const Run& r) { return gn_apply(a, r.B, r.s); },
-              "gn_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(cout) +
-                  (a.res ? " +res" : "") + (a.ln_g ? " +ln" : ""));
+  // block1's GroupNorm apply (+ scale / shift, SiLU): fused into block2's convolution when that runs
+  // in the row-streaming mode (its transform warps apply it to every input row in shared memory, so
+  // h1 never exists in HBM); a separate HBM pass otherwise.
+  GnApply a1{};
+  a1.raw = raw.p; a1.stats = st1; a1.gamma = g1; a1.beta = be1;
+  if (n->kind == PRG_NET_UNET) {
+    a1.ss = n->ss;
+    a1.ss_stride = n->ss_rows;
+    a1.ss_off = *ss_cursor;
+    *ss_cursor += 2 * cout;
   }
-  NET_TRY(add_conv(n, EPI_GN, h1, nullptr, 0, 3, 1, w2, 0, b2, raw, [=](ConvParams& p) {
-    p.stats = st2;
-    p.gs_log2 = gs_log2;
-  }));
+  a1.res = nullptr; a1.y = h1.p; a1.HW = HW; a1.C = cout;
+  Act raw2 = raw;             // block2's raw output
+  {
+    ConvOp op2;
+    ActSrc araw = src_of(raw);
+    NET_TRY(conv_op_plan(&op2, EPI_GN, n->maxB, araw, nullptr, 0, 3, 1, w2, 0, cout, src_of(h1)));
+    if (cout == 64 && conv_op_can_transform_input(op2) && getenv("PRG_NO_XF") == nullptr) {
+      raw2 = h1;              // raw1 is read while raw2 is written: they cannot share a buffer
+      float2* coef = n->gn_coef_buf;
+      n->add_op(CAT_GN, [a1, coef](const Run& r) { return gn_coef(a1, coef, r.B, r.s); },
+                "gn_coef c" + std::to_string(cout));
+      NET_TRY(conv_op_set_input_transform(op2, coef));
+      ConvParams& p = op2.params();
+      p.bias = b2;
+      p.stats = st2;
+      p.gs_log2 = gs_log2;
+      char buf[160], lab[256];
+      snprintf(lab, sizeof(lab), "conv %dx%d %d->%d k3 m0 c1 +gn_in [%s]", H, W, cout, cout,
+               conv_op_describe(op2, buf, sizeof(buf)));
+      n->add_op(CAT_CONV, [op2](const Run& r) mutable { return conv_op_run(op2, r.B, r.s); }, lab,
+                2.0 * H * W * (double)cout * 9 * cout);
+    } else {
+      n->add_op(CAT_GN, [a1](const Run& r) { return gn_apply(a1, r.B, r.s); },
+                "gn_apply " + std::to_string(H) + "x" + std::to_string(W) + " c" + std::to_string(cout));
+      NET_TRY(add_conv(n, EPI_GN, h1, nullptr, 0, 3, 1, w2, 0, b2, raw, [=](ConvParams& p) {
+        p.stats = st2;
+        p.gs_log2 = gs_log2;
+      }));
+    }
+  }
   const __half* res_ptr;
   int res_stride;
   // res_conv fused with the second GroupNorm apply (conv engine EPI_GNRES): y = res_conv(x) +
@@ -390,7 +414,7 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
     Act y = new_act(n, H, W, cout);
     if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
     GnApply a{};
-    a.raw = raw.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr; a.HW = HW; a.C = cout;
+    a.raw = raw2.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr; a.HW = HW; a.C = cout;
     float2* coef = n->gn_coef_buf;
     n->add_op(CAT_GN, [a, coef](const Run& r) { return gn_coef(a, coef, r.B, r.s); },
               "gn_coef c" + std::to_string(cout));
@@ -401,7 +425,7 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
       NET_TRY(conv_op_plan(&op, EPI_GNRES, n->maxB, a0, x1 ? &a1 : nullptr, 0, 1, 1, wr, 0, cout, src_of(y)));
       ConvParams& p = op.params();
       p.bias = br;
-      p.res = raw.p;
+      p.res = raw2.p;
       p.gn_coef = coef;
       if (fuse_ln_g != nullptr) {
         p.ln_g = fuse_ln_g;
@@ -435,14 +459,14 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
       set_error("final_res_block must have a res_conv");
       return PRG_ERR_BLOB;
     }
-    bo->stats2 = st2; bo->g2 = g2; bo->b2 = be2;
+    bo->stats2 = st2; bo->g2 = g2; bo->b2 = be2; bo->raw2 = raw2.p;
     return PRG_OK;
   }
   Act y = new_act(n, H, W, cout);
   if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
   {
     GnApply a{};
-    a.raw = raw.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr;
+    a.raw = raw2.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr;
     a.res = res_ptr; a.res_pix_stride = res_stride; a.y = y.p; a.HW = HW; a.C = cout;
     if (fuse_ln_g != nullptr) {   // PreNorm of the attention that consumes y, written to n->xn
       a.ln_g = fuse_ln_g;
@@ -745,7 +769,7 @@ int build(prg_net* n) {
     BlockOut bo{};
     NET_TRY(add_resblock(n, "final_res_block", x, &stem, n->dim, &ss_cursor, true, &bo));
     TailParams& t = n->tail;
-    t.raw = n->raw; t.stats = bo.stats2; t.gamma = bo.g2; t.beta = bo.b2; t.res = n->resb;
+    t.raw = bo.raw2; t.stats = bo.stats2; t.gamma = bo.g2; t.beta = bo.b2; t.res = n->resb;
     const std::string fc = n->kind == PRG_NET_UNET ? "final_conv" : "final_conv.0";
     t.fw = n->f32(fc + ".weight");
     t.fb = n->f32(fc + ".bias");
