@@ -284,7 +284,7 @@ def run_reference_gpu_arm(a, rank, world):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": workload_name(a), "batch_per_gpu": B, "image_size": a.size, "timesteps": T,
-                      "sample": "Unet.forward only (>99.9 % of the path), pairs/s = B / (T * step); eager "
+                      "sample": "Unet.forward only (>99.9 %% of the path), pairs/s = B / (T * step); eager "
                                 "torch %s, cuDNN benchmark on" % torch.__version__},
            "unet_step_ms": res["fp32"], "unet_step_ms_tf32": res["tf32"],
            "unet_step_tflops": UNET_FLOP_PER_IMAGE * B / (res["fp32"] * 1e-3) / 1e12,

@@ -495,37 +495,61 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
       int img, x0, y0, nr;
       decode_seg(seg, img, x0, y0, nr);
-      // (A, B) of this thread's eight channels for this image (k_gn_coef wrote them; L2 hits)
+      // (A, B) of this thread's eight channels for this image (k_gn_coef wrote them; L2 hits), halved:
+      // SiLU(t) = h + h tanh(h) with h = t / 2 = x (A / 2) + B / 2  (scaling by 1/2 is exact)
       float2 cA[4], cB[4];
       {
         const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + (size_t)img * 64 + grp * 8);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 ab = __ldg(cf + q);             // (A0, B0, A1, B1)
-          cA[q] = make_float2(ab.x, ab.z);
-          cB[q] = make_float2(ab.y, ab.w);
+          cA[q] = make_float2(0.5f * ab.x, 0.5f * ab.z);
+          cB[q] = make_float2(0.5f * ab.y, 0.5f * ab.w);
         }
       }
       // columns of the slot that lie inside the image: pixel pp <-> x = x0 - 1 + pp
       const int pp_lo = (x0 == 0) ? 1 : 0;
       const int pp_hi = min(kHaloPix, p.Wo - x0 + 1);   // exclusive
+      constexpr int kCells = (kHaloPix + kXfThreads / 8 - 1) / (kXfThreads / 8);   // 9 cells per thread and row
+      const bool exact = (P.dbg_flags & 128) != 0;     // A/B switch: ex2 + rcp SiLU as in k_gn_apply
       for (int r = 0; r < nr + 2; ++r) {
         mbar_wait(&ctl->full[stage], phase);
         const int y = y0 - 1 + r;
         if (y >= 0 && y < p.Ho) {
           uint8_t* slot = sA + (size_t)stage * P.a_slot;
-#pragma unroll 3
-          for (int pp = p0; pp < kHaloPix; pp += kXfThreads / 8) {
-            if (pp < pp_lo || pp >= pp_hi) continue;
-            uint4* cell = reinterpret_cast<uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4));
-            uint4 v = *cell;
-            __half2* h = reinterpret_cast<__half2*>(&v);
+          // the whole row's cells of this thread in flight together: one warp per scheduler does this
+          // work, so the latency of the LDS -> FMA -> MUFU -> FMA -> STS chain is covered by
+          // instruction-level parallelism only
+          uint4 v[kCells];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 yv = xf_silu2(__ffma2_rn(__half22float2(h[q]), cA[q], cB[q]));
-              h[q] = __floats2half2_rn(yv.x, yv.y);
+          for (int q = 0; q < kCells; ++q) {
+            const int pp = p0 + q * (kXfThreads / 8);
+            if (pp >= pp_lo && pp < pp_hi)
+              v[q] = *reinterpret_cast<const uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4));
+          }
+#pragma unroll
+          for (int q = 0; q < kCells; ++q) {
+            __half2* h = reinterpret_cast<__half2*>(&v[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hv = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
+              float2 yv;
+              if (exact) {
+                yv = xf_silu2(__fadd2_rn(hv, hv));
+              } else {
+                float tx, ty;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(hv.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(hv.y));
+                yv = __ffma2_rn(hv, make_float2(tx, ty), hv);
+              }
+              h[e] = __floats2half2_rn(yv.x, yv.y);
             }
-            *cell = v;
+          }
+#pragma unroll
+          for (int q = 0; q < kCells; ++q) {
+            const int pp = p0 + q * (kXfThreads / 8);
+            if (pp >= pp_lo && pp < pp_hi)
+              *reinterpret_cast<uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4)) = v[q];
           }
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to tcgen05.mma

@@ -203,6 +203,12 @@ __device__ __forceinline__ void rp_pixel_generic(float z0, int r, int c, const R
   splat(x, y, z, m.k, H, W, zslot);
 }
 
+// the same, out of line: the rare pixels of a fast map that leave the validated ranges
+__device__ __noinline__ void rp_pixel_slow(float z0, int r, int c, const RpMap& m, int H, int W,
+                                           unsigned* __restrict__ zslot) {
+  rp_pixel_generic<false>(z0, r, c, m, H, W, zslot);
+}
+
 // Splat item: pixels [px0, px0 + kRpItemPx) of one map.  Thread t takes pixels px0 + t + 256 j.
 template <bool kScalarBmm>
 __device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, unsigned* __restrict__ zslot,
@@ -227,15 +233,23 @@ __device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, un
   const float nan = __int_as_float(0x7fc00000);
   const float Wf = (float)W, step = (float)kRpThreads;   // rows / columns are carried as floats (exact below 2^24)
   float ra = (float)r, ca = (float)c;
-#pragma unroll 2
-  for (int j = 0; j < kRpItemPx / (2 * kRpThreads); ++j) {
+  // all sixteen loads of the item first: 64 bytes in flight per thread (the kernel is otherwise bound
+  // by the latency of its own reads -- 1024 threads per SM with one or two loads each cover only
+  // a third of the bandwidth-delay product)
+  constexpr int kPer = kRpItemPx / kRpThreads;
+  float dv[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int iq = i + q * kRpThreads;
+    dv[q] = (iq < HW) ? __ldcs(dimg + iq) : nan;
+  }
+#pragma unroll
+  for (int j = 0; j < kPer / 2; ++j) {
     if (i >= HW) break;
     // pixel A = i, pixel B = i + 256
     float rb = ra, cb = ca + step;
     while (cb >= Wf) { cb -= Wf; rb += 1.f; }
-    const int ib = i + kRpThreads;
-    const float da = __ldcs(dimg + i);
-    const float db = (ib < HW) ? __ldcs(dimg + ib) : nan;
+    const float da = dv[2 * j], db = dv[2 * j + 1];
     // valid <=> inside the clip; the clip is inside [0, 1e9], so d > 1e-9 completes depth_in_range
     const bool va = da > lo && da < hi, vb = db > lo && db < hi;
     const float2 d = make_float2(da, db);
@@ -265,8 +279,8 @@ __device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, un
     // valid pixels outside the validated ranges (tiny depths, extreme depth after the transform):
     // the scalar path (rare)
     if ((va && !sa) || (vb && !sb)) {
-      if (va && !sa) rp_pixel_generic<false>(da, (int)ra, (int)ca, m, H, W, zslot);
-      if (vb && !sb) rp_pixel_generic<false>(db, (int)rb, (int)cb, m, H, W, zslot);
+      if (va && !sa) rp_pixel_slow(da, (int)ra, (int)ca, m, H, W, zslot);
+      if (vb && !sb) rp_pixel_slow(db, (int)rb, (int)cb, m, H, W, zslot);
     }
     i += 2 * kRpThreads;
     ca = cb + step; ra = rb;
@@ -279,8 +293,18 @@ __device__ __forceinline__ void rp_finalize_item(unsigned* __restrict__ zslot, f
                                                  uint8_t* __restrict__ mout, int px0, int HW) {
   const int end = min(px0 + kRpItemPx, HW);
   if ((HW & 3) == 0) {
-    for (int i = px0 + (int)threadIdx.x * 4; i < end; i += kRpThreads * 4) {
-      uint4 v = __ldcg(reinterpret_cast<const uint4*>(zslot + i));
+    constexpr int kIt = kRpItemPx / (kRpThreads * 4);
+    uint4 vv[kIt];
+#pragma unroll
+    for (int q = 0; q < kIt; ++q) {                       // all loads of the item in flight together
+      const int i = px0 + ((int)threadIdx.x + q * kRpThreads) * 4;
+      if (i < end) vv[q] = __ldcg(reinterpret_cast<const uint4*>(zslot + i));
+    }
+#pragma unroll
+    for (int q = 0; q < kIt; ++q) {
+      const int i = px0 + ((int)threadIdx.x + q * kRpThreads) * 4;
+      if (i >= end) break;
+      uint4 v = vv[q];
       uchar4 mk;
       mk.x = v.x != kEmpty; mk.y = v.y != kEmpty; mk.z = v.z != kEmpty; mk.w = v.w != kEmpty;
       v.x = mk.x ? v.x : 0u; v.y = mk.y ? v.y : 0u; v.z = mk.z ? v.z : 0u; v.w = mk.w ? v.w : 0u;
@@ -429,6 +453,97 @@ k_pc2depth_splat(const float* __restrict__ pc, const uint8_t* __restrict__ valid
 }
 
 // ------------------------------------------------------------------ depth2pc (dense)
+// (q & ~sign) | (a & sign) in one LOP3: the sign the division gives a zero quotient (b > 0)
+__device__ __forceinline__ float sign_of(float q, float a) {
+#ifdef __CUDA_ARCH__
+  unsigned r;
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=r"(r) : "r"(__float_as_uint(q)), "r"(__float_as_uint(a)));
+  return __uint_as_float(r);
+#else
+  return __uint_as_float((__float_as_uint(q) & 0x7fffffffu) | (__float_as_uint(a) & 0x80000000u));
+#endif
+}
+
+// Vector path (W % 4 == 0, so the four pixels of a thread share a row and every access is 16-byte
+// aligned): the arithmetic of two pixels per instruction on the packed fp32x2 pipe, no row wraps.
+__global__ void __launch_bounds__(256)
+k_depth2pc_vec(const float* __restrict__ depth, const float* __restrict__ K, float lo, float hi,
+               int use_clip, float invalid, float* __restrict__ pc, uint8_t* __restrict__ valid,
+               int HW, int W) {
+  const int b = blockIdx.y;
+  const Intr k = load_intr(K, b);
+  const float* dimg = depth + (size_t)b * HW;
+  float* pimg = pc + (size_t)b * HW * 3;
+  uint8_t* vimg = valid + (size_t)b * HW;
+  __shared__ float4 sT[8][96];     // per-warp transpose: every store instruction writes 512 contiguous bytes
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_w = 1.f / (float)W;
+  const bool clip_bounds = use_clip && lo >= 0.f && hi <= 1e9f;
+  const float2 ncx = make_float2(-k.cx, -k.cx), nfx = make_float2(-k.fx, -k.fx), nfy = make_float2(-k.fy, -k.fy);
+  const float2 rfx = make_float2(k.rfx, k.rfx), rfy = make_float2(k.rfy, k.rfy);
+  for (int base4 = blockIdx.x * blockDim.x; base4 * 4 < HW; base4 += gridDim.x * blockDim.x) {
+    const int i = (base4 + (int)threadIdx.x) * 4;
+    const bool in = i < HW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) v = __ldcs(reinterpret_cast<const float4*>(dimg + i));
+    int r, c0;
+    row_col(in ? i : 0, W, inv_w, r, c0);
+    const float d[4] = {v.x, v.y, v.z, v.w};
+    bool ok[4];
+    float z[4];
+    bool safe = k.fast;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ok[j] = use_clip ? (d[j] > lo && d[j] < hi) : true;
+      z[j] = ok[j] ? d[j] : invalid;
+      safe = safe && (!ok[j] || (clip_bounds ? z[j] > 1e-9f : depth_in_range(z[j])));
+    }
+    float o[12];
+    if (safe) {
+      const float c0f = (float)c0;
+      const float ry = __fsub_rn((float)r, k.cy);
+      const float2 ry2 = make_float2(ry, ry);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 z2 = make_float2(z[2 * h], z[2 * h + 1]);
+        const float2 xn = __fmul2_rn(__fadd2_rn(make_float2(c0f + (float)(2 * h), c0f + (float)(2 * h + 1)), ncx), z2);
+        const float2 yn = __fmul2_rn(ry2, z2);
+        const float2 x = div_exact2(xn, nfx, rfx), y = div_exact2(yn, nfy, rfy);
+        o[(2 * h) * 3 + 0] = sign_of(x.x, xn.x); o[(2 * h) * 3 + 1] = sign_of(y.x, yn.x);
+        o[(2 * h + 1) * 3 + 0] = sign_of(x.y, xn.y); o[(2 * h + 1) * 3 + 1] = sign_of(y.y, yn.y);
+      }
+    } else {         // extreme depths or intrinsics somewhere in these four pixels: IEEE divisions
+#pragma unroll
+      for (int j = 0; j < 4; ++j) unproject_ieee(r, c0 + j, z[j], k, o[j * 3 + 0], o[j * 3 + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j * 3 + 0] = ok[j] ? o[j * 3 + 0] : invalid;
+      o[j * 3 + 1] = ok[j] ? o[j * 3 + 1] : invalid;
+      o[j * 3 + 2] = z[j];
+    }
+    const int w0 = (base4 + warp * 32) * 4;           // first pixel of this warp
+    if (w0 + 127 < HW) {                              // the whole warp inside the image: coalesced path
+      sT[warp][lane * 3 + 0] = make_float4(o[0], o[1], o[2], o[3]);
+      sT[warp][lane * 3 + 1] = make_float4(o[4], o[5], o[6], o[7]);
+      sT[warp][lane * 3 + 2] = make_float4(o[8], o[9], o[10], o[11]);
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(pimg + (size_t)w0 * 3);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) __stcs(dst + q * 32 + lane, sT[warp][q * 32 + lane]);
+      __syncwarp();
+      *reinterpret_cast<uchar4*>(vimg + i) = make_uchar4(ok[0], ok[1], ok[2], ok[3]);
+    } else if (in) {
+      float4* dst = reinterpret_cast<float4*>(pimg + (size_t)i * 3);
+      __stcs(dst + 0, make_float4(o[0], o[1], o[2], o[3]));
+      __stcs(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
+      __stcs(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
+      *reinterpret_cast<uchar4*>(vimg + i) = make_uchar4(ok[0], ok[1], ok[2], ok[3]);
+    }
+  }
+}
+
+// Generic path (any width; a thread's four pixels may span rows).
 __global__ void __launch_bounds__(256)
 k_depth2pc(const float* __restrict__ depth, const float* __restrict__ K, float lo, float hi,
            int use_clip, float invalid, float* __restrict__ pc, uint8_t* __restrict__ valid,
@@ -858,8 +973,12 @@ extern "C" __attribute__((visibility("default"))) int prg_depth2pc_f32(const flo
   if (B == 0) return PRG_OK;
   const int HW = H * W;
   dim3 g(grid_for(HW, 256, 4), B);
-  k_depth2pc<<<g, 256, 0, (cudaStream_t)stream>>>(depth, K, clip_lo, clip_hi, use_clip, invalid, pc,
-                                                 valid, HW, W);
+  if ((W & 3) == 0)
+    k_depth2pc_vec<<<g, 256, 0, (cudaStream_t)stream>>>(depth, K, clip_lo, clip_hi, use_clip, invalid, pc,
+                                                       valid, HW, W);
+  else
+    k_depth2pc<<<g, 256, 0, (cudaStream_t)stream>>>(depth, K, clip_lo, clip_hi, use_clip, invalid, pc,
+                                                   valid, HW, W);
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }

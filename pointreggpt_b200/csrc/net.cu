@@ -157,6 +157,8 @@ struct prg_net {
   SamplerCtx* ctx_dev = nullptr;
   std::map<int, cudaGraphExec_t> step_graphs;   // batch size -> instantiated graph of one step
   std::map<int, int> step_graph_launches;       // batch size -> kernel launches inside that graph
+  cudaStream_t cap_stream = nullptr;            // capture stream (the caller's may be the legacy default stream)
+  bool graph_failed = false;                    // capture / instantiation failed once: plain launches
 
   template <typename T>
   T* dalloc(size_t count) {
@@ -888,6 +890,7 @@ EXPORT void prg_net_destroy(prg_net* n) {
   if (n->ts_dev) cudaFree(n->ts_dev);
   if (n->steps_dev) cudaFree(n->steps_dev);
   for (auto& g : n->step_graphs) cudaGraphExecDestroy(g.second);
+  if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
   delete n;
 }
 
@@ -1003,7 +1006,7 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
   // One step = the same launch sequence whatever the step: conditioning row of step *step_idx, the
   // U-Net trunk on x_state, the tail (final 1x1 + DDNM + posterior / DDIM update, in place on
   // x_state), step_idx += 1.
-  auto issue_step = [&]() -> int {
+  auto issue_step = [&](cudaStream_t s) -> int {
     NET_TRY(cond_mlp_step(n->mlp_w, n->mlp_b, n->act_t_all, n->ss_p, n->ss, n->ss_rows, 8 * n->dim, B, s,
                           n->step_idx, 4 * n->dim));
     Run r{B, s, n->x_state, nullptr, 0, pcond, 1};
@@ -1029,30 +1032,42 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
     if (it != n->step_graphs.end()) exec = it->second;
   }
   for (int i = 0; i < nsteps; ++i) {
-    if (exec == nullptr && !no_graph && i == 1 && nsteps >= 4) {
+    if (exec == nullptr && !no_graph && !n->graph_failed && i == 1 && nsteps >= 4) {
       // first long call at this batch size: step 0 ran directly (every kernel is configured and
-      // loaded), now record the same launches once.  Nothing executes during the capture.
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(s, &cs);
-      if (cs == cudaStreamCaptureStatusNone) {
+      // loaded), now record the same launches once -- on a stream of our own, because the caller's
+      // may be the legacy default stream, which cannot be captured.  Nothing executes during the
+      // capture; the graph is then launched on the caller's stream.
+      if (n->cap_stream == nullptr &&
+          cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        n->graph_failed = true;
+      }
+      if (!n->graph_failed) {
         const int every = g_prof.every;
         g_prof.every = 0;              // no event records inside the capture
         const uint64_t fw = n->forwards, lc = g_launches.load();
         cudaGraph_t graph = nullptr;
-        PRG_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const int rc = issue_step();
-        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        int rc = PRG_OK;
+        cudaError_t ce = cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal);
+        if (ce == cudaSuccess) {
+          rc = issue_step(n->cap_stream);
+          ce = cudaStreamEndCapture(n->cap_stream, &graph);     // always ends the capture
+        }
         g_prof.every = every;
         n->forwards = fw;
-        const uint64_t recorded = g_launches.load() - lc;   // kernel launches of one step
+        const uint64_t recorded = g_launches.load() - lc;       // kernel launches of one step
         g_launches.fetch_sub(recorded);
-        if (rc != PRG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-        PRG_CUDA_OK(ce);
-        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        PRG_CUDA_OK(ie);
-        n->step_graphs[B] = exec;
-        n->step_graph_launches[B] = (int)recorded;
+        if (ce == cudaSuccess && rc == PRG_OK && graph != nullptr)
+          ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ce != cudaSuccess || rc != PRG_OK || exec == nullptr) {
+          cudaGetLastError();          // capture unavailable here: plain launches from now on
+          exec = nullptr;
+          n->graph_failed = true;
+        } else {
+          n->step_graphs[B] = exec;
+          n->step_graph_launches[B] = (int)recorded;
+        }
       }
     }
     const bool sampled = g_prof.every > 0 && (n->forwards % (uint64_t)g_prof.every) == 0;
@@ -1061,7 +1076,7 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
       n->forwards++;
       count_launch(n->step_graph_launches[B]);
     } else {
-      NET_TRY(issue_step());
+      NET_TRY(issue_step(s));
     }
   }
   PRG_CUDA_OK(cudaMemcpyAsync(out, n->x_state, npx * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -106,6 +106,28 @@ def random_sample_pose(batch_size, center=(0, 0, 3), rng=None):
     return T.astype(np.float32)
 
 
+def random_sample_transform(intrinsic, image_size=256):
+    """Pure random rotation that keeps the optical axis inside the old view (SDD:377-414): pitch / yaw
+    bounded by the field of view, free roll, zero translation.  Same numpy RNG call order as the
+    reference (rand, rand, rand, randn)."""
+    from scipy.spatial.transform import Rotation
+    batch_size = intrinsic.shape[0]
+    h, w = image_size, image_size
+    fx, fy = intrinsic[..., 0, 0], intrinsic[..., 1, 1]
+    cx, cy = intrinsic[..., 0, 2], intrinsic[..., 1, 2]
+    theta_min, theta_max = -np.arctan((h - cy) / fy), np.arctan(cy / fy)      # about the x axis
+    phi_min, phi_max = -np.arctan(cx / fx), np.arctan((w - cx) / fx)          # about the y axis
+    theta = np.random.rand(batch_size) * (theta_max - theta_min) + theta_min
+    phi = np.random.rand(batch_size) * (phi_max - phi_min) + phi_min
+    psi = np.random.rand(batch_size) * 2 * np.pi - np.pi
+    rot = Rotation.from_euler("XYZ", np.stack((theta, phi, psi), axis=-1), degrees=False).as_matrix()
+    trans = np.random.randn(batch_size, 3) / 3 * 0
+    T = np.stack([np.eye(4) for _ in range(batch_size)])
+    T[..., :3, :3] = rot
+    T[..., :3, 3] = trans
+    return T.astype(np.float32)
+
+
 def num_to_groups(num, divisor):
     """SDD:538-544."""
     arr = [divisor] * (num // divisor)

@@ -1,13 +1,12 @@
 """`Tester` under the reference's name (SDD:1829-2247), the parts on the generation path:
-`load`, `sample_uncondition` and `sample` -- successive conditional generation: an unconditional
-first view, then each next view conditioned on the previous one reprojected 0.5 m forward, with the
-occlusion filter (SDD:1961-2065).  FID / Inception scoring and the dataset-driven `generate` are not
-part of the hot path (SURVEY 8 f3 covers `sample`).
+`load`, `sample_uncondition`, `sample` -- successive conditional generation: an unconditional first
+view, then each next view conditioned on the previous one reprojected 0.5 m forward, with the
+occlusion filter (SDD:1961-2065) -- and `generate` -- scene fusion: every next view is conditioned on
+the z-buffer of the voxel-merged cloud of all previous views seen from a random rotation
+(SDD:2099-2247).  FID / Inception scoring is not part of the path.
 
 Differences forced by the offline environment: accelerate / ema_pytorch replaced as in
 `Generator`; PNGs are written with PIL (8-bit grey) instead of matplotlib; PLYs by `cloud.write_ply`.
-
-STAGED: uses `occlusion_filter`, whose kernel has not run on hardware yet (tests/test_zz_staged_gpu.py).
 """
 import math
 import os
@@ -133,6 +132,67 @@ class Tester(object):
                     self._save_view(b_idx * self.batch_size + s, sample_idx,
                                     images_last[s, 0].cpu().numpy(), images_rpj[s, 0].cpu().numpy(),
                                     image[0].cpu().numpy(), K[s], absolute_pose[s])
+            strips.append(torch.cat(views, dim=-1))
+        all_images = torch.cat(strips, dim=0)
+        _save_grey(str(self.samples_folder / 'overview.png'),
+                   torch.cat(list(all_images[:, 0]), dim=0).cpu().numpy())
+        return all_images
+
+
+    @torch.no_grad()
+    def generate(self, num_scenes, num_samples, voxel_size=0.005):
+        """SDD:2099-2247: scene fusion.  View 0 is unconditional; its cloud (clip 0.5-3.5 m, voxel
+        `voxel_size`) seeds the scene memory.  For every further view a random in-view rotation is
+        composed onto the camera pose, the scene memory is z-buffered into that camera
+        (`pc2depth_tensor`, pose applied in the kernel), the model samples with that condition, and the
+        new view's cloud -- moved back to the first camera, `(pc - t) @ R` -- is merged into the memory
+        by voxel down-sampling.  Per scene a 25 mm cloud `scene-{i}.ply` is written at the end.
+        Returns the (num_scenes, 1, S, num_samples * S) strip of all views."""
+        model = self.ema.ema_model
+        dev = self.device
+        S = self.image_size
+        strips = []
+        for b_idx, batch in enumerate(geometry.num_to_groups(num_scenes, self.batch_size)):
+            K = self._intrinsics(batch)
+            Kt = torch.tensor(K).to(dev)
+            param_cond = geometry.param_vector(Kt)
+            absolute_pose = np.stack([np.eye(4) for _ in range(batch)]).astype(np.float32)
+            images = model.sample(param_cond=param_cond, disable_tqdm=True)
+            views = [images]
+            zero = np.zeros((S, S), np.float32)
+            pc0, counts = geometry.point_cloud_batch(images, Kt, scale=10.0, clip=CLOUD_CLIP)
+            counts = counts.cpu().tolist()
+            memory = []
+            for s in range(batch):
+                _save_grey(str(self.samples_folder / f'scene-{b_idx * self.batch_size + s}-sample-0.png'),
+                           np.concatenate([zero, zero, images[s, 0].cpu().numpy()], axis=-1))
+                memory.append(cloud.voxel_down_sample(pc0[s, :counts[s]], voxel_size).to(torch.float32))
+            for sample_idx in range(1, num_samples):
+                relative_pose = geometry.random_sample_transform(K, image_size=S)          # SDD:2156-2158
+                absolute_pose = relative_pose @ absolute_pose
+                pose_t = torch.tensor(absolute_pose).to(dev)
+                offsets = torch.tensor(np.cumsum([0] + [m.shape[0] for m in memory]))
+                images_rpj, mask_rpj = geometry.pc2depth_ragged(torch.cat(memory), offsets, Kt,
+                                                                image_size=[S, S], pose=pose_t)
+                images_rpj = images_rpj * 0.1
+                img_cond = geometry.normalize_to_neg_one_to_one(
+                    torch.cat([images_rpj, mask_rpj.to(images_rpj.dtype)], dim=1))
+                images_last = images
+                images = model.sample(param_cond=param_cond, img_cond=img_cond, disable_tqdm=True)
+                views.append(images)
+                pc_new, counts = geometry.point_cloud_batch(images, Kt, pose=pose_t, scale=10.0,
+                                                            clip=CLOUD_CLIP)
+                counts = counts.cpu().tolist()
+                for s in range(batch):
+                    _save_grey(str(self.samples_folder /
+                                   f'scene-{b_idx * self.batch_size + s}-sample-{sample_idx}.png'),
+                               np.concatenate([images_last[s, 0].cpu().numpy(), images_rpj[s, 0].cpu().numpy(),
+                                               images[s, 0].cpu().numpy()], axis=-1))
+                    merged = torch.cat([memory[s].to(torch.float64), pc_new[s, :counts[s]]], dim=0)
+                    memory[s] = cloud.voxel_down_sample(merged, voxel_size).to(torch.float32)
+            for s in range(batch):
+                cloud.write_ply(str(self.samples_folder / f'scene-{b_idx * self.batch_size + s}.ply'),
+                                cloud.voxel_down_sample(memory[s], 0.025))
             strips.append(torch.cat(views, dim=-1))
         all_images = torch.cat(strips, dim=0)
         _save_grey(str(self.samples_folder / 'overview.png'),

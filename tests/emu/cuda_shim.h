@@ -15,6 +15,7 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(x)
 struct float4 { float x, y, z, w; };

@@ -97,7 +97,8 @@ extern "C" void emu_pc2depth(const float* pc, const uint8_t* valid, const int64_
 struct DArgs { const float *depth, *K; float lo, hi; int use_clip; float invalid; float* pc; uint8_t* valid; int HW, W; };
 static void call_d2pc(void* p) {
   DArgs& a = *(DArgs*)p;
-  k_depth2pc(a.depth, a.K, a.lo, a.hi, a.use_clip, a.invalid, a.pc, a.valid, a.HW, a.W);
+  if ((a.W & 3) == 0) k_depth2pc_vec(a.depth, a.K, a.lo, a.hi, a.use_clip, a.invalid, a.pc, a.valid, a.HW, a.W);   // as prg_depth2pc_f32
+  else k_depth2pc(a.depth, a.K, a.lo, a.hi, a.use_clip, a.invalid, a.pc, a.valid, a.HW, a.W);
 }
 extern "C" void emu_depth2pc(const float* depth, const float* K, float lo, float hi, int use_clip, float invalid,
                              float* pc, uint8_t* valid, int B, int H, int W, int gx) {

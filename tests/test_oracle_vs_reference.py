@@ -285,3 +285,25 @@ def test_network_oracle_other_architectures_bit_exact(ref, dim, mults, size, bat
     with torch.no_grad():
         assert torch.equal(net(x, t, pc), R.unet_forward({k: v.detach() for k, v in net.state_dict().items()}, x, t, pc))
         assert torch.equal(m(d), R.maskunet_forward({k: v.detach() for k, v in m.state_dict().items()}, d))
+
+
+def test_host_samplers_match_the_reference_rng_stream(ref):
+    """random_sample_pose / random_sample_intrinsic / random_sample_transform / intrinsic_transform of
+    the product package against the reference's functions under the same numpy seed (same draws in
+    the same order -> identical matrices)."""
+    sdd, _ = ref
+    from pointreggpt_b200 import geometry as pg
+    for seed in (0, 5, 99):
+        np.random.seed(seed)
+        Kr = sdd.random_sample_intrinsic(7)
+        Pr = sdd.random_sample_pose(7)
+        Ktr = sdd.intrinsic_transform(Kr, resize=256, centercrop=256).astype(np.float32)
+        Tr = sdd.random_sample_transform(Ktr, image_size=256)
+        np.random.seed(seed)
+        Ko = pg.random_sample_intrinsic(7)
+        Po = pg.random_sample_pose(7)
+        Kto = pg.intrinsic_transform(Ko, resize=256, centercrop=256).astype(np.float32)
+        To = pg.random_sample_transform(Kto, image_size=256)
+        assert np.array_equal(Kr, Ko) and np.array_equal(Pr, Po) and np.array_equal(Ktr, Kto)
+        assert np.array_equal(Tr, To) and To.dtype == np.float32
+        assert np.all(To[:, :3, 3] == 0)

@@ -275,3 +275,29 @@ def test_reproject_tiny_and_narrow_maps(shape):
     a, b = gpc.cpu().numpy(), opc
     assert np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))
     assert np.array_equal(gv.cpu().numpy(), ov)
+
+
+def test_tester_generate_scene_fusion(tmp_path):
+    """Tester.generate (SDD:2099-2247): every further view is conditioned on the z-buffer of the
+    voxel-merged cloud of the previous views under a random in-view rotation; files as the reference
+    names them; the fused 25 mm cloud of a scene stays inside the 0.5-3.5 m clip it was built from."""
+    from pointreggpt_b200 import nets
+    from pointreggpt_b200.diffusion import GaussianDiffusion
+    from pointreggpt_b200.tester import Tester
+    torch.manual_seed(0)
+    np.random.seed(0)
+    unet = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1)
+    diff = GaussianDiffusion(unet, image_size=128, timesteps=8, sampling_timesteps=2, objective="pred_x0",
+                             beta_schedule="sigmoid", ddim_sampling_eta=1.0)
+    t = Tester(diff, batch_size=2, results_folder=str(tmp_path / "res"), samples_folder=str(tmp_path / "out"))
+    strip = t.generate(num_scenes=3, num_samples=3)
+    assert strip.shape == (3, 1, 128, 3 * 128) and torch.isfinite(strip).all()
+    assert strip.min() >= 0 and strip.max() <= 1
+    for scene in range(3):
+        for k in range(3):
+            assert (tmp_path / "out" / ("scene-%d-sample-%d.png" % (scene, k))).is_file()
+        pts = cloud.read_ply(str(tmp_path / "out" / ("scene-%d.ply" % scene)))
+        assert pts.shape[1] == 3 and np.isfinite(pts).all()
+        if pts.shape[0]:
+            assert np.linalg.norm(pts, axis=1).max() < 3.5 * 2.0     # clip 3.5 m depth, 128-px field of view
+    assert (tmp_path / "out" / "overview.png").is_file()
