@@ -954,10 +954,14 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
   // the param_cond half of every block MLP once (SDD:925, 932, 709-713 are separable per half)
   {
     if (nsteps > n->act_t_cap) {
+      // the recorded step graphs hold these pointers: drop them with the buffers
+      PRG_CUDA_OK(cudaStreamSynchronize(s));
+      for (auto& g : n->step_graphs) cudaGraphExecDestroy(g.second);
+      n->step_graphs.clear();
       if (n->act_t_all) { cudaFree(n->act_t_all); cudaFree(n->ts_dev); }
       n->act_t_all = nullptr;
       n->ts_dev = nullptr;
-      const int cap = nsteps + 16;
+      const int cap = std::max(nsteps, 1024) + 16;
       if (cudaMalloc(&n->act_t_all, (size_t)cap * 4 * n->dim * sizeof(float)) != cudaSuccess ||
           cudaMalloc(&n->ts_dev, (size_t)cap * sizeof(int)) != cudaSuccess) {
         set_error("out of device memory for the per-step time embeddings");
@@ -975,13 +979,17 @@ EXPORT int prg_sampler_run(prg_net* n, const prg_step* steps, int nsteps, const 
   // the step list, the step counter and this call's pointers go to the device
   {
     if (nsteps > n->steps_cap) {
+      PRG_CUDA_OK(cudaStreamSynchronize(s));
+      for (auto& g : n->step_graphs) cudaGraphExecDestroy(g.second);
+      n->step_graphs.clear();
       if (n->steps_dev) cudaFree(n->steps_dev);
       n->steps_dev = nullptr;
-      if (cudaMalloc(&n->steps_dev, (size_t)(nsteps + 16) * sizeof(StepDev)) != cudaSuccess) {
+      const int cap = std::max(nsteps, 1024) + 16;
+      if (cudaMalloc(&n->steps_dev, (size_t)cap * sizeof(StepDev)) != cudaSuccess) {
         set_error("out of device memory for the step list");
         return PRG_ERR_CUDA;
       }
-      n->steps_cap = nsteps + 16;
+      n->steps_cap = cap;
     }
     std::vector<StepDev> sd(nsteps);
     int slab = 1;

@@ -8,7 +8,7 @@ import torch
 from pointreggpt_b200 import geometry, synthetic
 
 dev = torch.device("cuda", 0)
-B, H, W = 256, 480, 640
+B, H, W = 128, 480, 640
 d = (synthetic.synthetic_depth_batch(0, 8, H, W) * 10).repeat(B // 8, 1, 1, 1).contiguous().to(dev)
 K = torch.tensor(synthetic.synthetic_intrinsics(B, None)).to(dev)
 P = torch.tensor(synthetic.synthetic_poses(B)).to(dev)
