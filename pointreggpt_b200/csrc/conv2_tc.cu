@@ -44,7 +44,7 @@ constexpr int kHaloPix = kBlockM + 2;              // 130 pixels per ring row
 constexpr int kHaloBytes = kHaloPix * 128;         // 16640 B written by TMA
 constexpr int kHaloSlot = 17 * 1024;               // slot pitch (1024-aligned)
 constexpr int kThreads = 320;                     // TMA warp + MMA warp + 8 epilogue warps
-constexpr int kXfThreads = 128;                   // XF: + 4 transform warps (GroupNorm apply on the ring slot)
+constexpr int kXfThreads = 192;                   // XF: + 6 transform warps (GroupNorm apply on the ring slot): 512 threads, 128 registers each
 constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 227 * 1024;
@@ -487,9 +487,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     }
   } else if (XF && warp >= kThreads / 32) {
     // =============================== input transform (XF) ========================
-    const int xt = (int)threadIdx.x - kThreads;      // 0..127
+    const int xt = (int)threadIdx.x - kThreads;      // 0..kXfThreads - 1
     const int grp = xt & 7;                          // logical 16-byte chunk = channels 8 grp .. 8 grp + 7
-    const int p0 = xt >> 3;                          // first pixel of the slot this thread touches (then + 16)
+    const int p0 = xt >> 3;                          // first pixel of the slot this thread touches (then + kXfThreads / 8)
     int stage = 0;
     uint32_t phase = 0;
     for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
@@ -510,7 +510,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       // columns of the slot that lie inside the image: pixel pp <-> x = x0 - 1 + pp
       const int pp_lo = (x0 == 0) ? 1 : 0;
       const int pp_hi = min(kHaloPix, p.Wo - x0 + 1);   // exclusive
-      constexpr int kCells = (kHaloPix + kXfThreads / 8 - 1) / (kXfThreads / 8);   // 9 cells per thread and row
+      constexpr int kCells = (kHaloPix + kXfThreads / 8 - 1) / (kXfThreads / 8);   // 6 cells per thread and row
       const bool exact = (P.dbg_flags & 128) != 0;     // A/B switch: ex2 + rcp SiLU as in k_gn_apply
       for (int r = 0; r < nr + 2; ++r) {
         mbar_wait(&ctl->full[stage], phase);
@@ -527,22 +527,43 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             if (pp >= pp_lo && pp < pp_hi)
               v[q] = *reinterpret_cast<const uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4));
           }
+          if (exact) {
 #pragma unroll
-          for (int q = 0; q < kCells; ++q) {
-            __half2* h = reinterpret_cast<__half2*>(&v[q]);
+            for (int q = 0; q < kCells; ++q) {
+              __half2* h = reinterpret_cast<__half2*>(&v[q]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 hv = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
-              float2 yv;
-              if (exact) {
-                yv = xf_silu2(__fadd2_rn(hv, hv));
-              } else {
-                float tx, ty;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(hv.x));
-                asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(hv.y));
-                yv = __ffma2_rn(hv, make_float2(tx, ty), hv);
+              for (int e = 0; e < 4; ++e) {
+                const float2 hv = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
+                const float2 yv = xf_silu2(__fadd2_rn(hv, hv));
+                h[e] = __floats2half2_rn(yv.x, yv.y);
               }
-              h[e] = __floats2half2_rn(yv.x, yv.y);
+            }
+          } else {
+            // all cells of the row in three stages, so that the MUFU results are consumed long after
+            // they were issued (two warps per scheduler: little else hides the MUFU latency)
+            float2 hv[kCells][4];
+            float tx[kCells][4], ty[kCells][4];
+#pragma unroll
+            for (int u = 0; u < kCells; ++u) {
+              const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hv[u][e] = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
+            }
+#pragma unroll
+            for (int u = 0; u < kCells; ++u)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                asm volatile("tanh.approx.f32 %0, %1;" : "=f"(tx[u][e]) : "f"(hv[u][e].x));
+                asm volatile("tanh.approx.f32 %0, %1;" : "=f"(ty[u][e]) : "f"(hv[u][e].y));
+              }
+#pragma unroll
+            for (int u = 0; u < kCells; ++u) {
+              __half2* h = reinterpret_cast<__half2*>(&v[u]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 yv = __ffma2_rn(hv[u][e], make_float2(tx[u][e], ty[u][e]), hv[u][e]);
+                h[e] = __floats2half2_rn(yv.x, yv.y);
+              }
             }
           }
 #pragma unroll

@@ -150,7 +150,8 @@ __device__ __forceinline__ void splat(float x, float y, float z, const Intr& k, 
 //     lane to nearest like the scalar instructions: bit-identical), rounding + bounds test is one
 //     F2I.RN (round-half-even, saturating) and one unsigned compare per coordinate.
 constexpr int kRpThreads = 256;
-constexpr int kRpItemPx = 4096;
+constexpr int kRpItemPx = 16384;     // pixels per work item
+constexpr int kRpSubPx = 4096;       // an item is walked in sub-blocks of 16 pixels per thread
 constexpr float kPoseMax = 1e4f;
 
 struct RpMap {
@@ -236,7 +237,9 @@ __device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, un
   // all sixteen loads of the item first: 64 bytes in flight per thread (the kernel is otherwise bound
   // by the latency of its own reads -- 1024 threads per SM with one or two loads each cover only
   // a third of the bandwidth-delay product)
-  constexpr int kPer = kRpItemPx / kRpThreads;
+  constexpr int kPer = kRpSubPx / kRpThreads;
+#pragma unroll 1
+  for (int sub = 0; sub < kRpItemPx / kRpSubPx && i < HW; ++sub) {
   float dv[kPer];
 #pragma unroll
   for (int q = 0; q < kPer; ++q) {
@@ -286,6 +289,7 @@ __device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, un
     ca = cb + step; ra = rb;
     while (ca >= Wf) { ca -= Wf; ra += 1.f; }
   }
+  }
 }
 
 // Finalise item: pixels [px0, px0 + kRpItemPx) of one map: depth (0 where empty) and mask out, slot reset.
@@ -293,16 +297,17 @@ __device__ __forceinline__ void rp_finalize_item(unsigned* __restrict__ zslot, f
                                                  uint8_t* __restrict__ mout, int px0, int HW) {
   const int end = min(px0 + kRpItemPx, HW);
   if ((HW & 3) == 0) {
-    constexpr int kIt = kRpItemPx / (kRpThreads * 4);
+    constexpr int kIt = kRpSubPx / (kRpThreads * 4);
+    for (int sub0 = px0; sub0 < end; sub0 += kRpSubPx) {
     uint4 vv[kIt];
 #pragma unroll
-    for (int q = 0; q < kIt; ++q) {                       // all loads of the item in flight together
-      const int i = px0 + ((int)threadIdx.x + q * kRpThreads) * 4;
+    for (int q = 0; q < kIt; ++q) {                       // the sub-block's loads in flight together
+      const int i = sub0 + ((int)threadIdx.x + q * kRpThreads) * 4;
       if (i < end) vv[q] = __ldcg(reinterpret_cast<const uint4*>(zslot + i));
     }
 #pragma unroll
     for (int q = 0; q < kIt; ++q) {
-      const int i = px0 + ((int)threadIdx.x + q * kRpThreads) * 4;
+      const int i = sub0 + ((int)threadIdx.x + q * kRpThreads) * 4;
       if (i >= end) break;
       uint4 v = vv[q];
       uchar4 mk;
@@ -311,6 +316,7 @@ __device__ __forceinline__ void rp_finalize_item(unsigned* __restrict__ zslot, f
       __stcs(reinterpret_cast<uint4*>(dout + i), v);
       *reinterpret_cast<uchar4*>(mout + i) = mk;
       *reinterpret_cast<uint4*>(zslot + i) = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+    }
     }
   } else {
     for (int i = px0 + (int)threadIdx.x; i < end; i += kRpThreads) {
@@ -329,25 +335,27 @@ struct RpPlan {
   long long total;  // work items of the call
 };
 
-// Item counters: release / acquire at device scope.  (The host emulation of the tests runs the items
-// one after another, where every dependency is already satisfied.)
+// Item counters, release / acquire at device scope, counted in WARPS: the warps of a CTA walk the same
+// items but never meet -- no CTA barrier anywhere (a profile of the first version, which closed every
+// item with __syncthreads + fence + atomic by thread 0, showed the warps stalled on those barriers for
+// five of every six issue slots).  Every thread polls for itself (one broadcast load per warp).
+// (The host emulation of the tests runs the items one after another, where every dependency is
+// already satisfied.)
+constexpr int kRpWarps = kRpThreads / 32;
 __device__ __forceinline__ void rp_wait(const int* cnt, int need) {
 #ifdef __CUDA_ARCH__
-  if (threadIdx.x == 0) {
-    while (true) {
-      int v;
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-      if (v >= need) break;
-      __nanosleep(64);
-    }
+  while (true) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+    if (v >= need) break;
+    __nanosleep(64);
   }
-  __syncthreads();
 #endif
 }
 __device__ __forceinline__ void rp_signal(int* cnt) {
 #ifdef __CUDA_ARCH__
-  __syncthreads();                 // the item's REDs / stores of every thread ...
-  if (threadIdx.x == 0) {
+  __syncwarp();                    // the warp's REDs / stores of this item ...
+  if ((threadIdx.x & 31) == 0) {
     __threadfence();               // ... are ordered before the counter (cumulative fence)
     atomicAdd(cnt, 1);
   }
@@ -384,19 +392,19 @@ __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict
   asm volatile("" : "+l"(zslot));   // keep the slot base in one register pair (index arithmetic stays 32-bit)
 #endif
   if (!fin) {
-    if (map >= pl.R) rp_wait(cnt_fin + (map - pl.R), (int)I);      // the slot's previous map is out
+    if (map >= pl.R) rp_wait(cnt_fin + (map - pl.R), (int)I * kRpWarps);   // the slot's previous map is out
     const RpMap m = rp_load_map(K, pose, map, lo, hi);
     rp_splat_item<kScalarBmm>(depth + (size_t)map * pl.HW, zslot, j * kRpItemPx, pl.HW, pl.H, pl.W, lo, hi, m);
     rp_signal(cnt_splat + map);
   } else {
-    rp_wait(cnt_splat + map, (int)I);                               // every pixel of the map has been splatted
+    rp_wait(cnt_splat + map, (int)I * kRpWarps);                    // every pixel of the map has been splatted
     rp_finalize_item(zslot, depth_out + (size_t)map * pl.HW, mask_out + (size_t)map * pl.HW, j * kRpItemPx, pl.HW);
     rp_signal(cnt_fin + map);
   }
 }
 
 template <bool kScalarBmm>
-__global__ void __launch_bounds__(kRpThreads)
+__global__ void __launch_bounds__(kRpThreads, 3)
 k_reproject_fused(const float* __restrict__ depth, const float* __restrict__ K, const float* __restrict__ pose,
                   float lo, float hi, unsigned* __restrict__ scratch, float* __restrict__ depth_out,
                   uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat, int* __restrict__ cnt_fin,
