@@ -141,6 +141,14 @@ __device__ __forceinline__ float2 xf_silu2(float2 t) {
   return __fmul2_rn(t, make_float2(xf_rcp(d.x), xf_rcp(d.y)));
 }
 
+// SiLU(t) = h + h tanh(h), h = t / 2: one MUFU operation per element instead of two (ex2 + rcp)
+__device__ __forceinline__ float silu_tanh(float t) {
+  const float h = 0.5f * t;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+
 template <int BN, int EPI, int CG = 1, int XF = 0>
 __global__ void __launch_bounds__(kThreads + XF * kXfThreads, 1)
 k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -189,7 +197,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     }
     mbar_init(&ctl->wfull, 1);
     if (XF)
-      for (int s = 0; s < P.stages; ++s) mbar_init(&ctl->xfull[s], kXfThreads);
+      for (int s = 0; s < P.stages; ++s) mbar_init(&ctl->xfull[s], 32);   // the one warp that transforms the row
     for (int a = 0; a < 8; ++a) {
       mbar_init(&ctl->tmem_full[a], 1);
       mbar_init(&ctl->tmem_empty[a], (BN == 64 ? kEpiThreads / 2 : kEpiThreads) * CG);
@@ -487,15 +495,22 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     }
   } else if (XF && warp >= kThreads / 32) {
     // =============================== input transform (XF) ========================
-    const int xt = (int)threadIdx.x - kThreads;      // 0..kXfThreads - 1
-    const int grp = xt & 7;                          // logical 16-byte chunk = channels 8 grp .. 8 grp + 7
-    const int p0 = xt >> 3;                          // first pixel of the slot this thread touches (then + kXfThreads / 8)
-    int stage = 0;
-    uint32_t phase = 0;
+    // Row-parallel: transform warp w owns the ring rows g = w, w + 6, w + 12, ... (g counts the rows the
+    // producer loads, in order) and transforms each of them alone, so six rows are in flight at
+    // once and the latency chain of a row (barrier wait -> LDS -> FMA -> MUFU -> FMA -> STS -> proxy
+    // fence -> arrive) overlaps with five others instead of being paid once per row by everybody.
+    constexpr int kXfWarps = kXfThreads / 32;
+    const int xw = warp - kThreads / 32;             // 0..5
+    const int grp = lane & 7;                        // logical 16-byte chunk = channels 8 grp .. 8 grp + 7
+    const int pq = lane >> 3;                        // pixel of the slot this lane touches first (then + 4)
+    constexpr int kCells = (kHaloPix + 3) / 4;       // 33 cells per lane and row
+    constexpr int kBatch = 6;                        // cells in flight per lane
+    const bool exact = (P.dbg_flags & 128) != 0;     // A/B switch: ex2 + rcp SiLU as in k_gn_apply
+    long long g = 0;                                 // ring row counter (all rows of all segments of this CTA)
     for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
       int img, x0, y0, nr;
       decode_seg(seg, img, x0, y0, nr);
-      // (A, B) of this thread's eight channels for this image (k_gn_coef wrote them; L2 hits), halved:
+      // (A, B) of this lane's eight channels for this image (k_gn_coef wrote them; L2 hits), halved:
       // SiLU(t) = h + h tanh(h) with h = t / 2 = x (A / 2) + B / 2  (scaling by 1/2 is exact)
       float2 cA[4], cB[4];
       {
@@ -510,72 +525,71 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       // columns of the slot that lie inside the image: pixel pp <-> x = x0 - 1 + pp
       const int pp_lo = (x0 == 0) ? 1 : 0;
       const int pp_hi = min(kHaloPix, p.Wo - x0 + 1);   // exclusive
-      constexpr int kCells = (kHaloPix + kXfThreads / 8 - 1) / (kXfThreads / 8);   // 6 cells per thread and row
-      const bool exact = (P.dbg_flags & 128) != 0;     // A/B switch: ex2 + rcp SiLU as in k_gn_apply
-      for (int r = 0; r < nr + 2; ++r) {
+      for (int r = 0; r < nr + 2; ++r, ++g) {
+        if ((int)(g % kXfWarps) != xw) continue;
+        const int stage = (int)(g % P.stages);
+        const uint32_t phase = (uint32_t)((g / P.stages) & 1);
         mbar_wait(&ctl->full[stage], phase);
         const int y = y0 - 1 + r;
         if (y >= 0 && y < p.Ho) {
           uint8_t* slot = sA + (size_t)stage * P.a_slot;
-          // the whole row's cells of this thread in flight together: one warp per scheduler does this
-          // work, so the latency of the LDS -> FMA -> MUFU -> FMA -> STS chain is covered by
-          // instruction-level parallelism only
-          uint4 v[kCells];
+#pragma unroll 1
+          for (int c0 = 0; c0 < kCells; c0 += kBatch) {
+            uint4 v[kBatch];
+            bool on[kBatch];
 #pragma unroll
-          for (int q = 0; q < kCells; ++q) {
-            const int pp = p0 + q * (kXfThreads / 8);
-            if (pp >= pp_lo && pp < pp_hi)
-              v[q] = *reinterpret_cast<const uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4));
-          }
-          if (exact) {
+            for (int u = 0; u < kBatch; ++u) {
+              const int pp = pq + 4 * (c0 + u);
+              on[u] = (c0 + u < kCells) && pp >= pp_lo && pp < pp_hi;
+              if (on[u]) v[u] = *reinterpret_cast<const uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4));
+            }
+            if (exact) {
 #pragma unroll
-            for (int q = 0; q < kCells; ++q) {
-              __half2* h = reinterpret_cast<__half2*>(&v[q]);
+              for (int u = 0; u < kBatch; ++u) {
+                __half2* h = reinterpret_cast<__half2*>(&v[u]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 hv = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
-                const float2 yv = xf_silu2(__fadd2_rn(hv, hv));
-                h[e] = __floats2half2_rn(yv.x, yv.y);
+                for (int e = 0; e < 4; ++e) {
+                  const float2 hv = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
+                  const float2 yv = xf_silu2(__fadd2_rn(hv, hv));
+                  h[e] = __floats2half2_rn(yv.x, yv.y);
+                }
               }
-            }
-          } else {
-            // all cells of the row in three stages, so that the MUFU results are consumed long after
-            // they were issued (two warps per scheduler: little else hides the MUFU latency)
-            float2 hv[kCells][4];
-            float tx[kCells][4], ty[kCells][4];
+            } else {
+              // three stages over the batch, so that the MUFU results are consumed long after issue
+              float2 hv[kBatch][4];
+              float tx[kBatch][4], ty[kBatch][4];
 #pragma unroll
-            for (int u = 0; u < kCells; ++u) {
-              const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+              for (int u = 0; u < kBatch; ++u) {
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) hv[u][e] = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
-            }
-#pragma unroll
-            for (int u = 0; u < kCells; ++u)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                asm volatile("tanh.approx.f32 %0, %1;" : "=f"(tx[u][e]) : "f"(hv[u][e].x));
-                asm volatile("tanh.approx.f32 %0, %1;" : "=f"(ty[u][e]) : "f"(hv[u][e].y));
+                for (int e = 0; e < 4; ++e) hv[u][e] = __ffma2_rn(__half22float2(h[e]), cA[e], cB[e]);
               }
 #pragma unroll
-            for (int u = 0; u < kCells; ++u) {
-              __half2* h = reinterpret_cast<__half2*>(&v[u]);
+              for (int u = 0; u < kBatch; ++u)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 yv = __ffma2_rn(hv[u][e], make_float2(tx[u][e], ty[u][e]), hv[u][e]);
-                h[e] = __floats2half2_rn(yv.x, yv.y);
+                for (int e = 0; e < 4; ++e) {
+                  asm volatile("tanh.approx.f32 %0, %1;" : "=f"(tx[u][e]) : "f"(hv[u][e].x));
+                  asm volatile("tanh.approx.f32 %0, %1;" : "=f"(ty[u][e]) : "f"(hv[u][e].y));
+                }
+#pragma unroll
+              for (int u = 0; u < kBatch; ++u) {
+                __half2* h = reinterpret_cast<__half2*>(&v[u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 yv = __ffma2_rn(hv[u][e], make_float2(tx[u][e], ty[u][e]), hv[u][e]);
+                  h[e] = __floats2half2_rn(yv.x, yv.y);
+                }
               }
             }
-          }
 #pragma unroll
-          for (int q = 0; q < kCells; ++q) {
-            const int pp = p0 + q * (kXfThreads / 8);
-            if (pp >= pp_lo && pp < pp_hi)
-              *reinterpret_cast<uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4)) = v[q];
+            for (int u = 0; u < kBatch; ++u) {
+              const int pp = pq + 4 * (c0 + u);
+              if (on[u]) *reinterpret_cast<uint4*>(slot + pp * 128 + ((grp ^ (pp & 7)) << 4)) = v[u];
+            }
           }
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to tcgen05.mma
         mbar_arrive(&ctl->xfull[stage]);
-        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -765,8 +779,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               const float4 ab = __ldg(cf + q * 4 + j);
               const float2 r2 = __half22float2(h[j]);
               const float t0 = fmaf(r2.x, ab.x, ab.y), t1 = fmaf(r2.y, ab.z, ab.w);
-              f[q * 8 + j * 2 + 0] += __fdividef(t0, 1.f + __expf(-t0));
-              f[q * 8 + j * 2 + 1] += __fdividef(t1, 1.f + __expf(-t1));
+              f[q * 8 + j * 2 + 0] += silu_tanh(t0);
+              f[q * 8 + j * 2 + 1] += silu_tanh(t1);
             }
           }
         }
@@ -982,8 +996,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             const float4 ab = __ldg(cf + q * 4 + j);        // (A, B) of two consecutive channels
             const float2 r2 = __half22float2(h[j]);
             const float t0 = fmaf(r2.x, ab.x, ab.y), t1 = fmaf(r2.y, ab.z, ab.w);
-            f[q * 8 + j * 2 + 0] += __fdividef(t0, 1.f + __expf(-t0));
-            f[q * 8 + j * 2 + 1] += __fdividef(t1, 1.f + __expf(-t1));
+            f[q * 8 + j * 2 + 0] += silu_tanh(t0);
+            f[q * 8 + j * 2 + 1] += silu_tanh(t1);
           }
         }
         if (p.has_ln_out) {

@@ -150,7 +150,8 @@ __device__ __forceinline__ void splat(float x, float y, float z, const Intr& k, 
 //     lane to nearest like the scalar instructions: bit-identical), rounding + bounds test is one
 //     F2I.RN (round-half-even, saturating) and one unsigned compare per coordinate.
 constexpr int kRpThreads = 256;
-constexpr int kRpItemPx = 16384;     // pixels per work item
+constexpr int kRpItemPx = 4096;      // pixels per work item: the resident CTAs together hold grid x 4096 pixels in
+                                     // flight, which must stay well below the D maps that separate dependent items
 constexpr int kRpSubPx = 4096;       // an item is walked in sub-blocks of 16 pixels per thread
 constexpr float kPoseMax = 1e4f;
 
@@ -896,11 +897,11 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
   RpPlan pl;
   pl.B = B; pl.H = H; pl.W = W; pl.HW = H * W;
   pl.items = (pl.HW + kRpItemPx - 1) / kRpItemPx;
-  // ring: as many maps as fit 24 MB (L2-resident next to the streaming traffic), at least 2, at most 64
+  // ring: as many maps as fit 24 MB (L2-resident next to the streaming traffic), at least 2, at most 96
   {
     const size_t per_map = (size_t)pl.HW * sizeof(unsigned);
     long long r = (long long)((24u << 20) / per_map);
-    r = std::max(2ll, std::min(64ll, r));
+    r = std::max(2ll, std::min(96ll, r));
     pl.R = (int)std::min<long long>(r, std::max(2, B));
     pl.D = std::max(1, std::min(pl.R / 2, B));
     if (pl.D >= pl.R) pl.D = pl.R - 1;

@@ -408,8 +408,11 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
   // 192 vs 67 + 80 us at 128x128: the SiLU turns the conv epilogue (8 warps per SM) into the
   // MUFU / issue bound part, while k_gn_apply hides the same work behind 32 resident warps.
   // Opt-in (PRG_GNRES=1) until the epilogue has more warps to spread it over.
+  // PRG_GNRES: unset = off; "1" = every eligible block; "256" = blocks at >= 256-pixel rows only
+  const char* gnres_env = getenv("PRG_GNRES");
+  const int gnres_min_w = gnres_env == nullptr ? (1 << 30) : (atoi(gnres_env) > 1 ? atoi(gnres_env) : 0);
   const bool fuse_res = !last && n->has(pfx + ".res_conv.weight") && cout <= 512 &&
-                        (fuse_ln_g == nullptr || cout == 64) && getenv("PRG_GNRES") != nullptr;
+                        (fuse_ln_g == nullptr || cout == 64) && W >= gnres_min_w;
   if (fuse_res) {
     NET_PTR(wr, n->f16(pfx + ".res_conv.weight"));
     NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
