@@ -336,34 +336,38 @@ struct RpPlan {
   long long total;  // work items of the call
 };
 
-// Item counters, release / acquire at device scope, counted in WARPS: the warps of a CTA walk the same
-// items but never meet -- no CTA barrier anywhere (a profile of the first version, which closed every
-// item with __syncthreads + fence + atomic by thread 0, showed the warps stalled on those barriers for
-// five of every six issue slots).  Every thread polls for itself (one broadcast load per warp).
+// Item counters: release / acquire at device scope, one signal per CTA and item.
 // (The host emulation of the tests runs the items one after another, where every dependency is
 // already satisfied.)
-constexpr int kRpWarps = kRpThreads / 32;
 __device__ __forceinline__ void rp_wait(const int* cnt, int need) {
 #ifdef __CUDA_ARCH__
-  while (true) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-    if (v >= need) break;
-    __nanosleep(64);
+  if (threadIdx.x == 0) {
+    while (true) {
+      int v;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+      if (v >= need) break;
+      __nanosleep(32);
+    }
   }
+  __syncthreads();
 #endif
 }
 __device__ __forceinline__ void rp_signal(int* cnt) {
 #ifdef __CUDA_ARCH__
-  __syncwarp();                    // the warp's REDs / stores of this item ...
-  if ((threadIdx.x & 31) == 0) {
+  __syncthreads();                 // the item's REDs / stores of every thread ...
+  if (threadIdx.x == 0) {
     __threadfence();               // ... are ordered before the counter (cumulative fence)
     atomicAdd(cnt, 1);
   }
 #endif
 }
 
-// Work item p of the call (see the order described above).
+// Work item p of the call.  Order: round k = [splat item 0 of map k, finalise item 0 of map k - D,
+// splat item 1 of map k, finalise item 1 of map k - D, ...] -- the two kinds ALTERNATE, and the grid
+// size is odd, so every CTA (which takes items p, p + grid, p + 2 grid, ...) alternates between a
+// splat and a finalise item and all CTAs advance at the same pace.  (With the kinds in blocks a CTA
+// did a dozen expensive splat items in a row, then a dozen cheap finalise items; CTAs drifted tens of
+// rounds apart and spent their time polling for maps the laggards had not finished.)
 template <bool kScalarBmm>
 __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict__ depth, const float* __restrict__ K,
                                             const float* __restrict__ pose, float lo, float hi,
@@ -374,16 +378,16 @@ __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict
   const long long head = (long long)pl.D * I, mid = (long long)(pl.B - pl.D) * 2 * I;
   int map, j;
   bool fin;
-  if (p < head) {
+  if (p < head) {                       // first D rounds: nothing to finalise yet
     map = (int)(p / I); j = (int)(p - map * I); fin = false;
   } else if (p < head + mid) {
     const long long q = p - head;
     const int k = (int)(q / (2 * I));
     const int w = (int)(q - (long long)k * 2 * I);
-    fin = w >= I;
+    fin = (w & 1) != 0;
+    j = w >> 1;
     map = fin ? k : pl.D + k;
-    j = fin ? w - (int)I : w;
-  } else {
+  } else {                              // last D rounds: nothing left to splat
     const long long q = p - head - mid;
     const int k = (int)(q / I);
     map = pl.B - pl.D + k; j = (int)(q - k * I); fin = true;
@@ -393,12 +397,12 @@ __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict
   asm volatile("" : "+l"(zslot));   // keep the slot base in one register pair (index arithmetic stays 32-bit)
 #endif
   if (!fin) {
-    if (map >= pl.R) rp_wait(cnt_fin + (map - pl.R), (int)I * kRpWarps);   // the slot's previous map is out
+    if (map >= pl.R) rp_wait(cnt_fin + (map - pl.R), (int)I);      // the slot's previous map is out
     const RpMap m = rp_load_map(K, pose, map, lo, hi);
     rp_splat_item<kScalarBmm>(depth + (size_t)map * pl.HW, zslot, j * kRpItemPx, pl.HW, pl.H, pl.W, lo, hi, m);
     rp_signal(cnt_splat + map);
   } else {
-    rp_wait(cnt_splat + map, (int)I * kRpWarps);                    // every pixel of the map has been splatted
+    rp_wait(cnt_splat + map, (int)I);                               // every pixel of the map has been splatted
     rp_finalize_item(zslot, depth_out + (size_t)map * pl.HW, mask_out + (size_t)map * pl.HW, j * kRpItemPx, pl.HW);
     rp_signal(cnt_fin + map);
   }
@@ -932,6 +936,7 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
     int occ2 = 0;
     PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_reproject_fused<true>, kRpThreads, 0));
     z.grid = num_sms() * std::max(1, std::min(occ, occ2));   // every CTA resident: the item order relies on it
+    z.grid -= 1 - (z.grid & 1);                               // odd: every CTA alternates splat / finalise items
   }
   if (z.used && z.last != s) PRG_CUDA_OK(cudaStreamWaitEvent(s, z.done, 0));
   PRG_CUDA_OK(cudaMemsetAsync(z.counters, 0, need_cnt * sizeof(int), s));

@@ -17,7 +17,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 struct float4 { float x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
 struct dim3 { unsigned x, y, z; };
