@@ -725,7 +725,7 @@ def run_dataset(a):
             cursor[0] += n
             done = gen.generate(lo, lo + n, num_samples=1, has_refine_step=False, depth_correction=mask,
                                 base_seed=0)
-            assert done == n
+            assert done == n * world          # generate() returns the all-reduced count of finished scenes
         for _ in range(a.warmup):
             step()
         ctx.barrier()

@@ -336,86 +336,151 @@ struct RpPlan {
   long long total;  // work items of the call
 };
 
-// Item counters: release / acquire at device scope, one signal per CTA and item.
-// (The host emulation of the tests runs the items one after another, where every dependency is
-// already satisfied.)
-__device__ __forceinline__ void rp_wait(const int* cnt, int need) {
-#ifdef __CUDA_ARCH__
-  if (threadIdx.x == 0) {
-    while (true) {
-      int v;
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-      if (v >= need) break;
-      __nanosleep(32);
-    }
-  }
-  __syncthreads();
-#endif
-}
-__device__ __forceinline__ void rp_signal(int* cnt) {
-#ifdef __CUDA_ARCH__
-  __syncthreads();                 // the item's REDs / stores of every thread ...
-  if (threadIdx.x == 0) {
-    __threadfence();               // ... are ordered before the counter (cumulative fence)
-    atomicAdd(cnt, 1);
-  }
-#endif
-}
-
-// Work item p of the call.  Order: round k = [splat item 0 of map k, finalise item 0 of map k - D,
+// ---- item order and synchronisation ------------------------------------------------------
+// Order of the work items of a call: round k = [splat item 0 of map k, finalise item 0 of map k - D,
 // splat item 1 of map k, finalise item 1 of map k - D, ...] -- the two kinds ALTERNATE, and the grid
 // size is odd, so every CTA (which takes items p, p + grid, p + 2 grid, ...) alternates between a
 // splat and a finalise item and all CTAs advance at the same pace.  (With the kinds in blocks a CTA
 // did a dozen expensive splat items in a row, then a dozen cheap finalise items; CTAs drifted tens of
 // rounds apart and spent their time polling for maps the laggards had not finished.)
+struct RpItem {
+  int map, j;
+  bool fin;
+  const int* wait_cnt;   // counter this item depends on (nullptr = none) ...
+  int wait_need;         // ... and the value it must have reached
+  int* done_cnt;         // counter this item signals
+};
+
+__device__ __forceinline__ RpItem rp_decode(long long p, int* cnt_splat, int* cnt_fin, const RpPlan& pl) {
+  const long long I = pl.items;
+  const long long head = (long long)pl.D * I, mid = (long long)(pl.B - pl.D) * 2 * I;
+  RpItem it;
+  if (p < head) {                       // first D rounds: nothing to finalise yet
+    it.map = (int)(p / I); it.j = (int)(p - it.map * I); it.fin = false;
+  } else if (p < head + mid) {
+    const long long q = p - head;
+    const int k = (int)(q / (2 * I));
+    const int w = (int)(q - (long long)k * 2 * I);
+    it.fin = (w & 1) != 0;
+    it.j = w >> 1;
+    it.map = it.fin ? k : pl.D + k;
+  } else {                              // last D rounds: nothing left to splat
+    const long long q = p - head - mid;
+    const int k = (int)(q / I);
+    it.map = pl.B - pl.D + k; it.j = (int)(q - k * I); it.fin = true;
+  }
+  if (it.fin) {                         // every pixel of the map has been splatted
+    it.wait_cnt = cnt_splat + it.map; it.wait_need = (int)I; it.done_cnt = cnt_fin + it.map;
+  } else {                              // the slot's previous map is out
+    it.wait_cnt = it.map >= pl.R ? cnt_fin + (it.map - pl.R) : nullptr; it.wait_need = (int)I;
+    it.done_cnt = cnt_splat + it.map;
+  }
+  return it;
+}
+
+__device__ __forceinline__ int rp_peek(const int* cnt) {
+  int v = 0x7fffffff;
+#ifdef __CUDA_ARCH__
+  if (cnt != nullptr) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+#endif
+  return v;
+}
+
+// The pixel work of item `it` for the calling thread (worker threads 0 .. kRpThreads - 1).
+template <bool kScalarBmm>
+__device__ __forceinline__ void rp_work(const RpItem& it, const float* __restrict__ depth, const float* __restrict__ K,
+                                        const float* __restrict__ pose, float lo, float hi,
+                                        unsigned* __restrict__ scratch, float* __restrict__ depth_out,
+                                        uint8_t* __restrict__ mask_out, const RpPlan& pl) {
+  unsigned* zslot = scratch + (size_t)(it.map % pl.R) * pl.HW;
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+l"(zslot));   // keep the slot base in one register pair (index arithmetic stays 32-bit)
+#endif
+  if (!it.fin) {
+    const RpMap m = rp_load_map(K, pose, it.map, lo, hi);
+    rp_splat_item<kScalarBmm>(depth + (size_t)it.map * pl.HW, zslot, it.j * kRpItemPx, pl.HW, pl.H, pl.W, lo, hi, m);
+  } else {
+    rp_finalize_item(zslot, depth_out + (size_t)it.map * pl.HW, mask_out + (size_t)it.map * pl.HW, it.j * kRpItemPx, pl.HW);
+  }
+}
+
+// Host emulation of the tests: the items one after another (every dependency is then already satisfied).
 template <bool kScalarBmm>
 __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict__ depth, const float* __restrict__ K,
                                             const float* __restrict__ pose, float lo, float hi,
                                             unsigned* __restrict__ scratch, float* __restrict__ depth_out,
                                             uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat,
                                             int* __restrict__ cnt_fin, const RpPlan& pl) {
-  const long long I = pl.items;
-  const long long head = (long long)pl.D * I, mid = (long long)(pl.B - pl.D) * 2 * I;
-  int map, j;
-  bool fin;
-  if (p < head) {                       // first D rounds: nothing to finalise yet
-    map = (int)(p / I); j = (int)(p - map * I); fin = false;
-  } else if (p < head + mid) {
-    const long long q = p - head;
-    const int k = (int)(q / (2 * I));
-    const int w = (int)(q - (long long)k * 2 * I);
-    fin = (w & 1) != 0;
-    j = w >> 1;
-    map = fin ? k : pl.D + k;
-  } else {                              // last D rounds: nothing left to splat
-    const long long q = p - head - mid;
-    const int k = (int)(q / I);
-    map = pl.B - pl.D + k; j = (int)(q - k * I); fin = true;
-  }
-  unsigned* zslot = scratch + (size_t)(map % pl.R) * pl.HW;
-#ifdef __CUDA_ARCH__
-  asm volatile("" : "+l"(zslot));   // keep the slot base in one register pair (index arithmetic stays 32-bit)
-#endif
-  if (!fin) {
-    if (map >= pl.R) rp_wait(cnt_fin + (map - pl.R), (int)I);      // the slot's previous map is out
-    const RpMap m = rp_load_map(K, pose, map, lo, hi);
-    rp_splat_item<kScalarBmm>(depth + (size_t)map * pl.HW, zslot, j * kRpItemPx, pl.HW, pl.H, pl.W, lo, hi, m);
-    rp_signal(cnt_splat + map);
-  } else {
-    rp_wait(cnt_splat + map, (int)I);                               // every pixel of the map has been splatted
-    rp_finalize_item(zslot, depth_out + (size_t)map * pl.HW, mask_out + (size_t)map * pl.HW, j * kRpItemPx, pl.HW);
-    rp_signal(cnt_fin + map);
-  }
+  const RpItem it = rp_decode(p, cnt_splat, cnt_fin, pl);
+  rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
 }
 
+// The kernel: eight worker warps + ONE SIGNALLING WARP per CTA.  Publishing an item ("all its REDs /
+// stores are visible device-wide") needs a fence that waits for the CTA's outstanding memory operations
+// (~1.5 us) -- with thread 0 of the workers doing it, the whole CTA waited for that fence at the next
+// barrier (4 of 5 stalled issue slots in the ncu capture of that version).  Here the workers only
+// `bar.arrive` on a named barrier when they are done with an item and go on; the signalling warp
+// `bar.sync`s on it, fences, bumps the item's counter and publishes its progress in shared memory.
+// Two named barriers alternate; a worker starts item k only when the signaller is through item k - 2
+// (so a barrier is never armed twice), which bounds the skew between the warps to one item.
+// Dependencies: every worker warp polls for itself (one broadcast load), and it peeks at the NEXT
+// item's counter before working on the current one, so that the L2 round trip of the poll is hidden.
+constexpr int kRpCtaThreads = kRpThreads + 32;
+
 template <bool kScalarBmm>
-__global__ void __launch_bounds__(kRpThreads, 3)
+__global__ void __launch_bounds__(kRpCtaThreads, 3)
 k_reproject_fused(const float* __restrict__ depth, const float* __restrict__ K, const float* __restrict__ pose,
                   float lo, float hi, unsigned* __restrict__ scratch, float* __restrict__ depth_out,
                   uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat, int* __restrict__ cnt_fin,
                   const RpPlan pl) {
-  for (long long p = blockIdx.x; p < pl.total; p += gridDim.x)
-    rp_run_item<kScalarBmm>(p, depth, K, pose, lo, hi, scratch, depth_out, mask_out, cnt_splat, cnt_fin, pl);
+#ifdef __CUDA_ARCH__
+  __shared__ volatile int s_signalled;          // items of this CTA the signalling warp is through
+  if (threadIdx.x == 0) s_signalled = 0;
+  __syncthreads();
+  const bool signaller = threadIdx.x >= kRpThreads;
+  if (signaller) {
+    int k = 0;
+    for (long long p = blockIdx.x; p < pl.total; p += gridDim.x, ++k) {
+      const RpItem it = rp_decode(p, cnt_splat, cnt_fin, pl);
+      if (k & 1) asm volatile("bar.sync 2, %0;" ::"n"(kRpCtaThreads) : "memory");   // all workers done with item k
+      else asm volatile("bar.sync 1, %0;" ::"n"(kRpCtaThreads) : "memory");
+      if (threadIdx.x == kRpThreads) {
+        __threadfence();                        // their REDs / stores before the counter (cumulative)
+        atomicAdd(it.done_cnt, 1);
+        s_signalled = k + 1;
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  int k = 0;
+  long long p = blockIdx.x;
+  if (p >= pl.total) return;
+  int seen;
+  {
+    const RpItem first = rp_decode(p, cnt_splat, cnt_fin, pl);
+    seen = rp_peek(first.wait_cnt);
+  }
+  for (; p < pl.total; p += gridDim.x, ++k) {
+    const RpItem it = rp_decode(p, cnt_splat, cnt_fin, pl);
+    // dependency of this item (usually satisfied by the peek made one item ago)
+    while (seen < it.wait_need) {
+      __nanosleep(32);
+      seen = rp_peek(it.wait_cnt);
+    }
+    // the barrier of this item's parity must have been consumed for item k - 2
+    if (k >= 2) {
+      while (s_signalled < k - 1) __nanosleep(20);
+    }
+    seen = 0x7fffffff;
+    if (p + gridDim.x < pl.total)               // peek at the next item's counter: in flight during this item
+      seen = rp_peek(rp_decode(p + gridDim.x, cnt_splat, cnt_fin, pl).wait_cnt);
+    rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
+    __syncwarp();
+    if (k & 1) asm volatile("bar.arrive 2, %0;" ::"n"(kRpCtaThreads) : "memory");
+    else asm volatile("bar.arrive 1, %0;" ::"n"(kRpCtaThreads) : "memory");
+  }
+#endif
 }
 
 __global__ void __launch_bounds__(256)
@@ -932,9 +997,9 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
   if (z.done == nullptr) PRG_CUDA_OK(cudaEventCreateWithFlags(&z.done, cudaEventDisableTiming));
   if (z.grid == 0) {
     int occ = 0;
-    PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_reproject_fused<false>, kRpThreads, 0));
+    PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_reproject_fused<false>, kRpCtaThreads, 0));
     int occ2 = 0;
-    PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_reproject_fused<true>, kRpThreads, 0));
+    PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_reproject_fused<true>, kRpCtaThreads, 0));
     z.grid = num_sms() * std::max(1, std::min(occ, occ2));   // every CTA resident: the item order relies on it
     z.grid -= 1 - (z.grid & 1);                               // odd: every CTA alternates splat / finalise items
   }
@@ -942,10 +1007,10 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
   PRG_CUDA_OK(cudaMemsetAsync(z.counters, 0, need_cnt * sizeof(int), s));
   const int grid = (int)std::min<long long>(z.grid, pl.total);
   if ((long long)pl.HW * 9 < 400)     // maps of at most 44 pixels: ATen's scalar bmm rounding (see rigid())
-    k_reproject_fused<true><<<grid, kRpThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
+    k_reproject_fused<true><<<grid, kRpCtaThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
                                                        z.counters, z.counters + B, pl);
   else
-    k_reproject_fused<false><<<grid, kRpThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
+    k_reproject_fused<false><<<grid, kRpCtaThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
                                                         z.counters, z.counters + B, pl);
   PRG_LAUNCH_CHECK();
   PRG_CUDA_OK(cudaEventRecord(z.done, s));
