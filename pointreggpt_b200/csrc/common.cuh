@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
 #include <string>
 
@@ -73,6 +74,36 @@ struct PtrDeviceGuard {
     if (switched) cudaSetDevice(prev);
   }
 };
+
+// ---- programmatic dependent launch ---------------------------------------------------------
+// Every kernel of a network evaluation starts with pdl_trigger() (the next kernel of the stream may
+// be scheduled as soon as this grid's CTAs are all running or gone) and calls pdl_wait() before it
+// touches anything a predecessor wrote (until then: barrier initialisation, TMEM allocation,
+// tensor-map prefetch, weight / bias loads).  So the prologue of kernel i + 1 overlaps the tail of
+// kernel i -- 127 times per sampler step, inside the step's CUDA graph as programmatic edges.
+// A kernel launched without the attribute sees both instructions as no-ops.
+extern bool g_pdl_enabled;     // PRG_NO_PDL=1 or a profiled evaluation: plain stream order
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

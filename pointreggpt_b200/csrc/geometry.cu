@@ -415,17 +415,29 @@ __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict
   rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
 }
 
-// The kernel: eight worker warps + ONE SIGNALLING WARP per CTA.  Publishing an item ("all its REDs /
-// stores are visible device-wide") needs a fence that waits for the CTA's outstanding memory operations
-// (~1.5 us) -- with thread 0 of the workers doing it, the whole CTA waited for that fence at the next
-// barrier (4 of 5 stalled issue slots in the ncu capture of that version).  Here the workers only
-// `bar.arrive` on a named barrier when they are done with an item and go on; the signalling warp
-// `bar.sync`s on it, fences, bumps the item's counter and publishes its progress in shared memory.
-// Two named barriers alternate; a worker starts item k only when the signaller is through item k - 2
-// (so a barrier is never armed twice), which bounds the skew between the warps to one item.
-// Dependencies: every worker warp polls for itself (one broadcast load), and it peeks at the NEXT
-// item's counter before working on the current one, so that the L2 round trip of the poll is hidden.
+// The kernel: eight worker warps + ONE HELPER THREAD per CTA (lane 0 of a ninth warp).
+//  * Publishing an item ("all its REDs / stores are visible device-wide") needs a fence that waits for
+//    the CTA's outstanding memory operations (~1.5 us).  With thread 0 of the workers doing it, the whole
+//    CTA waited for that fence at the next barrier (4 of 5 stalled issue slots in the ncu capture of that
+//    version).  Here each worker warp arrives on a shared-memory mbarrier when it is done with an item and
+//    goes on; the helper sees the phase complete, fences, bumps the item's counter.
+//  * Dependencies are polled by the helper as well, a few items ahead, and published through shared
+//    memory (`s_ready`): ONE polling thread per CTA.  (Polling from every warp put 8 x 443 spinning
+//    readers on a handful of counter lines in L2 and slowed the atomics that would have released them:
+//    1.06-1.6 ms instead of 0.86.)
+//  Two mbarriers alternate; a worker starts item k only when the helper is through item k - 2 (so a
+//  barrier never collects arrivals of two items), which bounds the skew between the warps to one item.
 constexpr int kRpCtaThreads = kRpThreads + 32;
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned rp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool rp_mbar_test(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(rp_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+#endif
 
 template <bool kScalarBmm>
 __global__ void __launch_bounds__(kRpCtaThreads, 3)
@@ -434,51 +446,55 @@ k_reproject_fused(const float* __restrict__ depth, const float* __restrict__ K, 
                   uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat, int* __restrict__ cnt_fin,
                   const RpPlan pl) {
 #ifdef __CUDA_ARCH__
-  __shared__ volatile int s_signalled;          // items of this CTA the signalling warp is through
-  if (threadIdx.x == 0) s_signalled = 0;
+  __shared__ unsigned long long s_done[2];      // mbarriers: the eight worker warps are through item k (k & 1)
+  __shared__ volatile int s_signalled;          // items of this CTA the helper has published
+  __shared__ volatile int s_ready;              // items of this CTA whose dependency is satisfied
+  if (threadIdx.x == 0) {
+    s_signalled = 0;
+    s_ready = 0;
+    for (int b = 0; b < 2; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rp_smem_u32(&s_done[b])), "r"(kRpThreads / 32) : "memory");
+  }
   __syncthreads();
-  const bool signaller = threadIdx.x >= kRpThreads;
-  if (signaller) {
-    int k = 0;
-    for (long long p = blockIdx.x; p < pl.total; p += gridDim.x, ++k) {
-      const RpItem it = rp_decode(p, cnt_splat, cnt_fin, pl);
-      if (k & 1) asm volatile("bar.sync 2, %0;" ::"n"(kRpCtaThreads) : "memory");   // all workers done with item k
-      else asm volatile("bar.sync 1, %0;" ::"n"(kRpCtaThreads) : "memory");
-      if (threadIdx.x == kRpThreads) {
-        __threadfence();                        // their REDs / stores before the counter (cumulative)
-        atomicAdd(it.done_cnt, 1);
-        s_signalled = k + 1;
+  if (blockIdx.x >= pl.total) return;
+  const int nitems = (int)((pl.total - 1 - blockIdx.x) / gridDim.x) + 1;
+  if (threadIdx.x >= kRpThreads) {
+    if (threadIdx.x != kRpThreads) return;
+    // ---- helper thread
+    int ks = 0, kp = 0;
+    RpItem is = rp_decode(blockIdx.x, cnt_splat, cnt_fin, pl), ip = is;
+    while (ks < nitems) {
+      bool progressed = false;
+      if (kp < nitems && kp < ks + 6) {           // poll a few items ahead of the signalling front
+        if (rp_peek(ip.wait_cnt) >= ip.wait_need) {
+          __threadfence_block();
+          s_ready = ++kp;
+          if (kp < nitems) ip = rp_decode(blockIdx.x + (long long)kp * gridDim.x, cnt_splat, cnt_fin, pl);
+          progressed = true;
+        }
       }
-      __syncwarp();
+      if (rp_mbar_test(&s_done[ks & 1], (unsigned)(ks >> 1) & 1u)) {
+        __threadfence();                          // the workers' REDs / stores before the counter (cumulative)
+        atomicAdd(is.done_cnt, 1);
+        s_signalled = ++ks;
+        if (ks < nitems) is = rp_decode(blockIdx.x + (long long)ks * gridDim.x, cnt_splat, cnt_fin, pl);
+        progressed = true;
+      }
+      if (!progressed) __nanosleep(40);
     }
     return;
   }
-  int k = 0;
-  long long p = blockIdx.x;
-  if (p >= pl.total) return;
-  int seen;
-  {
-    const RpItem first = rp_decode(p, cnt_splat, cnt_fin, pl);
-    seen = rp_peek(first.wait_cnt);
-  }
-  for (; p < pl.total; p += gridDim.x, ++k) {
-    const RpItem it = rp_decode(p, cnt_splat, cnt_fin, pl);
-    // dependency of this item (usually satisfied by the peek made one item ago)
-    while (seen < it.wait_need) {
-      __nanosleep(32);
-      seen = rp_peek(it.wait_cnt);
-    }
-    // the barrier of this item's parity must have been consumed for item k - 2
-    if (k >= 2) {
-      while (s_signalled < k - 1) __nanosleep(20);
-    }
-    seen = 0x7fffffff;
-    if (p + gridDim.x < pl.total)               // peek at the next item's counter: in flight during this item
-      seen = rp_peek(rp_decode(p + gridDim.x, cnt_splat, cnt_fin, pl).wait_cnt);
+  // ---- worker warps
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < nitems; ++k) {
+    const RpItem it = rp_decode(blockIdx.x + (long long)k * gridDim.x, cnt_splat, cnt_fin, pl);
+    // dependency satisfied (helper polled it) and this item's barrier free (helper is through item k - 2)
+    while (s_ready < k + 1 || s_signalled < k - 1) __nanosleep(20);
+    __threadfence_block();
     rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
     __syncwarp();
-    if (k & 1) asm volatile("bar.arrive 2, %0;" ::"n"(kRpCtaThreads) : "memory");
-    else asm volatile("bar.arrive 1, %0;" ::"n"(kRpCtaThreads) : "memory");
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rp_smem_u32(&s_done[k & 1])) : "memory");
   }
 #endif
 }
