@@ -1,5 +1,6 @@
 // Error reporting / versioning / launch accounting of libprg.so.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -7,6 +8,7 @@ namespace prg {
 
 static thread_local char t_error[1024] = "";
 std::atomic<uint64_t> g_launches{0};
+bool g_pdl_enabled = getenv("PRG_NO_PDL") == nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

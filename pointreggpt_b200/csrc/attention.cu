@@ -45,6 +45,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_attn_mid(const __half* __restrict__ qkv, __half* __restrict__ out, int n) {
+  pdl_trigger();
+  pdl_wait();
   // [64 rows][4 chunks of 16 B], chunk ^= (row >> 1) & 3
   __shared__ __align__(16) __half sK[64 * 32];
   __shared__ __align__(16) __half sV[64 * 32];
@@ -173,7 +175,7 @@ int attn_mid(const __half* qkv, __half* out, int B, int n, cudaStream_t s) {
     return PRG_ERR_ARG;
   }
   dim3 g(n / 64, 4, B);
-  k_attn_mid<<<g, 128, 0, s>>>(qkv, out, n);
+  PRG_CUDA_OK(launch_pdl(k_attn_mid, g, dim3(128), 0, s, qkv, out, n));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }

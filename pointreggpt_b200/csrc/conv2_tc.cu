@@ -155,6 +155,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
         const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
         const __grid_constant__ CUtensorMap tmO3, const Conv2Params P) {
+  pdl_trigger();
   const ConvParams& p = P.c;
   constexpr int kBBytes = (BN / CG) * kBlockK * 2;   // B rows this CTA stages per K block
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -222,6 +223,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   else __syncthreads();
   tc_fence_after();
+  pdl_wait();                        // everything above touched weights only, no data of a preceding kernel
   const uint32_t taddr = ctl->tmem_addr;
 
   // item -> coordinates (per-tap mode)
@@ -1412,8 +1414,8 @@ static int launch2(const Conv2Launch& L, cudaStream_t stream) {
                                      kSmemBudget));
     configured = kSmemBudget;
   }
-  k_conv2<BN, EPI><<<L.grid, kThreads, L.smem, stream>>>(L.tmA0, L.tmA1, L.tmB, L.tmO[0], L.tmO[1],
-                                                       L.tmO[2], L.tmO[3], L.P);
+  PRG_CUDA_OK(launch_pdl(k_conv2<BN, EPI>, dim3(L.grid), dim3(kThreads), L.smem, stream, L.tmA0, L.tmA1, L.tmB, L.tmO[0],
+                         L.tmO[1], L.tmO[2], L.tmO[3], L.P));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -1426,8 +1428,8 @@ static int launch2_xf(const Conv2Launch& L, cudaStream_t stream) {
                                      kSmemBudget));
     configured = kSmemBudget;
   }
-  k_conv2<BN, EPI, 1, 1><<<L.grid, kThreads + kXfThreads, L.smem, stream>>>(L.tmA0, L.tmA1, L.tmB, L.tmO[0], L.tmO[1],
-                                                                           L.tmO[2], L.tmO[3], L.P);
+  PRG_CUDA_OK(launch_pdl(k_conv2<BN, EPI, 1, 1>, dim3(L.grid), dim3(kThreads + kXfThreads), L.smem, stream, L.tmA0, L.tmA1,
+                         L.tmB, L.tmO[0], L.tmO[1], L.tmO[2], L.tmO[3], L.P));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -1446,13 +1448,15 @@ static int launch2_pair(const Conv2Launch& L, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl_enabled ? 2 : 1;
   PRG_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv2<BN, EPI, 2>, L.tmA0, L.tmA1, L.tmB, L.tmO[0], L.tmO[1], L.tmO[2],
                                  L.tmO[3], L.P));
   PRG_LAUNCH_CHECK();

@@ -56,6 +56,8 @@ template <int CIN, bool AUG>
 __global__ void __launch_bounds__(256)
 k_stem_tc(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
           __half* __restrict__ y, int S, int B) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int KT = 49 * CIN;                 // taps
   constexpr int KR = 3 * KT;                   // real K of the split GEMM
   constexpr int KS = (KR + 15) / 16;           // k-steps
@@ -246,7 +248,7 @@ static int stem_tc_launch(const float* x, const float* w, const float* bias, __h
   const int patches = tiles_x * tiles_x * B;
   int grid = num_sms() * 2;
   if (grid > patches) grid = patches;
-  k_stem_tc<CIN, AUG><<<grid, 256, smem, s>>>(x, w, bias, y, S, B);
+  PRG_CUDA_OK(launch_pdl(k_stem_tc<CIN, AUG>, grid, dim3(256), smem, s, x, w, bias, y, S, B));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -269,6 +271,8 @@ int stem_mask(const float* depth01, const float* w, const float* bias, __half* y
 __global__ void __launch_bounds__(512)
 k_cond_embed(CondWeights w, const int64_t* __restrict__ time, int time_scalar,
              const float* __restrict__ pcond, float* __restrict__ cond_act) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int dim = w.dim, hid = 4 * w.dim;
   float* emb = sm;            // [dim]
@@ -319,7 +323,7 @@ k_cond_embed(CondWeights w, const int64_t* __restrict__ time, int time_scalar,
 int cond_embed(const CondWeights& w, const int64_t* time, int time_scalar, const float* pcond,
                float* cond_act, int B, cudaStream_t s) {
   const size_t smem = sizeof(float) * (w.dim + 8 * w.dim + w.pdim);
-  k_cond_embed<<<B, 512, smem, s>>>(w, time, time_scalar, pcond, cond_act);
+  PRG_CUDA_OK(launch_pdl(k_cond_embed, dim3(B), dim3(512), smem, s, w, time, time_scalar, pcond, cond_act));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -385,6 +389,8 @@ __global__ void __launch_bounds__(256)
 k_cond_mlp_step(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ act_t,
                 const float* __restrict__ ss_p, float* __restrict__ ss, int rows, int Ktot, int K, int B,
                 const int* __restrict__ step_idx, int act_stride) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   if (step_idx != nullptr) act_t += (size_t)(*step_idx) * act_stride;   // this step's time embedding
@@ -411,8 +417,8 @@ int cond_mlp_param(const float* W, const float* cond_act, float* ss_p, int rows,
 }
 int cond_mlp_step(const float* W, const float* bias, const float* act_t, const float* ss_p, float* ss,
                   int rows, int Ktot, int B, cudaStream_t s, const int* step_idx, int act_stride) {
-  k_cond_mlp_step<<<(rows * 32 + 255) / 256, 256, 0, s>>>(W, bias, act_t, ss_p, ss, rows, Ktot, Ktot / 2, B,
-                                                         step_idx, act_stride);
+  PRG_CUDA_OK(launch_pdl(k_cond_mlp_step, dim3((rows * 32 + 255) / 256), dim3(256), 0, s, W, bias, act_t, ss_p, ss, rows,
+                         Ktot, Ktot / 2, B, step_idx, act_stride));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -421,6 +427,8 @@ int cond_mlp_step(const float* W, const float* bias, const float* act_t, const f
 __global__ void __launch_bounds__(256)
 k_cond_mlp(const float* __restrict__ W, const float* __restrict__ bias,
            const float* __restrict__ cond_act, float* __restrict__ ss, int rows, int K) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   if (warp >= rows) return;
@@ -436,7 +444,7 @@ k_cond_mlp(const float* __restrict__ W, const float* __restrict__ bias,
 int cond_mlp(const float* W, const float* bias, const float* cond_act, float* ss, int rows, int K,
              int B, cudaStream_t s) {
   dim3 g((rows * 32 + 255) / 256, B);
-  k_cond_mlp<<<g, 256, 0, s>>>(W, bias, cond_act, ss, rows, K);
+  PRG_CUDA_OK(launch_pdl(k_cond_mlp, g, dim3(256), 0, s, W, bias, cond_act, ss, rows, K));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -481,6 +489,8 @@ __device__ __forceinline__ void gn_coeffs(const long long* stats, const float* g
 __global__ void __launch_bounds__(256)
 k_gn_coef(const long long* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
           const float* __restrict__ ss, int ss_stride, int ss_off, int C, int HW, float2* __restrict__ coef) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* sA = sm;
   float* sB = sm + C;
@@ -491,8 +501,8 @@ k_gn_coef(const long long* __restrict__ stats, const float* __restrict__ gamma, 
 }
 
 int gn_coef(const GnApply& a, float2* coef, int B, cudaStream_t s) {
-  k_gn_coef<<<B, 256, 2 * a.C * sizeof(float), s>>>(a.stats, a.gamma, a.beta, a.ss, a.ss_stride, a.ss_off, a.C,
-                                                     a.HW, coef);
+  PRG_CUDA_OK(launch_pdl(k_gn_coef, dim3(B), dim3(256), 2 * a.C * sizeof(float), s, a.stats, a.gamma, a.beta, a.ss,
+                         a.ss_stride, a.ss_off, a.C, a.HW, coef));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -500,6 +510,8 @@ int gn_coef(const GnApply& a, float2* coef, int B, cudaStream_t s) {
 template <bool LN>
 __global__ void __launch_bounds__(256, LN ? 3 : 4)
 k_gn_apply(GnApply a, int total_blocks, int nblk) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* sA = sm;
   float* sB = sm + a.C;
@@ -635,9 +647,9 @@ int gn_apply(const GnApply& a, int B, cudaStream_t s) {
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
   if (ln)
-    k_gn_apply<true><<<grid, 256, 3 * a.C * sizeof(float), s>>>(a, total, nblk);
+    PRG_CUDA_OK(launch_pdl(k_gn_apply<true>, dim3(grid), dim3(256), 3 * a.C * sizeof(float), s, a, total, nblk));
   else
-    k_gn_apply<false><<<grid, 256, 3 * a.C * sizeof(float), s>>>(a, total, nblk);
+    PRG_CUDA_OK(launch_pdl(k_gn_apply<false>, dim3(grid), dim3(256), 3 * a.C * sizeof(float), s, a, total, nblk));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -649,6 +661,8 @@ template <int C>
 __global__ void __launch_bounds__(256)
 k_ln_apply(const __half* __restrict__ x, const float* __restrict__ g,
            const __half* __restrict__ res, __half* __restrict__ y, int64_t npix) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int PER = C / 32;  // channels per lane (2, 4, 8 or 16), contiguous
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -716,10 +730,10 @@ int ln_apply(const __half* x, const float* g, const __half* res, __half* y, int6
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   switch (C) {
-    case 64: k_ln_apply<64><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
-    case 128: k_ln_apply<128><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
-    case 256: k_ln_apply<256><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
-    case 512: k_ln_apply<512><<<(int)blocks, 256, 0, s>>>(x, g, res, y, npix); break;
+    case 64: PRG_CUDA_OK(launch_pdl(k_ln_apply<64>, dim3((int)blocks), dim3(256), 0, s, x, g, res, y, npix)); break;
+    case 128: PRG_CUDA_OK(launch_pdl(k_ln_apply<128>, dim3((int)blocks), dim3(256), 0, s, x, g, res, y, npix)); break;
+    case 256: PRG_CUDA_OK(launch_pdl(k_ln_apply<256>, dim3((int)blocks), dim3(256), 0, s, x, g, res, y, npix)); break;
+    case 512: PRG_CUDA_OK(launch_pdl(k_ln_apply<512>, dim3((int)blocks), dim3(256), 0, s, x, g, res, y, npix)); break;
     default:
       set_error("ln_apply: unsupported channel count %d", C);
       return PRG_ERR_ARG;
@@ -780,16 +794,22 @@ int fill_normal(float* x, int B, int64_t per_image, const unsigned long long* se
 // network tail: GN+SiLU(block2) + res, final 1x1 (64 -> 1), then forward / sigmoid / sampler step
 // 8 lanes per pixel (8 channels each), 4 pixels per warp -> 512 contiguous bytes per warp load.
 // ------------------------------------------------------------------------------------------
-__global__ void k_step_advance(int* step_idx) { *step_idx += 1; }
+__global__ void k_step_advance(int* step_idx) {
+  pdl_trigger();
+  pdl_wait();
+  *step_idx += 1;
+}
 
 int step_advance(int* step_idx, cudaStream_t s) {
-  k_step_advance<<<1, 1, 0, s>>>(step_idx);
+  PRG_CUDA_OK(launch_pdl(k_step_advance, dim3(1), dim3(1), 0, s, step_idx));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
 
 __global__ void __launch_bounds__(256)
 k_net_tail(TailParams t) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sA[64], sB[64], sW[64];
   const int b = blockIdx.y;
   if (t.mode == 2 && t.steps != nullptr) {
@@ -883,7 +903,7 @@ int net_tail(const TailParams& t, int B, cudaStream_t s) {
   const int cap = num_sms() * 8;
   if (gx > cap) gx = cap;
   dim3 g(gx, B);
-  k_net_tail<<<g, 256, 0, s>>>(t);
+  PRG_CUDA_OK(launch_pdl(k_net_tail, g, dim3(256), 0, s, t));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }

@@ -415,7 +415,7 @@ __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict
   rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
 }
 
-// The kernel: eight worker warps + ONE HELPER THREAD per CTA (lane 0 of a ninth warp).
+// The kernel: eight worker warps + TWO HELPER THREADS per CTA (lanes 0 and 1 of a ninth warp).
 //  * Publishing an item ("all its REDs / stores are visible device-wide") needs a fence that waits for
 //    the CTA's outstanding memory operations (~1.5 us).  With thread 0 of the workers doing it, the whole
 //    CTA waited for that fence at the next barrier (4 of 5 stalled issue slots in the ncu capture of that
@@ -425,8 +425,8 @@ __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict
 //    memory (`s_ready`): ONE polling thread per CTA.  (Polling from every warp put 8 x 443 spinning
 //    readers on a handful of counter lines in L2 and slowed the atomics that would have released them:
 //    1.06-1.6 ms instead of 0.86.)
-//  Two mbarriers alternate; a worker starts item k only when the helper is through item k - 2 (so a
-//  barrier never collects arrivals of two items), which bounds the skew between the warps to one item.
+//  Four mbarriers rotate; a worker starts item k only when the signaller is through item k - 4 (so a
+//  barrier never collects arrivals of two items), which bounds how far the workers run ahead.
 constexpr int kRpCtaThreads = kRpThreads + 32;
 
 #ifdef __CUDA_ARCH__
@@ -446,41 +446,39 @@ k_reproject_fused(const float* __restrict__ depth, const float* __restrict__ K, 
                   uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat, int* __restrict__ cnt_fin,
                   const RpPlan pl) {
 #ifdef __CUDA_ARCH__
-  __shared__ unsigned long long s_done[2];      // mbarriers: the eight worker warps are through item k (k & 1)
-  __shared__ volatile int s_signalled;          // items of this CTA the helper has published
+  constexpr int kRing = 4;                      // mbarriers in rotation = items a worker may run ahead of the signaller
+  __shared__ unsigned long long s_done[kRing];  // mbarriers: the eight worker warps are through item k (k % kRing)
+  __shared__ volatile int s_signalled;          // items of this CTA the signaller has published
   __shared__ volatile int s_ready;              // items of this CTA whose dependency is satisfied
   if (threadIdx.x == 0) {
     s_signalled = 0;
     s_ready = 0;
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < kRing; ++b)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rp_smem_u32(&s_done[b])), "r"(kRpThreads / 32) : "memory");
   }
   __syncthreads();
   if (blockIdx.x >= pl.total) return;
   const int nitems = (int)((pl.total - 1 - blockIdx.x) / gridDim.x) + 1;
   if (threadIdx.x >= kRpThreads) {
-    if (threadIdx.x != kRpThreads) return;
-    // ---- helper thread
-    int ks = 0, kp = 0;
-    RpItem is = rp_decode(blockIdx.x, cnt_splat, cnt_fin, pl), ip = is;
-    while (ks < nitems) {
-      bool progressed = false;
-      if (kp < nitems && kp < ks + 6) {           // poll a few items ahead of the signalling front
-        if (rp_peek(ip.wait_cnt) >= ip.wait_need) {
-          __threadfence_block();
-          s_ready = ++kp;
-          if (kp < nitems) ip = rp_decode(blockIdx.x + (long long)kp * gridDim.x, cnt_splat, cnt_fin, pl);
-          progressed = true;
-        }
-      }
-      if (rp_mbar_test(&s_done[ks & 1], (unsigned)(ks >> 1) & 1u)) {
+    // ---- helper warp: lane 0 publishes finished items, lane 1 polls dependencies ahead (the two lanes
+    // diverge for the whole kernel; independent thread scheduling interleaves them, so the poller's L2
+    // round trips and the signaller's fences do not wait for each other)
+    if (threadIdx.x == kRpThreads) {
+      for (int ks = 0; ks < nitems; ++ks) {
+        const RpItem is = rp_decode(blockIdx.x + (long long)ks * gridDim.x, cnt_splat, cnt_fin, pl);
+        while (!rp_mbar_test(&s_done[ks % kRing], (unsigned)(ks / kRing) & 1u)) __nanosleep(40);
         __threadfence();                          // the workers' REDs / stores before the counter (cumulative)
         atomicAdd(is.done_cnt, 1);
-        s_signalled = ++ks;
-        if (ks < nitems) is = rp_decode(blockIdx.x + (long long)ks * gridDim.x, cnt_splat, cnt_fin, pl);
-        progressed = true;
+        s_signalled = ks + 1;
       }
-      if (!progressed) __nanosleep(40);
+    } else if (threadIdx.x == kRpThreads + 1) {
+      for (int kp = 0; kp < nitems; ++kp) {
+        const RpItem ip = rp_decode(blockIdx.x + (long long)kp * gridDim.x, cnt_splat, cnt_fin, pl);
+        while (s_signalled + 8 < kp) __nanosleep(100);        // no need to run far ahead of the work
+        while (rp_peek(ip.wait_cnt) < ip.wait_need) __nanosleep(40);
+        __threadfence_block();
+        s_ready = kp + 1;
+      }
     }
     return;
   }
@@ -488,13 +486,13 @@ k_reproject_fused(const float* __restrict__ depth, const float* __restrict__ K, 
   const int lane = threadIdx.x & 31;
   for (int k = 0; k < nitems; ++k) {
     const RpItem it = rp_decode(blockIdx.x + (long long)k * gridDim.x, cnt_splat, cnt_fin, pl);
-    // dependency satisfied (helper polled it) and this item's barrier free (helper is through item k - 2)
-    while (s_ready < k + 1 || s_signalled < k - 1) __nanosleep(20);
+    // dependency satisfied (polled by the helper) and this item's barrier free (signaller through item k - kRing)
+    while (s_ready < k + 1 || s_signalled < k - (kRing - 1)) __nanosleep(20);
     __threadfence_block();
     rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
     __syncwarp();
     if (lane == 0)
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rp_smem_u32(&s_done[k & 1])) : "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rp_smem_u32(&s_done[k % kRing])) : "memory");
   }
 #endif
 }

@@ -91,6 +91,7 @@ __host__ __device__ inline int range_begin(int c, int total, int grid) {
 __global__ void __launch_bounds__(kThreads, 1)
 k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
         const Params P) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -129,6 +130,7 @@ k_kvctx(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtenso
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                 // everything above touched no data of a preceding kernel
   const uint32_t taddr = ctl->tmem_addr;
   // TMEM columns: [K0 | V0 | K1 | V1], 128 each; D2 of tile i, half 0 / 1 reuses K(i & 1) / V(i & 1)
   auto k_cols = [&](int b) { return taddr + (uint32_t)(b * 256); };
@@ -363,6 +365,8 @@ constexpr int kMaxChunks = 64;      // partial slots per image (two pixel halves
 __global__ void __launch_bounds__(256)
 k_linattn_fold(const float* __restrict__ partials, const float* __restrict__ wout,
                __half* __restrict__ weff, int C, int cpi, float inv_n) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sS[kMaxChunks][32];   // exp(m_k - m) per chunk and channel of this head
   __shared__ float sN[32];               // 1 / (z n)
   __shared__ float sC[32 * 33];          // combined context [d][e]
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
        const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
        const QParams P) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -514,6 +519,7 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                 // everything above touched no data of a preceding kernel (bias / gain are weights)
   const uint32_t taddr = ctl->tmem_addr;     // columns: [Dq0 | Dq1 | Do0 (C) | Do1 (C)]
 
   auto tile_xy = [&](int t, int& img, int& x0, int& y0) {
@@ -947,10 +953,10 @@ int kvctx_run(KvCtxOp& op, int B, const float* wout, __half* weff, int C, cudaSt
     PRG_CUDA_OK(cudaFuncSetAttribute(k_kvctx, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured = 1;
   }
-  k_kvctx<<<grid, kThreads, L.smem, s>>>(L.tmX, L.tmW, P);
+  PRG_CUDA_OK(launch_pdl(k_kvctx, dim3(grid), dim3(kThreads), L.smem, s, L.tmX, L.tmW, P));
   PRG_LAUNCH_CHECK();
   dim3 g(B, 4);
-  k_linattn_fold<<<g, 256, 0, s>>>(P.partials, wout, weff, C, 2 * L.cpi, 1.f / (float)(P.tpi * 128));
+  PRG_CUDA_OK(launch_pdl(k_linattn_fold, g, dim3(256), 0, s, P.partials, wout, weff, C, 2 * L.cpi, 1.f / (float)(P.tpi * 128)));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }
@@ -1047,7 +1053,7 @@ static int qout_launch(const QOutLaunch& L, int grid, cudaStream_t s) {
     PRG_CUDA_OK(cudaFuncSetAttribute(k_qout<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured = 1;
   }
-  k_qout<C><<<grid, kThreads, L.smem, s>>>(L.tmX, L.tmW, L.tmE, L.tmO, L.P);
+  PRG_CUDA_OK(launch_pdl(k_qout<C>, dim3(grid), dim3(kThreads), L.smem, s, L.tmX, L.tmW, L.tmE, L.tmO, L.P));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
 }

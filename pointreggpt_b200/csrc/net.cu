@@ -803,6 +803,11 @@ int run_trunk(prg_net* n, const Run& r) {
     return PRG_OK;
   }
   g_prof.forwards++;
+  struct PdlOff {           // per-launch events need plain stream order
+    bool prev = g_pdl_enabled;
+    PdlOff() { g_pdl_enabled = false; }
+    ~PdlOff() { g_pdl_enabled = prev; }
+  } pdl_off;
   for (size_t i = 0; i < n->ops.size(); ++i) {
     Profiler::Rec rec{g_prof.get(), g_prof.get(), n->op_cat[i],
                       g_prof.op_id((n->kind == PRG_NET_UNET ? "U" : "M") + n->op_label[i], n->op_flops[i])};
@@ -818,6 +823,9 @@ int run_trunk(prg_net* n, const Run& r) {
 int run_tail(prg_net* n, const TailParams& t, int B, cudaStream_t s) {
   const bool prof = g_prof.every > 0 && ((n->forwards - 1) % (uint64_t)g_prof.every) == 0;
   if (!prof) return net_tail(t, B, s);
+  const bool pdl_prev = g_pdl_enabled;
+  g_pdl_enabled = false;
+  struct Restore { bool v; ~Restore() { g_pdl_enabled = v; } } restore{pdl_prev};
   Profiler::Rec rec{g_prof.get(), g_prof.get(), CAT_TAIL,
                     g_prof.op_id(n->kind == PRG_NET_UNET ? "Utail" : "Mtail", 0)};
   cudaEventRecord(rec.a, s);
