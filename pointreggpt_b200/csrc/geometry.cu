@@ -9,6 +9,7 @@
 // All fp32 arithmetic uses the _rn intrinsics so nvcc can neither contract nor
 // reorder it; the z-buffer is an order-independent atomicMin on the bit pattern of
 // the (strictly positive) depth, so the result is deterministic and bit-exact.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -983,8 +984,9 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
   // ring: as many maps as fit 24 MB (L2-resident next to the streaming traffic), at least 2, at most 96
   {
     const size_t per_map = (size_t)pl.HW * sizeof(unsigned);
-    long long r = (long long)((24u << 20) / per_map);
-    r = std::max(2ll, std::min(96ll, r));
+    static const long long ring_mb = getenv("PRG_RP_RING_MB") ? std::max(1, atoi(getenv("PRG_RP_RING_MB"))) : 24;   // tuning
+    long long r = (long long)((size_t)(ring_mb << 20) / per_map);
+    r = std::max(2ll, std::min(192ll, r));
     pl.R = (int)std::min<long long>(r, std::max(2, B));
     pl.D = std::max(1, std::min(pl.R / 2, B));
     if (pl.D >= pl.R) pl.D = pl.R - 1;
