@@ -686,7 +686,7 @@ def run_geometry(a):
                                          "%d MB" % (px * 4 >> 20, px * 22 >> 20),
                    "parallelism": "maps sharded by rank, no collective"},
         "hbm_gbs": both, "clocks": clk, "e2e": e2e, "gpu_launches": launches, "checked": checked,
-        "roofline": {"bound": "hbm", "kernel": "reprojection (memset + k_reproject_splat + k_zbuf_finalize per call) "
+        "roofline": {"bound": "hbm", "kernel": "k_reproject_fused (one persistent launch per call: splat + z-buffer ring in L2 + finalise) "
                      "and k_depth2pc; CUDA events around every call in the timed region",
                      "achieved": both, "peak": peak, "unit": "GB/s", "frac": both / peak, "traffic": None,
                      "peak_source": src,

@@ -135,25 +135,43 @@ __device__ __forceinline__ void splat(float x, float y, float z, const Intr& k, 
 
 // ------------------------------------------------------------------ reproject
 // One persistent kernel, 9 bytes of DRAM traffic per pixel (4 read, 4 + 1 written):
-//   * the z-buffer of a map lives in a small ring of scratch slots (R maps, <= 24 MB) that stays in
+//   * the z-buffer of a map lives in a small ring of scratch slots (R maps, <= 48 MB) that stays in
 //     the 126 MB L2 for the whole call: atomicMin (RED) goes to L2, depth_out / mask_out are written
 //     exactly once by the finalisation, which also hands the slot back filled with 0xFFFFFFFF -- no
 //     fill pass, no read-modify-write of the output;
-//   * work items (4096 pixels) are dealt round-robin to the resident CTAs in this order: round k =
-//     [splat items of map k] then [finalise items of map k - D]; finalise(m) waits until all splat
-//     items of map m have signalled, splat(m) waits until finalise(m - R) has freed its slot.  Every
-//     wait targets an item EARLIER in the order, so with all CTAs resident the smallest unfinished
-//     item can always run: no deadlock, no grid-wide barrier, no launch gaps between maps;
+//   * a work item SPLATS a pixel range of map k and FINALISES the same range of map k - D (R = 2 D):
+//     the two halves are independent, so the finalisation's slot loads are issued before the splat
+//     arithmetic and consumed after it; ONE counter per round k carries both dependencies (see RpItem).
+//     Items are claimed from a ticket counter; every wait targets a smaller ticket, so with all CTAs
+//     resident the smallest unfinished item can always run: no deadlock, no grid-wide barrier, no
+//     launch gaps between maps;
 //   * lanes own CONSECUTIVE pixels: neighbouring pixels land on neighbouring targets, so a warp's 32
 //     RED operations fall into a few 32-byte sectors (measured 3.6 RED/clk/SM against 1.4 when a lane
 //     owns four consecutive pixels -- tools/microbench/zbuf_atomics.cu);
 //   * the arithmetic of two pixels runs on the packed fp32x2 pipe (FADD2 / FMUL2 / FFMA2 round each
 //     lane to nearest like the scalar instructions: bit-identical), rounding + bounds test is one
-//     F2I.RN (round-half-even, saturating) and one unsigned compare per coordinate.
-constexpr int kRpThreads = 256;
-constexpr int kRpItemPx = 4096;      // pixels per work item: the resident CTAs together hold grid x 4096 pixels in
-                                     // flight, which must stay well below the D maps that separate dependent items
-constexpr int kRpSubPx = 4096;       // an item is walked in sub-blocks of 16 pixels per thread
+//     F2I.RN (round-half-even, saturating) and one unsigned compare per coordinate; the RED itself is
+//     unconditional (see rp_red_min), so a sub-block's arithmetic is branch-free.
+// Launch shape (tuning builds with other values: tools/build_variant.sh).  Measured on 500 maps of
+// 640x480 (profiles/r2_reproject_ncu.txt): the kernel is bound by per-warp latency chains, not by
+// occupancy -- 15 fat worker warps per SM (122 registers: both load batches and the finalisation's loads
+// stay in registers) beat 27 thin ones (72 registers, spills).
+#ifndef PRG_RP_THREADS
+#define PRG_RP_THREADS 480           // worker threads per CTA (+ one helper warp = 512)
+#endif
+#ifndef PRG_RP_CTAS_PER_SM
+#define PRG_RP_CTAS_PER_SM 1
+#endif
+#ifndef PRG_RP_FENCE
+#define PRG_RP_FENCE 1               // scheduling fence between the pixel pairs of a sub-block (see rp_splat_sub)
+#endif
+constexpr int kRpThreads = PRG_RP_THREADS;
+constexpr int kRpPer = 8;                       // pixels per thread and sub-block (one batch of loads in flight)
+constexpr int kRpSubPx = kRpPer * kRpThreads;   // an item is walked in sub-blocks; the loads of the next one are
+                                                // issued before the arithmetic of the current one
+constexpr int kRpItemPx = 4 * kRpSubPx;         // pixels per work item: the resident CTAs together hold grid x item
+                                                // pixels in flight, which must stay well below the D maps that
+                                                // separate dependent items
 constexpr float kPoseMax = 1e4f;
 
 struct RpMap {
@@ -212,56 +230,102 @@ __device__ __noinline__ void rp_pixel_slow(float z0, int r, int c, const RpMap& 
   rp_pixel_generic<false>(z0, r, c, m, H, W, zslot);
 }
 
-// Splat item: pixels [px0, px0 + kRpItemPx) of one map.  Thread t takes pixels px0 + t + 256 j.
-template <bool kScalarBmm>
-__device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, unsigned* __restrict__ zslot,
-                                              int px0, int HW, int H, int W, float lo, float hi,
-                                              const RpMap& m) {
-  const int t = threadIdx.x;
-  int i = px0 + t;
-  if (i >= HW) return;
-  int r = i / W, c = i - r * W;                  // one division per item and thread; then incremental
-  if (kScalarBmm || !m.fast) {
-    for (int j = 0; j < kRpItemPx / kRpThreads && i < HW; ++j, i += kRpThreads) {
-      const float z0 = __ldcs(dimg + i);
-      if (z0 > lo && z0 < hi) rp_pixel_generic<kScalarBmm>(z0, r, c, m, H, W, zslot);
-      c += kRpThreads;
-      while (c >= W) { c -= W; ++r; }
+// z-buffer update of one pixel WITHOUT a branch or a predicate: a pixel that must not be drawn sends
+// the identity of min (0xFFFFFFFF) to its own source position (in range, lane-consecutive) instead.  The
+// unrolled arithmetic of a sub-block is then ONE basic block, which lets ptxas interleave the dependency
+// chains of its pixel pairs (with a branch around every RED the chains ran one after another: 2.5 of 12
+// cycles per issued instruction were fixed-latency waits, 1.4 branch resolution).  RED.MIN on the GLOBAL
+// window: the generic-address form the compiler picks when it loses track of the address space resolves
+// the window per lane first.
+__device__ __forceinline__ void rp_red_min(unsigned* __restrict__ zslot, unsigned long long zglobal, int ri, int ci,
+                                           int H, int W, bool ok, unsigned zbits, int own_index) {
+  ok = ok && (unsigned)ci < (unsigned)W && (unsigned)ri < (unsigned)H;
+#ifdef __CUDA_ARCH__
+  (void)zslot;
+  const unsigned idx = ok ? (unsigned)(ri * W + ci) : (unsigned)own_index;
+  const unsigned val = ok ? zbits : kEmpty;
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tred.relaxed.gpu.global.min.u32 [a], %2;\n\t}\n"
+               ::"l"(zglobal), "r"(idx), "r"(val));
+#else
+  (void)own_index; (void)zglobal;
+  if (ok) atomicMin(zslot + (unsigned)(ri * W + ci), zbits);
+#endif
+}
+
+// per-thread state of the fast path: map constants broadcast into both lanes of packed registers, and
+// the (row, column) of the thread's current pixel PAIR (A = i, B = i + kRpThreads) carried as floats
+// (exact below 2^24).  2 * kRpThreads pixels further = dr2 rows and dc2 < W columns, so ONE conditional
+// wrap per step is enough for any width.
+struct RpFast {
+  float2 ncx, ncy, rfx, rfy, nfx, nfy, fx2, fy2, cx2, cy2;
+  float2 nW2, dc2, dr2;
+  float Wf;
+  float2 c2, r2;
+};
+
+struct RpSteps {          // kRpThreads and 2 * kRpThreads pixels as (rows, columns < W) of the map
+  int d1r, d1c, d2r, d2c;
+};
+__host__ __device__ inline RpSteps rp_steps(int W) {
+  RpSteps st;
+  st.d1r = kRpThreads / W; st.d1c = kRpThreads - st.d1r * W;
+  st.d2r = (2 * kRpThreads) / W; st.d2c = 2 * kRpThreads - st.d2r * W;
+  return st;
+}
+
+__device__ __forceinline__ void rp_fast_init(RpFast& f, const Intr& k, int W, const RpSteps& st, int i0) {
+  f.ncx = f2(-k.cx); f.ncy = f2(-k.cy); f.rfx = f2(k.rfx); f.rfy = f2(k.rfy); f.nfx = f2(-k.fx); f.nfy = f2(-k.fy);
+  f.fx2 = f2(k.fx); f.fy2 = f2(k.fy); f.cx2 = f2(k.cx); f.cy2 = f2(k.cy);
+  f.Wf = (float)W;
+  f.nW2 = f2(-f.Wf); f.dc2 = f2((float)st.d2c); f.dr2 = f2((float)st.d2r);
+  const int r0 = i0 / W, c0 = i0 - r0 * W;
+  int cb = c0 + st.d1c, rb = r0 + st.d1r;
+  if (cb >= W) { cb -= W; ++rb; }
+  f.c2 = make_float2((float)c0, (float)cb);
+  f.r2 = make_float2((float)r0, (float)rb);
+}
+
+__device__ __forceinline__ void rp_fast_step(RpFast& f) {      // next pair: 2 * kRpThreads pixels further
+  f.c2 = __fadd2_rn(f.c2, f.dc2);
+  f.r2 = __fadd2_rn(f.r2, f.dr2);
+  const float2 wrap = make_float2(f.c2.x >= f.Wf ? 1.f : 0.f, f.c2.y >= f.Wf ? 1.f : 0.f);
+  f.c2 = __ffma2_rn(wrap, f.nW2, f.c2);
+  f.r2 = __fadd2_rn(f.r2, wrap);
+}
+
+// One full sub-block (pixels base + q * kRpThreads, q < kRpPer, all inside the map) of the fast path.
+__device__ __forceinline__ void rp_splat_sub(const float (&dv)[kRpPer], const float* __restrict__ dimg,
+                                             unsigned* __restrict__ zslot, unsigned long long zglobal, int base,
+                                             int H, int W, float lo, float hi, const RpMap& m, RpFast& f) {
+#ifdef __CUDA_ARCH__
+  {  // nothing inside the clip in the whole warp (background): only advance the position
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < kRpPer; ++q) any = any || (dv[q] > lo && dv[q] < hi);
+    if (!__any_sync(__activemask(), any)) {
+#pragma unroll
+      for (int j = 0; j < kRpPer / 2; ++j) rp_fast_step(f);
+      return;
     }
-    return;
   }
-  const Intr& k = m.k;
-  const float2 ncx = f2(-k.cx), ncy = f2(-k.cy), rfx = f2(k.rfx), rfy = f2(k.rfy), nfx = f2(-k.fx), nfy = f2(-k.fy);
-  const float2 fx2 = f2(k.fx), fy2 = f2(k.fy), cx2 = f2(k.cx), cy2 = f2(k.cy);
-  const float nan = __int_as_float(0x7fc00000);
-  const float Wf = (float)W, step = (float)kRpThreads;   // rows / columns are carried as floats (exact below 2^24)
-  float ra = (float)r, ca = (float)c;
-  // all sixteen loads of the item first: 64 bytes in flight per thread (the kernel is otherwise bound
-  // by the latency of its own reads -- 1024 threads per SM with one or two loads each cover only
-  // a third of the bandwidth-delay product)
-  constexpr int kPer = kRpSubPx / kRpThreads;
-#pragma unroll 1
-  for (int sub = 0; sub < kRpItemPx / kRpSubPx && i < HW; ++sub) {
-  float dv[kPer];
+#endif
+  bool slow = false;
 #pragma unroll
-  for (int q = 0; q < kPer; ++q) {
-    const int iq = i + q * kRpThreads;
-    dv[q] = (iq < HW) ? __ldcs(dimg + iq) : nan;
-  }
-#pragma unroll
-  for (int j = 0; j < kPer / 2; ++j) {
-    if (i >= HW) break;
-    // pixel A = i, pixel B = i + 256
-    float rb = ra, cb = ca + step;
-    while (cb >= Wf) { cb -= Wf; rb += 1.f; }
+  for (int j = 0; j < kRpPer / 2; ++j) {
+#if defined(__CUDA_ARCH__) && PRG_RP_FENCE
+    // a scheduling fence every two pairs: with the whole sub-block as one region ptxas interleaved all
+    // eight pixels, ran out of predicate registers and kept them as bits of a general register (a third
+    // of the instructions were that bookkeeping); two pairs are four independent chains already
+    if (j > 0 && (j & 1) == 0) __syncwarp();
+#endif
     const float da = dv[2 * j], db = dv[2 * j + 1];
     // valid <=> inside the clip; the clip is inside [0, 1e9], so d > 1e-9 completes depth_in_range
     const bool va = da > lo && da < hi, vb = db > lo && db < hi;
     const float2 d = make_float2(da, db);
     // x = ((c - cx) * z) / fx, y = ((r - cy) * z) / fy   (SDD:196-197).  No sign fix-up as in
     // div_exact_signed: with d > 1e-9 a numerator is zero only as the exact +0 of c - cx.
-    const float2 x = div_exact2(__fmul2_rn(__fadd2_rn(make_float2(ca, cb), ncx), d), nfx, rfx);
-    const float2 y = div_exact2(__fmul2_rn(__fadd2_rn(make_float2(ra, rb), ncy), d), nfy, rfy);
+    const float2 x = div_exact2(__fmul2_rn(__fadd2_rn(f.c2, f.ncx), d), f.nfx, f.rfx);
+    const float2 y = div_exact2(__fmul2_rn(__fadd2_rn(f.r2, f.ncy), d), f.nfy, f.rfy);
     // matmul(pc, R^T) + t  (SDD:279): fma(z, r2, fma(y, r1, x * r0)) + t
     const float2 X = __fadd2_rn(__ffma2_rn(d, f2(m.P[2]), __ffma2_rn(y, f2(m.P[1]), __fmul2_rn(x, f2(m.P[0])))), f2(m.P[3]));
     const float2 Y = __fadd2_rn(__ffma2_rn(d, f2(m.P[6]), __ffma2_rn(y, f2(m.P[5]), __fmul2_rn(x, f2(m.P[4])))), f2(m.P[7]));
@@ -271,45 +335,81 @@ __device__ __forceinline__ void rp_splat_item(const float* __restrict__ dimg, un
     // round-half-even + saturation then IS torch.round + the bounds test on the integer index.
     const bool sa = va && da > 1e-9f && Z.x > 1e-6f && Z.x < 1e12f;
     const bool sb = vb && db > 1e-9f && Z.y > 1e-6f && Z.y < 1e12f;
-    const float2 rz = make_float2(frcp_rn_normal(sa ? Z.x : 1.f), frcp_rn_normal(sb ? Z.y : 1.f));
+    // (the reciprocal of a depth outside that range may be anything: such a pixel draws nothing below)
+    const float2 rz = make_float2(frcp_rn_normal(Z.x), frcp_rn_normal(Z.y));
     const float2 nZ = make_float2(-Z.x, -Z.y);
-    const float2 u = __fadd2_rn(div_exact2(__fmul2_rn(X, fx2), nZ, rz), cx2);
-    const float2 v = __fadd2_rn(div_exact2(__fmul2_rn(Y, fy2), nZ, rz), cy2);
-    const int cia = __float2int_rn(u.x), ria = __float2int_rn(v.x);
-    const int cib = __float2int_rn(u.y), rib = __float2int_rn(v.y);
-    if (sa && (unsigned)cia < (unsigned)W && (unsigned)ria < (unsigned)H)
-      atomicMin(zslot + (unsigned)(ria * W + cia), __float_as_uint(Z.x));
-    if (sb && (unsigned)cib < (unsigned)W && (unsigned)rib < (unsigned)H)
-      atomicMin(zslot + (unsigned)(rib * W + cib), __float_as_uint(Z.y));
-    // valid pixels outside the validated ranges (tiny depths, extreme depth after the transform):
-    // the scalar path (rare)
-    if ((va && !sa) || (vb && !sb)) {
-      if (va && !sa) rp_pixel_slow(da, (int)ra, (int)ca, m, H, W, zslot);
-      if (vb && !sb) rp_pixel_slow(db, (int)rb, (int)cb, m, H, W, zslot);
-    }
-    i += 2 * kRpThreads;
-    ca = cb + step; ra = rb;
-    while (ca >= Wf) { ca -= Wf; ra += 1.f; }
+    const float2 u = __fadd2_rn(div_exact2(__fmul2_rn(X, f.fx2), nZ, rz), f.cx2);
+    const float2 v = __fadd2_rn(div_exact2(__fmul2_rn(Y, f.fy2), nZ, rz), f.cy2);
+    rp_red_min(zslot, zglobal, __float2int_rn(v.x), __float2int_rn(u.x), H, W, sa, __float_as_uint(Z.x), base + 2 * j * kRpThreads);
+    rp_red_min(zslot, zglobal, __float2int_rn(v.y), __float2int_rn(u.y), H, W, sb, __float_as_uint(Z.y), base + (2 * j + 1) * kRpThreads);
+    // valid pixels outside the validated ranges (tiny depths, extreme depth after the transform) are
+    // only noted here (rare)
+    slow = slow || (va && !sa) || (vb && !sb);
+    rp_fast_step(f);
   }
+  if (slow) {
+    // ... and then ALL valid pixels of the thread's sub-block take the scalar path: it is bit-identical
+    // to the fast one where both apply, and min is idempotent, so drawing a pixel twice changes nothing
+    for (int q = 0; q < kRpPer; ++q) {
+      const int i = base + q * kRpThreads;
+      const float z0 = __ldcs(dimg + i);
+      if (z0 > lo && z0 < hi) rp_pixel_slow(z0, i / W, i % W, m, H, W, zslot);
+    }
   }
 }
 
-// Finalise item: pixels [px0, px0 + kRpItemPx) of one map: depth (0 where empty) and mask out, slot reset.
-__device__ __forceinline__ void rp_finalize_item(unsigned* __restrict__ zslot, float* __restrict__ dout,
-                                                 uint8_t* __restrict__ mout, int px0, int HW) {
-  const int end = min(px0 + kRpItemPx, HW);
+__device__ __forceinline__ void rp_load_sub(float (&dv)[kRpPer], const float* __restrict__ dimg, int base) {
+#pragma unroll
+  for (int q = 0; q < kRpPer; ++q) dv[q] = __ldcs(dimg + base + q * kRpThreads);
+}
+
+// Pixels [c0, e) of one map, one at a time through the scalar helpers (any intrinsics / pose, tiny maps,
+// the partial chunk at the end of a map whose size is not a multiple of kRpChunkPx).  Thread t takes
+// pixels c0 + t + kRpThreads j.
+template <bool kScalarBmm>
+__device__ __forceinline__ void rp_splat_range(const float* __restrict__ dimg, unsigned* __restrict__ zslot,
+                                               int c0, int e, int H, int W, float lo, float hi, const RpMap& m) {
+  int i = c0 + (int)threadIdx.x;
+  if (i >= e) return;
+  int r = i / W, c = i - r * W;
+  for (; i < e; i += kRpThreads) {
+    const float z0 = __ldcs(dimg + i);
+    if (z0 > lo && z0 < hi) rp_pixel_generic<kScalarBmm>(z0, r, c, m, H, W, zslot);
+    c += kRpThreads;
+    while (c >= W) { c -= W; ++r; }
+  }
+}
+
+// the same out of line, for the rest of a fast map's last chunk
+__device__ __noinline__ void rp_splat_rest(const float* __restrict__ dimg, unsigned* __restrict__ zslot, int c0, int e,
+                                           int H, int W, float lo, float hi, const RpMap& m) {
+  rp_splat_range<false>(dimg, zslot, c0, e, H, W, lo, hi, m);
+}
+
+// Finalisation of pixels [c0, min(c0 + kRpChunkPx, end)) of one map, in two halves: the loads of the
+// z-buffer slot (L2) are issued BEFORE the splat arithmetic of the same work item and consumed after it,
+// so their latency is covered by the thread itself rather than by occupancy.  Depth (0 where empty) and
+// mask out, slot reset to empty.
+constexpr int kRpChunkPx = 2 * kRpSubPx;                     // 16 pixels per thread
+constexpr int kRpFinIt = kRpChunkPx / (kRpThreads * 4);      // 128-bit accesses per thread and chunk
+
+__device__ __forceinline__ void rp_finalize_load(uint4 (&vv)[kRpFinIt], const unsigned* __restrict__ zslot, int c0,
+                                                 int end, int HW) {
+  if ((HW & 3) != 0) return;
+#pragma unroll
+  for (int q = 0; q < kRpFinIt; ++q) {
+    const int i = c0 + ((int)threadIdx.x + q * kRpThreads) * 4;
+    if (i < end) vv[q] = __ldcg(reinterpret_cast<const uint4*>(zslot + i));
+  }
+}
+
+__device__ __forceinline__ void rp_finalize_store(const uint4 (&vv)[kRpFinIt], unsigned* __restrict__ zslot,
+                                                  float* __restrict__ dout, uint8_t* __restrict__ mout, int c0,
+                                                  int end, int HW) {
   if ((HW & 3) == 0) {
-    constexpr int kIt = kRpSubPx / (kRpThreads * 4);
-    for (int sub0 = px0; sub0 < end; sub0 += kRpSubPx) {
-    uint4 vv[kIt];
 #pragma unroll
-    for (int q = 0; q < kIt; ++q) {                       // the sub-block's loads in flight together
-      const int i = sub0 + ((int)threadIdx.x + q * kRpThreads) * 4;
-      if (i < end) vv[q] = __ldcg(reinterpret_cast<const uint4*>(zslot + i));
-    }
-#pragma unroll
-    for (int q = 0; q < kIt; ++q) {
-      const int i = sub0 + ((int)threadIdx.x + q * kRpThreads) * 4;
+    for (int q = 0; q < kRpFinIt; ++q) {
+      const int i = c0 + ((int)threadIdx.x + q * kRpThreads) * 4;
       if (i >= end) break;
       uint4 v = vv[q];
       uchar4 mk;
@@ -317,11 +417,11 @@ __device__ __forceinline__ void rp_finalize_item(unsigned* __restrict__ zslot, f
       v.x = mk.x ? v.x : 0u; v.y = mk.y ? v.y : 0u; v.z = mk.z ? v.z : 0u; v.w = mk.w ? v.w : 0u;
       __stcs(reinterpret_cast<uint4*>(dout + i), v);
       *reinterpret_cast<uchar4*>(mout + i) = mk;
-      *reinterpret_cast<uint4*>(zslot + i) = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-    }
+      __stcg(reinterpret_cast<uint4*>(zslot + i), make_uint4(kEmpty, kEmpty, kEmpty, kEmpty));
     }
   } else {
-    for (int i = px0 + (int)threadIdx.x; i < end; i += kRpThreads) {
+    const int e = min(c0 + kRpChunkPx, end);
+    for (int i = c0 + (int)threadIdx.x; i < e; i += kRpThreads) {
       const unsigned v = __ldcg(zslot + i);
       mout[i] = v != kEmpty;
       reinterpret_cast<unsigned*>(dout)[i] = v != kEmpty ? v : 0u;
@@ -332,50 +432,32 @@ __device__ __forceinline__ void rp_finalize_item(unsigned* __restrict__ zslot, f
 
 struct RpPlan {
   int B, H, W, HW;
-  int items;        // work items per map and phase
-  int R, D;         // ring slots, finalisation lag (D < R, D <= B)
-  long long total;  // work items of the call
+  RpSteps st;       // rp_steps(W)
+  int item_px;      // pixels per work item (a multiple of kRpChunkPx)
+  int items;        // work items per round
+  int R, D;         // ring slots and finalisation lag, R = 2 D
+  long long total;  // work items of the call = (B + D) * items
 };
 
 // ---- item order and synchronisation ------------------------------------------------------
-// Order of the work items of a call: round k = [splat item 0 of map k, finalise item 0 of map k - D,
-// splat item 1 of map k, finalise item 1 of map k - D, ...] -- the two kinds ALTERNATE, and the grid
-// size is odd, so every CTA (which takes items p, p + grid, p + 2 grid, ...) alternates between a
-// splat and a finalise item and all CTAs advance at the same pace.  (With the kinds in blocks a CTA
-// did a dozen expensive splat items in a row, then a dozen cheap finalise items; CTAs drifted tens of
-// rounds apart and spent their time polling for maps the laggards had not finished.)
+// Round k (k = 0 .. B + D - 1) consists of `items` FUSED work items: item j splats pixels
+// [j * item_px, (j + 1) * item_px) of map k (if k < B) and finalises the same pixel range of map k - D
+// (if k >= D).  Map m lives in ring slot m % R with R = 2 D, so ONE counter per round carries both
+// dependencies: done[k - D] == items says that every pixel of map k - D has been splatted (its
+// finalisation may start) and that map k - 2 D has been finalised (its slot, which is map k's, is empty).
+// The two halves of an item touch different slots and are independent, which is what the interleaving
+// of rp_finalize_load / splat / rp_finalize_store uses.
 struct RpItem {
-  int map, j;
-  bool fin;
-  const int* wait_cnt;   // counter this item depends on (nullptr = none) ...
-  int wait_need;         // ... and the value it must have reached
-  int* done_cnt;         // counter this item signals
+  int round, j;
+  int map_s, map_f;      // map to splat / to finalise, -1 = none
 };
 
-__device__ __forceinline__ RpItem rp_decode(long long p, int* cnt_splat, int* cnt_fin, const RpPlan& pl) {
-  const long long I = pl.items;
-  const long long head = (long long)pl.D * I, mid = (long long)(pl.B - pl.D) * 2 * I;
+__device__ __forceinline__ RpItem rp_decode(long long p, const RpPlan& pl) {
   RpItem it;
-  if (p < head) {                       // first D rounds: nothing to finalise yet
-    it.map = (int)(p / I); it.j = (int)(p - it.map * I); it.fin = false;
-  } else if (p < head + mid) {
-    const long long q = p - head;
-    const int k = (int)(q / (2 * I));
-    const int w = (int)(q - (long long)k * 2 * I);
-    it.fin = (w & 1) != 0;
-    it.j = w >> 1;
-    it.map = it.fin ? k : pl.D + k;
-  } else {                              // last D rounds: nothing left to splat
-    const long long q = p - head - mid;
-    const int k = (int)(q / I);
-    it.map = pl.B - pl.D + k; it.j = (int)(q - k * I); it.fin = true;
-  }
-  if (it.fin) {                         // every pixel of the map has been splatted
-    it.wait_cnt = cnt_splat + it.map; it.wait_need = (int)I; it.done_cnt = cnt_fin + it.map;
-  } else {                              // the slot's previous map is out
-    it.wait_cnt = it.map >= pl.R ? cnt_fin + (it.map - pl.R) : nullptr; it.wait_need = (int)I;
-    it.done_cnt = cnt_splat + it.map;
-  }
+  it.round = (int)(p / pl.items);
+  it.j = (int)(p - (long long)it.round * pl.items);
+  it.map_s = it.round < pl.B ? it.round : -1;
+  it.map_f = it.round >= pl.D ? it.round - pl.D : -1;
   return it;
 }
 
@@ -387,21 +469,55 @@ __device__ __forceinline__ int rp_peek(const int* cnt) {
   return v;
 }
 
-// The pixel work of item `it` for the calling thread (worker threads 0 .. kRpThreads - 1).
+// The pixel work of a fused item for the calling thread (worker threads 0 .. kRpThreads - 1); `m` is
+// only read when there is a map to splat.  Thread t takes pixels px0 + t + kRpThreads j of the splat
+// half and four consecutive pixels per 128-bit access of the finalisation half.
+//
+// Fast maps run a software pipeline over the item's chunks (a chunk = two sub-blocks of eight pixels
+// per thread): the depth loads of the NEXT sub-block and the slot loads of the chunk's finalisation are
+// in flight during the arithmetic of the current sub-block, so a warp covers its own memory latency
+// (15 fat warps per SM do better than 27 thin ones, see the launch shape above).
 template <bool kScalarBmm>
-__device__ __forceinline__ void rp_work(const RpItem& it, const float* __restrict__ depth, const float* __restrict__ K,
-                                        const float* __restrict__ pose, float lo, float hi,
+__device__ __forceinline__ void rp_work(int map_s, int map_f, int j, const RpMap& m,
+                                        const float* __restrict__ depth, float lo, float hi,
                                         unsigned* __restrict__ scratch, float* __restrict__ depth_out,
                                         uint8_t* __restrict__ mask_out, const RpPlan& pl) {
-  unsigned* zslot = scratch + (size_t)(it.map % pl.R) * pl.HW;
+  const int t = threadIdx.x;
+  const int px0 = j * pl.item_px, end = min(px0 + pl.item_px, pl.HW);
+  const int H = pl.H, W = pl.W, HW = pl.HW;
+  const float* dimg = depth + (size_t)max(map_s, 0) * HW;
+  unsigned* zs = scratch + (size_t)(max(map_s, 0) % pl.R) * HW;
+  unsigned* zf = scratch + (size_t)(max(map_f, 0) % pl.R) * HW;
+  float* dout = depth_out + (size_t)max(map_f, 0) * HW;
+  uint8_t* mout = mask_out + (size_t)max(map_f, 0) * HW;
+  int c0 = px0;
+  if (!kScalarBmm && map_s >= 0 && m.fast && c0 + kRpSubPx <= end) {
+    RpFast f;
+    rp_fast_init(f, m.k, W, pl.st, c0 + t);
+    unsigned long long zglobal = 0;
 #ifdef __CUDA_ARCH__
-  asm volatile("" : "+l"(zslot));   // keep the slot base in one register pair (index arithmetic stays 32-bit)
+    zglobal = __cvta_generic_to_global(zs);
+    asm volatile("" : "+l"(zglobal));     // keep the slot base in one register pair (else it is re-derived per pixel)
 #endif
-  if (!it.fin) {
-    const RpMap m = rp_load_map(K, pose, it.map, lo, hi);
-    rp_splat_item<kScalarBmm>(depth + (size_t)it.map * pl.HW, zslot, it.j * kRpItemPx, pl.HW, pl.H, pl.W, lo, hi, m);
-  } else {
-    rp_finalize_item(zslot, depth_out + (size_t)it.map * pl.HW, mask_out + (size_t)it.map * pl.HW, it.j * kRpItemPx, pl.HW);
+    float dva[kRpPer], dvb[kRpPer];
+    rp_load_sub(dva, dimg, c0 + t);
+    for (; c0 + kRpSubPx <= end; c0 += kRpChunkPx) {
+      const bool two = c0 + kRpChunkPx <= end;    // false only in the last chunk of a map: one full sub-block + a rest
+      uint4 fv[kRpFinIt];
+      if (map_f >= 0) rp_finalize_load(fv, zf, c0, end, HW);
+      if (two) rp_load_sub(dvb, dimg, c0 + kRpSubPx + t);
+      rp_splat_sub(dva, dimg, zs, zglobal, c0 + t, H, W, lo, hi, m, f);
+      if (c0 + kRpChunkPx + kRpSubPx <= end) rp_load_sub(dva, dimg, c0 + kRpChunkPx + t);
+      if (two) rp_splat_sub(dvb, dimg, zs, zglobal, c0 + kRpSubPx + t, H, W, lo, hi, m, f);
+      else rp_splat_rest(dimg, zs, c0 + kRpSubPx, end, H, W, lo, hi, m);
+      if (map_f >= 0) rp_finalize_store(fv, zf, dout, mout, c0, end, HW);
+    }
+  }
+  for (; c0 < end; c0 += kRpChunkPx) {      // everything else (see rp_splat_range)
+    uint4 fv[kRpFinIt];
+    if (map_f >= 0) rp_finalize_load(fv, zf, c0, end, HW);
+    if (map_s >= 0) rp_splat_range<kScalarBmm>(dimg, zs, c0, min(c0 + kRpChunkPx, end), H, W, lo, hi, m);
+    if (map_f >= 0) rp_finalize_store(fv, zf, dout, mout, c0, end, HW);
   }
 }
 
@@ -410,25 +526,39 @@ template <bool kScalarBmm>
 __device__ __forceinline__ void rp_run_item(long long p, const float* __restrict__ depth, const float* __restrict__ K,
                                             const float* __restrict__ pose, float lo, float hi,
                                             unsigned* __restrict__ scratch, float* __restrict__ depth_out,
-                                            uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat,
-                                            int* __restrict__ cnt_fin, const RpPlan& pl) {
-  const RpItem it = rp_decode(p, cnt_splat, cnt_fin, pl);
-  rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
+                                            uint8_t* __restrict__ mask_out, const RpPlan& pl) {
+  const RpItem it = rp_decode(p, pl);
+  RpMap m;
+  if (it.map_s >= 0) m = rp_load_map(K, pose, it.map_s, lo, hi);
+  rp_work<kScalarBmm>(it.map_s, it.map_f, it.j, m, depth, lo, hi, scratch, depth_out, mask_out, pl);
 }
 
-// The kernel: eight worker warps + TWO HELPER THREADS per CTA (lanes 0 and 1 of a ninth warp).
+// The kernel: kRpThreads / 32 worker warps + TWO HELPER THREADS per CTA (lanes 0 and 1 of one more warp).
 //  * Publishing an item ("all its REDs / stores are visible device-wide") needs a fence that waits for
 //    the CTA's outstanding memory operations (~1.5 us).  With thread 0 of the workers doing it, the whole
 //    CTA waited for that fence at the next barrier (4 of 5 stalled issue slots in the ncu capture of that
 //    version).  Here each worker warp arrives on a shared-memory mbarrier when it is done with an item and
-//    goes on; the helper sees the phase complete, fences, bumps the item's counter.
-//  * Dependencies are polled by the helper as well, a few items ahead, and published through shared
-//    memory (`s_ready`): ONE polling thread per CTA.  (Polling from every warp put 8 x 443 spinning
-//    readers on a handful of counter lines in L2 and slowed the atomics that would have released them:
-//    1.06-1.6 ms instead of 0.86.)
-//  Four mbarriers rotate; a worker starts item k only when the signaller is through item k - 4 (so a
-//  barrier never collects arrivals of two items), which bounds how far the workers run ahead.
+//    goes on; the helper sees the phase complete, fences, bumps the round's counter.
+//  * The other helper lane CLAIMS the CTA's next item from a global ticket counter (one item ahead of the
+//    workers), decodes it (64-bit division), loads the map's intrinsics / pose, polls the item's
+//    dependency and publishes all of that through a shared-memory ring (`s_slot`, `s_ready`): the worker
+//    threads find their item decoded (with every worker decoding and loading for itself, half of the
+//    executed instructions of a 16-pixel-per-thread item were not pixel work), and ONE thread per CTA
+//    polls.  (Polling from every warp put 8 x 443 spinning readers on a handful of counter lines in L2
+//    and slowed the atomics that would have released them: 1.06-1.6 ms instead of 0.86.)
+//  * Tickets are handed out in increasing order and every wait targets an item with a smaller ticket,
+//    so the smallest unfinished item can always run (all CTAs are resident).
+//  Four mbarriers rotate; a worker starts its k-th item only when the signaller is through the (k - 4)-th
+//  (so a barrier never collects arrivals of two items), which bounds how far the workers run ahead.
 constexpr int kRpCtaThreads = kRpThreads + 32;
+constexpr int kRpClaimAhead = 1;       // the poller claims the CTA's (k + 1)-th item when the workers start the k-th
+constexpr int kRpItemRing = 8;         // published items in shared memory (> kRing + kRpClaimAhead + 1)
+
+struct RpSlot {
+  int round;        // -1: no more work
+  int j, map_s, map_f;
+  RpMap m;
+};
 
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ unsigned rp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -441,56 +571,73 @@ __device__ __forceinline__ bool rp_mbar_test(unsigned long long* bar, unsigned p
 #endif
 
 template <bool kScalarBmm>
-__global__ void __launch_bounds__(kRpCtaThreads, 3)
+__global__ void __launch_bounds__(kRpCtaThreads, PRG_RP_CTAS_PER_SM)
 k_reproject_fused(const float* __restrict__ depth, const float* __restrict__ K, const float* __restrict__ pose,
                   float lo, float hi, unsigned* __restrict__ scratch, float* __restrict__ depth_out,
-                  uint8_t* __restrict__ mask_out, int* __restrict__ cnt_splat, int* __restrict__ cnt_fin,
-                  const RpPlan pl) {
+                  uint8_t* __restrict__ mask_out, int* __restrict__ done, unsigned long long* __restrict__ ticket,
+                  const int flags, const int claim_ahead, const RpPlan pl) {
 #ifdef __CUDA_ARCH__
   constexpr int kRing = 4;                      // mbarriers in rotation = items a worker may run ahead of the signaller
-  __shared__ unsigned long long s_done[kRing];  // mbarriers: the eight worker warps are through item k (k % kRing)
+  __shared__ unsigned long long s_done[kRing];  // mbarriers: the worker warps are through their k-th item (k % kRing)
+  __shared__ RpSlot s_slot[kRpItemRing];        // the CTA's k-th item (k % kRpItemRing), decoded
   __shared__ volatile int s_signalled;          // items of this CTA the signaller has published
-  __shared__ volatile int s_ready;              // items of this CTA whose dependency is satisfied
+  __shared__ volatile int s_ready;              // items of this CTA that are claimed, decoded and free to run
+  __shared__ volatile int s_started;            // items of this CTA the workers have started
   if (threadIdx.x == 0) {
     s_signalled = 0;
     s_ready = 0;
+    s_started = 0;
     for (int b = 0; b < kRing; ++b)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rp_smem_u32(&s_done[b])), "r"(kRpThreads / 32) : "memory");
   }
   __syncthreads();
-  if (blockIdx.x >= pl.total) return;
-  const int nitems = (int)((pl.total - 1 - blockIdx.x) / gridDim.x) + 1;
   if (threadIdx.x >= kRpThreads) {
-    // ---- helper warp: lane 0 publishes finished items, lane 1 polls dependencies ahead (the two lanes
+    // ---- helper warp: lane 0 publishes finished items, lane 1 claims / decodes / polls (the two lanes
     // diverge for the whole kernel; independent thread scheduling interleaves them, so the poller's L2
     // round trips and the signaller's fences do not wait for each other)
     if (threadIdx.x == kRpThreads) {
-      for (int ks = 0; ks < nitems; ++ks) {
-        const RpItem is = rp_decode(blockIdx.x + (long long)ks * gridDim.x, cnt_splat, cnt_fin, pl);
+      for (int ks = 0;; ++ks) {
+        while (s_ready < ks + 1) __nanosleep(40);
+        __threadfence_block();
+        const int round = s_slot[ks % kRpItemRing].round;
+        if (round < 0) break;
         while (!rp_mbar_test(&s_done[ks % kRing], (unsigned)(ks / kRing) & 1u)) __nanosleep(40);
-        __threadfence();                          // the workers' REDs / stores before the counter (cumulative)
-        atomicAdd(is.done_cnt, 1);
+        if (!(flags & 4)) __threadfence();        // the workers' REDs / stores before the counter (cumulative)
+        atomicAdd(done + round, 1);
         s_signalled = ks + 1;
       }
     } else if (threadIdx.x == kRpThreads + 1) {
-      for (int kp = 0; kp < nitems; ++kp) {
-        const RpItem ip = rp_decode(blockIdx.x + (long long)kp * gridDim.x, cnt_splat, cnt_fin, pl);
-        while (s_signalled + 8 < kp) __nanosleep(100);        // no need to run far ahead of the work
-        while (rp_peek(ip.wait_cnt) < ip.wait_need) __nanosleep(40);
+      for (int kp = 0;; ++kp) {
+        while (s_started + (claim_ahead - 1) < kp) __nanosleep(40);   // a claimed ticket blocks its dependents: stay close
+        long long p = (flags & 1) ? (long long)blockIdx.x + (long long)kp * gridDim.x
+                                  : (long long)atomicAdd(ticket, 1ull);
+        RpSlot& sl = s_slot[kp % kRpItemRing];
+        if (p >= pl.total) {
+          sl.round = -1;
+        } else {
+          const RpItem ip = rp_decode(p, pl);
+          sl.round = ip.round; sl.j = ip.j; sl.map_s = ip.map_s; sl.map_f = ip.map_f;
+          if (ip.map_s >= 0) sl.m = rp_load_map(K, pose, ip.map_s, lo, hi);
+          if (ip.round >= pl.D && !(flags & 2))   // (bit 1: timing experiments only -- results are wrong)
+            while (rp_peek(done + (ip.round - pl.D)) < pl.items) __nanosleep(40);
+        }
         __threadfence_block();
         s_ready = kp + 1;
+        if (p >= pl.total) break;
       }
     }
     return;
   }
   // ---- worker warps
   const int lane = threadIdx.x & 31;
-  for (int k = 0; k < nitems; ++k) {
-    const RpItem it = rp_decode(blockIdx.x + (long long)k * gridDim.x, cnt_splat, cnt_fin, pl);
-    // dependency satisfied (polled by the helper) and this item's barrier free (signaller through item k - kRing)
+  for (int k = 0;; ++k) {
+    // published by the helper and this item's barrier free (signaller through item k - kRing)
     while (s_ready < k + 1 || s_signalled < k - (kRing - 1)) __nanosleep(20);
     __threadfence_block();
-    rp_work<kScalarBmm>(it, depth, K, pose, lo, hi, scratch, depth_out, mask_out, pl);
+    const RpSlot& sl = s_slot[k % kRpItemRing];
+    if (sl.round < 0) break;
+    if (threadIdx.x == 0) s_started = k + 1;
+    rp_work<kScalarBmm>(sl.map_s, sl.map_f, sl.j, sl.m, depth, lo, hi, scratch, depth_out, mask_out, pl);
     __syncwarp();
     if (lane == 0)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rp_smem_u32(&s_done[k % kRing])) : "memory");
@@ -980,20 +1127,24 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
 
   RpPlan pl;
   pl.B = B; pl.H = H; pl.W = W; pl.HW = H * W;
-  pl.items = (pl.HW + kRpItemPx - 1) / kRpItemPx;
-  // ring: as many maps as fit 24 MB (L2-resident next to the streaming traffic), at least 2, at most 96
+  pl.st = rp_steps(W);
+  static const int item_px = getenv("PRG_RP_ITEM_PX") ? std::max(1, atoi(getenv("PRG_RP_ITEM_PX")) / kRpChunkPx) * kRpChunkPx : kRpItemPx;   // tuning
+  pl.item_px = item_px;
+  pl.items = (pl.HW + pl.item_px - 1) / pl.item_px;
+  // ring: as many maps as fit 48 MB (L2-resident next to the streaming traffic), an even number >= 2;
+  // a map is finalised D = R / 2 rounds after it was splatted
   {
     const size_t per_map = (size_t)pl.HW * sizeof(unsigned);
-    static const long long ring_mb = getenv("PRG_RP_RING_MB") ? std::max(1, atoi(getenv("PRG_RP_RING_MB"))) : 24;   // tuning
+    static const long long ring_mb = getenv("PRG_RP_RING_MB") ? std::max(1, atoi(getenv("PRG_RP_RING_MB"))) : 48;   // tuning
     long long r = (long long)((size_t)(ring_mb << 20) / per_map);
     r = std::max(2ll, std::min(192ll, r));
-    pl.R = (int)std::min<long long>(r, std::max(2, B));
-    pl.D = std::max(1, std::min(pl.R / 2, B));
-    if (pl.D >= pl.R) pl.D = pl.R - 1;
+    r = std::min<long long>(r, 2ll * B);
+    pl.D = (int)std::max(1ll, r / 2);
+    pl.R = 2 * pl.D;
   }
-  pl.total = 2ll * B * pl.items;
+  pl.total = (long long)(B + pl.D) * pl.items;
   const size_t need_words = (size_t)pl.R * pl.HW;
-  const size_t need_cnt = 2 * (size_t)B;
+  const size_t need_cnt = (size_t)(B + pl.D) + 2;      // [ticket (64 bit)] [one counter per round]
   if (z.ring_words < need_words || z.ncounters < need_cnt) {
     PRG_CUDA_OK(cudaDeviceSynchronize());          // nobody is using the old buffers
     if (z.ring_words < need_words) {
@@ -1016,18 +1167,22 @@ extern "C" __attribute__((visibility("default"))) int prg_reproject_f32(const fl
     PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_reproject_fused<false>, kRpCtaThreads, 0));
     int occ2 = 0;
     PRG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_reproject_fused<true>, kRpCtaThreads, 0));
-    z.grid = num_sms() * std::max(1, std::min(occ, occ2));   // every CTA resident: the item order relies on it
-    z.grid -= 1 - (z.grid & 1);                               // odd: every CTA alternates splat / finalise items
+    z.grid = num_sms() * std::max(1, std::min(occ, occ2));   // every CTA resident: the waits rely on it
   }
   if (z.used && z.last != s) PRG_CUDA_OK(cudaStreamWaitEvent(s, z.done, 0));
   PRG_CUDA_OK(cudaMemsetAsync(z.counters, 0, need_cnt * sizeof(int), s));
   const int grid = (int)std::min<long long>(z.grid, pl.total);
+  // bit 0: round-robin deal instead of tickets (A/B); bits 1, 2: timing experiments that BREAK the result
+  static const int flags = getenv("PRG_RP_FLAGS") ? atoi(getenv("PRG_RP_FLAGS")) : 0;
+  static const int claim_ahead = getenv("PRG_RP_AHEAD") ? std::max(1, std::min(3, atoi(getenv("PRG_RP_AHEAD")))) : kRpClaimAhead;
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(z.counters);
+  int* done = z.counters + 2;
   if ((long long)pl.HW * 9 < 400)     // maps of at most 44 pixels: ATen's scalar bmm rounding (see rigid())
     k_reproject_fused<true><<<grid, kRpCtaThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
-                                                       z.counters, z.counters + B, pl);
+                                                       done, ticket, flags, claim_ahead, pl);
   else
     k_reproject_fused<false><<<grid, kRpCtaThreads, 0, s>>>(depth, K, pose, clip_lo, clip_hi, z.ring, depth_out, mask_out,
-                                                        z.counters, z.counters + B, pl);
+                                                        done, ticket, flags, claim_ahead, pl);
   PRG_LAUNCH_CHECK();
   PRG_CUDA_OK(cudaEventRecord(z.done, s));
   z.last = s;

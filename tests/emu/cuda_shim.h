@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstring>
 #define __device__
+#define __host__
 #define __global__
 #define __forceinline__ inline
 #define __noinline__
@@ -33,6 +34,7 @@ static inline uchar4 make_uchar4(unsigned char a, unsigned char b, unsigned char
 template <class T> static inline T __ldcs(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 /* x86-64 SSE arithmetic rounds every operation to nearest even in its own precision */
@@ -72,5 +74,6 @@ static inline int __float2int_rn(float f) {
   return (int)nearbyintf(f);            /* default rounding mode: half to even */
 }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 static inline void __threadfence() {}
 static inline void __nanosleep(unsigned) {}

@@ -43,25 +43,25 @@ static void run_block(unsigned x, unsigned y, unsigned first, unsigned last, voi
 // the kernel deals them (every dependency of an item is an earlier item); ring of R slots, lag D as
 // the ABI entry plans them, but with a ring small enough that slots are reused even in tiny batches.
 extern "C" void emu_reproject(const float* depth, const float* K, const float* pose, float lo, float hi,
-                              float* out, uint8_t* mask, unsigned* scratch, int B, int H, int W, int R) {
+                              float* out, uint8_t* mask, unsigned* scratch, int B, int H, int W, int R, int item_chunks) {
   RpPlan pl;
   pl.B = B; pl.H = H; pl.W = W; pl.HW = H * W;
-  pl.items = (pl.HW + kRpItemPx - 1) / kRpItemPx;
-  pl.R = R < 2 ? 2 : R;
-  pl.D = pl.R / 2 < 1 ? 1 : pl.R / 2;
+  pl.st = rp_steps(W);
+  pl.item_px = item_chunks * kRpChunkPx;
+  pl.items = (pl.HW + pl.item_px - 1) / pl.item_px;
+  pl.D = R / 2 < 1 ? 1 : R / 2;
   if (pl.D > B) pl.D = B;
-  if (pl.D >= pl.R) pl.D = pl.R - 1;
-  pl.total = 2ll * B * pl.items;
+  pl.R = 2 * pl.D;
+  pl.total = (long long)(B + pl.D) * pl.items;
   memset(scratch, 0xFF, (size_t)pl.R * pl.HW * 4);
-  blockDim = {256, 1, 1};
+  blockDim = {(unsigned)kRpThreads, 1, 1};
   gridDim = {1, 1, 1};
   blockIdx = {0, 0, 0};
-  int dummy[2] = {0, 0};
   for (long long p = 0; p < pl.total; ++p)
-    for (unsigned t = 0; t < 256; ++t) {
+    for (unsigned t = 0; t < (unsigned)kRpThreads; ++t) {
       threadIdx = {t, 0, 0};
-      if ((long long)pl.HW * 9 < 400) rp_run_item<true>(p, depth, K, pose, lo, hi, scratch, out, mask, dummy, dummy, pl);
-      else rp_run_item<false>(p, depth, K, pose, lo, hi, scratch, out, mask, dummy, dummy, pl);
+      if ((long long)pl.HW * 9 < 400) rp_run_item<true>(p, depth, K, pose, lo, hi, scratch, out, mask, pl);
+      else rp_run_item<false>(p, depth, K, pose, lo, hi, scratch, out, mask, pl);
     }
   // the call must hand the ring back empty
   for (size_t i = 0; i < (size_t)pl.R * pl.HW; ++i)
@@ -256,7 +256,7 @@ def test_reproject_kernel_numerics(geom, shape, extreme):
     mask = np.empty((B, H, W), np.uint8)
     scratch = np.full((2, H, W), 0, np.uint32)            # ring of two slots: reused within the batch
     geom.emu_reproject(_vp(dm), _vp(K), _vp(P), ctypes.c_float(0.0), ctypes.c_float(10.0), _vp(out), _vp(mask),
-                       _vp(scratch), B, H, W, 2)
+                       _vp(scratch), B, H, W, 2, 1 + B % 2)
     assert _same_bits_or_nan(out.reshape(want_d.shape), want_d)
     assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m) and want_m.any()
 
@@ -404,7 +404,7 @@ def test_geometry_kernels_differential_fuzz(geom, seed):
         ring = 2 + trial % 3
         scratch = np.full((ring, H, W), 0, np.uint32)
         geom.emu_reproject(_vp(dm), _vp(K), _vp(P), ctypes.c_float(rclip[0]), ctypes.c_float(rclip[1]), _vp(out),
-                           _vp(mask), _vp(scratch), B, H, W, ring)
+                           _vp(mask), _vp(scratch), B, H, W, ring, 1 + trial % 3)
         assert _same_bits_or_nan(out.reshape(want_d.shape), want_d), ctx
         assert np.array_equal(mask.reshape(want_m.shape).astype(bool), want_m), ctx
 

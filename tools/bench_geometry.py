@@ -18,6 +18,7 @@ ap.add_argument("--maps", type=int, default=512)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--h", type=int, default=480)
 ap.add_argument("--w", type=int, default=640)
+ap.add_argument("--only", default="", help="reproject | depth2pc")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 B, H, W = a.maps, a.h, a.w
@@ -50,9 +51,11 @@ def timed(fn):
 
 
 px = B * H * W
-ms = timed(lambda: geometry.reproject_tensor(d, K, P))
-print("reproject_tensor %d maps %dx%d: %.3f ms  %.0f GB/s algorithmic (9 B/px)  %.2f of measured HBM peak %.0f; %.0f maps/s"
-      % (B, H, W, ms, px * 9 / ms / 1e6, px * 9 / ms / 1e6 / peak, peak, B / ms * 1e3))
-ms = timed(lambda: geometry.depth2pc_tensor(d, K, clip=[0, 10]))
-print("depth2pc_tensor  %d maps %dx%d: %.3f ms  %.0f GB/s algorithmic (17 B/px)  %.2f of measured HBM peak; %.0f maps/s"
-      % (B, H, W, ms, px * 17 / ms / 1e6, px * 17 / ms / 1e6 / peak, B / ms * 1e3))
+if a.only != "depth2pc":
+    ms = timed(lambda: geometry.reproject_tensor(d, K, P))
+    print("reproject_tensor %d maps %dx%d: %.3f ms  %.0f GB/s algorithmic (9 B/px)  %.2f of measured HBM peak %.0f; %.0f maps/s"
+          % (B, H, W, ms, px * 9 / ms / 1e6, px * 9 / ms / 1e6 / peak, peak, B / ms * 1e3))
+if a.only != "reproject":
+    ms = timed(lambda: geometry.depth2pc_tensor(d, K, clip=[0, 10]))
+    print("depth2pc_tensor  %d maps %dx%d: %.3f ms  %.0f GB/s algorithmic (17 B/px)  %.2f of measured HBM peak; %.0f maps/s"
+          % (B, H, W, ms, px * 17 / ms / 1e6, px * 17 / ms / 1e6 / peak, B / ms * 1e3))
