@@ -806,6 +806,56 @@ int step_advance(int* step_idx, cudaStream_t s) {
   return PRG_OK;
 }
 
+// What one pixel does with the network output `net`: forward / sigmoid (+ keep mask) / one sampler step.
+__device__ __forceinline__ void tail_pixel(const TailParams& t, float net, int b, int64_t p, size_t o) {
+  if (t.mode == 0) {
+    t.out[o] = net;
+    return;
+  }
+  if (t.mode == 1) {
+    const float pr = 1.f / (1.f + expf(-net));
+    if (t.out != nullptr) t.out[o] = pr;
+    if (t.keep != nullptr) t.keep[o] = pr > t.thresh;
+    return;
+  }
+  const float xt = t.x_t[o];
+  float x0 = net;
+  if (t.clip_x_start) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+  float pred_noise = 0.f;
+  if (t.sampler == 1 || t.sampler == 2 || t.sampler == 4)
+    pred_noise = __fdiv_rn(__fsub_rn(__fmul_rn(t.c0, xt), x0), t.c1);      // SDD:1158-1162
+  bool m = false;
+  if (t.img_cond != nullptr) {
+    const float mk = t.img_cond[((size_t)b * 2 + 1) * t.HW + p];
+    m = __fmul_rn(__fadd_rn(mk, 1.f), 0.5f) > 0.5f;                         // SDD:507-508
+    if (t.use_ddnm && m) x0 = t.img_cond[((size_t)b * 2 + 0) * t.HW + p];  // SDD:1218
+  }
+  float nz = 0.f;
+  if (t.add_noise)
+    nz = (t.noise != nullptr) ? t.noise[o] : philox_normal(t.seeds[b], t.noise_offset + (unsigned long long)p);
+  float xn;
+  if (t.sampler == 0 || t.sampler == 3) {
+    x0 = fminf(fmaxf(x0, -1.f), 1.f);                                       // SDD:1250-1251
+    const float mean = __fadd_rn(__fmul_rn(t.c0, x0), __fmul_rn(t.c1, xt));  // SDD:1174-1176
+    xn = __fadd_rn(mean, __fmul_rn(t.c2, nz));                              // SDD:1280
+    if (t.sampler == 3) xn = m ? xn : xt;                                   // SDD:1313-1314
+  } else if (t.sampler == 1) {
+    xn = __fadd_rn(__fadd_rn(__fmul_rn(x0, t.c2), __fmul_rn(t.c3, pred_noise)),
+                   __fmul_rn(t.c4, nz));                                   // SDD:1371-1373
+  } else if (t.sampler == 2) {
+    xn = x0;                                                                // SDD:1358-1360
+  } else {
+    xn = m ? x0 : xt;                                                       // SDD:1388-1389
+  }
+  if (t.unnormalize) xn = __fmul_rn(__fadd_rn(xn, 1.f), 0.5f);              // SDD:560-561
+  t.out[o] = xn;
+}
+
+// A warp walks blocks of 32 consecutive pixels.  Pass k (of eight) reduces pixels 4k .. 4k + 3 (eight lanes
+// per pixel, eight channels per lane: 512 contiguous bytes per warp load) and hands each result to lane
+// 4k + g; after the eight passes EVERY lane owns one pixel and runs the per-pixel stage -- Philox +
+// Box-Muller, DDNM, posterior / DDIM update -- so that part runs 32 lanes wide instead of on one lane
+// in eight (it was more than a third of the kernel inside the sampler loop).
 __global__ void __launch_bounds__(256)
 k_net_tail(TailParams t) {
   pdl_trigger();
@@ -831,76 +881,49 @@ k_net_tail(TailParams t) {
   if (threadIdx.x < 64) sW[threadIdx.x] = t.fw[threadIdx.x];
   __syncthreads();
   const float fb = __ldg(t.fb);
-  const int sub = threadIdx.x & 7;  // which 8-channel slice
-  const int c0 = sub * 8;
-  const int64_t pix_per_iter = ((int64_t)gridDim.x * blockDim.x) >> 3;
-  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < t.HW;
-       p += pix_per_iter) {
-    const size_t e = ((size_t)b * t.HW + p) * 64 + c0;
-    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(t.raw + e));
-    const uint4 r = __ldcs(reinterpret_cast<const uint4*>(t.res + e));
-    const __half2* hv = reinterpret_cast<const __half2*>(&v);
-    const __half2* hr = reinterpret_cast<const __half2*>(&r);
-    float dot = 0.f;
+  const int lane = threadIdx.x & 31;
+  const int c0 = (lane & 7) * 8;          // which 8-channel slice
+  float ca[8], cb[8], cw[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 a = __half22float2(hv[j]), q = __half22float2(hr[j]);
-      const float y0 = silu(fmaf(a.x, sA[c0 + 2 * j], sB[c0 + 2 * j])) + q.x;
-      const float y1 = silu(fmaf(a.y, sA[c0 + 2 * j + 1], sB[c0 + 2 * j + 1])) + q.y;
-      dot = fmaf(y0, sW[c0 + 2 * j], dot);
-      dot = fmaf(y1, sW[c0 + 2 * j + 1], dot);
-    }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    if (sub != 0) continue;
-    const float net = dot + fb;
-    const size_t o = (size_t)b * t.HW + p;
-    if (t.mode == 0) {
-      t.out[o] = net;
-    } else if (t.mode == 1) {
-      const float pr = 1.f / (1.f + expf(-net));
-      if (t.out != nullptr) t.out[o] = pr;
-      if (t.keep != nullptr) t.keep[o] = pr > t.thresh;
-    } else {
-      const float xt = t.x_t[o];
-      float x0 = net;
-      if (t.clip_x_start) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-      float pred_noise = 0.f;
-      if (t.sampler == 1 || t.sampler == 2 || t.sampler == 4)
-        pred_noise = __fdiv_rn(__fsub_rn(__fmul_rn(t.c0, xt), x0), t.c1);      // SDD:1158-1162
-      bool m = false;
-      if (t.img_cond != nullptr) {
-        const float mk = t.img_cond[((size_t)b * 2 + 1) * t.HW + p];
-        m = __fmul_rn(__fadd_rn(mk, 1.f), 0.5f) > 0.5f;                         // SDD:507-508
-        if (t.use_ddnm && m) x0 = t.img_cond[((size_t)b * 2 + 0) * t.HW + p];  // SDD:1218
+  for (int j = 0; j < 8; ++j) { ca[j] = sA[c0 + j]; cb[j] = sB[c0 + j]; cw[j] = sW[c0 + j]; }
+  const int64_t nblk = ((int64_t)t.HW + 31) >> 5;
+  for (int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk < nblk; blk += (int64_t)gridDim.x * 8) {
+    const int64_t p0 = blk * 32;
+    float mine = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t p = p0 + 4 * k + (lane >> 3);
+      float dot = 0.f;
+      if (p < t.HW) {
+        const size_t e = ((size_t)b * t.HW + p) * 64 + c0;
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(t.raw + e));
+        const uint4 r = __ldcs(reinterpret_cast<const uint4*>(t.res + e));
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+        const __half2* hr = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __half22float2(hv[j]), q = __half22float2(hr[j]);
+          const float y0 = silu(fmaf(a.x, ca[2 * j], cb[2 * j])) + q.x;
+          const float y1 = silu(fmaf(a.y, ca[2 * j + 1], cb[2 * j + 1])) + q.y;
+          dot = fmaf(y0, cw[2 * j], dot);
+          dot = fmaf(y1, cw[2 * j + 1], dot);
+        }
       }
-      float nz = 0.f;
-      if (t.add_noise)
-        nz = (t.noise != nullptr) ? t.noise[o] : philox_normal(t.seeds[b], t.noise_offset + (unsigned long long)p);
-      float xn;
-      if (t.sampler == 0 || t.sampler == 3) {
-        x0 = fminf(fmaxf(x0, -1.f), 1.f);                                       // SDD:1250-1251
-        const float mean = __fadd_rn(__fmul_rn(t.c0, x0), __fmul_rn(t.c1, xt));  // SDD:1174-1176
-        xn = __fadd_rn(mean, __fmul_rn(t.c2, nz));                              // SDD:1280
-        if (t.sampler == 3) xn = m ? xn : xt;                                   // SDD:1313-1314
-      } else if (t.sampler == 1) {
-        xn = __fadd_rn(__fadd_rn(__fmul_rn(x0, t.c2), __fmul_rn(t.c3, pred_noise)),
-                       __fmul_rn(t.c4, nz));                                   // SDD:1371-1373
-      } else if (t.sampler == 2) {
-        xn = x0;                                                                // SDD:1358-1360
-      } else {
-        xn = m ? x0 : xt;                                                       // SDD:1388-1389
-      }
-      if (t.unnormalize) xn = __fmul_rn(__fadd_rn(xn, 1.f), 0.5f);              // SDD:560-561
-      t.out[o] = xn;
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      const float got = __shfl_sync(0xffffffffu, dot, (lane & 3) * 8);   // pixel 4k + (lane & 3) of the block
+      if ((lane >> 2) == k) mine = got;
     }
+    const int64_t p = p0 + lane;
+    if (p < t.HW) tail_pixel(t, mine + fb, b, p, (size_t)b * t.HW + p);
   }
 }
 
 int net_tail(const TailParams& t, int B, cudaStream_t s) {
-  int gx = (int)(((int64_t)t.HW * 8 + 255) / 256);
-  const int cap = num_sms() * 8;
+  // a CTA = eight warps, a warp takes 32-pixel blocks; about eight resident CTAs per SM over the whole batch
+  int gx = (int)(((int64_t)t.HW + 255) / 256);
+  const int cap = std::max(1, (num_sms() * 8 + B - 1) / std::max(1, B));
   if (gx > cap) gx = cap;
   dim3 g(gx, B);
   PRG_CUDA_OK(launch_pdl(k_net_tail, g, dim3(256), 0, s, t));

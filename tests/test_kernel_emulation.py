@@ -509,8 +509,8 @@ extern "C" void emu_tail(const float* x_t, const float* img_cond, const float* n
 def tail(tmp_path_factory):
     """The sampler-step arithmetic of k_net_tail (mode 2), cut out of elementwise.cu verbatim."""
     src = open(os.path.join(ROOT, "pointreggpt_b200", "csrc", "elementwise.cu")).read()
-    a = src.index("      const float xt = t.x_t[o];")
-    b = src.index("      t.out[o] = xn;") + len("      t.out[o] = xn;")
+    a = src.index("  const float xt = t.x_t[o];")
+    b = src.index("  t.out[o] = xn;") + len("  t.out[o] = xn;")
     return _compile(tmp_path_factory.mktemp("emu"), "tail", TAIL_DRIVER_HEAD + src[a:b] + TAIL_DRIVER_TAIL)
 
 
