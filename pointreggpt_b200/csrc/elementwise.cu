@@ -851,6 +851,23 @@ __device__ __forceinline__ void tail_pixel(const TailParams& t, float net, int b
   t.out[o] = xn;
 }
 
+// sampler loop: this step's parameters come from the device-resident list (same launch for every step)
+__device__ __forceinline__ void tail_resolve_step(TailParams& t) {
+  if (t.mode != 2 || t.steps == nullptr) return;
+  const StepDev st = t.steps[*t.step_idx];
+  const SamplerCtx cx = *t.ctx;
+  t.sampler = st.kind;
+  t.add_noise = st.add_noise;
+  t.unnormalize = st.unnormalize;
+  t.c0 = st.c0; t.c1 = st.c1; t.c2 = st.c2; t.c3 = st.c3; t.c4 = st.c4;
+  t.img_cond = cx.img_cond;
+  t.noise = (cx.noise != nullptr && st.add_noise) ? cx.noise + (size_t)st.noise_slab * t.slab_stride : nullptr;
+  t.noise_offset = (unsigned long long)st.noise_slab * (unsigned long long)t.HW;
+  t.clip_x_start = (st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST || st.kind == PRG_STEP_REFINE_DDIM);
+  t.use_ddnm = (cx.img_cond != nullptr) &&
+               (st.kind == PRG_STEP_P_SAMPLE || st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST);
+}
+
 // A warp walks blocks of 32 consecutive pixels.  Pass k (of eight) reduces pixels 4k .. 4k + 3 (eight lanes
 // per pixel, eight channels per lane: 512 contiguous bytes per warp load) and hands each result to lane
 // 4k + g; after the eight passes EVERY lane owns one pixel and runs the per-pixel stage -- Philox +
@@ -862,21 +879,7 @@ k_net_tail(TailParams t) {
   pdl_wait();
   __shared__ float sA[64], sB[64], sW[64];
   const int b = blockIdx.y;
-  if (t.mode == 2 && t.steps != nullptr) {
-    // sampler loop: this step's parameters come from the device-resident list (same launch for every step)
-    const StepDev st = t.steps[*t.step_idx];
-    const SamplerCtx cx = *t.ctx;
-    t.sampler = st.kind;
-    t.add_noise = st.add_noise;
-    t.unnormalize = st.unnormalize;
-    t.c0 = st.c0; t.c1 = st.c1; t.c2 = st.c2; t.c3 = st.c3; t.c4 = st.c4;
-    t.img_cond = cx.img_cond;
-    t.noise = (cx.noise != nullptr && st.add_noise) ? cx.noise + (size_t)st.noise_slab * t.slab_stride : nullptr;
-    t.noise_offset = (unsigned long long)st.noise_slab * (unsigned long long)t.HW;
-    t.clip_x_start = (st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST || st.kind == PRG_STEP_REFINE_DDIM);
-    t.use_ddnm = (cx.img_cond != nullptr) &&
-                 (st.kind == PRG_STEP_P_SAMPLE || st.kind == PRG_STEP_DDIM || st.kind == PRG_STEP_DDIM_LAST);
-  }
+  tail_resolve_step(t);
   gn_coeffs(t.stats, t.gamma, t.beta, nullptr, 64, t.HW, b, sA, sB);
   if (threadIdx.x < 64) sW[threadIdx.x] = t.fw[threadIdx.x];
   __syncthreads();
@@ -929,6 +932,232 @@ int net_tail(const TailParams& t, int B, cudaStream_t s) {
   PRG_CUDA_OK(launch_pdl(k_net_tail, g, dim3(256), 0, s, t));
   PRG_LAUNCH_CHECK();
   return PRG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// ResnetBlock output in ONE streaming pass (SDD:731-734):  y = SiLU(GN(raw2)) + res_conv(cat(x0, x1))
+// [+ the PreNorm LayerNorm of y for the attention that follows].
+//
+// The separate form -- 1x1 conv on the tcgen05 engine (reads x, writes the shortcut tensor) followed by
+// k_gn_apply (reads raw2 and the shortcut, writes y) -- is two HBM-bound passes; the fused tcgen05
+// epilogue (EPI_GNRES) removed the shortcut tensor but put all the SiLU work on eight epilogue warps
+// and was no faster.  Here the 1x1 conv (16 K MACs per pixel at most) rides on mma.sync inside an
+// elementwise-style kernel with many resident warps: x, raw2 in, y out, nothing else.
+//
+// No shared-memory staging of activations: the k index of an MMA (and the n index of an n-tile) may be
+// permuted freely as long as both operands agree, so the fragments are chosen such that every lane
+// reads / writes 16 contiguous bytes of a pixel row:
+//   A (m16 x k16, k-step s of a 32-channel group): lane (g, t) supplies channels 8t + 4s + {0, 1} as
+//     k slots {2t, 2t+1} and 8t + 4s + {2, 3} as k slots {2t+8, 2t+9} of rows g and g + 8 -- one
+//     LDG.128 of channels 8t .. 8t+7 per row feeds both k-steps;
+//   B: W[ch][8t .. 8t+7] from shared memory (one LDS.128 feeds both k-steps);
+//   C (m16 x n8, n-tile jj of a 32-channel group): column c of the tile is channel 8 (c >> 1) + 2 jj +
+//     (c & 1), so lane (g, t) ends up with channels 8t .. 8t+7 of rows g and g + 8: raw2 in and y out are
+//     LDG.128 / STG.128.
+// ------------------------------------------------------------------------------------------
+//
+// TAIL = 1 (the network's final block, COUT = 64): y is not written at all -- it goes straight into the
+// final 1x1 conv (64 -> 1, a dot product over the four lanes that hold a pixel's channels) and the
+// per-pixel stage of the network tail (forward / sigmoid / sampler step, see tail_pixel).
+template <int COUT, int CIN, bool LN, bool TAIL>
+__global__ void __launch_bounds__(256, COUT == 64 ? 2 : 1)
+k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
+  pdl_trigger();
+  constexpr int NG = COUT / 32;            // output channel groups
+  constexpr int KG = CIN / 32;             // input channel groups
+  constexpr int kPitch = CIN * 2 + 64;     // bytes per weight row in shared memory (conflict-free LDS.128)
+  extern __shared__ __align__(16) uint8_t rsm[];
+  uint8_t* sW = rsm;
+  float2* sCoef = reinterpret_cast<float2*>(rsm + COUT * kPitch);
+  float* sBias = reinterpret_cast<float*>(sCoef + COUT);
+  float* sG = sBias + COUT;
+  // weights / bias / gain: not written by any kernel of the evaluation, so before the dependency wait
+  for (int i = threadIdx.x; i < COUT * (CIN / 8); i += 256) {
+    const int r = i / (CIN / 8), c = i - r * (CIN / 8);
+    *reinterpret_cast<uint4*>(sW + r * kPitch + c * 16) = __ldg(reinterpret_cast<const uint4*>(a.w + (size_t)r * CIN) + c);
+  }
+  for (int i = threadIdx.x; i < COUT; i += 256) {
+    sBias[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
+    sG[i] = LN ? __ldg(a.ln_g + i) : (TAIL ? __ldg(tp.fw + i) : 0.f);     // TAIL: weight of the final 1x1 conv
+  }
+  const float fb = TAIL ? __ldg(tp.fb) : 0.f;
+  pdl_wait();
+  if (TAIL) tail_resolve_step(tp);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int g_begin = (int)(((long long)blockIdx.x * total_blocks) / gridDim.x);
+  const int g_end = (int)(((long long)(blockIdx.x + 1) * total_blocks) / gridDim.x);
+  // weight row of n-tile jj (of group ng) for this lane's B fragment: channel 32 ng + 8 (g >> 1) + 2 jj + (g & 1)
+  const uint8_t* wrow = sW + (8 * (g >> 1) + (g & 1)) * kPitch + t * 16;
+  int b = -1;
+  for (int blk = g_begin; blk < g_end; ++blk) {
+    const int gb = blk / nblk, pb = blk - gb * nblk;
+    if (gb != b) {
+      b = gb;
+      __syncthreads();                     // everyone is done with the previous image's coefficients
+      for (int i = threadIdx.x; i < COUT; i += 256) sCoef[i] = a.coef[(size_t)b * COUT + i];
+      __syncthreads();
+    }
+    const size_t row0 = (size_t)b * a.HW + (size_t)pb * 128 + warp * 16 + g;    // pixel rows row0 and row0 + 8
+    // ---- every load of the tile first
+    uint4 xa[KG], xb[KG], ra[NG], rb[NG];
+#pragma unroll
+    for (int kg = 0; kg < KG; ++kg) {
+      const int c = kg * 32;
+      const __half* src = (c < a.c0) ? a.x0 + row0 * a.c0 + c : a.x1 + row0 * a.c1 + (c - a.c0);
+      const size_t step = (c < a.c0) ? (size_t)8 * a.c0 : (size_t)8 * a.c1;
+      xa[kg] = __ldcs(reinterpret_cast<const uint4*>(src) + t);
+      xb[kg] = __ldcs(reinterpret_cast<const uint4*>(src + step) + t);
+    }
+#pragma unroll
+    for (int ng = 0; ng < NG; ++ng) {
+      const __half* src = a.raw + row0 * COUT + ng * 32;
+      ra[ng] = __ldcs(reinterpret_cast<const uint4*>(src) + t);
+      rb[ng] = __ldcs(reinterpret_cast<const uint4*>(src + 8 * COUT) + t);
+    }
+    // ---- shortcut 1x1 conv
+    float acc[NG * 4][4];
+#pragma unroll
+    for (int j = 0; j < NG * 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int kg = 0; kg < KG; ++kg) {
+      const uint32_t f0[4] = {xa[kg].x, xb[kg].x, xa[kg].y, xb[kg].y};
+      const uint32_t f1[4] = {xa[kg].z, xb[kg].z, xa[kg].w, xb[kg].w};
+#pragma unroll
+      for (int j = 0; j < NG * 4; ++j) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(wrow + ((j >> 2) * 32 + (j & 3) * 2) * kPitch + kg * 64);
+        hmma16816(acc[j], f0, wv.x, wv.y);
+        hmma16816(acc[j], f1, wv.z, wv.w);
+      }
+    }
+    // ---- y = SiLU(A raw + B) + shortcut + bias, rounded to fp16 (kept in acc for the LayerNorm)
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int ng = 0; ng < NG; ++ng) {
+      const int ch = ng * 32 + t * 8;
+      const __half2* h0 = reinterpret_cast<const __half2*>(&ra[ng]);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&rb[ng]);
+      uint32_t o0[4], o1[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 cf = *reinterpret_cast<const float4*>(sCoef + ch + 2 * jj);     // (A, B) of two channels
+        const float2 bi = *reinterpret_cast<const float2*>(sBias + ch + 2 * jj);
+        const float2 cA = make_float2(cf.x, cf.z), cB = make_float2(cf.y, cf.w);
+        float* c = acc[ng * 4 + jj];
+        float2 y0 = silu2(__ffma2_rn(__half22float2(h0[jj]), cA, cB));
+        float2 y1 = silu2(__ffma2_rn(__half22float2(h1[jj]), cA, cB));
+        y0 = __fadd2_rn(y0, __fadd2_rn(make_float2(c[0], c[1]), bi));
+        y1 = __fadd2_rn(y1, __fadd2_rn(make_float2(c[2], c[3]), bi));
+        if (TAIL) {                       // final 1x1 conv: this lane's share of the two pixels' dot products
+          const float2 fw = *reinterpret_cast<const float2*>(sG + ch + 2 * jj);
+          sum0 = fmaf(y0.y, fw.y, fmaf(y0.x, fw.x, sum0));
+          sum1 = fmaf(y1.y, fw.y, fmaf(y1.x, fw.x, sum1));
+          continue;
+        }
+        const __half2 q0 = __floats2half2_rn(y0.x, y0.y), q1 = __floats2half2_rn(y1.x, y1.y);
+        o0[jj] = *reinterpret_cast<const uint32_t*>(&q0);
+        o1[jj] = *reinterpret_cast<const uint32_t*>(&q1);
+        if (LN) {
+          const float2 r0 = __half22float2(q0), r1 = __half22float2(q1);
+          c[0] = r0.x; c[1] = r0.y; c[2] = r1.x; c[3] = r1.y;
+          sum0 += r0.x + r0.y;
+          sum1 += r1.x + r1.y;
+        }
+      }
+      if (TAIL) continue;
+      __half* dst = a.y + row0 * COUT + ch;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+      *reinterpret_cast<uint4*>(dst + 8 * COUT) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    }
+    if (TAIL) {
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      // lane t = 0 finishes the pixel of row g, lane t = 1 the pixel of row g + 8
+      if (t < 2) {
+        const int64_t p = (int64_t)pb * 128 + warp * 16 + g + 8 * t;
+        tail_pixel(tp, (t == 0 ? sum0 : sum1) + fb, b, p, (size_t)b * a.HW + p);
+      }
+      continue;
+    }
+    if (LN) {
+      // channel LayerNorm of the fp16-rounded y (what the attention's PreNorm would read back), two-pass
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float mean0 = sum0 * (1.f / COUT), mean1 = sum1 * (1.f / COUT);
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NG * 4; ++j) {
+        const float d0 = acc[j][0] - mean0, d1 = acc[j][1] - mean0, d2 = acc[j][2] - mean1, d3 = acc[j][3] - mean1;
+        q0 = fmaf(d0, d0, q0); q0 = fmaf(d1, d1, q0);
+        q1 = fmaf(d2, d2, q1); q1 = fmaf(d3, d3, q1);
+      }
+      q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      const float rs0 = rsqrtf(q0 * (1.f / COUT) + 1e-5f), rs1 = rsqrtf(q1 * (1.f / COUT) + 1e-5f);
+#pragma unroll
+      for (int ng = 0; ng < NG; ++ng) {
+        const int ch = ng * 32 + t * 8;
+        uint32_t o0[4], o1[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float2 gn = *reinterpret_cast<const float2*>(sG + ch + 2 * jj);
+          const float* c = acc[ng * 4 + jj];
+          const __half2 l0 = __floats2half2_rn((c[0] - mean0) * rs0 * gn.x, (c[1] - mean0) * rs0 * gn.y);
+          const __half2 l1 = __floats2half2_rn((c[2] - mean1) * rs1 * gn.x, (c[3] - mean1) * rs1 * gn.y);
+          o0[jj] = *reinterpret_cast<const uint32_t*>(&l0);
+          o1[jj] = *reinterpret_cast<const uint32_t*>(&l1);
+        }
+        __half* dst = a.ln_out + row0 * COUT + ch;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<uint4*>(dst + 8 * COUT) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+      }
+    }
+  }
+}
+
+// (the 192 -> 128 instantiation exists and is correct, but at 250 registers / 8 warps per SM it measured
+// 160 us against 68 + 79 us for the two-pass form at 128-pixel rows, so the planner only asks for 128 -> 64)
+bool res1x1_gn_supported(int cout, int c0, int c1, int HW) {
+  return HW % 128 == 0 && c0 % 32 == 0 && c1 % 32 == 0 && cout == 64 && c0 + c1 == 128;
+}
+
+template <int COUT, int CIN>
+static int res1x1_gn_launch(const ResGn& a, const TailParams* tail, int B, cudaStream_t s) {
+  const int nblk = a.HW / 128, total = nblk * B;
+  const size_t smem = (size_t)COUT * (CIN * 2 + 64) + COUT * (sizeof(float2) + 2 * sizeof(float));
+  int grid = num_sms() * (COUT == 64 ? 2 : 1);          // one resident wave
+  if (grid > total) grid = total;
+  if (grid < 1) grid = 1;
+  const TailParams tp = tail ? *tail : TailParams{};
+  auto go = [&](auto kern) -> int {
+    PRG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
+    PRG_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(256), smem, s, a, tp, total, nblk));
+    PRG_LAUNCH_CHECK();
+    return PRG_OK;
+  };
+  if (tail != nullptr) {
+    if (COUT != 64) { set_error("res1x1_gn: the fused tail needs 64 channels"); return PRG_ERR_ARG; }
+    return go(k_res1x1_gn<64, 128, false, true>);
+  }
+  if (a.ln_out != nullptr) return go(k_res1x1_gn<COUT, CIN, true, false>);
+  return go(k_res1x1_gn<COUT, CIN, false, false>);
+}
+
+int res1x1_gn(const ResGn& a, int B, cudaStream_t s) {
+  if (!res1x1_gn_supported(a.Cout, a.c0, a.c1, a.HW)) {
+    set_error("res1x1_gn: unsupported shape (Cout %d, Cin %d + %d, HW %d)", a.Cout, a.c0, a.c1, a.HW);
+    return PRG_ERR_ARG;
+  }
+  if (a.Cout == 64) return res1x1_gn_launch<64, 128>(a, nullptr, B, s);
+  return res1x1_gn_launch<128, 192>(a, nullptr, B, s);
+}
+
+int net_tail_fused(const TailParams& t, const ResGn& a, int B, cudaStream_t s) {
+  if (a.Cout != 64 || !res1x1_gn_supported(a.Cout, a.c0, a.c1, a.HW) || t.HW != a.HW) {
+    set_error("net_tail_fused: unsupported shape (Cout %d, Cin %d + %d, HW %d)", a.Cout, a.c0, a.c1, a.HW);
+    return PRG_ERR_ARG;
+  }
+  return res1x1_gn_launch<64, 128>(a, &t, B, s);
 }
 
 }  // namespace prg

@@ -57,6 +57,23 @@ int gn_apply(const GnApply& a, int B, cudaStream_t s);
 // coef[b][c] = (A, B) with y = SiLU(A * raw + B) (uses stats / gamma / beta / ss / HW / C of `a`).
 int gn_coef(const GnApply& a, float2* coef, int B, cudaStream_t s);
 
+// ---- ResnetBlock output in one pass (SDD:731-734): y = SiLU(A raw + B) + res_conv(cat(x0, x1)) + bias
+// [+ ln_out = LN_c(y) * ln_g].  (A, B) per (image, channel) come from gn_coef.
+struct ResGn {
+  const __half *x0, *x1;      // cat(x0, x1) along channels; contiguous NHWC (pixel stride = channel count)
+  int c0, c1;                 // channel counts (multiples of 32; c1 = 0 and x1 = nullptr without a skip input)
+  const __half* w;            // res_conv weight [Cout][c0 + c1] fp16
+  const float* bias;          // [Cout] or nullptr
+  const __half* raw;          // block2's raw conv output (B, HW, Cout)
+  const float2* coef;         // from gn_coef
+  __half* y;                  // (B, HW, Cout)
+  const float* ln_g;          // optional fused channel LayerNorm of y: gain ...
+  __half* ln_out;             // ... and destination
+  int HW, Cout;
+};
+bool res1x1_gn_supported(int cout, int c0, int c1, int HW);
+int res1x1_gn(const ResGn& a, int B, cudaStream_t s);
+
 // ---- channel LayerNorm with gain (SDD:619-628): y = LN_c(x) * g [+ res] -----------------------
 int ln_apply(const __half* x, const float* g, const __half* res, __half* y, int64_t npix, int C,
              cudaStream_t s);
@@ -117,6 +134,9 @@ struct TailParams {
 // step_idx += 1 (last node of the per-step graph)
 int step_advance(int* step_idx, cudaStream_t s);
 int net_tail(const TailParams& t, int B, cudaStream_t s);
+// the same with the final block's shortcut 1x1 conv + GroupNorm apply computed inside (t.raw / t.stats /
+// t.gamma / t.beta / t.res are not used: `a` carries x0, x1, raw, the weights and the gn_coef output)
+int net_tail_fused(const TailParams& t, const ResGn& a, int B, cudaStream_t s);
 
 // N(0,1) draws from one Philox stream per image (key = seeds_dev[b], counter = offset + index)
 int fill_normal(float* x, int B, int64_t per_image, const unsigned long long* seeds_dev,

@@ -26,9 +26,9 @@ using namespace prg;
 
 namespace {
 
-enum OpCat { CAT_CONV = 0, CAT_GN, CAT_LN, CAT_CTX, CAT_QOUT, CAT_ATTN, CAT_STEM, CAT_COND, CAT_TAIL, CAT_COUNT };
+enum OpCat { CAT_CONV = 0, CAT_GN, CAT_LN, CAT_CTX, CAT_QOUT, CAT_ATTN, CAT_STEM, CAT_COND, CAT_TAIL, CAT_RESGN, CAT_COUNT };
 const char* const kCatNames[CAT_COUNT] = {"conv_tc", "gn_apply", "ln_apply", "linattn_kvctx",
-                                          "linattn_qout", "attn_mid", "stem", "cond", "tail"};
+                                          "linattn_qout", "attn_mid", "stem", "cond", "tail", "res1x1_gn"};
 
 // Sampled per-op timing with CUDA events on the launching stream (bench.py's roofline leg).
 struct Profiler {
@@ -146,6 +146,8 @@ struct prg_net {
 
   // tail (filled by the builder)
   TailParams tail{};
+  bool tail_fused = false;      // the tail kernel also runs the final block's shortcut conv + GroupNorm apply
+  ResGn tail_rg{};
   __half* stem_out = nullptr;
   float* x_state = nullptr;  // sampler state (maxB, S*S) f32
   unsigned long long* seeds_dev = nullptr;  // sampler: per-image Philox keys (maxB)
@@ -313,6 +315,8 @@ int ilog2i(int v) {
 }
 
 struct BlockOut {
+  bool fused_tail = false;  // final block: shortcut conv + GroupNorm apply run inside the tail kernel (`rg`)
+  ResGn rg{};
   Act y;                 // output (unused for the final block)
   const long long* stats2;  // final block: statistics of block2
   const float *g2, *b2;
@@ -401,6 +405,34 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
   }
   const __half* res_ptr;
   int res_stride;
+  // Shortcut 1x1 conv + second GroupNorm apply + residual add (+ the attention's PreNorm LayerNorm) as ONE
+  // streaming mma.sync pass (k_res1x1_gn): the shortcut tensor never exists, x / raw2 are read once and
+  // y written once.  Where the shapes allow it (the up path at 256- and 128-pixel rows: 128 -> 64 and
+  // 192 -> 128 with contiguous sources); PRG_NO_RESGN=1 keeps the two-pass form for A/B runs.
+  if (!last && n->has(pfx + ".res_conv.weight") && getenv("PRG_NO_RESGN") == nullptr && getenv("PRG_GNRES") == nullptr &&
+      x0.pix_stride == x0.C && (x1 == nullptr || x1->pix_stride == x1->C) &&
+      res1x1_gn_supported(cout, x0.C, x1 ? x1->C : 0, HW)) {
+    NET_PTR(wr, n->f16(pfx + ".res_conv.weight"));
+    NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
+    Act y = new_act(n, H, W, cout);
+    if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
+    GnApply a{};
+    a.raw = raw2.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr; a.HW = HW; a.C = cout;
+    float2* coef = n->gn_coef_buf;
+    n->add_op(CAT_GN, [a, coef](const Run& r) { return gn_coef(a, coef, r.B, r.s); },
+              "gn_coef c" + std::to_string(cout));
+    ResGn rg{};
+    rg.x0 = x0.p; rg.c0 = x0.C;
+    rg.x1 = x1 ? x1->p : nullptr; rg.c1 = x1 ? x1->C : 0;
+    rg.w = wr; rg.bias = br; rg.raw = raw2.p; rg.coef = coef; rg.y = y.p; rg.HW = HW; rg.Cout = cout;
+    if (fuse_ln_g != nullptr) { rg.ln_g = fuse_ln_g; rg.ln_out = n->xn; }
+    n->add_op(CAT_RESGN, [rg](const Run& r) { return res1x1_gn(rg, r.B, r.s); },
+              "res1x1_gn " + std::to_string(H) + "x" + std::to_string(W) + " " + std::to_string(cin) + "->" +
+                  std::to_string(cout) + (rg.ln_g ? " +ln" : ""),
+              2.0 * H * W * (double)cout * cin);
+    bo->y = y;
+    return PRG_OK;
+  }
   // res_conv fused with the second GroupNorm apply (conv engine EPI_GNRES): y = res_conv(x) +
   // SiLU(GN(raw2)); the shortcut tensor never reaches HBM.  With a PreNorm LayerNorm to emit this
   // needs the whole channel row in one thread, i.e. Cout = 64.
@@ -443,6 +475,26 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
                 2.0 * H * W * (double)cout * cin);
     }
     bo->y = y;
+    return PRG_OK;
+  }
+  if (last && n->has(pfx + ".res_conv.weight") && getenv("PRG_NO_RESGN") == nullptr &&
+      x0.pix_stride == x0.C && (x1 == nullptr || x1->pix_stride == x1->C) &&
+      res1x1_gn_supported(cout, x0.C, x1 ? x1->C : 0, HW)) {
+    // final block: the same fusion inside the network tail (k_res1x1_gn<TAIL>): neither the shortcut
+    // tensor nor y is ever written
+    NET_PTR(wr, n->f16(pfx + ".res_conv.weight"));
+    NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
+    GnApply a{};
+    a.raw = raw2.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr; a.HW = HW; a.C = cout;
+    float2* coef = n->gn_coef_buf;
+    n->add_op(CAT_GN, [a, coef](const Run& r) { return gn_coef(a, coef, r.B, r.s); },
+              "gn_coef c" + std::to_string(cout));
+    ResGn& rg = bo->rg;
+    rg.x0 = x0.p; rg.c0 = x0.C;
+    rg.x1 = x1 ? x1->p : nullptr; rg.c1 = x1 ? x1->C : 0;
+    rg.w = wr; rg.bias = br; rg.raw = raw2.p; rg.coef = coef; rg.y = nullptr; rg.HW = HW; rg.Cout = cout;
+    bo->fused_tail = true;
+    bo->stats2 = st2; bo->g2 = g2; bo->b2 = be2; bo->raw2 = raw2.p;
     return PRG_OK;
   }
   if (n->has(pfx + ".res_conv.weight")) {
@@ -775,6 +827,8 @@ int build(prg_net* n) {
     NET_TRY(add_resblock(n, "final_res_block", x, &stem, n->dim, &ss_cursor, true, &bo));
     TailParams& t = n->tail;
     t.raw = bo.raw2; t.stats = bo.stats2; t.gamma = bo.g2; t.beta = bo.b2; t.res = n->resb;
+    n->tail_fused = bo.fused_tail;
+    n->tail_rg = bo.rg;
     const std::string fc = n->kind == PRG_NET_UNET ? "final_conv" : "final_conv.0";
     t.fw = n->f32(fc + ".weight");
     t.fb = n->f32(fc + ".bias");
@@ -822,14 +876,14 @@ int run_trunk(prg_net* n, const Run& r) {
 
 int run_tail(prg_net* n, const TailParams& t, int B, cudaStream_t s) {
   const bool prof = g_prof.every > 0 && ((n->forwards - 1) % (uint64_t)g_prof.every) == 0;
-  if (!prof) return net_tail(t, B, s);
+  if (!prof) return n->tail_fused ? net_tail_fused(t, n->tail_rg, B, s) : net_tail(t, B, s);
   const bool pdl_prev = g_pdl_enabled;
   g_pdl_enabled = false;
   struct Restore { bool v; ~Restore() { g_pdl_enabled = v; } } restore{pdl_prev};
   Profiler::Rec rec{g_prof.get(), g_prof.get(), CAT_TAIL,
                     g_prof.op_id(n->kind == PRG_NET_UNET ? "Utail" : "Mtail", 0)};
   cudaEventRecord(rec.a, s);
-  const int rc = net_tail(t, B, s);
+  const int rc = n->tail_fused ? net_tail_fused(t, n->tail_rg, B, s) : net_tail(t, B, s);
   cudaEventRecord(rec.b, s);
   g_prof.recs.push_back(rec);
   return rc;
