@@ -102,6 +102,9 @@ struct Conv2Params {
   int halo, wres, n_tiles, stages;
   int pair;             // per-tap mode, BN = 128: an item is TWO adjacent M tiles sharing every B stage
   int nsrc;             // halo mode: 1, or 2 = cat(x0, x1) of two 64-channel sources streamed row by row
+  int cls_bind;         // halo mode, folded x2 upsample ("rows3"): CTA i works on parity class i & 3 only -- its
+                        // class's weights (K columns cls * num_kb * 64 ...) stay resident, its input window is
+                        // shifted by (py, px) and only the dx = 0, 1 taps are issued (see conv2_plan)
   int direct_store;     // BN = 64 epilogue writes global memory itself (no staging slabs / TMA store)
   int total_items;      // per-tap: m_tiles * n_tiles * classes ; halo: number of row segments
   int m_tiles;          // per-tap: tiles_x * tiles_y * B
@@ -161,6 +164,10 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int item0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // per-tap item walk
   const int istep = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // row-streaming segment walk; with cls_bind the grid is four interleaved groups, one per parity class
+  const int cls_b = P.cls_bind ? (int)(blockIdx.x & 3u) : 0;
+  const int seg0 = P.cls_bind ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
+  const int sstep = P.cls_bind ? (int)(gridDim.x >> 2) : (int)gridDim.x;
   // fp16 staging.  BN = 64: eight per-warp 4 KB slabs.  BN >= 128: ONE 64-channel box (16 KB) that
   // the epilogue fills and stores BN/64 times per tile -- the shared memory this frees buys a
   // fourth load stage, and these layers are bound by the bytes in flight, not by the epilogue.
@@ -266,14 +273,14 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             // dy = 2, 1, 0 are one contiguous N = 192 B operand
             const int wtap = kb / chunks, wcc = kb - wtap * chunks;   // halo: per source, per dx, dy = 2, 1, 0
             const int blk = P.halo ? wcc * 9 + (wtap % 3) * 3 + (2 - wtap / 3) : nt * num_kb + kb;
-            tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)blk * kBBytes, kb * kBlockK, nt * BN, 0);
+            tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)blk * kBBytes, (cls_b * num_kb + kb) * kBlockK, nt * BN, 0);
           }
       }
       int stage = 0;
       uint32_t phase = 0;
       int dbg_row = 0;
       if (P.halo) {
-        for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+        for (int seg = seg0; seg < P.total_items; seg += sstep) {
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
           for (int r = 0; r < nr + 2; ++r) {
@@ -283,7 +290,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               ++dbg_row;
               mbar_arrive_expect_tx(&ctl->full[stage], kHaloBytes);
               tma_load_4d(src == 0 ? &tmA0 : &tmA1, &ctl->full[stage], sA + (size_t)stage * P.a_slot, 0,
-                          x0 - 1, y0 - 1 + r, img);
+                          x0 - 1 + (cls_b & 1), y0 - 1 + r + (cls_b >> 1), img);
               if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -377,7 +384,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       // (dx, k16) -- split in two only where the slot ring wraps, and on the very first
       // (dx, k16) = (0, 0) step, where the new target (dy = 0) must overwrite, not accumulate.
       constexpr uint32_t idesc0 = idesc_f16(kBlockM, 0);   // + (N >> 3) << 17
-      for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+      for (int seg = seg0; seg < P.total_items; seg += sstep) {
         int img, x0, y0, nr;
         decode_seg(seg, img, x0, y0, nr);
         for (int ri = 0; ri < nr + 2; ++ri) {
@@ -420,18 +427,21 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
                 umma_f16(taddr_u + sn * 64u, da0, db0 + (uint64_t)(n_old * kBlk), idesc0 | (8u << 17), 0u);
               }
             }
+            const int smax = P.cls_bind ? 8 : 12;                   // rows3: the dx = 2 taps are zero, skip them
             if (c1 == cnt) {
               const uint32_t id = idesc0 | ((uint32_t)(cnt * 8) << 17);
 #pragma unroll
               for (int s = 1; s < 12; ++s)
-                umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + (uint64_t)((s >> 2) * 3 * kBlk + (s & 3) * 2),
-                         id, 1u);
+                if (s < smax)
+                  umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + (uint64_t)((s >> 2) * 3 * kBlk + (s & 3) * 2),
+                           id, 1u);
             } else {
               const uint32_t id1 = idesc0 | ((uint32_t)(c1 * 8) << 17);
               const uint32_t id2 = idesc0 | ((uint32_t)((cnt - c1) * 8) << 17);
               const uint64_t db1 = db0 + (uint64_t)(c1 * kBlk);
 #pragma unroll
               for (int s = 1; s < 12; ++s) {
+                if (s >= smax) break;
                 const uint64_t bo = (uint64_t)((s >> 2) * 3 * kBlk + (s & 3) * 2);
                 umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + bo, id1, 1u);
                 umma_f16(taddr_u, da0 + (uint64_t)(2 * s), db1 + bo, id2, 1u);
@@ -509,7 +519,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     constexpr int kBatch = 6;                        // cells in flight per lane
     const bool exact = (P.dbg_flags & 128) != 0;     // A/B switch: ex2 + rcp SiLU as in k_gn_apply
     long long g = 0;                                 // ring row counter (all rows of all segments of this CTA)
-    for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+    for (int seg = seg0; seg < P.total_items; seg += sstep) {
       int img, x0, y0, nr;
       decode_seg(seg, img, x0, y0, nr);
       // (A, B) of this lane's eight channels for this image (k_gn_coef wrote them; L2 hits), halved:
@@ -1092,10 +1102,10 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 
     if constexpr (BN == 64) {
       if (P.halo) {
-        for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+        for (int seg = seg0; seg < P.total_items; seg += sstep) {
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
-          for (int j = 0; j < nr; ++j) do_tile64(img, x0, y0 + j, 0);
+          for (int j = 0; j < nr; ++j) do_tile64(img, x0, y0 + j, cls_b);
         }
       } else {
         for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
@@ -1106,7 +1116,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       if (lane == 0) bulk_wait0();
     } else {
       if (P.halo) {
-        for (int seg = blockIdx.x; seg < P.total_items; seg += gridDim.x) {
+        for (int seg = seg0; seg < P.total_items; seg += sstep) {
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
           for (int j = 0; j < nr; ++j) do_tile(img, x0, y0 + j, 0, 0);
@@ -1230,9 +1240,30 @@ static void halo_segments(Conv2Params* P, int B, int sms) {
   P->total_items = B * strips * P->segs_per_strip;
 }
 
-static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode,
+// rows3 = 1: the folded nearest-x2 upsample + 3x3 conv, 128 -> 64 channels, as FOUR class-bound row-streaming
+// convolutions in one launch.  Parity class (py, px) of the output is a 2x2-tap conv on the low-res input;
+// written as a 3x3 conv whose ky = 2 / kx = 2 taps are zero on the input shifted by (py, px), it runs on the
+// two-source row-streaming kernel (the 128 input channels = two 64-channel sources of the same tensor):
+// every input row is loaded once per class instead of once per tap, the class's weights stay resident, and
+// the zero kx = 2 taps are not issued.  `w` = [64][4 classes][3][3][128] (packing.upsample_rows3_weight).
+// s0 is the 128-channel input; the per-tap form of this layer was TMA-bound at a third of the tensor rate.
+static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0_in, const ActSrc* s1_in, int mode,
                       int ksize, int classes, const __half* w, int w_batched, int Cout,
-                      const ActSrc& out) {
+                      const ActSrc& out, int rows3 = 0) {
+  ActSrc s0 = s0_in, s1v;
+  const ActSrc* s1 = s1_in;
+  if (rows3) {
+    if (s0_in.C != 128 || s1_in != nullptr || Cout != 64 || mode != 0 || ksize != 3 || classes != 4 || w_batched ||
+        epi != EPI_BIAS || s0_in.W % kBlockM != 0 || num_sms() < 4) {
+      set_error("conv_plan: the class-bound row-streaming upsample needs 128 -> 64 channels, rows of 128 pixels");
+      return PRG_ERR_ARG;
+    }
+    s0.C = 64;
+    s1v = s0;
+    s1v.ptr = s0.ptr + 64;
+    s1 = &s1v;
+    classes = 1;            // per CTA: one class, planned like a 3x3 two-source conv
+  }
   memset(L, 0, sizeof(*L));
   Conv2Params& P = L->P;
   ConvParams& p = P.c;
@@ -1267,7 +1298,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   p.cin0 = s0.C;
   p.classes = classes;
   p.w_batched = w_batched;
-  p.out_scale = (classes == 4) ? 2 : 1;
+  p.out_scale = (classes == 4 || rows3) ? 2 : 1;
   L->epi = epi;
 
   int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
@@ -1305,6 +1336,11 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
                         w_all + kCtlBytes + 1024 + 4 * kHaloSlot <= kSmemBudget;
   P.nsrc = 1;
   P.direct_store = 0;
+  P.cls_bind = 0;
+  if (rows3 && !halo2_ok) {
+    set_error("conv_plan: class-bound row-streaming upsample not plannable here");
+    return PRG_ERR_ARG;
+  }
   if (halo2_ok) {
     P.halo = 1;
     P.wres = 1;
@@ -1340,12 +1376,16 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   L->smem = P.w_bytes + stages * per_stage + fixed_used;
 
   const int sms = num_sms();
-  if (P.halo) {
+  if (rows3) {
+    P.cls_bind = 1;
+    halo_segments(&P, B, sms / 4);                 // per class: a quarter of the CTAs
+    L->grid = 4 * std::min(P.total_items, sms / 4);
+  } else if (P.halo) {
     halo_segments(&P, B, sms);
   } else {
     P.total_items = (P.m_tiles >> (P.pair | (L->cg == 2))) * P.n_tiles * classes;
   }
-  L->grid = (L->cg == 2) ? 2 * std::min(P.total_items, sms / 2) : std::min(P.total_items, sms);
+  if (!rows3) L->grid = (L->cg == 2) ? 2 * std::min(P.total_items, sms / 2) : std::min(P.total_items, sms);
 
   // ---- tensor maps: activations
   for (int si = 0; si < 2; ++si) {
@@ -1373,7 +1413,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0, const Ac
   }
   // ---- weights: [nb][Cout][classes*ntaps*cin]
   {
-    const uint64_t ktot = (uint64_t)classes * ntaps * cin;
+    const uint64_t ktot = (uint64_t)(rows3 ? 4 : classes) * ntaps * cin;
     uint64_t dims[3] = {ktot, (uint64_t)Cout, (uint64_t)(w_batched ? B : 1)};
     uint64_t str[2] = {ktot * 2, ktot * 2 * Cout};
     uint32_t box[3] = {64, (uint32_t)(bn / L->cg), 1};
@@ -1517,6 +1557,18 @@ int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1,
   return PRG_OK;
 }
 
+int conv_op_plan_upsample_rows3(ConvOp* op, int B, const ActSrc& s0, const __half* w_rows3, const ActSrc& out) {
+  Conv2Launch* L = new Conv2Launch();
+  int rc = conv2_plan(L, EPI_BIAS, B, s0, nullptr, 0, 3, 4, w_rows3, 0, 64, out, 1);
+  if (rc) {
+    delete L;
+    return rc;
+  }
+  delete reinterpret_cast<Conv2Launch*>(op->impl);
+  op->impl = L;
+  return PRG_OK;
+}
+
 bool conv_op_can_transform_input(const ConvOp& op) {
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
   return L->P.halo && L->P.nsrc == 1 && L->bn == 64 && L->epi == EPI_GN && L->cg == 1 && !(conv_flags() & 64);
@@ -1558,6 +1610,11 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
   Conv2Params& P = L.P;
   P.c.B = B;
   P.m_tiles = P.c.tiles_x * P.c.tiles_y * B;
+  if (P.cls_bind) {
+    halo_segments(&P, B, num_sms() / 4);
+    L.grid = 4 * std::min(P.total_items, num_sms() / 4);
+    return conv2_run(L, stream);
+  }
   if (P.halo)
     halo_segments(&P, B, num_sms());
   else
@@ -1568,8 +1625,8 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
 
 const char* conv_op_describe(const ConvOp& op, char* buf, int n) {
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
-  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d cg=%d xf=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
-           L->P.halo, L->P.wres, L->P.pair, L->cg, L->xf, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
+  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d cg=%d xf=%d rows3=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
+           L->P.halo, L->P.wres, L->P.pair, L->cg, L->xf, L->P.cls_bind, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
   return buf;
 }
 

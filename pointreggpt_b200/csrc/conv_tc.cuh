@@ -71,6 +71,10 @@ struct ConvOp {
 // out: destination tensor (H, W = full output size, C = Cout, pix_stride).
 int conv_op_plan(ConvOp* op, int epi, int B, const ActSrc& s0, const ActSrc* s1, int mode, int ksize,
                  int classes, const __half* w, int w_batched, int Cout, const ActSrc& out);
+// The folded nearest-x2 upsample + 3x3 conv for 128 -> 64 channels on rows of 128 (or 256, ...) input pixels as
+// four class-bound row-streaming convolutions in one launch (see conv2_plan).  s0 = the 128-channel low-res
+// input, w_rows3 = [64][4][3][3][128] fp16 (packing.upsample_rows3_weight), out = the full-size output.
+int conv_op_plan_upsample_rows3(ConvOp* op, int B, const ActSrc& s0, const __half* w_rows3, const ActSrc& out);
 int conv_op_run(ConvOp& op, int B, cudaStream_t stream);
 // Row-streaming N = 64 EPI_GN plans with one source can apply y = SiLU(A[b][c] * x + B[b][c]) to their
 // INPUT on the fly (the GroupNorm apply of the producing Block; coef = [B][64] (A, B) from gn_coef()),

@@ -810,7 +810,20 @@ int build(prg_net* n) {
       NET_PTR(bu, n->f32(p + ".3.1.bias"));
       Act y = new_act(n, x.H * 2, x.W * 2, cin);
       if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
-      NET_TRY(add_conv(n, EPI_BIAS, x, nullptr, 0, 3, 4, wu, 0, bu, y));
+      const __half* w3 = n->has(p + ".3.1.weight.rows3") ? n->f16(p + ".3.1.weight.rows3") : nullptr;
+      if (w3 != nullptr && x.C == 128 && cin == 64 && x.W % 128 == 0 && getenv("PRG_NO_ROWS3") == nullptr) {
+        // 128 -> 64 at rows of >= 128 input pixels: four class-bound row-streaming convs in one launch
+        ConvOp op;
+        NET_TRY(conv_op_plan_upsample_rows3(&op, n->maxB, src_of(x), w3, src_of(y)));
+        op.params().bias = bu;
+        char buf[160], lab[256];
+        snprintf(lab, sizeof(lab), "conv %dx%d %d->%d k3 m0 c4 [%s]", y.H, y.W, x.C, cin,
+                 conv_op_describe(op, buf, sizeof(buf)));
+        n->add_op(CAT_CONV, [op](const Run& r) mutable { return conv_op_run(op, r.B, r.s); }, lab,
+                  2.0 * y.H * y.W * (double)cin * 9 * x.C);
+      } else {
+        NET_TRY(add_conv(n, EPI_BIAS, x, nullptr, 0, 3, 4, wu, 0, bu, y));
+      }
       x = y;
     } else {
       NET_PTR(wu, n->f16(p + ".3.weight"));

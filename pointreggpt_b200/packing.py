@@ -54,6 +54,17 @@ def upsample_fold_weight(w):
     return out.reshape(co, 16 * ci).contiguous()
 
 
+def upsample_rows3_weight(w):
+    """The folded upsample conv once more, for the class-bound row-streaming kernel (conv2_tc.cu, rows3):
+    per parity class a 3x3 conv on the input shifted by (py, px) whose ky = 2 / kx = 2 taps are zero.
+    Returns (Cout, 4 classes * 9 taps * Cin), k = ((cls * 3 + ky) * 3 + kx) * Cin + c."""
+    co, ci = w.shape[0], w.shape[1]
+    f = upsample_fold_weight(w).reshape(co, 4, 2, 2, ci)
+    out = torch.zeros(co, 4, 3, 3, ci, dtype=torch.float32)
+    out[:, :, :2, :2] = f
+    return out.reshape(co, 36 * ci).contiguous()
+
+
 class BlobWriter:
     def __init__(self):
         self.entries = []
@@ -173,6 +184,8 @@ def _pack_trunk(w, sd, kind, groups):
         p = "ups.%d.3" % i
         if (p + ".1.weight") in sd:
             w.add(p + ".1.weight", upsample_fold_weight(sd[p + ".1.weight"].float()), "f16")
+            if tuple(sd[p + ".1.weight"].shape[:2]) == (64, 128):
+                w.add(p + ".1.weight.rows3", upsample_rows3_weight(sd[p + ".1.weight"].float()), "f16")
             w.add(p + ".1.bias", sd[p + ".1.bias"], "f32")
         else:
             w.add(p + ".weight", conv_weight_kmajor(sd[p + ".weight"].float()), "f16")
