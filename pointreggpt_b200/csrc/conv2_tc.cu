@@ -398,7 +398,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && ri >= 2 && src == 0 &&
                           tcount + (uint32_t)ri - 2u < 64u;
           if (tr) P.trace[(tcount + ri - 2) * 8 + 0] = clock64();   // last input row + slot ready
-          const int j_lo = max(ri - 2, 0), j_hi = min(ri, nr - 1);
+          // rows3: the dy = 2 taps are zero as well, so row ri only feeds the output rows ri - 1 and ri
+          // (N = 128 instead of 192; the last row of a segment feeds nothing)
+          const int j_lo = max(ri - (P.cls_bind ? 1 : 2), 0), j_hi = min(ri, nr - 1);
           const uint32_t row_lo = (sA_u + (uint32_t)stage * P.a_slot) >> 4;
           const uint32_t w_lo = (sW_u >> 4) + (uint32_t)(src * 9) * (kBBytes >> 4);   // this source's taps
           const bool last_src = (src == P.nsrc - 1);
@@ -416,7 +418,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             // step 0: targets that already hold a partial sum accumulate, the new one (j = ri, first
             // source only) overwrites its slot
             const int n_old = (ri < nr && src == 0) ? cnt - 1 : cnt;  // old targets come first
-            {
+            if (cnt > 0) {
               const int o1 = min(n_old, c1);                         // old targets before the wrap
               if (o1 > 0) umma_f16(d0, da0, db0, idesc0 | ((uint32_t)(o1 * 8) << 17), 1u);
               if (n_old > o1)
@@ -428,7 +430,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               }
             }
             const int smax = P.cls_bind ? 8 : 12;                   // rows3: the dx = 2 taps are zero, skip them
-            if (c1 == cnt) {
+            if (cnt <= 0) {
+              // nothing to issue (rows3, last row of the segment)
+            } else if (c1 == cnt) {
               const uint32_t id = idesc0 | ((uint32_t)(cnt * 8) << 17);
 #pragma unroll
               for (int s = 1; s < 12; ++s)
