@@ -968,8 +968,9 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
   constexpr int kPitch = CIN * 2 + 64;     // bytes per weight row in shared memory (conflict-free LDS.128)
   extern __shared__ __align__(16) uint8_t rsm[];
   uint8_t* sW = rsm;
-  float2* sCoef = reinterpret_cast<float2*>(rsm + COUT * kPitch);
-  float* sBias = reinterpret_cast<float*>(sCoef + COUT);
+  float* sCA = reinterpret_cast<float*>(rsm + COUT * kPitch);     // y = SiLU(sCA[c] * raw + sCB[c]) + ...
+  float* sCB = sCA + COUT;
+  float* sBias = sCB + COUT;
   float* sG = sBias + COUT;
   // weights / bias / gain: not written by any kernel of the evaluation, so before the dependency wait
   for (int i = threadIdx.x; i < COUT * (CIN / 8); i += 256) {
@@ -995,7 +996,7 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
     if (gb != b) {
       b = gb;
       __syncthreads();                     // everyone is done with the previous image's coefficients
-      for (int i = threadIdx.x; i < COUT; i += 256) sCoef[i] = a.coef[(size_t)b * COUT + i];
+      gn_coeffs(a.stats, a.gamma, a.beta, nullptr, COUT, a.HW, b, sCA, sCB);   // block2's GroupNorm as (A, B) per channel
       __syncthreads();
     }
     const size_t row0 = (size_t)b * a.HW + (size_t)pb * 128 + warp * 16 + g;    // pixel rows row0 and row0 + 8
@@ -1040,9 +1041,9 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
       uint32_t o0[4], o1[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const float4 cf = *reinterpret_cast<const float4*>(sCoef + ch + 2 * jj);     // (A, B) of two channels
+        const float2 cA = *reinterpret_cast<const float2*>(sCA + ch + 2 * jj);       // two channels
+        const float2 cB = *reinterpret_cast<const float2*>(sCB + ch + 2 * jj);
         const float2 bi = *reinterpret_cast<const float2*>(sBias + ch + 2 * jj);
-        const float2 cA = make_float2(cf.x, cf.z), cB = make_float2(cf.y, cf.w);
         float* c = acc[ng * 4 + jj];
         float2 y0 = silu2(__ffma2_rn(__half22float2(h0[jj]), cA, cB));
         float2 y1 = silu2(__ffma2_rn(__half22float2(h1[jj]), cA, cB));
@@ -1124,7 +1125,7 @@ bool res1x1_gn_supported(int cout, int c0, int c1, int HW) {
 template <int COUT, int CIN>
 static int res1x1_gn_launch(const ResGn& a, const TailParams* tail, int B, cudaStream_t s) {
   const int nblk = a.HW / 128, total = nblk * B;
-  const size_t smem = (size_t)COUT * (CIN * 2 + 64) + COUT * (sizeof(float2) + 2 * sizeof(float));
+  const size_t smem = (size_t)COUT * (CIN * 2 + 64) + COUT * 4 * sizeof(float);
   int grid = num_sms() * (COUT == 64 ? 2 : 1);          // one resident wave
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;

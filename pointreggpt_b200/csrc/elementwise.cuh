@@ -57,15 +57,17 @@ int gn_apply(const GnApply& a, int B, cudaStream_t s);
 // coef[b][c] = (A, B) with y = SiLU(A * raw + B) (uses stats / gamma / beta / ss / HW / C of `a`).
 int gn_coef(const GnApply& a, float2* coef, int B, cudaStream_t s);
 
-// ---- ResnetBlock output in one pass (SDD:731-734): y = SiLU(A raw + B) + res_conv(cat(x0, x1)) + bias
-// [+ ln_out = LN_c(y) * ln_g].  (A, B) per (image, channel) come from gn_coef.
+// ---- ResnetBlock output in one pass (SDD:731-734): y = SiLU(GN(raw)) + res_conv(cat(x0, x1)) + bias
+// [+ ln_out = LN_c(y) * ln_g].  The GroupNorm affine per (image, channel) is derived inside the kernel from
+// the integer statistics block2's conv epilogue left behind.
 struct ResGn {
   const __half *x0, *x1;      // cat(x0, x1) along channels; contiguous NHWC (pixel stride = channel count)
   int c0, c1;                 // channel counts (multiples of 32; c1 = 0 and x1 = nullptr without a skip input)
   const __half* w;            // res_conv weight [Cout][c0 + c1] fp16
   const float* bias;          // [Cout] or nullptr
   const __half* raw;          // block2's raw conv output (B, HW, Cout)
-  const float2* coef;         // from gn_coef
+  const long long* stats;     // its GroupNorm statistics [B][8][2] (fixed point, see conv_tc.cuh) ...
+  const float *gamma, *beta;  // ... and affine
   __half* y;                  // (B, HW, Cout)
   const float* ln_g;          // optional fused channel LayerNorm of y: gain ...
   __half* ln_out;             // ... and destination

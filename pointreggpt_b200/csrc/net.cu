@@ -416,15 +416,11 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
     NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
     Act y = new_act(n, H, W, cout);
     if (!y.p) { set_error("out of device memory"); return PRG_ERR_CUDA; }
-    GnApply a{};
-    a.raw = raw2.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr; a.HW = HW; a.C = cout;
-    float2* coef = n->gn_coef_buf;
-    n->add_op(CAT_GN, [a, coef](const Run& r) { return gn_coef(a, coef, r.B, r.s); },
-              "gn_coef c" + std::to_string(cout));
     ResGn rg{};
     rg.x0 = x0.p; rg.c0 = x0.C;
     rg.x1 = x1 ? x1->p : nullptr; rg.c1 = x1 ? x1->C : 0;
-    rg.w = wr; rg.bias = br; rg.raw = raw2.p; rg.coef = coef; rg.y = y.p; rg.HW = HW; rg.Cout = cout;
+    rg.w = wr; rg.bias = br; rg.raw = raw2.p; rg.stats = st2; rg.gamma = g2; rg.beta = be2;
+    rg.y = y.p; rg.HW = HW; rg.Cout = cout;
     if (fuse_ln_g != nullptr) { rg.ln_g = fuse_ln_g; rg.ln_out = n->xn; }
     n->add_op(CAT_RESGN, [rg](const Run& r) { return res1x1_gn(rg, r.B, r.s); },
               "res1x1_gn " + std::to_string(H) + "x" + std::to_string(W) + " " + std::to_string(cin) + "->" +
@@ -484,15 +480,11 @@ int add_resblock(prg_net* n, const std::string& pfx, const Act& x0, const Act* x
     // tensor nor y is ever written
     NET_PTR(wr, n->f16(pfx + ".res_conv.weight"));
     NET_PTR(br, n->f32(pfx + ".res_conv.bias"));
-    GnApply a{};
-    a.raw = raw2.p; a.stats = st2; a.gamma = g2; a.beta = be2; a.ss = nullptr; a.HW = HW; a.C = cout;
-    float2* coef = n->gn_coef_buf;
-    n->add_op(CAT_GN, [a, coef](const Run& r) { return gn_coef(a, coef, r.B, r.s); },
-              "gn_coef c" + std::to_string(cout));
     ResGn& rg = bo->rg;
     rg.x0 = x0.p; rg.c0 = x0.C;
     rg.x1 = x1 ? x1->p : nullptr; rg.c1 = x1 ? x1->C : 0;
-    rg.w = wr; rg.bias = br; rg.raw = raw2.p; rg.coef = coef; rg.y = nullptr; rg.HW = HW; rg.Cout = cout;
+    rg.w = wr; rg.bias = br; rg.raw = raw2.p; rg.stats = st2; rg.gamma = g2; rg.beta = be2;
+    rg.y = nullptr; rg.HW = HW; rg.Cout = cout;
     bo->fused_tail = true;
     bo->stats2 = st2; bo->g2 = g2; bo->b2 = be2; bo->raw2 = raw2.p;
     return PRG_OK;
