@@ -101,6 +101,8 @@ struct Conv2Params {
   ConvParams c;
   int halo, wres, n_tiles, stages;
   int pair;             // per-tap mode, BN = 128: an item is TWO adjacent M tiles sharing every B stage
+  int dxs;              // pair mode, 3x3, rows of 128 pixels: the three dx taps of a (dy, K block) share ONE
+                        // 130-pixel halo row per tile (shifted views, as in the row-streaming mode)
   int nsrc;             // halo mode: 1, or 2 = cat(x0, x1) of two 64-channel sources streamed row by row
   int cls_bind;         // halo mode, folded x2 upsample ("rows3"): CTA i works on parity class i & 3 only -- its
                         // class's weights (K columns cls * num_kb * 64 ...) stay resident, its input window is
@@ -304,6 +306,28 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const int wz = p.w_batched ? it.img : 0;
           const int wk0 = it.cls * num_kb * kBlockK;
           const Item i2 = P.pair ? decode(item, 1) : it;
+          if (P.dxs) {
+            // stages in the order (ky, K block, kx); the kx = 0 stage carries the two tiles' halo rows
+            // (130 pixels from x0 - 1), all three carry their tap's B block
+            for (int g = 0; g < 3 * chunks; ++g) {
+              const int ky = g / chunks, cc = g - ky * chunks;
+              const CUtensorMap* tm = cc < p.chunks0 ? &tmA0 : &tmA1;
+              const int ch = (cc < p.chunks0 ? cc : cc - p.chunks0) * kBlockK;
+              for (int kx = 0; kx < 3; ++kx) {
+                mbar_wait(&ctl->empty[stage], phase ^ 1);
+                uint8_t* a_dst = sA + (size_t)stage * P.a_slot;
+                mbar_arrive_expect_tx(&ctl->full[stage], (kx == 0 ? 2 * kHaloBytes : 0) + kBBytes);
+                if (kx == 0) {
+                  tma_load_4d(tm, &ctl->full[stage], a_dst, ch, it.x0 - 1, it.y0 + ky - 1, it.img);
+                  tma_load_4d(tm, &ctl->full[stage], a_dst + kHaloSlot, ch, i2.x0 - 1, i2.y0 + ky - 1, i2.img);
+                }
+                tma_load_3d(&tmB, &ctl->full[stage], sB + (size_t)stage * kBBytes,
+                            wk0 + ((ky * 3 + kx) * chunks + cc) * kBlockK, it.n_tile * BN, wz);
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+              }
+            }
+            continue;
+          }
           for (int kb = 0; kb < num_kb; ++kb) {
             const int tap = kb / chunks, cc = kb - tap * chunks;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
@@ -470,6 +494,43 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         tc_fence_after();
         const uint32_t d_addr = taddr_u + ((acc * BN) << P.pair);
         const uint32_t w_base = sW_u + (uint32_t)(it.n_tile * num_kb) * kBBytes;
+        if (CG == 1 && P.dxs) {
+          for (int g = 0; g < 3 * chunks; ++g) {
+            uint32_t a_grp = 0;
+            int st[3];
+            for (int kx = 0; kx < 3; ++kx) {
+              mbar_wait(&ctl->full[stage], phase);
+              tc_fence_after();
+              st[kx] = stage;
+              if (kx == 0) a_grp = sA_u + (uint32_t)stage * P.a_slot;
+              const uint32_t b_addr = sB_u + (uint32_t)stage * kBBytes;
+              if (elect_one()) {
+                const uint64_t da = mkdesc(a_grp + (uint32_t)kx * 128u);          // view shifted by kx pixels
+                const uint64_t da2 = mkdesc(a_grp + kHaloSlot + (uint32_t)kx * 128u);
+                const uint64_t db = mkdesc(b_addr);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                           (g > 0 || kx > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16(d_addr + BN, da2 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                           (g > 0 || kx > 0 || k > 0) ? 1u : 0u);
+                if (kx == 2) {
+                  // the halo rows of the kx = 0 stage were read by all three taps: release the group together
+                  umma_commit(&ctl->empty[st[0]]);
+                  umma_commit(&ctl->empty[st[1]]);
+                  umma_commit(&ctl->empty[st[2]]);
+                  if (g == 3 * chunks - 1) umma_commit(&ctl->tmem_full[acc]);
+                }
+              }
+              __syncwarp();
+              if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          ++tcount;
+          continue;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
@@ -1215,13 +1276,12 @@ struct Conv2Launch {
   int xf;   // 1 = input transform warps (GroupNorm apply of the producing Block on the ring slot)
 };
 
-static int g_conv_flags = -1;  // PRG_CONV_FLAGS bit0: disable the halo-ring mode (A/B measurements)
+// PRG_CONV_FLAGS (A/B measurements; read whenever a layer is planned): bit 0 no row-streaming mode, 1 no
+// per-tap pair mode, 4 no CTA-pair kernel, 5 no two-source row-streaming, 6 no input transform, 7 ex2 + rcp
+// SiLU in the transform warps, 8 no shared halo rows in the pair-mode 3x3 convs
 static int conv_flags() {
-  if (g_conv_flags < 0) {
-    const char* e = getenv("PRG_CONV_FLAGS");
-    g_conv_flags = e ? atoi(e) : 0;
-  }
-  return g_conv_flags;
+  const char* e = getenv("PRG_CONV_FLAGS");
+  return e ? atoi(e) : 0;
 }
 
 // Segment length for the halo mode: MMA time scales with the rows a CTA owns; the two extra halo
@@ -1363,14 +1423,23 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0_in, const
   // flight (not L2 bandwidth) bound the kernel; two M tiles per B stage need a third less
   P.pair = (bn == 128 && !P.halo && !P.wres && mode == 0 && epi != EPI_QKV && !(conv_flags() & 2) &&
             (p.tiles_x * p.tiles_y) % 2 == 0) ? 1 : 0;
-  P.a_slot = P.halo ? kHaloSlot : (kABytes << P.pair);
+  // 3x3 pair-mode layers on rows of 128 pixels: the three dx taps share one halo row per tile and (dy, K block)
+  // -- 82 KB through TMA per 1536 MMA cycles instead of 144 KB (these layers were TMA-bound at ~970 TFLOP/s)
+  P.dxs = (P.pair && mode == 0 && ksize == 3 && classes == 1 && tile_w == kBlockM && !(conv_flags() & 256)) ? 1 : 0;
+  P.a_slot = P.halo ? kHaloSlot : P.dxs ? 2 * kHaloSlot : (kABytes << P.pair);
   // CTA pair: N = 256 per-tap layers are bound by the bytes each SM pulls through TMA; as a pair
   // each CTA stages only half of B
   L->cg = (bn == 256 && !P.halo && !P.wres && !P.pair && !w_batched && (epi == EPI_BIAS || epi == EPI_GN) &&
            (p.tiles_x * p.tiles_y) % 2 == 0 && !(conv_flags() & 16)) ? 2 : 1;
-  const int per_stage = P.a_slot + (P.wres ? 0 : b_bytes / L->cg);
+  int per_stage = P.a_slot + (P.wres ? 0 : b_bytes / L->cg);
   const int fixed_used = P.direct_store ? kCtlBytes + 1024 : fixed;
   int stages = (kSmemBudget - fixed_used - P.w_bytes) / per_stage;
+  if (P.dxs && stages < 4) {      // a (dy, K block) group holds three stages at once and the next one must be loadable
+    P.dxs = 0;
+    P.a_slot = kABytes << P.pair;
+    per_stage = P.a_slot + (P.wres ? 0 : b_bytes / L->cg);
+    stages = (kSmemBudget - fixed_used - P.w_bytes) / per_stage;
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     set_error("conv_plan: shared memory budget too small (%d stages)", stages);
@@ -1400,7 +1469,7 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0_in, const
     if (mode == 0) {
       uint64_t dims[4] = {(uint64_t)s->C, (uint64_t)s->W, (uint64_t)s->H, (uint64_t)B};
       uint64_t str[3] = {ps, ps * s->W, ps * s->W * s->H};
-      uint32_t box[4] = {64, (uint32_t)(P.halo ? kHaloPix : tile_w), (uint32_t)(P.halo ? 1 : tile_h), 1};
+      uint32_t box[4] = {64, (uint32_t)((P.halo || P.dxs) ? kHaloPix : tile_w), (uint32_t)(P.halo ? 1 : tile_h), 1};
       int rc = tmap_encode_f16(tm, s->ptr, 4, dims, str, box);
       if (rc) return rc;
     } else {
@@ -1629,8 +1698,8 @@ int conv_op_run(ConvOp& op, int B, cudaStream_t stream) {
 
 const char* conv_op_describe(const ConvOp& op, char* buf, int n) {
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(op.impl);
-  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d cg=%d xf=%d rows3=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
-           L->P.halo, L->P.wres, L->P.pair, L->cg, L->xf, L->P.cls_bind, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
+  snprintf(buf, n, "bn=%d epi=%d halo=%d wres=%d pair=%d dxs=%d cg=%d xf=%d rows3=%d stages=%d smem=%d kb=%d rseg=%d", L->bn, L->epi,
+           L->P.halo, L->P.wres, L->P.pair, L->P.dxs, L->cg, L->xf, L->P.cls_bind, L->P.stages, L->smem, L->P.num_kb, L->P.rseg);
   return buf;
 }
 

@@ -149,3 +149,43 @@ def test_generator_two_samples_per_scene_uses_scene_memory(tmp_path, monkeypatch
             assert (d / f).is_file(), f
         pts = cloud.read_ply(str(d / "sample-000001.cloud.ply"))
         assert pts.shape[0] > 50 and np.isfinite(pts).all()
+
+
+def test_fused_block_forms_agree_with_the_separate_ones(monkeypatch):
+    """The streaming shortcut kernel (k_res1x1_gn, incl. its fused-tail form) and the class-bound
+    row-streaming upsample conv against the forms they replace (1x1 conv on the engine + k_gn_apply +
+    k_net_tail; per-tap folded upsample), same weights, same input, 256x256 (the only size that takes
+    them).  Both forms are fp16-operand implementations of the same fp32 network; a change of summation order
+    in one layer re-draws the fp16 rounding noise of everything downstream, so two valid forms differ from
+    each other by about as much as each differs from the fp32 oracle (5.4e-4, tests/test_net_gpu.py) -- the
+    bound here is the same 1e-3 (+ 20 %), which still catches any real defect of either code path."""
+    torch.manual_seed(0)
+    net = nets.Unet(dim=64, param_cond_dim=4, dim_mults=(1, 2, 4, 8), channels=1).cuda()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 1, 256, 256, generator=g).cuda()
+    ic = (torch.rand(2, 2, 256, 256, generator=g) * 2 - 1).cuda()
+    t = torch.tensor([700, 20], dtype=torch.long).cuda()
+    pc = torch.randn(2, 4, generator=g).cuda()
+
+    def run(**env):
+        for k in ("PRG_NO_RESGN", "PRG_NO_ROWS3", "PRG_CONV_FLAGS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        net._release()                      # the plan reads the switches when the handle is built
+        out = net(x, t, pc, ic).float().cpu()
+        net._release()
+        return out
+
+    base = run()
+    no_rows3 = run(PRG_NO_ROWS3="1")
+    no_resgn = run(PRG_NO_RESGN="1")
+    both_off = run(PRG_NO_RESGN="1", PRG_NO_ROWS3="1")
+    no_dxs = run(PRG_CONV_FLAGS="256")           # per-tap pair convs without the shared halo rows
+    assert torch.isfinite(base).all()
+    e_rows3 = ((base - no_rows3).norm() / base.norm()).item()
+    e_resgn = ((base - no_resgn).norm() / base.norm()).item()
+    e_both = ((base - both_off).norm() / base.norm()).item()
+    e_dxs = ((base - no_dxs).norm() / base.norm()).item()
+    print("fused vs separate forms, rel-l2: rows3 %.2e, res1x1_gn %.2e, both %.2e, dxs %.2e" % (e_rows3, e_resgn, e_both, e_dxs))
+    assert max(e_rows3, e_resgn, e_both, e_dxs) <= 1.2e-3
