@@ -1278,7 +1278,8 @@ struct Conv2Launch {
 
 // PRG_CONV_FLAGS (A/B measurements; read whenever a layer is planned): bit 0 no row-streaming mode, 1 no
 // per-tap pair mode, 4 no CTA-pair kernel, 5 no two-source row-streaming, 6 no input transform, 7 ex2 + rcp
-// SiLU in the transform warps, 8 no shared halo rows in the pair-mode 3x3 convs
+// SiLU in the transform warps, 8 no shared halo rows in the pair-mode 3x3 convs, 10 streamed weights for the
+// 64 -> 64 stride-2 conv
 static int conv_flags() {
   const char* e = getenv("PRG_CONV_FLAGS");
   return e ? atoi(e) : 0;
@@ -1413,6 +1414,13 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0_in, const
   } else if (halo_ok) {
     P.halo = 1;
     P.wres = 1;
+  } else if (!w_batched && classes == 1 && mode == 1 && bn == 64 && P.n_tiles == 1 && epi == EPI_BIAS &&
+             !(conv_flags() & 1024) && w_all + kCtlBytes + 1024 + 5 * kABytes <= kSmemBudget) {
+    // 4x4 stride-2, 64 -> 64: all sixteen taps resident (128 KB), the epilogue stores to global memory itself
+    // (no room for staging slabs): 166 -> 155 us at 128x128 -- the layer is bound by the strided 5-D gathers of
+    // its A tiles, not by the bytes
+    P.wres = 1;
+    P.direct_store = 1;
   } else if (!w_batched && classes == 1 && w_all + fixed + 8 * kABytes <= kSmemBudget) {
     // resident weights only when enough A stages remain to keep ~128 KiB of loads in flight
     P.wres = 1;
