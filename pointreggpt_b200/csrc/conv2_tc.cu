@@ -167,9 +167,14 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   const int item0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // per-tap item walk
   const int istep = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // row-streaming segment walk; with cls_bind the grid is four interleaved groups, one per parity class
-  const int cls_b = P.cls_bind ? (int)(blockIdx.x & 3u) : 0;
-  const int seg0 = P.cls_bind ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
-  const int sstep = P.cls_bind ? (int)(gridDim.x >> 2) : (int)gridDim.x;
+  // (compile-time gates: the code of the two special modes exists only in the instantiations that can run them --
+  // the input-transform kernel sits at its register cap and lost 15 % when unrelated paths grew)
+  constexpr bool kRows3 = (BN == 64 && EPI == EPI_BIAS && CG == 1 && XF == 0);
+  constexpr bool kDxs = (BN == 128 && CG == 1 && XF == 0);
+  const bool cls_bind = kRows3 && P.cls_bind;
+  const int cls_b = cls_bind ? (int)(blockIdx.x & 3u) : 0;
+  const int seg0 = cls_bind ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
+  const int sstep = cls_bind ? (int)(gridDim.x >> 2) : (int)gridDim.x;
   // fp16 staging.  BN = 64: eight per-warp 4 KB slabs.  BN >= 128: ONE 64-channel box (16 KB) that
   // the epilogue fills and stores BN/64 times per tile -- the shared memory this frees buys a
   // fourth load stage, and these layers are bound by the bytes in flight, not by the epilogue.
@@ -306,7 +311,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const int wz = p.w_batched ? it.img : 0;
           const int wk0 = it.cls * num_kb * kBlockK;
           const Item i2 = P.pair ? decode(item, 1) : it;
-          if (P.dxs) {
+          if (kDxs && P.dxs) {
             // stages in the order (ky, K block, kx); the kx = 0 stage carries the two tiles' halo rows
             // (130 pixels from x0 - 1), all three carry their tap's B block
             for (int g = 0; g < 3 * chunks; ++g) {
@@ -424,7 +429,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           if (tr) P.trace[(tcount + ri - 2) * 8 + 0] = clock64();   // last input row + slot ready
           // rows3: the dy = 2 taps are zero as well, so row ri only feeds the output rows ri - 1 and ri
           // (N = 128 instead of 192; the last row of a segment feeds nothing)
-          const int j_lo = max(ri - (P.cls_bind ? 1 : 2), 0), j_hi = min(ri, nr - 1);
+          const int j_lo = max(ri - (cls_bind ? 1 : 2), 0), j_hi = min(ri, nr - 1);
           const uint32_t row_lo = (sA_u + (uint32_t)stage * P.a_slot) >> 4;
           const uint32_t w_lo = (sW_u >> 4) + (uint32_t)(src * 9) * (kBBytes >> 4);   // this source's taps
           const bool last_src = (src == P.nsrc - 1);
@@ -442,7 +447,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             // step 0: targets that already hold a partial sum accumulate, the new one (j = ri, first
             // source only) overwrites its slot
             const int n_old = (ri < nr && src == 0) ? cnt - 1 : cnt;  // old targets come first
-            if (cnt > 0) {
+            if (!kRows3 || cnt > 0) {
               const int o1 = min(n_old, c1);                         // old targets before the wrap
               if (o1 > 0) umma_f16(d0, da0, db0, idesc0 | ((uint32_t)(o1 * 8) << 17), 1u);
               if (n_old > o1)
@@ -453,8 +458,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
                 umma_f16(taddr_u + sn * 64u, da0, db0 + (uint64_t)(n_old * kBlk), idesc0 | (8u << 17), 0u);
               }
             }
-            const int smax = P.cls_bind ? 8 : 12;                   // rows3: the dx = 2 taps are zero, skip them
-            if (cnt <= 0) {
+            const int smax = cls_bind ? 8 : 12;                     // rows3: the dx = 2 taps are zero, skip them
+            if (kRows3 && cnt <= 0) {
               // nothing to issue (rows3, last row of the segment)
             } else if (c1 == cnt) {
               const uint32_t id = idesc0 | ((uint32_t)(cnt * 8) << 17);
@@ -494,7 +499,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         tc_fence_after();
         const uint32_t d_addr = taddr_u + ((acc * BN) << P.pair);
         const uint32_t w_base = sW_u + (uint32_t)(it.n_tile * num_kb) * kBBytes;
-        if (CG == 1 && P.dxs) {
+        if (kDxs && P.dxs) {
           for (int g = 0; g < 3 * chunks; ++g) {
             uint32_t a_grp = 0;
             int st[3];
