@@ -162,6 +162,11 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const __grid_constant__ CUtensorMap tmO3, const Conv2Params P) {
   pdl_trigger();
   const ConvParams& p = P.c;
+  // the input-transform kernel is always the single-source row-streaming form with resident weights and staged
+  // stores: as compile-time constants these remove every other mode from that instantiation (it sits at its
+  // register cap)
+  const int p_halo = XF ? 1 : P.halo, p_nsrc = XF ? 1 : P.nsrc, p_wres = XF ? 1 : P.wres;
+  const int p_pair = XF ? 0 : P.pair, p_direct = XF ? 0 : P.direct_store;
   constexpr int kBBytes = (BN / CG) * kBlockK * 2;   // B rows this CTA stages per K block
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int item0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // per-tap item walk
@@ -183,16 +188,16 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   // TMEM: BN = 64 owns all 512 columns (eight accumulators, halo mode walks them as a ring),
   // the wider tiles two accumulators.
   constexpr int kTmemCols = 512;
-  const uint32_t acc_mask = P.halo ? 7u : 1u;      // accumulator slots - 1
-  const int acc_log2 = P.halo ? 3 : 1;
+  const uint32_t acc_mask = p_halo ? 7u : 1u;      // accumulator slots - 1
+  const int acc_log2 = p_halo ? 3 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sW = smem;                               // resident weights (may be empty)
   uint8_t* sA = sW + P.w_bytes;                     // A ring
   uint8_t* sB = sA + P.stages * P.a_slot;           // streamed B ring (when !wres)
-  uint8_t* sO = sB + (P.wres ? 0 : P.stages * kBBytes);
-  Ctl* ctl = reinterpret_cast<Ctl*>(sO + (P.direct_store ? 0 : kOutBufs * kStageOut));
+  uint8_t* sO = sB + (p_wres ? 0 : P.stages * kBBytes);
+  Ctl* ctl = reinterpret_cast<Ctl*>(sO + (p_direct ? 0 : kOutBufs * kStageOut));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_w = 1 << p.tile_w_log2;
@@ -245,7 +250,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     Item it;
     it.n_tile = item % P.n_tiles;
     int m = item / P.n_tiles;
-    const int msh = (CG == 2) ? 1 : P.pair;       // pair mode / CTA pair: item m covers tiles 2m, 2m + 1
+    const int msh = (CG == 2) ? 1 : p_pair;       // pair mode / CTA pair: item m covers tiles 2m, 2m + 1
     const int m_items = P.m_tiles >> msh;
     it.cls = m / m_items;
     m = ((m - it.cls * m_items) << msh) + sub;
@@ -272,26 +277,26 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      if (P.wres) {
+      if (p_wres) {
         mbar_arrive_expect_tx(&ctl->wfull, (uint32_t)P.w_bytes);
         for (int nt = 0; nt < P.n_tiles; ++nt)
           for (int kb = 0; kb < num_kb; ++kb) {
             // halo mode: tap (dy, dx) goes to block dx*3 + (2 - dy), so that for one dx the taps
             // dy = 2, 1, 0 are one contiguous N = 192 B operand
             const int wtap = kb / chunks, wcc = kb - wtap * chunks;   // halo: per source, per dx, dy = 2, 1, 0
-            const int blk = P.halo ? wcc * 9 + (wtap % 3) * 3 + (2 - wtap / 3) : nt * num_kb + kb;
+            const int blk = p_halo ? wcc * 9 + (wtap % 3) * 3 + (2 - wtap / 3) : nt * num_kb + kb;
             tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)blk * kBBytes, (cls_b * num_kb + kb) * kBlockK, nt * BN, 0);
           }
       }
       int stage = 0;
       uint32_t phase = 0;
       int dbg_row = 0;
-      if (P.halo) {
+      if (p_halo) {
         for (int seg = seg0; seg < P.total_items; seg += sstep) {
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
           for (int r = 0; r < nr + 2; ++r) {
-            for (int src = 0; src < P.nsrc; ++src) {
+            for (int src = 0; src < p_nsrc; ++src) {
               mbar_wait(&ctl->empty[stage], phase ^ 1);
               if (P.trace != nullptr && blockIdx.x == 0 && dbg_row < 96) P.trace[512 + 2 * dbg_row] = clock64();
               ++dbg_row;
@@ -310,7 +315,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           if (p.classes == 4) { pad_y = 1 - (it.cls >> 1); pad_x = 1 - (it.cls & 1); }
           const int wz = p.w_batched ? it.img : 0;
           const int wk0 = it.cls * num_kb * kBlockK;
-          const Item i2 = P.pair ? decode(item, 1) : it;
+          const Item i2 = p_pair ? decode(item, 1) : it;
           if (kDxs && P.dxs) {
             // stages in the order (ky, K block, kx); the kx = 0 stage carries the two tiles' halo rows
             // (130 pixels from x0 - 1), all three carry their tap's B block
@@ -358,7 +363,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               if (++stage == P.stages) { stage = 0; phase ^= 1; }
               continue;
             }
-            mbar_arrive_expect_tx(&ctl->full[stage], (kABytes << P.pair) + (P.wres ? 0 : kBBytes));
+            mbar_arrive_expect_tx(&ctl->full[stage], (kABytes << p_pair) + (p_wres ? 0 : kBBytes));
             if (p.mode == 0) {
               const int ky = tap / p.kw, kx = tap - ky * p.kw;
               const int dy = ky - pad_y, dx = kx - pad_x;
@@ -368,7 +373,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               else
                 tma_load_4d(&tmA1, &ctl->full[stage], a_dst, (cc - p.chunks0) * kBlockK, it.x0 + dx,
                             it.y0 + dy, it.img);
-              if (P.pair) {   // second M tile of the item, same tap / channel chunk
+              if (p_pair) {   // second M tile of the item, same tap / channel chunk
                 if (cc < p.chunks0)
                   tma_load_4d(&tmA0, &ctl->full[stage], a_dst + kABytes, cc * kBlockK, i2.x0 + dx,
                               i2.y0 + dy, i2.img);
@@ -382,7 +387,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               tma_load_5d(&tmA0, &ctl->full[stage], a_dst, rx * p.cin0 + cc * kBlockK, it.x0 + qx,
                           ry, it.y0 + qy, it.img);
             }
-            if (!P.wres)
+            if (!p_wres)
               tma_load_3d(&tmB, &ctl->full[stage], sB + (size_t)stage * kBBytes, wk0 + kb * kBlockK,
                           it.n_tile * BN, wz);
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -393,7 +398,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     constexpr uint32_t idesc = idesc_f16(kBlockM, BN);
-    if (P.wres) mbar_wait(&ctl->wfull, 0);
+    if (p_wres) mbar_wait(&ctl->wfull, 0);
     // warp-reductions return provably uniform values: lets the compiler keep the TMEM address
     // and the descriptors in uniform registers instead of re-broadcasting them per MMA
     const uint32_t taddr_u = __reduce_or_sync(0xffffffffu, taddr);
@@ -405,7 +410,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     int stage = 0;
     uint32_t phase = 0;
     uint32_t tcount = 0;  // tiles issued by this CTA
-    if (P.halo) {
+    if (p_halo) {
       // Row-streaming 3x3: input row ri (image row y0 - 1 + ri) of a segment contributes to the
       // output rows j = ri - dy (dy = 0, 1, 2).  Their accumulators are neighbouring 64-column
       // TMEM slots ((tiles so far + j) & 7), and the weights of one dx are stacked [dy=2; dy=1;
@@ -417,7 +422,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         int img, x0, y0, nr;
         decode_seg(seg, img, x0, y0, nr);
         for (int ri = 0; ri < nr + 2; ++ri) {
-         for (int src = 0; src < P.nsrc; ++src) {
+         for (int src = 0; src < p_nsrc; ++src) {
           mbar_wait(XF ? &ctl->xfull[stage] : &ctl->full[stage], phase);
           if (ri < nr && src == 0) {   // slot of the new target must have been drained
             const uint32_t tn = tcount + (uint32_t)ri;
@@ -432,7 +437,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           const int j_lo = max(ri - (cls_bind ? 1 : 2), 0), j_hi = min(ri, nr - 1);
           const uint32_t row_lo = (sA_u + (uint32_t)stage * P.a_slot) >> 4;
           const uint32_t w_lo = (sW_u >> 4) + (uint32_t)(src * 9) * (kBBytes >> 4);   // this source's taps
-          const bool last_src = (src == P.nsrc - 1);
+          const bool last_src = (src == p_nsrc - 1);
           if (elect_one()) {
             // Descriptors of step s = dx*4 + k: A = row + 2*s (dx*128 B + k*32 B, in 16-byte
             // units), B = first target's block + dx*3 blocks + 2*k.  All twelve are the row's base
@@ -497,7 +502,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const uint32_t acc = tcount & 1;
         mbar_wait(&ctl->tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_addr = taddr_u + ((acc * BN) << P.pair);
+        const uint32_t d_addr = taddr_u + ((acc * BN) << p_pair);
         const uint32_t w_base = sW_u + (uint32_t)(it.n_tile * num_kb) * kBBytes;
         if (kDxs && P.dxs) {
           for (int g = 0; g < 3 * chunks; ++g) {
@@ -540,7 +545,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = sA_u + (uint32_t)stage * P.a_slot;
-          const uint32_t b_addr = P.wres ? w_base + (uint32_t)kb * kBBytes
+          const uint32_t b_addr = p_wres ? w_base + (uint32_t)kb * kBBytes
                                          : sB_u + (uint32_t)stage * kBBytes;
           if (elect_one()) {
             const uint64_t da = mkdesc(a_addr);
@@ -558,7 +563,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
               for (int k = 0; k < kBlockK / 16; ++k)
                 umma_f16(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                          (kb > 0 || k > 0) ? 1u : 0u);
-              if (P.pair) {   // the second M tile reuses the B stage
+              if (p_pair) {   // the second M tile reuses the B stage
                 const uint64_t da2 = mkdesc(a_addr + kABytes);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k)
@@ -702,7 +707,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       mbar_wait(&ctl->tmem_full[acc], (tcount >> acc_log2) & 1);
       tc_fence_after();
       if (tr) P.trace[tcount * 8 + 5] = clock64();       // accumulator complete
-      const uint32_t trow = taddr + ((acc * BN) << P.pair) + (uint32_t)(sub * BN) +
+      const uint32_t trow = taddr + ((acc * BN) << p_pair) + (uint32_t)(sub * BN) +
                             ((uint32_t)(quarter * 32) << 16);
       const float* sbias = ctl->bias + n0;
 
@@ -1100,7 +1105,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           ln_r = rsqrtf(((ss4[0] + ss4[1]) + (ss4[2] + ss4[3])) * (1.f / 64.f) + 1e-5f);
         }
       }
-      if (P.direct_store) {
+      if (p_direct) {
         // no staging: this thread writes its pixel's 64 channels (one 128-byte line) itself -- the
         // shared memory goes to the 147 KB of resident weights of the two-source conv instead
         uint4* gdst = reinterpret_cast<uint4*>(p.out + off);
@@ -1171,7 +1176,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
     };
 
     if constexpr (BN == 64) {
-      if (P.halo) {
+      if (p_halo) {
         for (int seg = seg0; seg < P.total_items; seg += sstep) {
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
@@ -1185,7 +1190,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       }
       if (lane == 0) bulk_wait0();
     } else {
-      if (P.halo) {
+      if (p_halo) {
         for (int seg = seg0; seg < P.total_items; seg += sstep) {
           int img, x0, y0, nr;
           decode_seg(seg, img, x0, y0, nr);
@@ -1198,9 +1203,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls);
             continue;
           }
-          for (int sub = 0; sub <= P.pair; ++sub) {
+          for (int sub = 0; sub <= p_pair; ++sub) {
             const Item it = decode(item, sub);
-            do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls, sub, sub == P.pair);
+            do_tile(it.img, it.x0, it.y0, it.n_tile, it.cls, sub, sub == p_pair);
           }
         }
       }
