@@ -960,10 +960,11 @@ int net_tail(const TailParams& t, int B, cudaStream_t s) {
 // final 1x1 conv (64 -> 1, a dot product over the four lanes that hold a pixel's channels) and the
 // per-pixel stage of the network tail (forward / sigmoid / sampler step, see tail_pixel).
 template <int COUT, int CIN, bool LN, bool TAIL>
-__global__ void __launch_bounds__(256, COUT == 64 ? 2 : 1)
+__global__ void __launch_bounds__(256, 2)
 k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
   pdl_trigger();
-  constexpr int NG = COUT / 32;            // output channel groups
+  constexpr int NH = COUT / 64;            // the output channels are produced in halves of 64 (two 32-channel groups):
+                                           // 32 accumulator registers at a time, so that 16 warps per SM fit at COUT = 128
   constexpr int KG = CIN / 32;             // input channel groups
   constexpr int kPitch = CIN * 2 + 64;     // bytes per weight row in shared memory (conflict-free LDS.128)
   extern __shared__ __align__(16) uint8_t rsm[];
@@ -988,7 +989,7 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
   const int g = lane >> 2, t = lane & 3;
   const int g_begin = (int)(((long long)blockIdx.x * total_blocks) / gridDim.x);
   const int g_end = (int)(((long long)(blockIdx.x + 1) * total_blocks) / gridDim.x);
-  // weight row of n-tile jj (of group ng) for this lane's B fragment: channel 32 ng + 8 (g >> 1) + 2 jj + (g & 1)
+  // weight row of n-tile jj of 32-channel group ng for this lane's B fragment: channel 32 ng + 8 (g >> 1) + 2 jj + (g & 1)
   const uint8_t* wrow = sW + (8 * (g >> 1) + (g & 1)) * kPitch + t * 16;
   int b = -1;
   for (int blk = g_begin; blk < g_end; ++blk) {
@@ -1000,75 +1001,85 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
       __syncthreads();
     }
     const size_t row0 = (size_t)b * a.HW + (size_t)pb * 128 + warp * 16 + g;    // pixel rows row0 and row0 + 8
-    // ---- every load of the tile first
-    uint4 xa[KG], xb[KG], ra[NG], rb[NG];
+    float sum0 = 0.f, sum1 = 0.f;          // LN: channel sums of the two rows; TAIL: their dot products with the final weight
+    uint32_t pk0[LN ? NH * 8 : 1], pk1[LN ? NH * 8 : 1];     // LN: the fp16-rounded y of this lane (packed pairs)
 #pragma unroll
-    for (int kg = 0; kg < KG; ++kg) {
-      const int c = kg * 32;
-      const __half* src = (c < a.c0) ? a.x0 + row0 * a.c0 + c : a.x1 + row0 * a.c1 + (c - a.c0);
-      const size_t step = (c < a.c0) ? (size_t)8 * a.c0 : (size_t)8 * a.c1;
-      xa[kg] = __ldcs(reinterpret_cast<const uint4*>(src) + t);
-      xb[kg] = __ldcs(reinterpret_cast<const uint4*>(src + step) + t);
-    }
+    for (int hf = 0; hf < NH; ++hf) {
+      // ---- every load of the half first (the x loads of the second half hit L1 / L2)
+      uint4 xa[KG], xb[KG], ra[2], rb[2];
 #pragma unroll
-    for (int ng = 0; ng < NG; ++ng) {
-      const __half* src = a.raw + row0 * COUT + ng * 32;
-      ra[ng] = __ldcs(reinterpret_cast<const uint4*>(src) + t);
-      rb[ng] = __ldcs(reinterpret_cast<const uint4*>(src + 8 * COUT) + t);
-    }
-    // ---- shortcut 1x1 conv
-    float acc[NG * 4][4];
-#pragma unroll
-    for (int j = 0; j < NG * 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-    for (int kg = 0; kg < KG; ++kg) {
-      const uint32_t f0[4] = {xa[kg].x, xb[kg].x, xa[kg].y, xb[kg].y};
-      const uint32_t f1[4] = {xa[kg].z, xb[kg].z, xa[kg].w, xb[kg].w};
-#pragma unroll
-      for (int j = 0; j < NG * 4; ++j) {
-        const uint4 wv = *reinterpret_cast<const uint4*>(wrow + ((j >> 2) * 32 + (j & 3) * 2) * kPitch + kg * 64);
-        hmma16816(acc[j], f0, wv.x, wv.y);
-        hmma16816(acc[j], f1, wv.z, wv.w);
-      }
-    }
-    // ---- y = SiLU(A raw + B) + shortcut + bias, rounded to fp16 (kept in acc for the LayerNorm)
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int ng = 0; ng < NG; ++ng) {
-      const int ch = ng * 32 + t * 8;
-      const __half2* h0 = reinterpret_cast<const __half2*>(&ra[ng]);
-      const __half2* h1 = reinterpret_cast<const __half2*>(&rb[ng]);
-      uint32_t o0[4], o1[4];
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const float2 cA = *reinterpret_cast<const float2*>(sCA + ch + 2 * jj);       // two channels
-        const float2 cB = *reinterpret_cast<const float2*>(sCB + ch + 2 * jj);
-        const float2 bi = *reinterpret_cast<const float2*>(sBias + ch + 2 * jj);
-        float* c = acc[ng * 4 + jj];
-        float2 y0 = silu2(__ffma2_rn(__half22float2(h0[jj]), cA, cB));
-        float2 y1 = silu2(__ffma2_rn(__half22float2(h1[jj]), cA, cB));
-        y0 = __fadd2_rn(y0, __fadd2_rn(make_float2(c[0], c[1]), bi));
-        y1 = __fadd2_rn(y1, __fadd2_rn(make_float2(c[2], c[3]), bi));
-        if (TAIL) {                       // final 1x1 conv: this lane's share of the two pixels' dot products
-          const float2 fw = *reinterpret_cast<const float2*>(sG + ch + 2 * jj);
-          sum0 = fmaf(y0.y, fw.y, fmaf(y0.x, fw.x, sum0));
-          sum1 = fmaf(y1.y, fw.y, fmaf(y1.x, fw.x, sum1));
-          continue;
-        }
-        const __half2 q0 = __floats2half2_rn(y0.x, y0.y), q1 = __floats2half2_rn(y1.x, y1.y);
-        o0[jj] = *reinterpret_cast<const uint32_t*>(&q0);
-        o1[jj] = *reinterpret_cast<const uint32_t*>(&q1);
-        if (LN) {
-          const float2 r0 = __half22float2(q0), r1 = __half22float2(q1);
-          c[0] = r0.x; c[1] = r0.y; c[2] = r1.x; c[3] = r1.y;
-          sum0 += r0.x + r0.y;
-          sum1 += r1.x + r1.y;
+      for (int kg = 0; kg < KG; ++kg) {
+        const int c = kg * 32;
+        const __half* src = (c < a.c0) ? a.x0 + row0 * a.c0 + c : a.x1 + row0 * a.c1 + (c - a.c0);
+        const size_t step = (c < a.c0) ? (size_t)8 * a.c0 : (size_t)8 * a.c1;
+        if (NH == 1) {
+          xa[kg] = __ldcs(reinterpret_cast<const uint4*>(src) + t);
+          xb[kg] = __ldcs(reinterpret_cast<const uint4*>(src + step) + t);
+        } else {
+          xa[kg] = __ldg(reinterpret_cast<const uint4*>(src) + t);
+          xb[kg] = __ldg(reinterpret_cast<const uint4*>(src + step) + t);
         }
       }
-      if (TAIL) continue;
-      __half* dst = a.y + row0 * COUT + ch;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-      *reinterpret_cast<uint4*>(dst + 8 * COUT) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+#pragma unroll
+      for (int ng = 0; ng < 2; ++ng) {
+        const __half* src = a.raw + row0 * COUT + hf * 64 + ng * 32;
+        ra[ng] = __ldcs(reinterpret_cast<const uint4*>(src) + t);
+        rb[ng] = __ldcs(reinterpret_cast<const uint4*>(src + 8 * COUT) + t);
+      }
+      // ---- shortcut 1x1 conv, 64 output channels
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+      for (int kg = 0; kg < KG; ++kg) {
+        const uint32_t f0[4] = {xa[kg].x, xb[kg].x, xa[kg].y, xb[kg].y};
+        const uint32_t f1[4] = {xa[kg].z, xb[kg].z, xa[kg].w, xb[kg].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 wv = *reinterpret_cast<const uint4*>(wrow + (hf * 64 + (j >> 2) * 32 + (j & 3) * 2) * kPitch + kg * 64);
+          hmma16816(acc[j], f0, wv.x, wv.y);
+          hmma16816(acc[j], f1, wv.z, wv.w);
+        }
+      }
+      // ---- y = SiLU(A raw + B) + shortcut + bias, rounded to fp16
+#pragma unroll
+      for (int ng = 0; ng < 2; ++ng) {
+        const int ch = hf * 64 + ng * 32 + t * 8;
+        const __half2* h0 = reinterpret_cast<const __half2*>(&ra[ng]);
+        const __half2* h1 = reinterpret_cast<const __half2*>(&rb[ng]);
+        uint32_t o0[4], o1[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float2 cA = *reinterpret_cast<const float2*>(sCA + ch + 2 * jj);       // two channels
+          const float2 cB = *reinterpret_cast<const float2*>(sCB + ch + 2 * jj);
+          const float2 bi = *reinterpret_cast<const float2*>(sBias + ch + 2 * jj);
+          const float* c = acc[ng * 4 + jj];
+          float2 y0 = silu2(__ffma2_rn(__half22float2(h0[jj]), cA, cB));
+          float2 y1 = silu2(__ffma2_rn(__half22float2(h1[jj]), cA, cB));
+          y0 = __fadd2_rn(y0, __fadd2_rn(make_float2(c[0], c[1]), bi));
+          y1 = __fadd2_rn(y1, __fadd2_rn(make_float2(c[2], c[3]), bi));
+          if (TAIL) {                       // final 1x1 conv: this lane's share of the two pixels' dot products
+            const float2 fw = *reinterpret_cast<const float2*>(sG + ch + 2 * jj);
+            sum0 = fmaf(y0.y, fw.y, fmaf(y0.x, fw.x, sum0));
+            sum1 = fmaf(y1.y, fw.y, fmaf(y1.x, fw.x, sum1));
+            continue;
+          }
+          const __half2 q0 = __floats2half2_rn(y0.x, y0.y), q1 = __floats2half2_rn(y1.x, y1.y);
+          o0[jj] = *reinterpret_cast<const uint32_t*>(&q0);
+          o1[jj] = *reinterpret_cast<const uint32_t*>(&q1);
+          if (LN) {
+            const float2 r0 = __half22float2(q0), r1 = __half22float2(q1);
+            pk0[(hf * 2 + ng) * 4 + jj] = o0[jj];
+            pk1[(hf * 2 + ng) * 4 + jj] = o1[jj];
+            sum0 += r0.x + r0.y;
+            sum1 += r1.x + r1.y;
+          }
+        }
+        if (TAIL) continue;
+        __half* dst = a.y + row0 * COUT + ch;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<uint4*>(dst + 8 * COUT) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+      }
     }
     if (TAIL) {
       sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
@@ -1087,8 +1098,10 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
       const float mean0 = sum0 * (1.f / COUT), mean1 = sum1 * (1.f / COUT);
       float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < NG * 4; ++j) {
-        const float d0 = acc[j][0] - mean0, d1 = acc[j][1] - mean0, d2 = acc[j][2] - mean1, d3 = acc[j][3] - mean1;
+      for (int i = 0; i < NH * 8; ++i) {
+        const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&pk0[i]));
+        const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&pk1[i]));
+        const float d0 = r0.x - mean0, d1 = r0.y - mean0, d2 = r1.x - mean1, d3 = r1.y - mean1;
         q0 = fmaf(d0, d0, q0); q0 = fmaf(d1, d1, q0);
         q1 = fmaf(d2, d2, q1); q1 = fmaf(d3, d3, q1);
       }
@@ -1096,15 +1109,16 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
       q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
       const float rs0 = rsqrtf(q0 * (1.f / COUT) + 1e-5f), rs1 = rsqrtf(q1 * (1.f / COUT) + 1e-5f);
 #pragma unroll
-      for (int ng = 0; ng < NG; ++ng) {
-        const int ch = ng * 32 + t * 8;
+      for (int gi = 0; gi < NH * 2; ++gi) {
+        const int ch = gi * 32 + t * 8;
         uint32_t o0[4], o1[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const float2 gn = *reinterpret_cast<const float2*>(sG + ch + 2 * jj);
-          const float* c = acc[ng * 4 + jj];
-          const __half2 l0 = __floats2half2_rn((c[0] - mean0) * rs0 * gn.x, (c[1] - mean0) * rs0 * gn.y);
-          const __half2 l1 = __floats2half2_rn((c[2] - mean1) * rs1 * gn.x, (c[3] - mean1) * rs1 * gn.y);
+          const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&pk0[gi * 4 + jj]));
+          const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&pk1[gi * 4 + jj]));
+          const __half2 l0 = __floats2half2_rn((r0.x - mean0) * rs0 * gn.x, (r0.y - mean0) * rs0 * gn.y);
+          const __half2 l1 = __floats2half2_rn((r1.x - mean1) * rs1 * gn.x, (r1.y - mean1) * rs1 * gn.y);
           o0[jj] = *reinterpret_cast<const uint32_t*>(&l0);
           o1[jj] = *reinterpret_cast<const uint32_t*>(&l1);
         }
@@ -1116,17 +1130,16 @@ k_res1x1_gn(ResGn a, TailParams tp, int total_blocks, int nblk) {
   }
 }
 
-// (the 192 -> 128 instantiation exists and is correct, but at 250 registers / 8 warps per SM it measured
-// 160 us against 68 + 79 us for the two-pass form at 128-pixel rows, so the planner only asks for 128 -> 64)
 bool res1x1_gn_supported(int cout, int c0, int c1, int HW) {
-  return HW % 128 == 0 && c0 % 32 == 0 && c1 % 32 == 0 && cout == 64 && c0 + c1 == 128;
+  return HW % 128 == 0 && c0 % 32 == 0 && c1 % 32 == 0 &&
+         ((cout == 64 && c0 + c1 == 128) || (cout == 128 && c0 + c1 == 192));
 }
 
 template <int COUT, int CIN>
 static int res1x1_gn_launch(const ResGn& a, const TailParams* tail, int B, cudaStream_t s) {
   const int nblk = a.HW / 128, total = nblk * B;
   const size_t smem = (size_t)COUT * (CIN * 2 + 64) + COUT * 4 * sizeof(float);
-  int grid = num_sms() * (COUT == 64 ? 2 : 1);          // one resident wave
+  int grid = num_sms() * 2;                             // one resident wave
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
   const TailParams tp = tail ? *tail : TailParams{};
