@@ -284,7 +284,11 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             // halo mode: tap (dy, dx) goes to block dx*3 + (2 - dy), so that for one dx the taps
             // dy = 2, 1, 0 are one contiguous N = 192 B operand
             const int wtap = kb / chunks, wcc = kb - wtap * chunks;   // halo: per source, per dx, dy = 2, 1, 0
-            const int blk = p_halo ? wcc * 9 + (wtap % 3) * 3 + (2 - wtap / 3) : nt * num_kb + kb;
+            // rows3: only the ky, kx in {0, 1} taps are non-zero and ever read; they are kept compactly
+            // ([source][dx = 0, 1][dy = 1, 0]: 64 KB instead of 147 KB, which buys nine ring slots instead of four)
+            if (cls_bind && (wtap % 3 == 2 || wtap / 3 == 2)) continue;
+            const int blk = cls_bind ? wcc * 4 + (wtap % 3) * 2 + (1 - wtap / 3)
+                          : p_halo ? wcc * 9 + (wtap % 3) * 3 + (2 - wtap / 3) : nt * num_kb + kb;
             tma_load_3d(&tmB, &ctl->wfull, sW + (size_t)blk * kBBytes, (cls_b * num_kb + kb) * kBlockK, nt * BN, 0);
           }
       }
@@ -436,7 +440,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           // (N = 128 instead of 192; the last row of a segment feeds nothing)
           const int j_lo = max(ri - (cls_bind ? 1 : 2), 0), j_hi = min(ri, nr - 1);
           const uint32_t row_lo = (sA_u + (uint32_t)stage * P.a_slot) >> 4;
-          const uint32_t w_lo = (sW_u >> 4) + (uint32_t)(src * 9) * (kBBytes >> 4);   // this source's taps
+          const uint32_t w_lo = (sW_u >> 4) + (uint32_t)(src * (cls_bind ? 4 : 9)) * (kBBytes >> 4);   // this source's taps
           const bool last_src = (src == p_nsrc - 1);
           if (elect_one()) {
             // Descriptors of step s = dx*4 + k: A = row + 2*s (dx*128 B + k*32 B, in 16-byte
@@ -447,7 +451,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             const uint32_t sa = (tcount + (uint32_t)j_lo) & 7u;      // TMEM slot of the first target
             const int cnt = j_hi - j_lo + 1;
             const int c1 = min(cnt, 8 - (int)sa);                    // targets before the slot ring wraps
-            const uint64_t db0 = desc_hi | (uint64_t)(w_lo + (uint32_t)(2 - ri + j_lo) * kBlk);
+            const uint32_t dxs_blk = cls_bind ? 2u : 3u;             // weight blocks per dx (rows3: dy = 1, 0 only)
+            const uint64_t db0 = desc_hi | (uint64_t)(w_lo + (uint32_t)((cls_bind ? 1 : 2) - ri + j_lo) * kBlk);
             const uint32_t d0 = taddr_u + sa * 64u;
             // step 0: targets that already hold a partial sum accumulate, the new one (j = ri, first
             // source only) overwrites its slot
@@ -471,7 +476,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
               for (int s = 1; s < 12; ++s)
                 if (s < smax)
-                  umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + (uint64_t)((s >> 2) * 3 * kBlk + (s & 3) * 2),
+                  umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + (uint64_t)((s >> 2) * dxs_blk * kBlk + (s & 3) * 2),
                            id, 1u);
             } else {
               const uint32_t id1 = idesc0 | ((uint32_t)(c1 * 8) << 17);
@@ -480,7 +485,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
               for (int s = 1; s < 12; ++s) {
                 if (s >= smax) break;
-                const uint64_t bo = (uint64_t)((s >> 2) * 3 * kBlk + (s & 3) * 2);
+                const uint64_t bo = (uint64_t)((s >> 2) * dxs_blk * kBlk + (s & 3) * 2);
                 umma_f16(d0, da0 + (uint64_t)(2 * s), db0 + bo, id1, 1u);
                 umma_f16(taddr_u, da0 + (uint64_t)(2 * s), db1 + bo, id2, 1u);
               }
@@ -1395,7 +1400,8 @@ static int conv2_plan(Conv2Launch* L, int epi, int B, const ActSrc& s0_in, const
   const int fixed = stage_out + kCtlBytes + 1024;
 
   // ---- mode selection
-  const long long w_all = (long long)P.n_tiles * P.num_kb * b_bytes;   // all weights of one class
+  // all weights of one class (rows3: the 2 x 2 non-zero taps of the two sources only)
+  const long long w_all = rows3 ? 8ll * b_bytes : (long long)P.n_tiles * P.num_kb * b_bytes;
   P.halo = 0;
   P.wres = 0;
   const bool halo_ok = !w_batched && classes == 1 && mode == 0 && ksize == 3 && s1 == nullptr &&
