@@ -154,7 +154,7 @@ __device__ __forceinline__ float silu_tanh(float t) {
   return fmaf(h, th, h);
 }
 
-template <int BN, int EPI, int CG = 1, int XF = 0>
+template <int BN, int EPI, int CG = 1, int XF = 0, int R3 = 0>
 __global__ void __launch_bounds__(kThreads + XF * kXfThreads, 1)
 k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
@@ -165,8 +165,8 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   // the input-transform kernel is always the single-source row-streaming form with resident weights and staged
   // stores: as compile-time constants these remove every other mode from that instantiation (it sits at its
   // register cap)
-  const int p_halo = XF ? 1 : P.halo, p_nsrc = XF ? 1 : P.nsrc, p_wres = XF ? 1 : P.wres;
-  const int p_pair = XF ? 0 : P.pair, p_direct = XF ? 0 : P.direct_store;
+  const int p_halo = (XF || R3) ? 1 : P.halo, p_nsrc = XF ? 1 : R3 ? 2 : P.nsrc, p_wres = (XF || R3) ? 1 : P.wres;
+  const int p_pair = (XF || R3) ? 0 : P.pair, p_direct = XF ? 0 : R3 ? 1 : P.direct_store;
   constexpr int kBBytes = (BN / CG) * kBlockK * 2;   // B rows this CTA stages per K block
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int item0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // per-tap item walk
@@ -174,9 +174,11 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   // row-streaming segment walk; with cls_bind the grid is four interleaved groups, one per parity class
   // (compile-time gates: the code of the two special modes exists only in the instantiations that can run them --
   // the input-transform kernel sits at its register cap and lost 15 % when unrelated paths grew)
-  constexpr bool kRows3 = (BN == 64 && EPI == EPI_BIAS && CG == 1 && XF == 0);
+  constexpr bool kRows3 = (R3 == 1);      // its own instantiation: step counts / weight strides stay compile-time
+                                          // constants, so the MMA descriptors are base + constant (no dependent math)
   constexpr bool kDxs = (BN == 128 && CG == 1 && XF == 0);
-  const bool cls_bind = kRows3 && P.cls_bind;
+  constexpr bool cls_bind = kRows3;
+  // (R3 also fixes the launch shape: two-source row streaming, resident weights, direct stores)
   const int cls_b = cls_bind ? (int)(blockIdx.x & 3u) : 0;
   const int seg0 = cls_bind ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
   const int sstep = cls_bind ? (int)(gridDim.x >> 2) : (int)gridDim.x;
@@ -1557,6 +1559,19 @@ static int launch2(const Conv2Launch& L, cudaStream_t stream) {
   return PRG_OK;
 }
 
+static int launch2_rows3(const Conv2Launch& L, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < L.smem) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_conv2<64, EPI_BIAS, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemBudget));
+    configured = kSmemBudget;
+  }
+  PRG_CUDA_OK(launch_pdl(k_conv2<64, EPI_BIAS, 1, 0, 1>, dim3(L.grid), dim3(kThreads), L.smem, stream, L.tmA0, L.tmA1,
+                         L.tmB, L.tmO[0], L.tmO[1], L.tmO[2], L.tmO[3], L.P));
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
 template <int BN, int EPI>
 static int launch2_xf(const Conv2Launch& L, cudaStream_t stream) {
   static int configured = 0;
@@ -1601,6 +1616,11 @@ static int launch2_pair(const Conv2Launch& L, cudaStream_t stream) {
 }
 
 static int conv2_run(const Conv2Launch& L, cudaStream_t stream) {
+  if (L.P.cls_bind) {
+    if (L.bn == 64 && L.epi == EPI_BIAS && L.P.halo && L.P.nsrc == 2 && L.P.direct_store) return launch2_rows3(L, stream);
+    set_error("conv_run: class-bound plan without its kernel");
+    return PRG_ERR_ARG;
+  }
   if (L.xf) {
     if (L.bn == 64 && L.epi == EPI_GN && L.P.halo && L.P.nsrc == 1) return launch2_xf<64, EPI_GN>(L, stream);
     set_error("conv_run: the input transform exists for the row-streaming N = 64 EPI_GN kernel only");
