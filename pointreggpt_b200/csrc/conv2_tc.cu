@@ -165,6 +165,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   // the input-transform kernel is always the single-source row-streaming form with resident weights and staged
   // stores: as compile-time constants these remove every other mode from that instantiation (it sits at its
   // register cap)
+  // (R3 = 2: the two-source row-streaming conv with the launch shape fixed in the same way, rows3 code excluded)
   const int p_halo = (XF || R3) ? 1 : P.halo, p_nsrc = XF ? 1 : R3 ? 2 : P.nsrc, p_wres = (XF || R3) ? 1 : P.wres;
   const int p_pair = (XF || R3) ? 0 : P.pair, p_direct = XF ? 0 : R3 ? 1 : P.direct_store;
   constexpr int kBBytes = (BN / CG) * kBlockK * 2;   // B rows this CTA stages per K block
@@ -1559,6 +1560,19 @@ static int launch2(const Conv2Launch& L, cudaStream_t stream) {
   return PRG_OK;
 }
 
+template <int EPI>
+static int launch2_two_source(const Conv2Launch& L, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < L.smem) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_conv2<64, EPI, 1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = kSmemBudget;
+  }
+  PRG_CUDA_OK(launch_pdl(k_conv2<64, EPI, 1, 0, 2>, dim3(L.grid), dim3(kThreads), L.smem, stream, L.tmA0, L.tmA1,
+                         L.tmB, L.tmO[0], L.tmO[1], L.tmO[2], L.tmO[3], L.P));
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
 static int launch2_rows3(const Conv2Launch& L, cudaStream_t stream) {
   static int configured = 0;
   if (configured < L.smem) {
@@ -1620,6 +1634,10 @@ static int conv2_run(const Conv2Launch& L, cudaStream_t stream) {
     if (L.bn == 64 && L.epi == EPI_BIAS && L.P.halo && L.P.nsrc == 2 && L.P.direct_store) return launch2_rows3(L, stream);
     set_error("conv_run: class-bound plan without its kernel");
     return PRG_ERR_ARG;
+  }
+  if (L.bn == 64 && L.P.halo && L.P.nsrc == 2 && L.P.direct_store && L.P.wres && !L.xf) {
+    if (L.epi == EPI_GN) return launch2_two_source<EPI_GN>(L, stream);
+    if (L.epi == EPI_BIAS) return launch2_two_source<EPI_BIAS>(L, stream);
   }
   if (L.xf) {
     if (L.bn == 64 && L.epi == EPI_GN && L.P.halo && L.P.nsrc == 1) return launch2_xf<64, EPI_GN>(L, stream);
