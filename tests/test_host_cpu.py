@@ -69,6 +69,19 @@ def test_packing_layouts():
                     patch = xp[:, :, 1 + dy:1 + dy + 6, 1 + dx:1 + dx + 6]
                     out[:, :, py::2, px::2] += torch.einsum("oc,bchw->bohw", f[:, py * 2 + px, ty * 2 + tx], patch)
     assert torch.allclose(out, ref, atol=1e-5)
+    # the same once more as the class-bound row-streaming kernel sees it (conv2_tc.cu, rows3): per parity class a
+    # plain 3x3 conv (pad 1) whose ky = 2 / kx = 2 taps are zero, on the input shifted by (py, px)
+    r3 = packing.upsample_rows3_weight(w).reshape(5, 4, 3, 3, 3)          # [co][class][ky][kx][ci]
+    assert torch.count_nonzero(r3[:, :, 2]) == 0 and torch.count_nonzero(r3[:, :, :, 2]) == 0
+    out3 = torch.zeros_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            # out[y][x] = sum w[ky][kx] in[y + ky - 1 + py][x + kx - 1 + px], zero outside the image (TMA fill)
+            xq = torch.nn.functional.pad(x, (1, 2, 1, 2))
+            window = xq[:, :, py:py + 8, px:px + 8]
+            wk = r3[:, py * 2 + px].permute(0, 3, 1, 2).contiguous()      # (co, ci, ky, kx)
+            out3[:, :, py::2, px::2] = torch.nn.functional.conv2d(window, wk)
+    assert torch.allclose(out3, ref, atol=1e-5)
     ws = packing.standardize(w)
     assert torch.allclose(ws, R.standardize_weight(w))
 
