@@ -375,3 +375,58 @@ def test_default_sampling_stays_on_the_fused_device_loop(monkeypatch):
     calls.clear()
     d.sample(param_cond=pc, img_cond=ic)
     assert calls == [(6, False, False, 3)]
+
+
+def test_res1x1_gn_fragment_permutation_is_a_gemm():
+    """k_res1x1_gn (elementwise.cu) feeds mma.sync.m16n8k16 straight from global memory by permuting the k
+    index of the MMA and the n index of an n-tile so that every lane touches 16 contiguous bytes of a pixel
+    row.  This restates the kernel's lane -> element assignment against the PTX fragment layout and checks
+    that the accumulators the lanes end up with are the plain GEMM y[px][co] = sum_ci x[px][ci] w[co][ci],
+    with lane (g, t) holding channels 8t .. 8t+7 of rows g and g + 8 of each 32-channel group."""
+    rng = np.random.default_rng(0)
+    cin, cout = 128, 64
+    x = rng.integers(-3, 4, (16, cin)).astype(np.float64)        # 16 pixels of one warp tile
+    w = rng.integers(-3, 4, (cout, cin)).astype(np.float64)
+    want = x @ w.T
+
+    def mma(a_frag, b_frag):
+        """m16n8k16 from per-lane fragments: a_frag[lane] = 8 values (a0.lo, a0.hi, a1.., a2.., a3..),
+        b_frag[lane] = 4 values (b0.lo, b0.hi, b1.lo, b1.hi) -> c[lane] = (c0, c1, c2, c3)."""
+        A = np.zeros((16, 16)); B = np.zeros((16, 8))
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            for e in range(2):
+                A[g, 2 * t + e] = a_frag[lane][0 + e]            # a0: row g,     k 2t, 2t+1
+                A[g + 8, 2 * t + e] = a_frag[lane][2 + e]        # a1: row g + 8, k 2t, 2t+1
+                A[g, 2 * t + 8 + e] = a_frag[lane][4 + e]        # a2: row g,     k 2t+8, 2t+9
+                A[g + 8, 2 * t + 8 + e] = a_frag[lane][6 + e]    # a3: row g + 8, k 2t+8, 2t+9
+                B[2 * t + e, g] = b_frag[lane][0 + e]            # b0: k 2t, 2t+1,   n g
+                B[2 * t + 8 + e, g] = b_frag[lane][2 + e]        # b1: k 2t+8, 2t+9, n g
+        C = A @ B
+        return [(C[l >> 2, 2 * (l & 3)], C[l >> 2, 2 * (l & 3) + 1], C[(l >> 2) + 8, 2 * (l & 3)],
+                 C[(l >> 2) + 8, 2 * (l & 3) + 1]) for l in range(32)]
+
+    got = np.zeros((16, cout))
+    for ng in range(cout // 32):                                  # 32-channel output groups
+        for jj in range(4):                                       # n-tiles of the group
+            acc = [np.zeros(4) for _ in range(32)]
+            for kg in range(cin // 32):                           # 32-channel input groups
+                for s in range(2):                                # the two k-steps one LDG.128 / LDS.128 feeds
+                    a_frag, b_frag = [], []
+                    for lane in range(32):
+                        g, t = lane >> 2, lane & 3
+                        xa = x[g, 32 * kg + 8 * t:32 * kg + 8 * t + 8]          # the lane's 16 bytes of row g
+                        xb = x[g + 8, 32 * kg + 8 * t:32 * kg + 8 * t + 8]      # ... and of row g + 8
+                        # f0 = {xa.x, xb.x, xa.y, xb.y}, f1 = {xa.z, xb.z, xa.w, xb.w} (32-bit words = channel pairs)
+                        lo = 4 * s
+                        a_frag.append([xa[lo], xa[lo + 1], xb[lo], xb[lo + 1], xa[lo + 2], xa[lo + 3], xb[lo + 2], xb[lo + 3]])
+                        row = 32 * ng + 8 * (g >> 1) + 2 * jj + (g & 1)          # weight row of this lane's B fragment
+                        wv = w[row, 32 * kg + 8 * t:32 * kg + 8 * t + 8]
+                        b_frag.append([wv[lo], wv[lo + 1], wv[lo + 2], wv[lo + 3]])
+                    for lane, c in enumerate(mma(a_frag, b_frag)):
+                        acc[lane] += np.array(c)
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                ch = 32 * ng + 8 * t + 2 * jj                     # the epilogue's channel of acc[..][0] (and + 1)
+                got[g, ch], got[g, ch + 1], got[g + 8, ch], got[g + 8, ch + 1] = acc[lane]
+    assert np.array_equal(got, want)
