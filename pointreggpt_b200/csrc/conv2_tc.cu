@@ -166,8 +166,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
   // stores: as compile-time constants these remove every other mode from that instantiation (it sits at its
   // register cap)
   // (R3 = 2: the two-source row-streaming conv with the launch shape fixed in the same way, rows3 code excluded)
-  const int p_halo = (XF || R3) ? 1 : P.halo, p_nsrc = XF ? 1 : R3 ? 2 : P.nsrc, p_wres = (XF || R3) ? 1 : P.wres;
-  const int p_pair = (XF || R3) ? 0 : P.pair, p_direct = XF ? 0 : R3 ? 1 : P.direct_store;
+  // (R3 = 3: the single-source row-streaming conv, likewise)
+  const int p_halo = (XF || R3) ? 1 : P.halo, p_nsrc = (XF || R3 == 3) ? 1 : R3 ? 2 : P.nsrc, p_wres = (XF || R3) ? 1 : P.wres;
+  const int p_pair = (XF || R3) ? 0 : P.pair, p_direct = (XF || R3 == 3) ? 0 : R3 ? 1 : P.direct_store;
   constexpr int kBBytes = (BN / CG) * kBlockK * 2;   // B rows this CTA stages per K block
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int item0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // per-tap item walk
@@ -1561,6 +1562,19 @@ static int launch2(const Conv2Launch& L, cudaStream_t stream) {
 }
 
 template <int EPI>
+static int launch2_one_source(const Conv2Launch& L, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < L.smem) {
+    PRG_CUDA_OK(cudaFuncSetAttribute(k_conv2<64, EPI, 1, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = kSmemBudget;
+  }
+  PRG_CUDA_OK(launch_pdl(k_conv2<64, EPI, 1, 0, 3>, dim3(L.grid), dim3(kThreads), L.smem, stream, L.tmA0, L.tmA1,
+                         L.tmB, L.tmO[0], L.tmO[1], L.tmO[2], L.tmO[3], L.P));
+  PRG_LAUNCH_CHECK();
+  return PRG_OK;
+}
+
+template <int EPI>
 static int launch2_two_source(const Conv2Launch& L, cudaStream_t stream) {
   static int configured = 0;
   if (configured < L.smem) {
@@ -1638,6 +1652,10 @@ static int conv2_run(const Conv2Launch& L, cudaStream_t stream) {
   if (L.bn == 64 && L.P.halo && L.P.nsrc == 2 && L.P.direct_store && L.P.wres && !L.xf) {
     if (L.epi == EPI_GN) return launch2_two_source<EPI_GN>(L, stream);
     if (L.epi == EPI_BIAS) return launch2_two_source<EPI_BIAS>(L, stream);
+  }
+  if (L.bn == 64 && L.P.halo && L.P.nsrc == 1 && !L.P.direct_store && L.P.wres && !L.P.pair && !L.xf && L.cg == 1) {
+    if (L.epi == EPI_GN) return launch2_one_source<EPI_GN>(L, stream);
+    if (L.epi == EPI_BIAS) return launch2_one_source<EPI_BIAS>(L, stream);
   }
   if (L.xf) {
     if (L.bn == 64 && L.epi == EPI_GN && L.P.halo && L.P.nsrc == 1) return launch2_xf<64, EPI_GN>(L, stream);
