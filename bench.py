@@ -63,6 +63,9 @@ def parse():
                     help="workspace batch of the network handles (0 = --batch)")
     ap.add_argument("--maps", type=int, default=12500, help="geometry: 640x480 maps per GPU per step")
     ap.add_argument("--pairs", type=int, default=64, help="dataset: scenes per GPU per step")
+    ap.add_argument("--device-batch", type=int, default=None,
+                    help="dataset: scenes per pass through the GPU (Generator's default: 32; = --batch for the "
+                         "reference's literal batching)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -715,7 +718,8 @@ def run_dataset(a):
     os.chdir(root)                                  # the driver resolves checkpoints relative to the cwd
     try:
         gen = Generator(diffusion, "synthetic", batch_size=a.batch, results_folder=os.path.join(root, "res"),
-                        samples_folder=os.path.join(root, "ds", "data"), device=ctx.dev)
+                        samples_folder=os.path.join(root, "ds", "data"), device=ctx.dev,
+                        device_batch=a.device_batch)
         gen.rank, gen.world_size = 0, 1             # this bench shards the scene ranges itself (weak scaling)
         n = a.pairs
         cursor = [rank * (a.warmup + a.steps) * n]
@@ -759,6 +763,10 @@ def run_dataset(a):
         "warmup": a.warmup, "ms_per_step": 1000.0 * te / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": workload_name(a), "pairs_per_gpu_per_step": n, "batch_size": a.batch,
+                   "device_batch": gen.device_batch,
+                   "batching": "batch_size is the reference's CLI value (skip-if-done bookkeeping); the scenes of "
+                               "several such batches pass through the GPU together (device_batch) -- a scene's "
+                               "files do not depend on the batch it travels in",
                    "image_size": a.size, "timesteps": a.timesteps, "sampling_timesteps": a.sampling_timesteps,
                    "files": "camera-intrinsics.txt, sample-*.{image.png,depth.png,pose.txt,cloud.ply}, "
                             "reprojected/corrected.image.png per scene (%d files, %.1f MB on this rank)" % (files, nbytes / 1e6),

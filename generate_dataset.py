@@ -31,6 +31,8 @@ parser.add_argument('--random_init', action='store_true', help='seeded random we
 parser.add_argument('--seed', default=0, type=int, help='base seed of the per-scene pose / noise streams')
 parser.add_argument('--sampling_timesteps', default=250, type=int)
 parser.add_argument('--batch_size', default=4, type=int)
+parser.add_argument('--device_batch', default=None, type=int,
+                    help='scenes per pass through the GPU (default 32; results do not depend on it)')
 args = parser.parse_args()
 
 if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not torch.distributed.is_initialized():
@@ -51,7 +53,7 @@ elif os.path.isdir(args.data_root):
 else:
     raise FileNotFoundError("--data_root %r does not exist (use --synthetic for the synthetic source "
                             "frames)" % args.data_root)
-generator = Generator(diffusion, folder, batch_size=args.batch_size, ema_decay=0.995,
+generator = Generator(diffusion, folder, batch_size=args.batch_size, device_batch=args.device_batch, ema_decay=0.995,
                       results_folder='./successive_ddnm_diffusion_results',
                       samples_folder='./{}/data'.format(args.dataset_name), amp=False)
 depth_correction = MaskUnet(dim=64, dim_mults=(1, 2, 4, 8))

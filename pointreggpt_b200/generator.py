@@ -11,6 +11,9 @@ Differences, all forced by the offline environment or by the B200 design:
   * source frames come from the 3DMatch tree `folder`, or from the seeded synthetic generator when
     `folder == "synthetic"` (no dataset can be downloaded here); a missing tree is an error;
   * poses and sampler noise are keyed by (base_seed, scene, sample), see pointreggpt_b200.rng;
+  * `batch_size` keeps the reference's meaning for the skip-if-done bookkeeping, but the scenes of
+    several such batches run through the device together (`device_batch`, default 32): a scene's files
+    do not depend on the batch it travels in, and a B200 is at 60 % of its batch-32 throughput at batch 4;
   * files are written by a worker thread while the next batch runs on the GPU.
 """
 import copy
@@ -28,7 +31,7 @@ from . import cloud, dist as pdist, geometry, pipeline, rng, synthetic
 class Generator(object):
     def __init__(self, diffusion_model, folder, *, batch_size=16, ema_update_every=10,
                  ema_decay=0.995, results_folder='./results', samples_folder='./samples',
-                 amp=False, fp16=False, split_batches=True, device=None):
+                 amp=False, fp16=False, split_batches=True, device=None, device_batch=None):
         super().__init__()
         if amp or fp16:
             raise NotImplementedError("the reference runs generation with amp=False (GD:54); the "
@@ -44,6 +47,10 @@ class Generator(object):
         self.model = diffusion_model.to(self._device)
         self.channels = diffusion_model.channels
         self.batch_size = batch_size
+        # scenes per pass through the device (>= batch_size); PRG_DEVICE_BATCH overrides the default
+        if device_batch is None:
+            device_batch = int(os.environ.get("PRG_DEVICE_BATCH", "32"))
+        self.device_batch = max(int(device_batch), int(batch_size), 1)
         self.image_size = diffusion_model.image_size
         # ema_pytorch.EMA keeps an averaged copy as `ema_model`; generation samples from it
         # (SDD:2572).  Only the holder is needed here.
@@ -128,23 +135,30 @@ class Generator(object):
         done = 0
         writer = _Writer(dev)
         try:
+            # the reference's batches decide what is skipped (SDD:2371-2381: a batch is complete when the last
+            # sample of its last scene exists); the scenes of the remaining ones are coalesced
+            todo = []
             for b_idx, batch in enumerate(geometry.num_to_groups(hi - lo, self.batch_size)):
                 first = lo + b_idx * self.batch_size
                 last_ply = self.samples_folder / 'scene-{:0>6d}/sample-{:0>6d}.cloud.ply'.format(
                     first + batch - 1, num_samples // 2)
-                if os.path.isfile(last_ply):                                          # SDD:2371-2381
+                if os.path.isfile(last_ply):
                     print("Skip completed scene {:0>6d} - {:0>6d}.".format(first, first + batch - 1))
                     done += batch
                     continue
+                todo.extend(range(first, first + batch))
+            for g0 in range(0, len(todo), self.device_batch):
+                scenes = todo[g0:g0 + self.device_batch]
+                batch = len(scenes)
                 sdirs = []
                 depths, Ks = [], []
-                for s in range(batch):
-                    sdir = self.samples_folder / 'scene-{:0>6d}'.format(first + s)
+                for sc in scenes:
+                    sdir = self.samples_folder / 'scene-{:0>6d}'.format(sc)
                     if sdir.exists():
                         shutil.rmtree(str(sdir), ignore_errors=True)
                     sdir.mkdir(parents=True, exist_ok=True)
                     sdirs.append(sdir)
-                    d, K = self._source_frame(first + s, info_train)
+                    d, K = self._source_frame(sc, info_train)
                     depths.append(d)
                     Ks.append(K)
                 K_np = np.stack(Ks)
@@ -158,10 +172,10 @@ class Generator(object):
                 fragments = [None] * batch
                 frag_pose = [None] * batch
                 for sample_idx in range(num_samples):
-                    seeds = [rng.scene_seed(base_seed, first + s, sample_idx) for s in range(batch)]
+                    seeds = [rng.scene_seed(base_seed, sc, sample_idx) for sc in scenes]
                     pose_np = np.concatenate([
-                        geometry.random_sample_pose(1, rng=rng.scene_rng(base_seed, first + s, sample_idx))
-                        for s in range(batch)]).astype(np.float32)                    # SDD:2526
+                        geometry.random_sample_pose(1, rng=rng.scene_rng(base_seed, sc, sample_idx))
+                        for sc in scenes]).astype(np.float32)                         # SDD:2526
                     pose = torch.tensor(pose_np).pin_memory().to(dev, non_blocking=True)
                     if memory is None:
                         offsets = torch.arange(batch + 1, device=dev, dtype=torch.int64) * (S * S)

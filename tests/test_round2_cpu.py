@@ -195,7 +195,7 @@ def test_generate_dataset_cli_surface(tmp_path):
     r = run("--help")
     assert r.returncode == 0
     for flag in ("--resume", "--dataset_name", "--start_scene_index", "-start", "--stop_scene_index", "-stop",
-                 "--num_samples", "--synthetic", "--seed"):
+                 "--num_samples", "--synthetic", "--seed", "--batch_size", "--device_batch"):
         assert flag in r.stdout, flag
     r = run("--resume", "official", "--data_root", str(tmp_path / "missing"))
     assert r.returncode != 0 and "does not exist" in r.stderr

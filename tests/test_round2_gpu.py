@@ -113,9 +113,12 @@ def test_generated_scenes_do_not_depend_on_batching_or_range(tmp_path, monkeypat
     with torch.no_grad():
         mask.final_conv[0].bias.fill_(8.0)
     runs = {}
-    for tag, (start, stop, bs) in {"a": (5, 9, 2), "b": (6, 9, 3)}.items():
+    # a, b: the scenes of the reference's batches coalesced into one pass through the device (the default);
+    # d: the reference's literal batching (device_batch = batch_size)
+    for tag, (start, stop, bs, dbs) in {"a": (5, 9, 2, None), "b": (6, 9, 3, None), "d": (5, 9, 2, 2)}.items():
         gen = Generator(_diffusion(), "synthetic", batch_size=bs, results_folder=str(tmp_path / "res"),
-                        samples_folder=str(tmp_path / tag / "data"))
+                        samples_folder=str(tmp_path / tag / "data"), device_batch=dbs)
+        assert gen.device_batch == (32 if dbs is None else dbs)
         assert gen.generate(start, stop, num_samples=1, has_refine_step=False, depth_correction=mask,
                             base_seed=11) == stop - start
         runs[tag] = tmp_path / tag / "data"
@@ -124,7 +127,8 @@ def test_generated_scenes_do_not_depend_on_batching_or_range(tmp_path, monkeypat
                   "sample-000001.depth.png", "camera-intrinsics.txt"):
             a = (runs["a"] / ("scene-%06d" % idx) / f).read_bytes()
             b = (runs["b"] / ("scene-%06d" % idx) / f).read_bytes()
-            assert a == b, (idx, f)
+            d = (runs["d"] / ("scene-%06d" % idx) / f).read_bytes()
+            assert a == b and a == d, (idx, f)
     # and a different base seed gives a different pose
     p1 = np.loadtxt(str(runs["a"] / "scene-000006" / "sample-000001.pose.txt"))
     gen = Generator(_diffusion(), "synthetic", batch_size=2, results_folder=str(tmp_path / "res"),
