@@ -42,6 +42,30 @@ int main() {
     emu_overlap(q.data(), n, p.data(), n, 0.0375, ce, ws2.data(), 5);
     printf("n=%lld: %d voxels, %d overlapping points\n", n, voxels, ce[0]);
   }
+  // fused reprojection: exact-size heap buffers for depth, outputs and the ring; odd sizes exercise the
+  // partial chunk / partial sub-block paths, item sizes of one to three chunks
+  int rshapes[][3] = {{3,256,256},{2,480,640},{2,33,47},{1,5,7},{2,64,96},{1,1,1},{1,90,171},{2,121,127},{1,130,259}};
+  int trial = 0;
+  for (auto& s : rshapes) {
+    int B = s[0], H = s[1], W = s[2];
+    size_t n = (size_t)B * H * W;
+    for (int ring = 2; ring <= 4; ring += 2, ++trial) {
+      std::vector<float> d(n), o(n), K(B * 9, 0.f), P(B * 16, 0.f);
+      std::vector<uint8_t> m(n);
+      std::vector<unsigned> scratch((size_t)ring * H * W);
+      for (size_t i = 0; i < n; ++i) d[i] = (rng() % 7 == 0) ? 0.f : 0.5f + (rng() % 9000) * 0.001f;
+      for (int b = 0; b < B; ++b) {
+        K[b * 9 + 0] = 1.2f * W; K[b * 9 + 4] = 1.2f * W; K[b * 9 + 2] = 0.5f * W; K[b * 9 + 5] = 0.5f * H; K[b * 9 + 8] = 1.f;
+        for (int i = 0; i < 4; ++i) P[b * 16 + i * 5] = 1.f;
+        P[b * 16 + 3] = 0.05f * (b + 1); P[b * 16 + 7] = -0.03f; P[b * 16 + 11] = 0.1f;
+      }
+      emu_reproject(d.data(), K.data(), P.data(), 0.f, 10.f, o.data(), m.data(), scratch.data(), B, H, W, ring, 1 + trial % 3);
+      size_t hit = 0;
+      for (size_t i = 0; i < n; ++i) hit += m[i];
+      if (o[0] == -12345.f) { printf("reproject %dx%dx%d ring %d: ring not handed back empty\n", B, H, W, ring); return 1; }
+      printf("reproject %dx%dx%d ring %d item chunks %d: %zu pixels hit\n", B, H, W, ring, 1 + trial % 3, hit);
+    }
+  }
   puts("asan run complete");
   return 0;
 }
@@ -57,10 +81,13 @@ def main():
         return re.search(r"^" + name + r" = '''(.*?)'''", t, re.S | re.M).group(1)
 
     occ = g[g.index("constexpr int kOccRows"):g.index("// ------------------------------------------------------------------ point_cloud")]
+    geo = g[g.index("constexpr unsigned kEmpty"):g.index("// ------------------------------------------------------------------ occlusion_filter")]
+    geo = geo.replace("extern __shared__ int64_t s_off[];", "static int64_t s_off[4097];")
     vox = c[c.index("constexpr unsigned long long kVoxEmpty"):c.index("}  // namespace prg")]
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "emu.cpp")
-        open(src, "w").write('#include "cuda_shim.h"\n' + occ + driver("DRIVER") + vox + driver("VOX_DRIVER") + MAIN)
+        open(src, "w").write('#include "cuda_shim.h"\n' + geo + driver("GEOM_DRIVER") + occ + driver("DRIVER") + vox +
+                             driver("VOX_DRIVER") + MAIN)
         exe = os.path.join(d, "emu")
         subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
                                "-ffp-contract=off", "-I", os.path.join(ROOT, "tests", "emu"), "-o", exe, src])
