@@ -199,3 +199,52 @@ def test_generate_dataset_cli_surface(tmp_path):
         assert flag in r.stdout, flag
     r = run("--resume", "official", "--data_root", str(tmp_path / "missing"))
     assert r.returncode != 0 and "does not exist" in r.stderr
+
+
+def test_reprojection_ticket_protocol_is_deadlock_free_and_slot_safe():
+    """Model of k_reproject_fused's scheduling (geometry.cu, RpItem): tickets are claimed in increasing order by
+    whichever CTA is free; ticket p = (round k, item j) splats item j of map k (k < B) and finalises item j of map
+    k - D (k >= D); it may start once done[k - D] == items; a finished item bumps done[k].  With R = 2 D ring slots:
+    whatever the interleaving, every item runs, a slot is never splatted before its previous map is fully finalised
+    and never finalised before its own map is fully splatted."""
+    import random
+    for trial in range(200):
+        rnd = random.Random(trial)
+        B, items, D = rnd.randint(1, 9), rnd.randint(1, 5), rnd.randint(1, 4)
+        D = min(D, B)
+        R = 2 * D
+        total = (B + D) * items
+        ncta = rnd.randint(1, 7)
+        done = [0] * (B + D)
+        splat_left = {m: items for m in range(B)}      # items of map m still to splat
+        fin_left = {m: items for m in range(B)}        # items of map m still to finalise
+        next_ticket = 0
+        held = [None] * ncta                            # the ticket a CTA has claimed and not finished
+        finished = 0
+        steps = 0
+        while finished < total:
+            steps += 1
+            assert steps < 100000, "no progress: deadlock"
+            c = rnd.randrange(ncta)
+            if held[c] is None:
+                if next_ticket < total:
+                    held[c] = next_ticket
+                    next_ticket += 1
+                continue
+            k, j = divmod(held[c], items)
+            if k >= D and done[k - D] < items:
+                # blocked -- but then some smaller ticket is unfinished and runnable (checked globally below)
+                smaller = [h for h in held if h is not None and h < held[c]]
+                assert smaller or any(d < items for d in done[:k - D + 1])
+                continue
+            if k < B:                                   # splat half: slot k % R must be free of map k - R
+                assert k - R < 0 or fin_left[k - R] == 0, "slot reused before its map was finalised"
+                splat_left[k] -= 1
+            if k >= D:                                  # finalise half: map k - D fully splatted
+                assert splat_left[k - D] == 0, "finalised before every pixel was splatted"
+                fin_left[k - D] -= 1
+            done[k] += 1
+            held[c] = None
+            finished += 1
+        assert all(v == 0 for v in splat_left.values()) and all(v == 0 for v in fin_left.values())
+        assert all(d == items for d in done)
