@@ -710,15 +710,39 @@ k_ln_apply(const __half* __restrict__ x, const float* __restrict__ g,
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
     __half* dst = y + p * C + lane * PER;
+    if (PER >= 8) {
+      // 16-byte residual loads / stores (with 4-byte ones every warp store touched 32 sectors for 128 useful bytes)
 #pragma unroll
-    for (int j = 0; j < PER; j += 2) {
-      float o0 = (f[j] - mean) * rstd * gl[j], o1 = (f[j + 1] - mean) * rstd * gl[j + 1];
-      if (res != nullptr) {
-        const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(res + p * C + lane * PER + j));
-        o0 += r2.x;
-        o1 += r2.y;
+      for (int q = 0; q < PER / 8; ++q) {
+        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+        if (res != nullptr) rv = __ldg(reinterpret_cast<const uint4*>(res + p * C + lane * PER + q * 8));
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = (q * 8 + 2 * j) % PER;
+          float o0 = (f[c] - mean) * rstd * gl[c], o1 = (f[(c + 1) % PER] - mean) * rstd * gl[(c + 1) % PER];
+          if (res != nullptr) {
+            const float2 r2 = __half22float2(rh[j]);
+            o0 += r2.x;
+            o1 += r2.y;
+          }
+          const __half2 h = __floats2half2_rn(o0, o1);
+          o[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      *reinterpret_cast<__half2*>(dst + j) = __floats2half2_rn(o0, o1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < PER; j += 2) {
+        float o0 = (f[j] - mean) * rstd * gl[j], o1 = (f[j + 1] - mean) * rstd * gl[j + 1];
+        if (res != nullptr) {
+          const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(res + p * C + lane * PER + j));
+          o0 += r2.x;
+          o1 += r2.y;
+        }
+        *reinterpret_cast<__half2*>(dst + j) = __floats2half2_rn(o0, o1);
+      }
     }
   }
 }
