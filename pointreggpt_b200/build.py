@@ -18,6 +18,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
          "-DPRG_BUILDING"]
+# extra -D switches for diagnostic builds, e.g. PRG_BUILD_DEFINES="-DPRG_CONV_TRACE_BUILD" (tools/trace_conv.py)
+FLAGS += os.environ.get("PRG_BUILD_DEFINES", "").split()
 
 
 def _sources():

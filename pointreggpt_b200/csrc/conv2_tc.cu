@@ -162,6 +162,13 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         const __grid_constant__ CUtensorMap tmO3, const Conv2Params P) {
   pdl_trigger();
   const ConvParams& p = P.c;
+  // per-tile clock64 timeline of CTA 0 (tools/trace_conv.py): compiled in only with -DPRG_CONV_TRACE_BUILD, so the
+  // production kernels carry neither its tests nor its registers
+#ifdef PRG_CONV_TRACE_BUILD
+  long long* const p_trace = p_trace;
+#else
+  constexpr long long* p_trace = nullptr;
+#endif
   // the input-transform kernel is always the single-source row-streaming form with resident weights and staged
   // stores: as compile-time constants these remove every other mode from that instantiation (it sits at its
   // register cap)
@@ -306,7 +313,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           for (int r = 0; r < nr + 2; ++r) {
             for (int src = 0; src < p_nsrc; ++src) {
               mbar_wait(&ctl->empty[stage], phase ^ 1);
-              if (P.trace != nullptr && blockIdx.x == 0 && dbg_row < 96) P.trace[512 + 2 * dbg_row] = clock64();
+              if (p_trace != nullptr && blockIdx.x == 0 && dbg_row < 96) p_trace[512 + 2 * dbg_row] = clock64();
               ++dbg_row;
               mbar_arrive_expect_tx(&ctl->full[stage], kHaloBytes);
               tma_load_4d(src == 0 ? &tmA0 : &tmA1, &ctl->full[stage], sA + (size_t)stage * P.a_slot, 0,
@@ -437,9 +444,9 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             mbar_wait(&ctl->tmem_empty[tn & 7u], ((tn >> 3) & 1u) ^ 1u);
           }
           tc_fence_after();
-          const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0 && ri >= 2 && src == 0 &&
+          const bool tr = p_trace != nullptr && blockIdx.x == 0 && lane == 0 && ri >= 2 && src == 0 &&
                           tcount + (uint32_t)ri - 2u < 64u;
-          if (tr) P.trace[(tcount + ri - 2) * 8 + 0] = clock64();   // last input row + slot ready
+          if (tr) p_trace[(tcount + ri - 2) * 8 + 0] = clock64();   // last input row + slot ready
           // rows3: the dy = 2 taps are zero as well, so row ri only feeds the output rows ri - 1 and ri
           // (N = 128 instead of 192; the last row of a segment feeds nothing)
           const int j_lo = max(ri - (cls_bind ? 1 : 2), 0), j_hi = min(ri, nr - 1);
@@ -498,7 +505,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
             if (ri >= 2 && last_src) umma_commit(&ctl->tmem_full[(tcount + (uint32_t)(ri - 2)) & 7u]);
           }
           __syncwarp();
-          if (tr) P.trace[(tcount + ri - 2) * 8 + 2] = clock64();   // row's MMAs issued
+          if (tr) p_trace[(tcount + ri - 2) * 8 + 2] = clock64();   // row's MMAs issued
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
          }
         }
@@ -710,12 +717,12 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
         else if (kOutBufs == 2) bulk_wait_read1();
         else bulk_wait_read0();
       }
-      const bool tr = P.trace != nullptr && blockIdx.x == 0 && e == 0 && tcount < 64;
+      const bool tr = p_trace != nullptr && blockIdx.x == 0 && e == 0 && tcount < 64;
       epi_bar();
-      if (tr) P.trace[tcount * 8 + 4] = clock64();       // all epilogue warps arrived
+      if (tr) p_trace[tcount * 8 + 4] = clock64();       // all epilogue warps arrived
       mbar_wait(&ctl->tmem_full[acc], (tcount >> acc_log2) & 1);
       tc_fence_after();
-      if (tr) P.trace[tcount * 8 + 5] = clock64();       // accumulator complete
+      if (tr) p_trace[tcount * 8 + 5] = clock64();       // accumulator complete
       const uint32_t trow = taddr + ((acc * BN) << p_pair) + (uint32_t)(sub * BN) +
                             ((uint32_t)(quarter * 32) << 16);
       const float* sbias = ctl->bias + n0;
@@ -919,7 +926,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           bulk_commit();
         }
       }
-      if (tr) P.trace[tcount * 8 + 6] = clock64();       // accumulator drained
+      if (tr) p_trace[tcount * 8 + 6] = clock64();       // accumulator drained
       if (EPI == EPI_GN) {
         // one 64-bit fixed-point atomic per (group, moment) of this tile: order-independent.
         // Slots were each written exactly once above; summed here in a fixed order.
@@ -937,7 +944,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
                     (unsigned long long)__float2ll_rn(v * (float)kStatScale));
         }
       }
-      if (tr) P.trace[tcount * 8 + 7] = clock64();       // tile done
+      if (tr) p_trace[tcount * 8 + 7] = clock64();       // tile done
       if (EPI == EPI_QKV) {
         if (qkv_part == 1 && p.colmax != nullptr && e < 128) {
           atomicMax(&p.colmax[img * 128 + e], ctl->colmax[e]);
@@ -970,11 +977,11 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
 #pragma unroll
         for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q);
       }
-      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 2 + 4 * grp && lane == 0 && tcount < 64;
-      if (tr) P.trace[tcount * 8 + 4] = clock64();
+      const bool tr = p_trace != nullptr && blockIdx.x == 0 && warp == 2 + 4 * grp && lane == 0 && tcount < 64;
+      if (tr) p_trace[tcount * 8 + 4] = clock64();
       mbar_wait(&ctl->tmem_full[acc], (tcount >> acc_log2) & 1);
       tc_fence_after();
-      if (tr) P.trace[tcount * 8 + 5] = clock64();       // accumulator complete
+      if (tr) p_trace[tcount * 8 + 5] = clock64();       // accumulator complete
       const uint32_t trow = taddr + acc * BN + ((uint32_t)(quarter * 32) << 16);
       uint32_t v0[32], v1[32];
       tmem_ld32(trow, v0);
@@ -982,7 +989,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&ctl->tmem_empty[acc]);                // accumulator back to the MMA warp
-      if (tr) P.trace[tcount * 8 + 6] = clock64();       // accumulator drained
+      if (tr) p_trace[tcount * 8 + 6] = clock64();       // accumulator drained
       float f[64];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -1131,7 +1138,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           o.w = *reinterpret_cast<uint32_t*>(&h3);
           gdst[q] = o;
         }
-        if (tr) P.trace[tcount * 8 + 7] = clock64();
+        if (tr) p_trace[tcount * 8 + 7] = clock64();
         ++tcount;
         return;
       }
@@ -1180,7 +1187,7 @@ k_conv2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtens
           tma_store_4d(&tmO1, slab + 8 * 4096, 0, x0 + (px & (tile_w - 1)), y0 + (px >> p.tile_w_log2), img);
         bulk_commit();
       }
-      if (tr) P.trace[tcount * 8 + 7] = clock64();       // tile done
+      if (tr) p_trace[tcount * 8 + 7] = clock64();       // tile done
       ++tcount;
     };
 

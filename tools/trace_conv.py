@@ -1,3 +1,7 @@
+"""Per-tile clock64 timeline of CTA 0 of the row-streaming conv (prg_test_conv_f16 with PRG_CONV_TRACE=1).
+The trace stamps are compiled in only when the library was built with
+    PRG_BUILD_DEFINES="-DPRG_CONV_TRACE_BUILD" python -m pointreggpt_b200.build --force
+(the production kernels carry neither the tests nor the registers of the instrumentation)."""
 import os, sys
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
 import torch
