@@ -465,6 +465,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
        const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
        const QParams P) {
+  // per-tile clock64 timeline of CTA 0 (tools/trace_qout.py): compiled in only with -DPRG_QOUT_TRACE_BUILD
+#ifdef PRG_QOUT_TRACE_BUILD
+  long long* const p_trace = P.trace;
+#else
+  constexpr long long* p_trace = nullptr;
+#endif
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -572,7 +578,7 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
         const int b = i & 1;
         mbar_wait(&ctl->dq_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < 48) P.trace[i * 16 + 5] = clock64();
+        if (p_trace != nullptr && blockIdx.x == 0 && lane == 0 && i < 48) p_trace[i * 16 + 5] = clock64();
         const uint32_t dq = taddr_u + (uint32_t)(b * 128);
         for (int kb = 0; kb < P.num_kb; ++kb) {
           mbar_wait(&ctl->full[stage], phase);
@@ -612,11 +618,11 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
           cur_img = img;
         }
         const int bj = ring_b(j);
-        if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && j < 48) P.trace[j * 16 + 6] = clock64();
+        if (p_trace != nullptr && blockIdx.x == 0 && lane == 0 && j < 48) p_trace[j * 16 + 6] = clock64();
         mbar_wait(&ctl->q_ready[bj], ring_par(j));
         mbar_wait(&ctl->do_empty[bj], ring_par(j) ^ 1u);
         tc_fence_after();
-        if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && j < 48) P.trace[j * 16 + 7] = clock64();
+        if (p_trace != nullptr && blockIdx.x == 0 && lane == 0 && j < 48) p_trace[j * 16 + 7] = clock64();
         if (elect_one()) {
           const uint32_t dout = taddr_u + 256u + (uint32_t)(bj * C);
           const uint64_t dq_ = desc_hi | (uint64_t)((sQ_u + (uint32_t)bj * 32768u) >> 4);
@@ -651,14 +657,14 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
 
     auto softmax_tile = [&](int i) {
       const int b = i & 1;
-      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 48;
-      if (tr) P.trace[i * 16 + 0] = clock64();
+      const bool tr = p_trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 48;
+      if (tr) p_trace[i * 16 + 0] = clock64();
       mbar_wait(&ctl->dq_full[b], (uint32_t)(i >> 1) & 1u);
-      if (tr) P.trace[i * 16 + 1] = clock64();
+      if (tr) p_trace[i * 16 + 1] = clock64();
       const int bq = ring_b(i);
       if (i >= NB) mbar_wait(&ctl->q_free[bq], ring_par(i - NB));   // MMA2(i - NB) has read this Q tile
       tc_fence_after();
-      if (tr) P.trace[i * 16 + 2] = clock64();
+      if (tr) p_trace[i * 16 + 2] = clock64();
       uint8_t* qrow = sQ + (size_t)bq * 32768 + (size_t)hh * 16384 + (size_t)row * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {                // one head per 32-column chunk
@@ -701,10 +707,10 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
           *reinterpret_cast<uint4*>(qrow + (((c * 4 + q) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
-      if (tr) P.trace[i * 16 + 3] = clock64();
+      if (tr) p_trace[i * 16 + 3] = clock64();
       fence_proxy_async();
       mbar_arrive(&ctl->q_ready[bq]);
-      if (tr) P.trace[i * 16 + 4] = clock64();
+      if (tr) p_trace[i * 16 + 4] = clock64();
     };
 
     // residual row of tile i (this warp's channel half): fetched one softmax phase ahead of its use
@@ -725,11 +731,11 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
       const uint32_t dout = taddr + 256u + (uint32_t)(bo * C + hh * CH) + lane_off;
       const float* cb = sbias + hh * CH;
       const float* cg = sgain + hh * CH;
-      const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 48;
-      if (tr) P.trace[i * 16 + 8] = clock64();
+      const bool tr = p_trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 48;
+      if (tr) p_trace[i * 16 + 8] = clock64();
       mbar_wait(&ctl->do_full[bo], ring_par(i));
       tc_fence_after();
-      if (tr) P.trace[i * 16 + 9] = clock64();
+      if (tr) p_trace[i * 16 + 9] = clock64();
       // one sweep: S = sum x and Q = sum (x - a)^2 over this warp's channels (x = acc + bias, a = its
       // first value), exchanged with the partner warp and combined exactly:
       //   sum_h (x - mean)^2 = Q_h - 2 (mean - a_h) (S_h - n a_h) + n (mean - a_h)^2
@@ -765,7 +771,7 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
       }
       if (hh == 0 && lane == 0) bulk_wait_read0_();   // the slab's previous TMA store has read it
       pair_bar();
-      if (tr) P.trace[i * 16 + 10] = clock64();
+      if (tr) p_trace[i * 16 + 10] = clock64();
       float mean, rstd;
       {
         const float s0 = xch[lane], q0 = xch[32 + lane], a0 = xch[64 + lane];
@@ -776,7 +782,7 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
                          (q1 - 2.f * e1 * (s1 - CH * a1) + CH * e1 * e1);
         rstd = rsqrtf(fmaxf(m2, 0.f) * (1.f / C) + 1e-5f);
       }
-      if (tr) P.trace[i * 16 + 11] = clock64();
+      if (tr) p_trace[i * 16 + 11] = clock64();
       // normalise + gain + residual -> slab (this warp's channel half of each pixel row)
 #pragma unroll 1
       for (int c = 0; c < CH; c += 32) {
@@ -817,10 +823,10 @@ k_qout(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensor
           for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rp + c + 32) + q);
         }
       }
-      if (tr) P.trace[i * 16 + 12] = clock64();
+      if (tr) p_trace[i * 16 + 12] = clock64();
       fence_proxy_async();
       pair_bar();
-      if (tr) P.trace[i * 16 + 13] = clock64();
+      if (tr) p_trace[i * 16 + 13] = clock64();
       if (hh == 0 && lane == 0) {
         const int px = quarter * 32;
 #pragma unroll

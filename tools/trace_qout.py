@@ -1,5 +1,6 @@
 """Timeline of CTA 0 of the fused q/to_out kernel (PRG_QOUT_TRACE): one U-Net evaluation, the
-first C=64 LinearAttention prints its per-tile clock stamps to stderr."""
+first C=64 LinearAttention prints its per-tile clock stamps to stderr.  The stamps are compiled in only when
+the library was built with PRG_BUILD_DEFINES="-DPRG_QOUT_TRACE_BUILD" python -m pointreggpt_b200.build --force."""
 import os
 import sys
 
